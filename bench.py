@@ -1,0 +1,324 @@
+#!/usr/bin/env python3
+"""bench.py -- XC build throughput (Mgridpts/s) and per-SCF-iteration V_xc time on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C5] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one DFT_ComputeXC call (one SCF iteration's E_xc + V_xc build, what dft.py:205-208
+times) on synthetic inputs of the named molecule shape: geometry from the reference's atom_txt,
+STO-3G, PySCF-level-3-sized synthetic grid, seeded idempotent density matrix.
+With N > 1 ranks the grid points are sharded (strong scaling: the molecule is fixed) and the
+nao x nao partial V_xc and E_xc are all-reduced with NCCL inside the call.
+
+One JSON line is printed by rank 0.  `value` is device-timed with the inputs resident in HBM;
+`e2e` is the same metric through the C ABI with HOST buffers for the per-iteration inputs/outputs
+(dft.py:200 uploads D, dft.py:211 downloads V_xc), copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "xc_build_mgridpts_per_s"
+UNIT = "Mgridpts/s"
+
+
+# --------------------------------------------------------------------------- helpers
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples = index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                p = [x.strip() for x in out.strip().split(",")]
+                if len(p) >= 6:
+                    self.samples.append(p)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "MEASURED_PEAKS.json (of measured)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback of B200_PROFILING.md (of fallback)"
+
+
+def cpu_port_baseline(hp, sample_points):
+    """PySCF-numint-shaped CPU port (oracle/numint_port.py) on a bounded sample of the same workload."""
+    from oracle import numint_port, oracle as O
+    n = min(sample_points, hp.ngrid)
+    idx = slice(0, n)
+    xc = {"LDA": 0, "GGA": 1, "B3LYP": 2}[hp.functional]
+    ao, grad = O.eval_ao(hp.coords[idx], hp.basis, deriv=1)
+    w = hp.weights[idx]
+    numint_port.nr_rks(xc, hp.dm, ao[: min(n, 4096)], w[: min(n, 4096)], grad[:, : min(n, 4096)])  # warm BLAS
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        numint_port.nr_rks(xc, hp.dm, ao, w, grad)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": n / best / 1e6, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"first {n} grid points of the workload, best of 3, numpy/OpenBLAS dgemm + OpenMP pointwise "
+                      f"(PySCF-numint-shaped restatement; PySCF itself is not installable here)",
+            "seconds": best}
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference_arm(args, rank, world):
+    """The reference's own implementation of the path.  Its implementation IS CUDA
+    (/root/reference/src/dft_solver.cu), compiled unmodified for sm_100a into oracle/_ref/dft_ref.so by
+    oracle/Makefile; it runs on the same B200 through its own C ABI on a bounded sample of the workload
+    (it materialises a full (ngrid,nao) B matrix and takes O(nao^2) uncoalesced work per point).  If the
+    prebuilt .so did not travel, the oracle's CPU port is timed on the host cores instead."""
+    if rank != 0:
+        return
+    import ctypes
+    from quantum_compute_dft_b200 import cuda_rt, workload
+    from quantum_compute_dft_b200.cuda_rt import DeviceArray
+    hp = workload.host_problem(args.workload, scale=args.scale)
+    cfg = {"workload": f"{args.workload}: {hp.name}", "ngrid": hp.ngrid, "nao": hp.nao, "basis": "sto-3g",
+           "grid": "synthetic level-3-sized", "parallelism": "1 GPU (reference is single-GPU)"}
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "dft_ref.so")
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg}
+    if os.path.exists(ref_so) and cuda_rt.device_count() > 0:
+        cuda_rt.set_device(0)
+        n = min(hp.ngrid, args.ref_sample)
+        solver = workload.make_solver(hp.functional)     # only used for DFT_EvalAO (input generation)
+        hp_s = workload.HostProblem(hp.name, hp.functional, hp.mol, hp.basis, hp.coords[:n], hp.weights[:n], hp.dm)
+        dp = workload.device_problem(hp_s, solver)
+        lib = ctypes.CDLL(ref_so)
+        lib.DFT_CreateSolver.argtypes = [ctypes.c_int]; lib.DFT_CreateSolver.restype = ctypes.c_void_p
+        lib.DFT_ComputeXC.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_uint64] * 5
+        lib.DFT_ComputeXC.restype = ctypes.c_double
+        s = lib.DFT_CreateSolver(workload.FUNCTIONAL_TYPE[hp.functional])
+        call = lambda: lib.DFT_ComputeXC(s, n, hp.nao, dp.d_dm.data.ptr, dp.d_ao.data.ptr,
+                                         dp.d_ao_grad.data.ptr if dp.d_ao_grad else 0, dp.d_weights.data.ptr,
+                                         dp.d_vxc.data.ptr)
+        for _ in range(max(1, args.warmup)):
+            call()
+        cuda_rt.synchronize()
+        e0, e1 = cuda_rt.Event(), cuda_rt.Event()
+        e0.record(0)
+        for _ in range(args.steps):
+            call()
+        e1.record(0)
+        e1.synchronize()
+        ms = e0.elapsed_ms(e1) / args.steps
+        val = n / (ms * 1e-3) / 1e6
+        line.update({"value": val, "ms_per_step": ms,
+                     "cpu_baseline": {"value": val, "unit": UNIT, "cores": 0, "kind": "reference",
+                                      "sample": f"reference CUDA (dft_solver.cu, unmodified, sm_100a) on the same B200, "
+                                                f"first {n} of {hp.ngrid} grid points per step"},
+                     "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    else:
+        cb = cpu_port_baseline(hp, args.cpu_sample)
+        cb["kind"] = "port"
+        line.update({"value": cb["value"], "ms_per_step": cb["seconds"] * 1e3, "cpu_baseline": cb,
+                     "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C5", help="C1..C5 (BASELINE.json configs); default C5 = B3LYP on "
+                    "C33H56N7O17P3S, the configuration the metric's target is quoted on")
+    ap.add_argument("--scale", type=float, default=1.0, help="grid size factor (1.0 = PySCF level-3 point counts)")
+    ap.add_argument("--cpu-sample", type=int, default=60000)
+    ap.add_argument("--ref-sample", type=int, default=65536)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 generic, 2 TMA")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    from quantum_compute_dft_b200 import cuda_rt, workload
+    if cuda_rt.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    cuda_rt.set_device(local_rank)
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist   # plumbing only: rendezvous, barrier, max-over-ranks
+        dist.init_process_group("gloo", init_method="env://")
+
+    hp = workload.host_problem(args.workload, scale=args.scale)
+    solver = workload.make_solver(hp.functional)
+    solver.set_option("path", args.path)
+    if world > 1:
+        ids = [solver.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        solver.comm_init(rank, world, ids[0])
+    dp = workload.device_problem(hp, solver, rank, world)
+    nao, n_local = dp.nao, dp.ngrid
+
+    def step():
+        return solver.compute_xc(n_local, nao, dp.d_dm, dp.d_ao, dp.d_weights, dp.d_vxc, dp.d_ao_grad)
+
+    def barrier():
+        cuda_rt.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # inputs per rank vs L2 (126 MB): flush explicitly when they could stay cache-resident
+    P = 1 if hp.functional == "LDA" else 4
+    input_bytes = 8.0 * n_local * P * nao
+    need_flush = input_bytes < 4 * 126e6
+    flush_buf = cuda_rt.DeviceArray((48 * 1024 * 1024,), np.float64) if need_flush else None  # 384 MB
+
+    for _ in range(args.warmup):
+        step()
+    e_xc = step()
+
+    # ---- device-timed region: K steps, CUDA events on the engine's stream
+    stream = solver.stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = cuda_rt.Event(), cuda_rt.Event()
+    dens_ms = vxc_ms = 0.0
+    barrier()
+    if not need_flush:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+            dens_ms += solver.stat("density_ms"); vxc_ms += solver.stat("vxc_ms")
+        ev1.record(stream)
+        ev1.synchronize()
+        total_ms = ev0.elapsed_ms(ev1)
+    else:
+        total_ms = 0.0
+        for _ in range(args.steps):
+            flush_buf.fill_zero()          # evict L2 (384 MB > 126 MB), outside the timed events
+            cuda_rt.synchronize()
+            ev0.record(stream)
+            step()
+            ev1.record(stream)
+            ev1.synchronize()
+            total_ms += ev0.elapsed_ms(ev1)
+            dens_ms += solver.stat("density_ms"); vxc_ms += solver.stat("vxc_ms")
+    barrier()
+
+    # ---- end-to-end region: host buffers for the per-iteration input (D) and outputs (V_xc, E_xc)
+    h_dm = cuda_rt.PinnedArray((nao, nao)); h_dm.array[...] = hp.dm
+    h_v = cuda_rt.PinnedArray((nao, nao))
+    nbytes = nao * nao * 8
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cuda_rt.memcpy_async(dp.d_dm.data.ptr, h_dm.ptr, nbytes, cuda_rt.H2D, stream)   # dft.py:200
+        e_host = step()                                                                  # dft.py:206 (returns E_xc)
+        cuda_rt.memcpy_async(h_v.ptr, dp.d_vxc.data.ptr, nbytes, cuda_rt.D2H, stream)   # dft.py:211
+        cuda_rt.stream_synchronize(stream)
+    cuda_rt.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    times = np.array([total_ms, e2e_ms, dens_ms, vxc_ms], dtype=np.float64)
+    if dist is not None:
+        import torch
+        t = torch.from_numpy(times)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times = t.numpy()
+    total_ms, e2e_ms, dens_ms, vxc_ms = (float(x) for x in times)
+
+    if rank == 0:
+        K = args.steps
+        ms_step = total_ms / K
+        value = hp.ngrid / (ms_step * 1e-3) / 1e6
+        e2e_value = hp.ngrid / (e2e_ms / K * 1e-3) / 1e6
+        peaks, peak_src = measured_peaks()
+        flops_local = workload.algorithmic_flops(n_local, nao)
+        dens_avg, vxc_avg = dens_ms / K, vxc_ms / K
+        tensor_bound = nao >= 100      # crossover of FP64-tensor and HBM rooflines near nao ~ 100
+        if tensor_bound:
+            dom, dom_ms = ("vxc_kernel", vxc_avg) if vxc_avg >= dens_avg else ("density_kernel", dens_avg)
+            dmma_peak = solver.lib.DFT_MicrobenchDMMA(4096)
+            dfma_peak = solver.lib.DFT_MicrobenchDFMA(4096)
+            achieved = 0.5 * flops_local / (dom_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
+                        "frac": achieved / dmma_peak if dmma_peak > 0 else None, "traffic": None,
+                        "peak_source": "DFT_MicrobenchDMMA measured in this run (register-resident mma.sync m8n8k4 f64 "
+                                       "-> DMMA); MEASURED_PEAKS.json has no FP64 entry; nominal 37-40 TFLOP/s",
+                        "dfma_peak_tflops": dfma_peak,
+                        "whole_call_tflops": flops_local / (ms_step * 1e-3) / 1e12,
+                        "density_ms": dens_avg, "vxc_ms": vxc_avg,
+                        "algorithmic_flops_per_launch": 0.5 * flops_local}
+        else:
+            bytes_local = workload.algorithmic_bytes(n_local, nao, hp.functional)
+            achieved = bytes_local / (ms_step * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "whole call (density + vxc kernels)", "achieved": achieved,
+                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                        "peak_source": peak_src, "density_ms": dens_avg, "vxc_ms": vxc_avg,
+                        "algorithmic_bytes_per_call": bytes_local}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_port_baseline(hp, args.cpu_sample)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {hp.name}", "functional": hp.functional, "ngrid": hp.ngrid,
+                       "nao": nao, "basis": "sto-3g", "grid": "synthetic, PySCF level-3 point counts",
+                       "density": "seeded idempotent D = 2CC^T", "parallelism": f"grid-sharded x{world}",
+                       "l2": "explicit 384 MB flush between timed steps" if need_flush else
+                             "inputs per rank (%.1f GB) far larger than L2" % (input_bytes / 1e9),
+                       "path": int(solver.stat("path"))},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 8,
+                    "note": "per SCF iteration the driver uploads D (dft.py:200) and downloads V_xc (dft.py:211) + E_xc; "
+                            "AO planes stay resident across iterations as in dft.py:155-176"},
+            "gpu_launches": int(solver.stat("launches")) * K,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+            "per_scf_iter_vxc_ms": ms_step, "e_xc": e_xc,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        solver.comm_destroy()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

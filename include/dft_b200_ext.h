@@ -1,0 +1,76 @@
+// dft_b200_ext.h -- ADDITIVE C entry points of the B200-native XC engine.
+//
+// None of these exists in the reference; none changes the four symbols of
+// dft_solver.h.  They cover what BASELINE.json's north_star adds around the
+// drop-in path:
+//   (a) AO evaluation on the GPU  -> replaces numint.eval_ao at grid.py:30,38 and the
+//       H2D copies of the AO arrays at dft.py:155,172;
+//   (e) grid-sharded multi-GPU    -> one process per GPU, NCCL all-reduce of the
+//       nao x nao partial V_xc and the scalar E_xc inside DFT_ComputeXC;
+//   options / statistics / microbenchmarks used by bench.py for the roofline denominators.
+// All functions return 0 on success and a non-zero code on failure unless stated otherwise;
+// like the reference ABI they never throw.
+#pragma once
+#include "dft_solver.h"
+
+extern "C" {
+
+// ---- (a) AO evaluation --------------------------------------------------------------------
+// Values (deriv=0) or values + first derivatives (deriv=1) of contracted Cartesian s/p Gaussian
+// shells on ngrid points.  Writes exactly the layouts DFT_ComputeXC consumes:
+//   d_ao      (ngrid, nao)    row-major float64          (dft.py:155)
+//   d_ao_grad (3, ngrid, nao) planar x,y,z, or 0 if deriv=0 (dft.py:136-142,172)
+// d_coords is a DEVICE pointer to (ngrid,3) float64 Bohr coordinates.  The shell tables are HOST
+// arrays (they are tiny and are staged into shared memory by the kernel):
+//   shell_xyz (nshell,3), shell_l (0|1), shell_ao_off, shell_prim_off, shell_nprim,
+//   prim_exp / prim_coef (nprim_total; coefficient already includes the primitive norm).
+// A primitive contributes only where exp*r^2 <= exp_cutoff (PySCF-like screening); pass <= 0
+// for the default (60).
+int DFT_EvalAO(XCSolver* solver, int ngrid, unsigned long long d_coords_ptr,
+               int nshell, const double* shell_xyz, const int* shell_l,
+               const int* shell_ao_off, const int* shell_prim_off, const int* shell_nprim,
+               int nprim_total, const double* prim_exp, const double* prim_coef,
+               int nao, int deriv, double exp_cutoff,
+               unsigned long long d_ao_ptr, unsigned long long d_ao_grad_ptr);
+
+// ---- (e) multi-GPU: one process per GPU ---------------------------------------------------
+// Rank 0 calls DFT_CommGetUniqueId and ships the 128 bytes to the other ranks out of band
+// (bench.py uses a torch.distributed / TCP store broadcast); every rank then calls
+// DFT_CommInit.  From then on DFT_ComputeXC treats its (ngrid, d_ao, d_ao_grad, d_weights)
+// as THIS RANK's slice of the grid, all-reduces (sum) the nao*nao partial V_xc and E_xc over
+// NVLink, and every rank returns the global E_xc and holds the global V_xc.  NCCL is loaded
+// with dlopen("libnccl.so.2") on first use; a single-GPU caller never needs it.
+int DFT_CommGetUniqueId(void* out_id_128_bytes);
+int DFT_CommInit(XCSolver* solver, int rank, int nranks, const void* id_128_bytes);
+int DFT_CommDestroy(XCSolver* solver);
+
+// ---- options / statistics ------------------------------------------------------------------
+// keys: "exact_functionals" 0|1 (0 = reference bug-compatible potentials, default; 1 = potentials
+//       that are the exact derivatives of the energies, i.e. libxc/PySCF numint)
+//       "path" 0 auto | 1 generic (any alignment) | 2 TMA-fed
+//       "deterministic" 0|1 (default 1: fixed-order reductions, bit-reproducible results)
+int DFT_SetOption(XCSolver* solver, const char* key, double value);
+// keys: "density_ms", "vxc_ms", "reduce_ms", "total_ms" (CUDA-event times of the last
+//       DFT_ComputeXC on the engine's stream), "launches" (kernels launched by the last call),
+//       "path" (path actually taken), "workspace_bytes".
+double DFT_GetStat(XCSolver* solver, const char* key);
+
+// ---- convenience for callers that keep V_xc/E_xc on the device (no host sync) --------------
+// Same as DFT_ComputeXC but writes E_xc to the device double at d_exc_ptr, does not block the
+// host, and returns 0.  Work is enqueued on the engine stream; DFT_StreamSynchronize waits.
+int DFT_ComputeXCAsync(XCSolver* solver, int ngrid, int nao,
+                       unsigned long long d_dm_ptr, unsigned long long d_ao_ptr,
+                       unsigned long long d_ao_grad_ptr, unsigned long long d_weights_ptr,
+                       unsigned long long d_vxc_ptr, unsigned long long d_exc_ptr);
+int DFT_StreamSynchronize(XCSolver* solver);
+// Raw cudaStream_t of the engine (as an integer) so a harness can record CUDA events on it.
+unsigned long long DFT_GetStream(XCSolver* solver);
+
+// ---- roofline denominators measured in place (bench.py) -------------------------------------
+// Register-resident FP64 tensor-core (mma.sync m8n8k4 f64 -> SASS DMMA) and FP64 FMA peak
+// throughput in TFLOP/s on the current device; `iters` inner iterations per thread.
+double DFT_MicrobenchDMMA(int iters);
+double DFT_MicrobenchDFMA(int iters);
+
+const char* DFT_B200_Version(void);
+}

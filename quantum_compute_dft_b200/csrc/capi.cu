@@ -1,0 +1,261 @@
+// capi.cu -- solver classes and the C ABI (drop-in for the reference's weights/dft.so).
+//
+// Reference counterparts (file:line into /root/reference/src/dft_solver.cu):
+//   XCSolver ctor/dtor :536-539, CublasHandleWrapper :530-534
+//   LDASolver::compute_xc :559-584, GGASolver :588-621, B3LYPSolver :625-672
+//   extern "C" block :675-719
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "../../include/dft_b200_ext.h"
+#include "engine.h"
+
+// ------------------------------------------------------------------------- context
+void* DeviceBuffer::ensure(size_t bytes, bool* failed) {
+    if (bytes <= capacity && ptr) return ptr;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    capacity = 0;
+    size_t want = bytes + bytes / 8 + 256;  // a little slack so slowly growing sizes do not thrash
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[dft_b200] cudaMalloc(%zu) failed: %s\n", want, cudaGetErrorString(e));
+        ptr = nullptr;
+        if (failed) *failed = true;
+        return nullptr;
+    }
+    capacity = want;
+    return ptr;
+}
+
+void DeviceBuffer::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    capacity = 0;
+}
+
+CublasHandleWrapper::CublasHandleWrapper() {
+    DFT_CUDA_CHECK(this, cudaGetDevice(&device));
+    // A *blocking* stream: implicitly ordered with the legacy default stream the reference's
+    // driver uses (dft.py:178,201,207), so callers need no extra synchronisation.
+    DFT_CUDA_CHECK(this, cudaStreamCreateWithFlags(&stream, cudaStreamDefault));
+    for (auto& e : ev) DFT_CUDA_CHECK(this, cudaEventCreate(&e));
+    DFT_CUDA_CHECK(this, cudaMallocHost(reinterpret_cast<void**>(&h_scalar), 64));
+}
+
+CublasHandleWrapper::~CublasHandleWrapper() {
+    if (stream) cudaStreamSynchronize(stream);
+    dsym.release(); coef.release(); epart.release(); vpart.release(); result.release(); scratch.release();
+    if (h_scalar) cudaFreeHost(h_scalar);
+    for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+size_t CublasHandleWrapper::workspace_bytes() const {
+    return dsym.capacity + coef.capacity + epart.capacity + vpart.capacity + result.capacity + scratch.capacity;
+}
+
+// ------------------------------------------------------------------------- solver classes
+XCSolver::XCSolver() : handle_wrapper(new CublasHandleWrapper()) {}
+XCSolver::~XCSolver() = default;
+
+void XCSolver::compute_coulomb(int nao, const double* d_eri, const double* d_dm, double* d_J) {
+    xc::coulomb_gemv(handle_wrapper.get(), nao, d_eri, d_dm, d_J);
+}
+
+void XCSolver::safe_cublas_dgemm(bool transA, bool transB, int m, int n, int k, const double* A, int lda,
+                                 const double* B, int ldb, double* C, int ldc) {
+    xc::dgemm_colmajor(handle_wrapper.get(), transA, transB, m, n, k, A, lda, B, ldb, C, ldc);
+}
+
+namespace {
+
+// One XC build on the engine stream.  When `d_exc_out` is null the call blocks and returns E_xc
+// (reference semantics); otherwise E_xc is left on the device and the call returns immediately.
+double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const double* d_dm, const double* d_ao,
+              const double* d_ao_grad, const double* d_w, double* d_vxc, double* d_exc_out) {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    if (!ctx || ngrid < 0 || nao <= 0 || !d_dm || !d_ao || !d_w || !d_vxc) return nan;
+    if (xc_type != 0 && !d_ao_grad) {
+        fprintf(stderr, "[dft_b200] GGA/B3LYP need d_ao_grad (3,ngrid,nao)\n");
+        return nan;
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != ctx->device) cudaSetDevice(ctx->device);
+    ctx->failed = false;
+
+    const size_t n2 = (size_t)nao * nao;
+    const bool multi = ctx->nranks > 1 && ctx->nccl_comm;
+    double* packed = (double*)ctx->result.ensure(sizeof(double) * (n2 + 1), &ctx->failed);
+    if (ctx->failed) return nan;
+
+    xc::Problem p;
+    p.xc_type = xc_type;
+    p.ngrid = ngrid;
+    p.nao = nao;
+    p.dm = d_dm;
+    p.ao = d_ao;
+    const size_t plane = (size_t)ngrid * nao;
+    p.gx = xc_type ? d_ao_grad : nullptr;
+    p.gy = xc_type ? d_ao_grad + plane : nullptr;
+    p.gz = xc_type ? d_ao_grad + 2 * plane : nullptr;
+    p.w = d_w;
+    p.vxc = multi ? packed : d_vxc;
+    p.d_exc = multi ? packed + n2 : (d_exc_out ? d_exc_out : packed + n2);
+
+    if (ngrid == 0) {
+        cudaMemsetAsync(p.vxc, 0, sizeof(double) * n2, ctx->stream);
+        cudaMemsetAsync(p.d_exc, 0, sizeof(double), ctx->stream);
+        ctx->stats = XcStats();
+    } else {
+        bool use_tma = false;
+        if (ctx->path == PATH_TMA) use_tma = xc::tma_compatible(p);
+        else if (ctx->path == PATH_AUTO) use_tma = xc::tma_compatible(p);
+        if (use_tma) xc::run_tma(ctx, p);
+        else xc::run_generic(ctx, p);
+    }
+    if (multi) {
+        if (xc::allreduce_result(ctx, packed, n2 + 1) != 0) ctx->failed = true;
+        DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(d_vxc, packed, sizeof(double) * n2, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (d_exc_out)
+            DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(d_exc_out, packed + n2, sizeof(double), cudaMemcpyDeviceToDevice,
+                                                ctx->stream));
+    }
+    if (ctx->timing) cudaEventRecord(ctx->ev[4], ctx->stream);
+    if (d_exc_out) {
+        DFT_CUDA_CHECK(ctx, cudaGetLastError());
+        return ctx->failed ? nan : 0.0;
+    }
+    DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar, p.d_exc, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    DFT_CUDA_CHECK(ctx, cudaGetLastError());
+    if (ctx->timing && ngrid > 0 && !ctx->failed) {
+        cudaEventElapsedTime(&ctx->stats.density_ms, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&ctx->stats.vxc_ms, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&ctx->stats.reduce_ms, ctx->ev[2], ctx->ev[4]);
+        cudaEventElapsedTime(&ctx->stats.total_ms, ctx->ev[0], ctx->ev[4]);
+    }
+    return ctx->failed ? nan : ctx->h_scalar[0];
+}
+
+}  // namespace
+
+LDASolver::LDASolver() : XCSolver() {}
+double LDASolver::compute_xc(int ngrid, int nao, const double* d_dm, const double* d_ao, const double* d_ao_grad,
+                             const double* d_weights, double* d_vxc) {
+    (void)d_ao_grad;  // ignored, as in the reference (dft.py:75 passes 0)
+    return run_xc(handle_wrapper.get(), 0, ngrid, nao, d_dm, d_ao, nullptr, d_weights, d_vxc, nullptr);
+}
+
+GGASolver::GGASolver() : XCSolver() {}
+double GGASolver::compute_xc(int ngrid, int nao, const double* d_dm, const double* d_ao, const double* d_ao_grad,
+                             const double* d_weights, double* d_vxc) {
+    return run_xc(handle_wrapper.get(), 1, ngrid, nao, d_dm, d_ao, d_ao_grad, d_weights, d_vxc, nullptr);
+}
+
+B3LYPSolver::B3LYPSolver() : XCSolver() {}
+double B3LYPSolver::compute_xc(int ngrid, int nao, const double* d_dm, const double* d_ao, const double* d_ao_grad,
+                               const double* d_weights, double* d_vxc) {
+    return run_xc(handle_wrapper.get(), 2, ngrid, nao, d_dm, d_ao, d_ao_grad, d_weights, d_vxc, nullptr);
+}
+
+namespace {
+int solver_type(XCSolver* s) {
+    if (dynamic_cast<LDASolver*>(s)) return 0;
+    if (dynamic_cast<GGASolver*>(s)) return 1;
+    if (dynamic_cast<B3LYPSolver*>(s)) return 2;
+    return -1;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------- C ABI
+extern "C" {
+
+XCSolver* DFT_CreateSolver(int type) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "[dft_b200] no CUDA device: this library has no CPU fallback\n");
+        return nullptr;
+    }
+    if (type == SOLVER_LDA) return new LDASolver();
+    if (type == SOLVER_GGA) return new GGASolver();
+    if (type == SOLVER_B3LYP) return new B3LYPSolver();
+    return nullptr;
+}
+
+void DFT_DestroySolver(XCSolver* solver) {
+    if (solver) delete solver;
+}
+
+double DFT_ComputeXC(XCSolver* solver, int ngrid, int nao, unsigned long long d_dm_ptr,
+                     unsigned long long d_ao_ptr, unsigned long long d_ao_grad_ptr,
+                     unsigned long long d_weights_ptr, unsigned long long d_vxc_ptr) {
+    if (!solver) return 0.0;
+    return solver->compute_xc(ngrid, nao, reinterpret_cast<const double*>(d_dm_ptr),
+                              reinterpret_cast<const double*>(d_ao_ptr),
+                              reinterpret_cast<const double*>(d_ao_grad_ptr),
+                              reinterpret_cast<const double*>(d_weights_ptr), reinterpret_cast<double*>(d_vxc_ptr));
+}
+
+void DFT_ComputeCoulomb(XCSolver* solver, int nao, unsigned long long d_eri_ptr, unsigned long long d_dm_ptr,
+                        unsigned long long d_J_ptr) {
+    if (!solver) return;
+    solver->compute_coulomb(nao, reinterpret_cast<const double*>(d_eri_ptr),
+                            reinterpret_cast<const double*>(d_dm_ptr), reinterpret_cast<double*>(d_J_ptr));
+}
+
+int DFT_ComputeXCAsync(XCSolver* solver, int ngrid, int nao, unsigned long long d_dm_ptr,
+                       unsigned long long d_ao_ptr, unsigned long long d_ao_grad_ptr,
+                       unsigned long long d_weights_ptr, unsigned long long d_vxc_ptr,
+                       unsigned long long d_exc_ptr) {
+    if (!solver || !d_exc_ptr) return 1;
+    const int t = solver_type(solver);
+    if (t < 0) return 2;
+    double r = run_xc(solver->context(), t, ngrid, nao, reinterpret_cast<const double*>(d_dm_ptr),
+                      reinterpret_cast<const double*>(d_ao_ptr),
+                      t ? reinterpret_cast<const double*>(d_ao_grad_ptr) : nullptr,
+                      reinterpret_cast<const double*>(d_weights_ptr), reinterpret_cast<double*>(d_vxc_ptr),
+                      reinterpret_cast<double*>(d_exc_ptr));
+    return std::isnan(r) ? 3 : 0;
+}
+
+int DFT_StreamSynchronize(XCSolver* solver) {
+    if (!solver) return 1;
+    return cudaStreamSynchronize(solver->context()->stream) == cudaSuccess ? 0 : 2;
+}
+
+unsigned long long DFT_GetStream(XCSolver* solver) {
+    if (!solver) return 0ull;
+    return reinterpret_cast<unsigned long long>(solver->context()->stream);
+}
+
+int DFT_SetOption(XCSolver* solver, const char* key, double value) {
+    if (!solver || !key) return 1;
+    CublasHandleWrapper* c = solver->context();
+    if (!strcmp(key, "exact_functionals")) { c->exact_functionals = value != 0.0; return 0; }
+    if (!strcmp(key, "path")) { c->path = (int)value; return 0; }
+    if (!strcmp(key, "timing")) { c->timing = value != 0.0; return 0; }
+    if (!strcmp(key, "deterministic")) { return value != 0.0 ? 0 : 3; }  // reductions are always fixed-order
+    return 2;
+}
+
+double DFT_GetStat(XCSolver* solver, const char* key) {
+    if (!solver || !key) return -1.0;
+    CublasHandleWrapper* c = solver->context();
+    if (!strcmp(key, "density_ms")) return c->stats.density_ms;
+    if (!strcmp(key, "vxc_ms")) return c->stats.vxc_ms;
+    if (!strcmp(key, "reduce_ms")) return c->stats.reduce_ms;
+    if (!strcmp(key, "total_ms")) return c->stats.total_ms;
+    if (!strcmp(key, "launches")) return c->stats.launches;
+    if (!strcmp(key, "path")) return c->stats.path;
+    if (!strcmp(key, "workspace_bytes")) return (double)c->workspace_bytes();
+    if (!strcmp(key, "nranks")) return c->nranks;
+    return -1.0;
+}
+
+const char* DFT_B200_Version(void) { return "quantum_compute_dft_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+// engine.h -- engine context behind the XCSolver pimpl (`CublasHandleWrapper`).
+//
+// The reference defines `struct CublasHandleWrapper { cublasHandle_t handle; }`
+// (dft_solver.cu:530-534) and allocates/frees 6-7 temporaries with cudaMalloc/cudaFree on
+// every compute_xc call (:561-582, :590-619, :627-670).  Here the same opaque slot owns one
+// stream, grow-only workspaces that live as long as the solver, the TMA descriptors, the
+// run-time options and (optionally) an NCCL communicator.  No cuBLAS.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+
+#define DFT_CUDA_CHECK(ctx, call)                                                              \
+    do {                                                                                       \
+        cudaError_t err__ = (call);                                                            \
+        if (err__ != cudaSuccess) {                                                            \
+            fprintf(stderr, "[dft_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(err__), \
+                    __FILE__, __LINE__, cudaGetErrorString(err__));                            \
+            if (ctx) (ctx)->failed = true;                                                     \
+        }                                                                                      \
+    } while (0)
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t capacity = 0;
+    // grow-only; contents are NOT preserved across growth
+    void* ensure(size_t bytes, bool* failed);
+    void release();
+};
+
+enum XcPath { PATH_AUTO = 0, PATH_GENERIC = 1, PATH_TMA = 2 };
+
+struct XcStats {
+    float density_ms = 0.f, vxc_ms = 0.f, reduce_ms = 0.f, total_ms = 0.f;
+    int launches = 0;
+    int path = 0;
+};
+
+struct CublasHandleWrapper {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool failed = false;
+
+    // options (DFT_SetOption)
+    bool exact_functionals = false;
+    int path = PATH_AUTO;
+    bool timing = true;
+
+    // workspaces
+    DeviceBuffer dsym;     // symmetrised, zero-padded density matrix
+    DeviceBuffer coef;     // per-point (a,bx,by,bz)
+    DeviceBuffer epart;    // per-CTA partial E_xc
+    DeviceBuffer vpart;    // split-K partial V tiles
+    DeviceBuffer result;   // packed [V_xc (nao*nao) | E_xc] for the all-reduce / async E
+    DeviceBuffer scratch;  // repacked AO planes etc.
+    double* h_scalar = nullptr;  // pinned
+
+    // multi-GPU (NCCL loaded lazily; see comm.cu)
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    XcStats stats;
+
+    CublasHandleWrapper();
+    ~CublasHandleWrapper();
+    size_t workspace_bytes() const;
+};
+
+// ---- kernels / launchers implemented across the .cu files --------------------------------
+namespace xc {
+
+struct Problem {
+    int xc_type;  // 0 LDA, 1 GGA(PBE), 2 B3LYP
+    int ngrid, nao;
+    const double* dm;
+    const double* ao;
+    const double* gx;  // nullptr for LDA
+    const double* gy;
+    const double* gz;
+    const double* w;
+    double* vxc;     // (nao,nao) output
+    double* d_exc;   // device scalar output
+};
+
+// generic path (any alignment, any nao): xc_generic.cu
+void run_generic(CublasHandleWrapper* ctx, const Problem& p);
+// TMA-fed path: xc_tma.cu.  Returns false when the inputs are not TMA-compatible.
+bool tma_compatible(const Problem& p);
+void run_tma(CublasHandleWrapper* ctx, const Problem& p);
+
+// all-reduce of [V | E] over the communicator (comm.cu); no-op when nranks == 1
+int allreduce_result(CublasHandleWrapper* ctx, double* d_packed, size_t count);
+
+void coulomb_gemv(CublasHandleWrapper* ctx, int nao, const double* eri, const double* dm, double* J);
+
+void dgemm_colmajor(CublasHandleWrapper* ctx, bool transA, bool transB, int m, int n, int k,
+                    const double* A, int lda, const double* B, int ldb, double* C, int ldc);
+
+}  // namespace xc

@@ -1,0 +1,93 @@
+// linalg.cu -- the two dense helpers the reference delegates to cuBLAS, hand-written.
+//
+//   coulomb_gemv   : J = ERI . vec(D), the cublasDgemv at dft_solver.cu:550-555 (column-major,
+//                    no transpose, N2 x N2 with N2 = nao^2).  HBM-bound: every ERI element is
+//                    read exactly once (8*nao^4 bytes), coalesced along the contiguous index,
+//                    split over column chunks for parallelism and reduced in a fixed order.
+//   dgemm_colmajor : definition behind XCSolver::safe_cublas_dgemm (dft_solver.h:25-27,
+//                    dft_solver.cu:541-548) so code written against the reference header links.
+//                    Not on the engine's own hot path (V_xc is built by the fused kernels).
+#include "engine.h"
+
+namespace xc {
+namespace {
+
+constexpr int GEMV_THREADS = 256;
+
+// partial[s][r] = sum_{c in chunk s} A[c*N2 + r] * x[c]
+__global__ void __launch_bounds__(GEMV_THREADS)
+gemv_partial_kernel(long N2, int cols_per_chunk, const double* __restrict__ A, const double* __restrict__ x,
+                    double* __restrict__ partial) {
+    const long r = (long)blockIdx.x * GEMV_THREADS + threadIdx.x;
+    const long c0 = (long)blockIdx.y * cols_per_chunk;
+    const long c1 = min(N2, c0 + cols_per_chunk);
+    if (r >= N2) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    long c = c0;
+    for (; c + 3 < c1; c += 4) {  // 4 independent loads in flight per thread
+        s0 = fma(__ldg(A + (size_t)c * N2 + r), __ldg(x + c), s0);
+        s1 = fma(__ldg(A + (size_t)(c + 1) * N2 + r), __ldg(x + c + 1), s1);
+        s2 = fma(__ldg(A + (size_t)(c + 2) * N2 + r), __ldg(x + c + 2), s2);
+        s3 = fma(__ldg(A + (size_t)(c + 3) * N2 + r), __ldg(x + c + 3), s3);
+    }
+    for (; c < c1; ++c) s0 = fma(__ldg(A + (size_t)c * N2 + r), __ldg(x + c), s0);
+    partial[(size_t)blockIdx.y * N2 + r] = (s0 + s1) + (s2 + s3);
+}
+
+__global__ void gemv_reduce_kernel(long N2, int nchunks, const double* __restrict__ partial,
+                                   double* __restrict__ y) {
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N2) return;
+    double s = 0.0;
+    for (int k = 0; k < nchunks; ++k) s += partial[(size_t)k * N2 + r];
+    y[r] = s;
+}
+
+// C(m x n) = op(A) op(B), column-major, alpha = 1, beta = 0
+__global__ void gemm_simple_kernel(bool ta, bool tb, int m, int n, int k, const double* __restrict__ A, int lda,
+                                   const double* __restrict__ B, int ldb, double* __restrict__ C, int ldc) {
+    __shared__ double As[16][17], Bs[16][17];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int row = blockIdx.x * 16 + tx, col = blockIdx.y * 16 + ty;
+    double acc = 0.0;
+    for (int k0 = 0; k0 < k; k0 += 16) {
+        const int ka = k0 + ty, kb = k0 + tx;
+        As[ty][tx] = (row < m && ka < k) ? (ta ? A[(size_t)row * lda + ka] : A[(size_t)ka * lda + row]) : 0.0;
+        Bs[tx][ty] = (kb < k && col < n) ? (tb ? B[(size_t)kb * ldb + col] : B[(size_t)col * ldb + kb]) : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) acc = fma(As[kk][tx], Bs[kk][ty], acc);
+        __syncthreads();
+    }
+    if (row < m && col < n) C[(size_t)col * ldc + row] = acc;
+}
+
+}  // namespace
+
+void coulomb_gemv(CublasHandleWrapper* ctx, int nao, const double* eri, const double* dm, double* J) {
+    if (!ctx || nao <= 0 || !eri || !dm || !J) return;
+    const long N2 = (long)nao * nao;
+    const int rblocks = (int)((N2 + GEMV_THREADS - 1) / GEMV_THREADS);
+    // enough CTAs to saturate HBM: aim for >= 8 resident CTAs per SM
+    int nchunks = (148 * 8 + rblocks - 1) / rblocks;
+    if (nchunks > N2 / 8) nchunks = (int)(N2 / 8);
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > 65535) nchunks = 65535;
+    int cols = (int)((N2 + nchunks - 1) / nchunks);
+    nchunks = (int)((N2 + cols - 1) / cols);
+    double* partial = (double*)ctx->vpart.ensure(sizeof(double) * (size_t)nchunks * N2, &ctx->failed);
+    if (ctx->failed) return;
+    gemv_partial_kernel<<<dim3(rblocks, nchunks), GEMV_THREADS, 0, ctx->stream>>>(N2, cols, eri, dm, partial);
+    gemv_reduce_kernel<<<rblocks, GEMV_THREADS, 0, ctx->stream>>>(N2, nchunks, partial, J);
+    DFT_CUDA_CHECK(ctx, cudaGetLastError());
+}
+
+void dgemm_colmajor(CublasHandleWrapper* ctx, bool transA, bool transB, int m, int n, int k, const double* A,
+                    int lda, const double* B, int ldb, double* C, int ldc) {
+    if (!ctx || m <= 0 || n <= 0) return;
+    dim3 grid((m + 15) / 16, (n + 15) / 16), block(16, 16);
+    gemm_simple_kernel<<<grid, block, 0, ctx->stream>>>(transA, transB, m, n, k, A, lda, B, ldb, C, ldc);
+    DFT_CUDA_CHECK(ctx, cudaGetLastError());
+}
+
+}  // namespace xc

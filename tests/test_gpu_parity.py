@@ -1,0 +1,225 @@
+"""GPU parity: the engine, called through the C ABI, against the CPU oracle (and, where the
+prebuilt oracle/_ref/dft_ref.so travelled to the box, against the reference's own CUDA).
+
+Tolerances are BASELINE.json's: |dE_xc| <= 1e-8 Ha, max|d sym(V_xc)| <= 1e-9, all FP64.
+Parity is defined on sym(V) = (V + V^T)/2, the matrix the reference's driver forms (dft.py:212).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+E_TOL, V_TOL = 1e-8, 1e-9
+FUNCS = ["LDA", "GGA", "B3LYP"]
+XC = {"LDA": 0, "GGA": 1, "B3LYP": 2}
+
+
+def _run_engine(lib_path, functional, dm, ao, w, grad, options=None, reference_abi=False):
+    from quantum_compute_dft_b200.cuda_rt import DeviceArray
+    from quantum_compute_dft_b200.solver import DFTSolverWrapper
+    ngrid, nao = ao.shape
+    s = DFTSolverWrapper(lib_path, functional)
+    for k, v in (options or {}).items():
+        s.set_option(k, v)
+    d_dm, d_ao, d_w = DeviceArray.from_host(dm), DeviceArray.from_host(ao), DeviceArray.from_host(w)
+    d_g = DeviceArray.from_host(grad) if functional != "LDA" else None
+    d_v = DeviceArray((nao, nao), zero=True)
+    e = s.compute_xc(ngrid, nao, d_dm, d_ao, d_w, d_v, d_g)
+    v = d_v.get()
+    stats = {k: s.stat(k) for k in ("path", "launches")} if not reference_abi else {}
+    return e, v, stats
+
+
+def _run_reference_so(functional, dm, ao, w, grad):
+    """The reference's own CUDA (compiled unmodified for sm_100a by oracle/Makefile)."""
+    from quantum_compute_dft_b200.cuda_rt import DeviceArray
+    path = os.path.join(ROOT, "oracle", "_ref", "dft_ref.so")
+    if not os.path.exists(path):
+        return None
+    lib = ctypes.CDLL(path)
+    lib.DFT_CreateSolver.argtypes = [ctypes.c_int]; lib.DFT_CreateSolver.restype = ctypes.c_void_p
+    lib.DFT_DestroySolver.argtypes = [ctypes.c_void_p]
+    lib.DFT_ComputeXC.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_uint64] * 5
+    lib.DFT_ComputeXC.restype = ctypes.c_double
+    ngrid, nao = ao.shape
+    s = lib.DFT_CreateSolver(XC[functional])
+    d_dm, d_ao, d_w = DeviceArray.from_host(dm), DeviceArray.from_host(ao), DeviceArray.from_host(w)
+    d_g = DeviceArray.from_host(grad) if functional != "LDA" else None
+    d_v = DeviceArray((nao, nao), zero=True)
+    e = lib.DFT_ComputeXC(s, ngrid, nao, d_dm.data.ptr, d_ao.data.ptr, d_g.data.ptr if d_g else 0, d_w.data.ptr,
+                          d_v.data.ptr)
+    v = d_v.get()
+    lib.DFT_DestroySolver(s)
+    return e, v
+
+
+def _check(oracle, lib_path, functional, dm, ao, w, grad, mode=0, options=None, vs_reference=True):
+    e_o, v_o = oracle.compute_xc(XC[functional], dm, ao, w, grad, mode=mode)
+    e, v, stats = _run_engine(lib_path, functional, dm, ao, w, grad, options)
+    assert stats["launches"] > 0
+    assert abs(e - e_o) <= E_TOL, (functional, e, e_o)
+    np.testing.assert_allclose(0.5 * (v + v.T), oracle.sym(v_o), rtol=0, atol=V_TOL)
+    np.testing.assert_array_equal(v, v.T)          # the engine always writes the symmetric matrix
+    if vs_reference and mode == 0:
+        ref = _run_reference_so(functional, dm, ao, w, grad)
+        if ref is not None:
+            assert abs(e - ref[0]) <= E_TOL
+            np.testing.assert_allclose(0.5 * (v + v.T), 0.5 * (ref[1] + ref[1].T), rtol=0, atol=V_TOL)
+    return e, v
+
+
+def _random_case(rng, ngrid, nao, decay=True):
+    """Random AO-like planes with a realistic spread of magnitudes and a PSD density."""
+    scale = 10 ** rng.uniform(-6, 0, (ngrid, 1)) if decay else 1.0
+    ao = rng.standard_normal((ngrid, nao)) * scale
+    grad = rng.standard_normal((3, ngrid, nao)) * scale
+    C = rng.standard_normal((nao, max(1, nao // 2))) / np.sqrt(nao)
+    dm = 2.0 * C @ C.T
+    w = rng.uniform(0.0, 1.0, ngrid)
+    return dm, ao, w, grad
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+def test_h2_fixture_through_c_abi(oracle, engine_lib, h2_fixture, functional):
+    mol, basis, coords, w, dm = h2_fixture
+    ao, grad = oracle.eval_ao(coords, basis, deriv=1)
+    e, v = _check(oracle, engine_lib, functional, dm, ao, w, grad)
+    kat = {"LDA": (-0.683240084985, -0.448744125728, -0.302576546237),
+           "GGA": (-0.714211888015, -0.463813769518, -0.311372142021),
+           "B3LYP": (-0.591838579199, -0.379855055638, -0.254425920412)}[functional]
+    assert abs(e - kat[0]) < 1e-10 and abs(v[0, 0] - kat[1]) < 1e-10 and abs(v[0, 1] - kat[2]) < 1e-10
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+@pytest.mark.parametrize("molname,scale", [("H2O", 1.0), ("Benzene", 0.12), ("H2S", 0.3)])
+def test_molecules(oracle, engine_lib, functional, molname, scale):
+    from quantum_compute_dft_b200 import workload
+    hp = workload.host_problem(molname, scale=scale, functional=functional)
+    ao, grad = oracle.eval_ao(hp.coords, hp.basis, deriv=1)
+    _check(oracle, engine_lib, functional, hp.dm, ao, hp.weights, grad)
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+@pytest.mark.parametrize("ngrid,nao", [(1, 1), (3, 2), (63, 7), (64, 16), (65, 17), (257, 33), (1000, 64),
+                                       (999, 65), (2049, 100), (1500, 129), (4097, 152)])
+def test_ragged_shapes(oracle, engine_lib, functional, ngrid, nao):
+    rng = np.random.default_rng(ngrid * 1000 + nao)
+    dm, ao, w, grad = _random_case(rng, ngrid, nao)
+    _check(oracle, engine_lib, functional, dm, ao, w, grad)
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+def test_exact_functional_mode(oracle, engine_lib, functional):
+    rng = np.random.default_rng(11)
+    dm, ao, w, grad = _random_case(rng, 3000, 24)
+    _check(oracle, engine_lib, functional, dm, ao, w, grad, mode=1, options={"exact_functionals": 1})
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+def test_nonsymmetric_density_matrix(oracle, engine_lib, functional):
+    """The reference's loops use D as given; only its symmetric part can matter."""
+    rng = np.random.default_rng(12)
+    dm, ao, w, grad = _random_case(rng, 2000, 19)
+    dm = dm + 0.05 * rng.standard_normal(dm.shape)
+    _check(oracle, engine_lib, functional, dm, ao, w, grad)
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+def test_row_gate_and_zero_weights(oracle, engine_lib, functional):
+    """rho < 1e-12 rows contribute nothing (dft_solver.cu:318-324); zero-weight padding points too."""
+    rng = np.random.default_rng(13)
+    dm, ao, w, grad = _random_case(rng, 4000, 12)
+    ao[::3] *= 1e-9          # rho ~ 1e-18 -> gated
+    grad[:, ::3] *= 1e-9
+    w[::5] = 0.0
+    e, v = _check(oracle, engine_lib, functional, dm, ao, w, grad)
+    keep = np.ones(4000, bool); keep[::3] = False
+    e2, v2 = _check(oracle, engine_lib, functional, dm, ao[keep], w[keep], grad[:, keep])
+    assert abs(e - e2) < 1e-10 and np.max(np.abs(v - v2)) < 1e-10
+
+
+def test_empty_grid(engine_lib):
+    from quantum_compute_dft_b200.cuda_rt import DeviceArray
+    from quantum_compute_dft_b200.solver import DFTSolverWrapper
+    s = DFTSolverWrapper(engine_lib, "GGA")
+    d = DeviceArray.from_host(np.eye(3))
+    a = DeviceArray((1, 3), zero=True); g = DeviceArray((3, 1, 3), zero=True); w = DeviceArray((1,), zero=True)
+    v = DeviceArray.from_host(np.ones((3, 3)))
+    assert s.compute_xc(0, 3, d, a, w, v, g) == 0.0
+    assert np.all(v.get() == 0.0)
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+def test_idempotent_and_deterministic(engine_lib, functional):
+    """Same inputs -> bit-identical outputs, call after call and solver after solver."""
+    rng = np.random.default_rng(14)
+    dm, ao, w, grad = _random_case(rng, 20000, 36)
+    r = [_run_engine(engine_lib, functional, dm, ao, w, grad) for _ in range(3)]
+    for e, v, _ in r[1:]:
+        assert e == r[0][0]
+        np.testing.assert_array_equal(v, r[0][1])
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+def test_grid_additivity(engine_lib, functional):
+    """E_xc and V_xc are sums over grid points: two half-grids add up to the whole (the property the
+    multi-GPU sharding relies on), checked at a size the CPU oracle would take too long for."""
+    rng = np.random.default_rng(15)
+    dm, ao, w, grad = _random_case(rng, 60000, 152, decay=True)
+    e, v, _ = _run_engine(engine_lib, functional, dm, ao, w, grad)
+    h = 30002
+    e1, v1, _ = _run_engine(engine_lib, functional, dm, ao[:h], w[:h], np.ascontiguousarray(grad[:, :h]))
+    e2, v2, _ = _run_engine(engine_lib, functional, dm, ao[h:], w[h:], np.ascontiguousarray(grad[:, h:]))
+    assert abs(e - (e1 + e2)) <= 1e-9 * max(1.0, abs(e))
+    np.testing.assert_allclose(v, v1 + v2, rtol=0, atol=1e-9 * max(1.0, np.abs(v).max()))
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+def test_forced_generic_path_matches_auto(oracle, engine_lib, functional):
+    rng = np.random.default_rng(16)
+    dm, ao, w, grad = _random_case(rng, 5000, 36)
+    e0, v0, s0 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 1})
+    e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 0})
+    assert s0["path"] == 1
+    assert abs(e0 - e1) <= E_TOL
+    np.testing.assert_allclose(v0, v1, rtol=0, atol=V_TOL)
+
+
+def test_ao_evaluation_on_gpu(oracle, engine_lib):
+    """DFT_EvalAO against the CPU statement of numint.eval_ao (values and planar gradients)."""
+    from quantum_compute_dft_b200 import molgrid as M
+    from quantum_compute_dft_b200.cuda_rt import DeviceArray
+    from quantum_compute_dft_b200.solver import DFTSolverWrapper
+    s = DFTSolverWrapper(engine_lib, "GGA")
+    for name, scale in (("H2O", 0.2), ("H2S", 0.1), ("Benzene", 0.05), ("C33H56N7O17P3S", 0.004)):
+        mol = M.load_molecule(name)
+        basis = M.sto3g_basis(mol)
+        coords, _, _ = M.make_grid(mol, scale=scale)
+        ao_o, g_o = oracle.eval_ao(coords, basis, deriv=1)
+        d_c = DeviceArray.from_host(coords)
+        d_ao = DeviceArray(ao_o.shape); d_g = DeviceArray(g_o.shape)
+        s.eval_ao(d_c, basis, d_ao, d_g)
+        np.testing.assert_allclose(d_ao.get(), ao_o, rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(d_g.get(), g_o, rtol=1e-12, atol=1e-14)
+        d_ao2 = DeviceArray(ao_o.shape)
+        s.eval_ao(d_c, basis, d_ao2, None)
+        np.testing.assert_array_equal(d_ao2.get(), d_ao.get())
+
+
+def test_coulomb_through_c_abi(oracle, engine_lib):
+    from quantum_compute_dft_b200.cuda_rt import DeviceArray
+    from quantum_compute_dft_b200.solver import DFTSolverWrapper
+    rng = np.random.default_rng(17)
+    s = DFTSolverWrapper(engine_lib, "LDA")
+    for nao in (1, 2, 7, 13, 36):
+        eri = rng.standard_normal((nao * nao, nao * nao))
+        dm = rng.standard_normal((nao, nao))
+        d_e, d_d = DeviceArray.from_host(eri), DeviceArray.from_host(dm)
+        d_j = DeviceArray((nao, nao), zero=True)
+        s.compute_coulomb(nao, d_e, d_d, d_j)
+        s.synchronize()
+        np.testing.assert_allclose(d_j.get(), oracle.coulomb(eri, dm), rtol=1e-12, atol=1e-11)

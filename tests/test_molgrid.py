@@ -1,0 +1,81 @@
+"""Host input generators: STO-3G self-checks, overlap, grids, densities."""
+import numpy as np
+import pytest
+
+from quantum_compute_dft_b200 import molgrid as M
+
+
+def test_sto3g_contracted_norms():
+    for sym, sets in M._STO3G_EXP.items():
+        s_sets = [M._S1, M._S2, M._S3][:len(sets)]
+        p_sets = [None, M._P2, M._P3][:len(sets)]
+        for ex, cs, cp in zip(sets, s_sets, p_sets):
+            assert abs(M._contracted_self_overlap(0, ex, cs) - 1.0) < 2e-6
+            if cp is not None:
+                assert abs(M._contracted_self_overlap(1, ex, cp) - 1.0) < 2e-6
+
+
+def test_sto3g_universal_scaling_ratios():
+    ratios = {0: (20.2851, 3.6950), 1: (13.2316, 3.0747), 2: (9.1577, 2.5550)}
+    for sym, sets in M._STO3G_EXP.items():
+        for k, ex in enumerate(sets):
+            assert abs(ex[0] / ex[2] - ratios[k][0]) < 2e-3 and abs(ex[1] / ex[2] - ratios[k][1]) < 2e-3
+
+
+def test_nao_of_config_molecules():
+    expect = {"H2O": 7, "Benzene": 36, "DHA": 152, "C33H56N7O17P3S": 377}
+    for name, nao in expect.items():
+        mol = M.load_molecule(name)
+        assert M.sto3g_basis(mol).nao == nao
+    assert M.load_molecule("DHA").natm == 56 and M.load_molecule("C33H56N7O17P3S").nocc == 250
+
+
+def test_level3_grid_sizes():
+    expect = {"H2O": 34310, "Benzene": 143556, "DHA": 655136, "C33H56N7O17P3S": 1436406}
+    for name, ng in expect.items():
+        mol = M.load_molecule(name)
+        assert sum(M.atom_grid_sizes(s)[3] for s in mol.symbols) == ng
+
+
+def test_analytic_overlap_matches_quadrature_and_density_integrates(oracle):
+    mol = M.load_molecule("H2O")
+    basis = M.sto3g_basis(mol)
+    coords, w, _ = M.make_grid(mol, scale=1.0)
+    assert coords.shape[0] == 34310
+    ao = oracle.eval_ao(coords, basis)
+    Sq = np.einsum("g,gi,gj->ij", w, ao, ao)
+    S = M.overlap_matrix(basis)
+    np.testing.assert_allclose(np.diag(S), 1.0, atol=1e-12)
+    assert np.max(np.abs(Sq - S)) < 2e-4        # synthetic product-rule grid, not Lebedev
+    D = M.synthetic_density(S, mol.nocc)
+    np.testing.assert_allclose(np.trace(D @ S), 10.0, rtol=1e-12)
+    rho = np.einsum("gi,ij,gj->g", ao, D, ao)
+    assert rho.min() > -1e-12 and abs(np.dot(w, rho) - 10.0) < 5e-3
+
+
+def test_eval_ao_numpy_matches_oracle(oracle):
+    mol = M.load_molecule("H2S")
+    basis = M.sto3g_basis(mol)
+    coords, _, _ = M.make_grid(mol, scale=0.02)
+    a1, g1 = oracle.eval_ao(coords, basis, deriv=1)
+    a2, g2 = M.eval_ao_numpy(coords, basis, deriv=1)
+    np.testing.assert_allclose(a1, a2, rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(g1, g2, rtol=1e-13, atol=1e-14)
+    # gradient against central differences of the value
+    h = 1e-5
+    for c in range(3):
+        dp = coords.copy(); dp[:, c] += h
+        dm = coords.copy(); dm[:, c] -= h
+        fd = (oracle.eval_ao(dp, basis, exp_cutoff=1e9) - oracle.eval_ao(dm, basis, exp_cutoff=1e9)) / (2 * h)
+        ga = oracle.eval_ao(coords, basis, deriv=1, exp_cutoff=1e9)[1][c]
+        assert np.max(np.abs(fd - ga)) < 1e-5 * max(1.0, np.abs(ga).max())
+
+
+def test_shard_bounds_cover_grid():
+    from quantum_compute_dft_b200.solver import shard_bounds
+    for ng in (0, 1, 7, 34310, 1436406):
+        for n in (1, 2, 4, 8):
+            cuts = [shard_bounds(ng, r, n) for r in range(n)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == ng
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(n - 1))
+            assert all(lo % 2 == 0 for lo, _ in cuts)

@@ -1,0 +1,22 @@
+#!/bin/bash
+# Usage (on the GPU box, through gpurun): bash tools/gpu_session.sh <tag> <what...>
+# Runs a bounded sequence of checks; every step has its own timeout and log under gpurun_out/<tag>/.
+set -u
+TAG=${1:-s}; shift
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.csv 2>&1
+for what in "$@"; do
+  case $what in
+    tests)   timeout 900 python -m pytest tests -m gpu -x -q > $OUT/tests.log 2>&1; echo "tests rc=$?" | tee -a $OUT/summary.txt; tail -15 $OUT/tests.log ;;
+    golden)  timeout 300 python tools/make_reference_golden.py $OUT/golden > $OUT/golden.log 2>&1; echo "golden rc=$?" | tee -a $OUT/summary.txt; tail -20 $OUT/golden.log ;;
+    smoke)   timeout 300 python __graft_entry__.py --smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/summary.txt; tail -5 $OUT/smoke.log ;;
+    micro)   timeout 120 python -c "
+from quantum_compute_dft_b200.solver import load_library
+l=load_library()
+print('DMMA TFLOP/s', l.DFT_MicrobenchDMMA(8192)); print('DFMA TFLOP/s', l.DFT_MicrobenchDFMA(8192))" > $OUT/micro.log 2>&1; echo "micro rc=$?" | tee -a $OUT/summary.txt; cat $OUT/micro.log ;;
+    bench:*) W=${what#bench:}; timeout 600 python bench.py --workload $W --steps 5 --warmup 3 > $OUT/bench_$W.json 2> $OUT/bench_$W.err; echo "bench $W rc=$?" | tee -a $OUT/summary.txt; cat $OUT/bench_$W.json; tail -3 $OUT/bench_$W.err ;;
+    ref:*)   W=${what#ref:}; timeout 600 python bench.py --impl reference --workload $W --steps 2 --warmup 1 > $OUT/ref_$W.json 2> $OUT/ref_$W.err; echo "ref $W rc=$?" | tee -a $OUT/summary.txt; cat $OUT/ref_$W.json; tail -3 $OUT/ref_$W.err ;;
+    *) echo "unknown step $what" ;;
+  esac
+done
