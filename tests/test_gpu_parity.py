@@ -105,7 +105,11 @@ def test_molecules(oracle, engine_lib, functional, molname, scale):
 
 @pytest.mark.parametrize("functional", FUNCS)
 @pytest.mark.parametrize("ngrid,nao", [(1, 1), (3, 2), (63, 7), (64, 16), (65, 17), (257, 33), (1000, 64),
-                                       (999, 65), (2049, 100), (1500, 129), (4097, 152)])
+                                       (999, 65), (2049, 100), (1500, 129), (4097, 152),
+                                       # TMA-compatible shapes: even nao (direct maps) and odd nao with even
+                                       # ngrid (row-pair maps), one to three column tiles, ragged tails
+                                       (2, 7), (128, 7), (1000, 7), (34310, 7), (2048, 36), (3000, 31), (130, 96),
+                                       (2500, 97), (777, 128), (1302, 130), (2600, 191), (1800, 256), (1900, 377)])
 def test_ragged_shapes(oracle, engine_lib, functional, ngrid, nao):
     rng = np.random.default_rng(ngrid * 1000 + nao)
     dm, ao, w, grad = _random_case(rng, ngrid, nao)
@@ -176,6 +180,20 @@ def test_grid_additivity(engine_lib, functional):
     e2, v2, _ = _run_engine(engine_lib, functional, dm, ao[h:], w[h:], np.ascontiguousarray(grad[:, h:]))
     assert abs(e - (e1 + e2)) <= 1e-9 * max(1.0, abs(e))
     np.testing.assert_allclose(v, v1 + v2, rtol=0, atol=1e-9 * max(1.0, np.abs(v).max()))
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+@pytest.mark.parametrize("ngrid,nao", [(50000, 152), (40000, 377), (30000, 36), (70001, 64)])
+def test_tma_path_matches_generic_path_at_scale(engine_lib, functional, ngrid, nao):
+    """Many row blocks per CTA (persistent loop wraps), all column tiles, both map kinds -- at sizes where
+    the CPU oracle is slow; the generic path is itself oracle-checked above."""
+    rng = np.random.default_rng(ngrid + nao)
+    dm, ao, w, grad = _random_case(rng, ngrid, nao)
+    e0, v0, s0 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 1})
+    e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 0})
+    assert s0["path"] == 1 and s1["path"] == (2 if (nao % 2 == 0 or ngrid % 2 == 0) else 1)
+    assert abs(e0 - e1) <= E_TOL * max(1.0, abs(e0) * 1e-3)
+    np.testing.assert_allclose(v0, v1, rtol=0, atol=V_TOL * max(1.0, np.abs(v0).max() * 1e-3))
 
 
 @pytest.mark.parametrize("functional", FUNCS)
