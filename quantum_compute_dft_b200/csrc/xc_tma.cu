@@ -1,7 +1,9 @@
 // xc_tma.cu -- the fast XC path: TMA-fed, mbarrier-pipelined FP64 tensor-core (DMMA) kernels.
 //
-// Two persistent, warp-specialised kernels per XC build (one CTA per SM, 8 consumer warps in a
-// 2 x 4 grid + 1 TMA producer warp):
+// Two persistent, warp-specialised kernels per XC build.  One CTA per SM, 384 threads: two consumer
+// warpgroups (8 warps in a 2 x 4 grid, warp tile 64 x 32 at the widest) and one producer warpgroup
+// whose first lane drives TMA; `setmaxnreg` moves registers from the producer to the consumers
+// (40 / 232 per thread) so that 64 x 32 FP64 accumulator tiles fit without spills.
 //
 //   density_tma_kernel   subsystem (b)+(c): for each block of 128 grid points
 //        C = Phi_blk . Dsym                      DMMA tiles, operands streamed by TMA (SWIZZLE_128B)
@@ -19,16 +21,24 @@
 //
 // Shared-memory operand tiles are written by TMA with the 128-byte swizzle; fragment rows (density
 // kernel) or reduction rows (V kernel) are permuted so that every 64-bit fragment load is
-// bank-conflict free (see DESIGN.md "swizzle and fragment permutation").
+// bank-conflict free ("swizzle and fragment permutation").
 //
-// Row pitch of the caller's AO arrays is 8*nao bytes.  TMA needs 16-byte multiples, so for odd nao
-// the arrays are addressed as (ngrid/2) x (2 nao) "row pairs" and each tile is fetched with two box
-// loads (even rows, odd rows); rows of a tile are then a fixed permutation of grid points, which is
-// harmless for both contractions.  Inputs TMA cannot address at all (misaligned base pointers, odd
-// nao with odd ngrid) take the generic path (xc_generic.cu).
+// Odd nao.  The caller's AO rows are 8*nao bytes apart; TMA needs 16-byte aligned rows and box
+// starts.  For odd nao only every second row is aligned, so the grid is split into two
+// SUB-PROBLEMS that are each a clean 2-D tensor with pitch 2*nao:
+//     E: even rows g = 2j,   columns 0..nao-1, base = ptr
+//     O: odd rows  g = 2j+1, base = ptr + (nao-1)*8 (16-byte aligned), columns 0..nao where column 0
+//        is the last element of the previous row (finite junk) and column c >= 1 is AO index c-1.
+// Sub-problem O therefore works with every AO index shifted by one: it multiplies by a copy of
+// Dsym shifted by (1,1) (row/column 0 zero, so the junk column is annihilated) and accumulates a
+// V matrix shifted by (1,1), which the finalize kernel un-shifts.  Blocks, tiles and slices are
+// always uniform in parity, so the inner loops do not know about any of this.
+// Inputs TMA cannot address at all (misaligned base pointers, odd nao with odd ngrid) take the
+// generic path (xc_generic.cu).
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstring>
 
 #include "dmma.cuh"
 #include "engine.h"
@@ -39,13 +49,42 @@ namespace xc {
 namespace tmapath {
 
 constexpr int MB = 128;                     // grid rows per block (density kernel)
-constexpr int NCW = 8;                      // consumer warps, 2 (m) x 4 (n); warp tile 64 x 8NF
-constexpr int NCONS = NCW * 32;             // 256 consumer threads (<= 224 registers each)
-constexpr int NTHREADS = NCONS + 32;        // + 1 producer warp
+constexpr int NCW = 8;                      // consumer warps, 2 (m) x 4 (n)
+constexpr int NCONS = NCW * 32;             // 256 consumer threads = 2 warpgroups
+constexpr int NTHREADS = NCONS + 128;       // + 1 producer warpgroup
+constexpr int REGS_CONSUMER = 232;          // 384*168 = 256*232 + 128*40
+constexpr int REGS_PRODUCER = 40;
 constexpr int D_STAGES = 5;                 // density pipeline depth
 constexpr int V_STAGES = 2;                 // V pipeline depth (stages are 5 planes wide)
 constexpr int VK = 16;                      // grid rows per V chunk
 constexpr int A_TILE_BYTES = MB * 128;      // 128 rows x 16 doubles
+
+struct SubProblem {
+    int rows;    // rows of this sub-problem
+    int gmul;    // grid point of row j: g = gmul * j + gadd
+    int gadd;
+    int shift;   // AO index = column - shift (0 or 1)
+    int blk0;    // first density block of this sub-problem
+    int coef0;   // first row of this sub-problem in the coefficient array (padded to 128 rows)
+};
+
+struct DensityParams {
+    CUtensorMap map_a[2];   // Phi of each sub-problem, box 16 x 128
+    CUtensorMap map_d;      // [2][NP][KP] symmetrised density (plain, shifted), box 16 x NT
+    SubProblem sub[2];
+    int nsub, ngrid, nao, xc_mode, nblocks, ntiles, nk, NP;
+    const double *ao, *gx, *gy, *gz, *w;
+    double* coef;
+    double* exc_part;
+};
+
+struct VxcParams {
+    CUtensorMap map_p[2][4];  // planes of each sub-problem, box 16 x 16
+    SubProblem sub[2];
+    int nsub, ntiles, lda_half, rows_per_slice, slices_per_sub, NP;
+    const double* coef;
+    double* vpart;
+};
 
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
     double v;
@@ -59,6 +98,14 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_f64x2(uint32_t addr, double2 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void reg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 __device__ __forceinline__ xcfun::PointCoef eval_mode(int mode, double rho, double gx, double gy, double gz, double w) {
@@ -86,12 +133,8 @@ struct DensitySmem {
 };
 
 template <int NF, int NPL>
-__global__ void __maxnreg__(224)
-density_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_d,
-                   int ngrid, int nao, int paired, int xc_mode, int nblocks, int ntiles, int nk,
-                   const double* __restrict__ ao, const double* __restrict__ gx, const double* __restrict__ gy,
-                   const double* __restrict__ gz, const double* __restrict__ w, double* __restrict__ coef,
-                   double* __restrict__ exc_part) {
+__global__ void __launch_bounds__(NTHREADS, 1)
+density_tma_kernel(const __grid_constant__ DensityParams P) {
     using L = DensitySmem<NF>;
     constexpr int NT = L::NT;
     extern __shared__ unsigned char smem_raw[];
@@ -112,26 +155,28 @@ density_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     __syncthreads();
 
-    if (warp == NCW) {
-        // ===================== TMA producer (one elected lane) =====================
-        if (lane == 0) {
-            tma::prefetch_map(&map_a);
-            tma::prefetch_map(&map_d);
+    const int nblocks = P.nblocks, ntiles = P.ntiles, nk = P.nk;
+
+    if (warp >= NCW) {
+        // ===================== producer warpgroup: one elected lane drives TMA =====================
+        reg_dec<REGS_PRODUCER>();
+        if (warp == NCW && lane == 0) {
+            tma::prefetch_map(&P.map_a[0]);
+            if (P.nsub > 1) tma::prefetch_map(&P.map_a[1]);
+            tma::prefetch_map(&P.map_d);
             uint32_t it = 0;
-            for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+            for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+                const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
+                const int blk = b - P.sub[si].blk0;
+                const int drow0 = P.sub[si].shift * P.NP;
                 for (int nt = 0; nt < ntiles; ++nt) {
                     for (int kc = 0; kc < nk; ++kc, ++it) {
                         const uint32_t s = it % D_STAGES, ph = (it / D_STAGES) & 1u;
                         tma::mbar_wait(&empty[s], ph ^ 1u);
                         unsigned char* st = sm + s * L::STAGE_BYTES;
                         tma::mbar_arrive_expect_tx(&full[s], L::STAGE_BYTES);
-                        if (!paired) {
-                            tma::load_2d(st, &map_a, kc * 16, blk * MB, &full[s]);
-                        } else {  // even rows -> tile rows 0..63, odd rows -> 64..127
-                            tma::load_2d(st, &map_a, kc * 16, blk * (MB / 2), &full[s]);
-                            tma::load_2d(st + A_TILE_BYTES / 2, &map_a, nao + kc * 16, blk * (MB / 2), &full[s]);
-                        }
-                        tma::load_2d(st + A_TILE_BYTES, &map_d, kc * 16, nt * NT, &full[s]);
+                        tma::load_2d(st, &P.map_a[si], kc * 16, blk * MB, &full[s]);
+                        tma::load_2d(st + A_TILE_BYTES, &P.map_d, kc * 16, drow0 + nt * NT, &full[s]);
                     }
                 }
             }
@@ -140,6 +185,7 @@ density_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
 
     // ===================== consumers: 8 warps, warp tile 64 x (8 NF) =====================
+    reg_inc<REGS_CONSUMER>();
     const int wm = warp >> 2, wn = warp & 3;
     const int q = lane >> 2, qcol = lane & 3;
     const int perm = 2 * (q & 3) + (q >> 2);  // fragment row -> tile row: conflict-free with SWIZZLE_128B
@@ -156,10 +202,18 @@ density_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int j = 2 * qcol + e;
         ncol[e] = 2 * (j & 3) + (j >> 2);
     }
+    const int ngrid = P.ngrid, nao = P.nao;
+    const double* __restrict__ ao = P.ao;
+    const double* __restrict__ gx = P.gx;
+    const double* __restrict__ gy = P.gy;
+    const double* __restrict__ gz = P.gz;
 
     double e_acc = 0.0;
     uint32_t it = 0;
-    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
+        const int blk = b - P.sub[si].blk0;
+        const int rows = P.sub[si].rows, gmul = P.sub[si].gmul, gadd = P.sub[si].gadd, shift = P.sub[si].shift;
         for (int nt = 0; nt < ntiles; ++nt) {
             double acc[8][NF][2];
 #pragma unroll
@@ -174,15 +228,15 @@ density_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const uint32_t b_base = base + s * L::STAGE_BYTES + A_TILE_BYTES + b_row;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    double a[8], b[NF];
+                    double a[8], bf[NF];
 #pragma unroll
                     for (int mf = 0; mf < 8; ++mf) a[mf] = lds_f64(a_base + mf * 1024 + koff[ks]);
 #pragma unroll
-                    for (int nf = 0; nf < NF; ++nf) b[nf] = lds_f64(b_base + nf * 1024 + koff[ks]);
+                    for (int nf = 0; nf < NF; ++nf) bf[nf] = lds_f64(b_base + nf * 1024 + koff[ks]);
 #pragma unroll
                     for (int mf = 0; mf < 8; ++mf)
 #pragma unroll
-                        for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], b[nf]);
+                        for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
                 }
                 __syncwarp();
                 if (lane == 0) tma::mbar_arrive(&empty[s]);
@@ -190,22 +244,22 @@ density_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             // ---- fused epilogue: row-dots of C with Phi and grad Phi (global loads, L2-hot for Phi);
             //      the row sums of this column tile are folded into shared memory right away so that
             //      no row accumulator stays live across the k-loop (each red[] entry has one owner lane)
-            const int nbase = nt * NT + wn * 8 * NF;
+            const int nbase = nt * NT + wn * 8 * NF - shift;
 #pragma unroll
             for (int mf = 0; mf < 8; ++mf) {
                 const int r = wm * 64 + mf * 8 + perm;
-                const long g = (long)blk * MB + (paired ? (r < MB / 2 ? 2 * r : 2 * (r - MB / 2) + 1) : r);
+                const int j = blk * MB + r;
                 double rs[NPL];
 #pragma unroll
                 for (int p = 0; p < NPL; ++p) rs[p] = 0.0;
-                if (g < ngrid) {
-                    const size_t rowoff = (size_t)g * nao;
+                if (j < rows) {
+                    const size_t rowoff = (size_t)((long)gmul * j + gadd) * nao;
 #pragma unroll
                     for (int nf = 0; nf < NF; ++nf) {
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int n = nbase + nf * 8 + ncol[e];
-                            if (n >= nao) continue;
+                            if (n < 0 || n >= nao) continue;
                             const double cv = acc[mf][nf][e];
                             rs[0] = fma(cv, __ldg(ao + rowoff + n), rs[0]);
                             if (NPL == 4) {
@@ -231,9 +285,10 @@ density_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         tma::named_bar_sync(1, NCONS);
         if (tid < MB) {
             const int r = tid;
-            const long g = (long)blk * MB + (paired ? (r < MB / 2 ? 2 * r : 2 * (r - MB / 2) + 1) : r);
+            const int j = blk * MB + r;
             double2 c01 = make_double2(0.0, 0.0), c23 = make_double2(0.0, 0.0);
-            if (g < ngrid) {
+            if (j < rows) {
+                const long g = (long)gmul * j + gadd;
                 const double* rr = red + r * 16;
                 const double rho = (rr[0] + rr[4]) + (rr[8] + rr[12]);
                 double dx = 0.0, dy = 0.0, dz = 0.0;
@@ -242,13 +297,13 @@ density_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     dy = 2.0 * ((rr[2] + rr[6]) + (rr[10] + rr[14]));
                     dz = 2.0 * ((rr[3] + rr[7]) + (rr[11] + rr[15]));
                 }
-                const xcfun::PointCoef pc = eval_mode(xc_mode, rho, dx, dy, dz, __ldg(w + g));
+                const xcfun::PointCoef pc = eval_mode(P.xc_mode, rho, dx, dy, dz, __ldg(P.w + g));
                 c01 = make_double2(pc.a, pc.bx);
                 c23 = make_double2(pc.by, pc.bz);
                 e_acc += pc.exc;
             }
-            // coef rows are padded to nblocks*128: rows beyond ngrid are written as zeros
-            double2* cp = reinterpret_cast<double2*>(coef) + 2 * (size_t)g;
+            // coefficient rows are stored per sub-problem, padded to whole blocks (zeros past the end)
+            double2* cp = reinterpret_cast<double2*>(P.coef) + 2 * ((size_t)P.sub[si].coef0 + j);
             cp[0] = c01;
             cp[1] = c23;
         }
@@ -261,7 +316,7 @@ density_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (lane == 0) esum[warp] = e_acc;
     }
     tma::named_bar_sync(1, NCONS);
-    if (tid == 0) exc_part[blockIdx.x] = (esum[0] + esum[1]) + (esum[2] + esum[3]);
+    if (tid == 0) P.exc_part[blockIdx.x] = (esum[0] + esum[1]) + (esum[2] + esum[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -281,11 +336,8 @@ struct VxcSmem {
 };
 
 template <int NF, int NPL>
-__global__ void __maxnreg__(224)
-vxc_tma_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant__ CUtensorMap map_px,
-               const __grid_constant__ CUtensorMap map_py, const __grid_constant__ CUtensorMap map_pz,
-               int ngrid, int nao, int paired, int ntiles, int lda_half, int rows_per_slice, int NP,
-               const double* __restrict__ coef, double* __restrict__ vpart) {
+__global__ void __launch_bounds__(NTHREADS, 1)
+vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     using L = VxcSmem<NF, NPL>;
     constexpr int NT = L::NT;
     extern __shared__ unsigned char smem_raw[];
@@ -297,8 +349,9 @@ vxc_tma_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // output tile of this CTA
+    const int ntiles = P.ntiles;
     int tm, tn;
-    if (lda_half) {  // upper-triangular tile pairs, row-major
+    if (P.lda_half) {  // upper-triangular tile pairs, row-major
         int t = blockIdx.x;
         tm = 0;
         while (t >= ntiles - tm) { t -= ntiles - tm; ++tm; }
@@ -309,9 +362,12 @@ vxc_tma_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant
     }
     const bool diag = (tm == tn);
     const int m0 = tm * NT, n0 = tn * NT;
-    const long gbeg = (long)blockIdx.y * rows_per_slice;
-    const long gend = min((long)ngrid, gbeg + rows_per_slice);
-    const int nchunks = gend > gbeg ? (int)((gend - gbeg + VK - 1) / VK) : 0;
+    // grid slice of this CTA: rows [jbeg, jend) of sub-problem si
+    const int si = blockIdx.y / P.slices_per_sub;
+    const int sl = blockIdx.y % P.slices_per_sub;
+    const int jbeg = sl * P.rows_per_slice;
+    const int jend = min(P.sub[si].rows, jbeg + P.rows_per_slice);
+    const int nchunks = jend > jbeg ? (jend - jbeg + VK - 1) / VK : 0;
 
     if (tid == 0) {
         for (int s = 0; s < V_STAGES; ++s) {
@@ -322,38 +378,34 @@ vxc_tma_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant
     }
     __syncthreads();
 
-    if (warp == NCW) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            const CUtensorMap* maps[4] = {&map_p0, &map_px, &map_py, &map_pz};
-            for (int p = 0; p < NPL; ++p) tma::prefetch_map(maps[p]);
-            const uint32_t stage_tx = (uint32_t)((NPL + (diag ? 0 : 1)) * L::TILE_BYTES + VK * 32);
+    if (warp >= NCW) {
+        // ===================== producer warpgroup =====================
+        reg_dec<REGS_PRODUCER>();
+        if (warp == NCW && lane == 0) {
+            for (int p = 0; p < NPL; ++p) tma::prefetch_map(&P.map_p[si][p]);
+            const int ntile_loads = NPL + (diag ? 0 : 1);
+            const uint32_t stage_tx = (uint32_t)(ntile_loads * L::TILE_BYTES + VK * 32);
+            const double* coef = P.coef + 4 * (size_t)P.sub[si].coef0;
             for (int c = 0; c < nchunks; ++c) {
                 const uint32_t s = c % V_STAGES, ph = (c / V_STAGES) & 1u;
                 tma::mbar_wait(&empty[s], ph ^ 1u);
                 unsigned char* st = sm + s * L::STAGE_BYTES;
-                const long g0 = gbeg + (long)c * VK;
+                const int j0 = jbeg + c * VK;
                 tma::mbar_arrive_expect_tx(&full[s], stage_tx);
-                for (int p = 0; p < NPL + (diag ? 0 : 1); ++p) {
-                    const CUtensorMap* mp = (p < NPL) ? maps[p] : &map_p0;
+                for (int p = 0; p < ntile_loads; ++p) {
+                    const CUtensorMap* mp = &P.map_p[si][p < NPL ? p : 0];
                     const int col0 = (p < NPL) ? m0 : n0;
-                    unsigned char* dst = st + (p < NPL ? p : NPL) * L::TILE_BYTES;
-                    for (int b = 0; b < 2 * NF; ++b) {
-                        if (!paired) {
-                            tma::load_2d(dst + b * 2048, mp, col0 + 16 * b, (int)g0, &full[s]);
-                        } else {
-                            tma::load_2d(dst + b * 2048, mp, col0 + 16 * b, (int)(g0 >> 1), &full[s]);
-                            tma::load_2d(dst + b * 2048 + 1024, mp, nao + col0 + 16 * b, (int)(g0 >> 1), &full[s]);
-                        }
-                    }
+                    unsigned char* dst = st + p * L::TILE_BYTES;
+                    for (int b = 0; b < 2 * NF; ++b) tma::load_2d(dst + b * 2048, mp, col0 + 16 * b, j0, &full[s]);
                 }
-                tma::load_1d(st + L::COEF_OFF, coef + 4 * g0, VK * 32, &full[s]);
+                tma::load_1d(st + L::COEF_OFF, coef + 4 * (size_t)j0, VK * 32, &full[s]);
             }
         }
         return;
     }
 
     // ===================== consumers: 2 x 4 warps, warp tile (16 NF) x (8 NF) =====================
+    reg_inc<REGS_CONSUMER>();
     const int wm = warp >> 2, wn = warp & 3;
     const int q = lane >> 2, qcol = lane & 3;
     constexpr int MF = 2 * NF;
@@ -383,16 +435,17 @@ vxc_tma_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant
         const uint32_t bs = bs_base + (c & 1) * L::BS_BYTES;
         tma::mbar_wait(&full[s], ph);
         // ---- build B rows for this chunk: B = a Phi + bx dxPhi + by dyPhi + bz dzPhi
-        for (int task = tid; task < 256 * NF; task += NCONS) {
+#pragma unroll
+        for (int t = 0; t < NF; ++t) {
+            const int task = tid + t * NCONS;
             const int j = task & 7, rb = task >> 3;
             const int r = rb & 15, b = rb >> 4;
             const uint32_t off = (uint32_t)(b * 2048 + r * 128 + (((j ^ r) & 7) << 4));
-            const int gi = paired ? (r < 8 ? 2 * r : 2 * (r - 8) + 1) : r;
-            const double2 ca = lds_f64x2(st + L::COEF_OFF + gi * 32);
+            const double2 ca = lds_f64x2(st + L::COEF_OFF + r * 32);
             const double2 v0 = lds_f64x2(st + off);
             double2 o = make_double2(ca.x * v0.x, ca.x * v0.y);
             if (NPL == 4) {
-                const double2 cb = lds_f64x2(st + L::COEF_OFF + gi * 32 + 16);
+                const double2 cb = lds_f64x2(st + L::COEF_OFF + r * 32 + 16);
                 const double2 v1 = lds_f64x2(st + L::TILE_BYTES + off);
                 const double2 v2 = lds_f64x2(st + 2 * L::TILE_BYTES + off);
                 const double2 v3 = lds_f64x2(st + 3 * L::TILE_BYTES + off);
@@ -408,21 +461,22 @@ vxc_tma_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant
         const uint32_t phin = st + (diag ? 0 : NPL * L::TILE_BYTES);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            double a[MF], b[NF];
+            double a[MF], bf[NF];
 #pragma unroll
             for (int mf = 0; mf < MF; ++mf) a[mf] = lds_f64(bs + aoff + (uint32_t)((4 * ks * L::BPITCH + mf * 8) * 8));
 #pragma unroll
-            for (int nf = 0; nf < NF; ++nf) b[nf] = lds_f64(phin + boff[ks][nf]);
+            for (int nf = 0; nf < NF; ++nf) bf[nf] = lds_f64(phin + boff[ks][nf]);
 #pragma unroll
             for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
-                for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], b[nf]);
+                for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
         }
         __syncwarp();
         if (lane == 0) tma::mbar_arrive(&empty[s]);
     }
     // ---- partial tile out
-    double* out = vpart + (size_t)blockIdx.y * NP * NP;
+    const int NP = P.NP;
+    double* out = P.vpart + (size_t)blockIdx.y * NP * NP;
 #pragma unroll
     for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
@@ -433,24 +487,29 @@ vxc_tma_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant
         }
 }
 
-// out[i][j] = sum_s (T_s(i,j) + T_s(j,i)), T = M where the tile was computed (lda_half: the mirror
-// tile otherwise).  Fixed summation order -> bit-reproducible and exactly symmetric.
-__global__ void finalize_tma_kernel(int nao, int NP, int NT, int nslices, int lda_half,
+// out[i][j] = sum over slices of T(i+s, j+s) + T(j+s, i+s), s = column shift of the slice's
+// sub-problem; T = M where the tile was computed (lda_half: the mirror tile otherwise).
+// Fixed summation order -> bit-reproducible and exactly symmetric.
+__global__ void finalize_tma_kernel(int nao, int NP, int NT, int nsub, int slices_per_sub, int shift1, int lda_half,
                                     const double* __restrict__ vpart, double* __restrict__ vxc, int nepart,
                                     const double* __restrict__ epart, double* __restrict__ d_exc) {
     const size_t n2 = (size_t)nao * nao;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < n2) {
-        const int i = (int)(idx / nao), j = (int)(idx % nao);
-        size_t o1 = (size_t)i * NP + j, o2 = (size_t)j * NP + i;
-        if (lda_half) {
-            if (i / NT > j / NT) o1 = o2;
-            else if (j / NT > i / NT) o2 = o1;
-        }
+        const int i0 = (int)(idx / nao), j0 = (int)(idx % nao);
         double s = 0.0;
-        for (int sl = 0; sl < nslices; ++sl) {
-            const double* p = vpart + (size_t)sl * NP * NP;
-            s += p[o1] + p[o2];
+        for (int su = 0; su < nsub; ++su) {
+            const int sh = su ? shift1 : 0;
+            const int i = i0 + sh, j = j0 + sh;
+            size_t o1 = (size_t)i * NP + j, o2 = (size_t)j * NP + i;
+            if (lda_half) {
+                if (i / NT > j / NT) o1 = o2;
+                else if (j / NT > i / NT) o2 = o1;
+            }
+            for (int sl = 0; sl < slices_per_sub; ++sl) {
+                const double* p = vpart + (size_t)(su * slices_per_sub + sl) * NP * NP;
+                s += p[o1] + p[o2];
+            }
         }
         vxc[idx] = s;
     }
@@ -468,14 +527,16 @@ __global__ void finalize_tma_kernel(int nao, int NP, int NT, int nslices, int ld
     }
 }
 
-__global__ void symmetrize_pad_tma_kernel(int nao, int ld, int rows, const double* __restrict__ dm,
+// dsym[s][i][j] = 1/2 (D[i-s][j-s] + D[j-s][i-s]) inside the matrix, 0 elsewhere; s = 0..nshift-1
+__global__ void symmetrize_pad_tma_kernel(int nao, int ld, int rows, int nshift, const double* __restrict__ dm,
                                           double* __restrict__ dsym) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= ld || i >= rows) return;
+    const int i = blockIdx.y % rows, s = blockIdx.y / rows;
+    if (j >= ld || s >= nshift) return;
     double v = 0.0;
-    if (i < nao && j < nao) v = 0.5 * (dm[(size_t)i * nao + j] + dm[(size_t)j * nao + i]);
-    dsym[(size_t)i * ld + j] = v;
+    const int ii = i - s, jj = j - s;
+    if (ii >= 0 && jj >= 0 && ii < nao && jj < nao) v = 0.5 * (dm[(size_t)ii * nao + jj] + dm[(size_t)jj * nao + ii]);
+    dsym[((size_t)s * rows + i) * ld + j] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -522,24 +583,83 @@ static bool make_map(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t ro
     return true;
 }
 
-static bool make_plane_map(CUtensorMap* m, const double* ptr, int ngrid, int nao, bool paired, uint32_t box_rows) {
-    if (!paired) return make_map(m, ptr, (uint64_t)nao, (uint64_t)ngrid, (uint64_t)nao, box_rows);
-    return make_map(m, ptr, 2ull * nao, (uint64_t)ngrid / 2, 2ull * nao, box_rows);
+// Tensor map of plane `ptr` for sub-problem (parity) si of an (ngrid x nao) array: see file header.
+static bool make_sub_map(CUtensorMap* m, const double* ptr, int ngrid, int nao, bool split, int si, uint32_t box_rows) {
+    if (!split) return make_map(m, ptr, (uint64_t)nao, (uint64_t)ngrid, (uint64_t)nao, box_rows);
+    if (si == 0) return make_map(m, ptr, (uint64_t)nao, (uint64_t)(ngrid + 1) / 2, 2ull * nao, box_rows);
+    return make_map(m, ptr + (nao - 1), (uint64_t)nao + 1, (uint64_t)ngrid / 2, 2ull * nao, box_rows);
 }
 
 template <int NF, int NPL>
-static void launch(CublasHandleWrapper* ctx, const Problem& p, bool paired, int ntiles, int NP, int KP, int nsm,
-                   double* dsym, double* coef, double* epart, int nblocks, int grid1, int xc_mode) {
+static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     cudaStream_t st = ctx->stream;
     const int ngrid = p.ngrid, nao = p.nao;
     constexpr int NT = 32 * NF;
-    CUtensorMap map_a, map_d, mp[4];
-    bool ok = make_plane_map(&map_a, p.ao, ngrid, nao, paired, paired ? MB / 2 : MB);
-    ok = ok && make_map(&map_d, dsym, (uint64_t)KP, (uint64_t)NP, (uint64_t)KP, NT);
+    const bool split = (nao & 1) != 0;
+    const int nsub = split ? 2 : 1;
+    const int ncols = nao + (split ? 1 : 0);            // widest sub-problem
+    const int ntiles = (ncols + NT - 1) / NT;
+    const int NP = ntiles * NT;
+    const int KP = ((ncols + 15) / 16) * 16;
+
+    DensityParams dp;
+    VxcParams vp;
+    memset(&dp, 0, sizeof(dp));
+    memset(&vp, 0, sizeof(vp));
+    SubProblem sub[2];
+    memset(sub, 0, sizeof(sub));
+    if (!split) {
+        sub[0] = SubProblem{ngrid, 1, 0, 0, 0, 0};
+    } else {
+        sub[0] = SubProblem{(ngrid + 1) / 2, 2, 0, 0, 0, 0};
+        sub[1] = SubProblem{ngrid / 2, 2, 1, 1, 0, 0};
+    }
+    int nblocks = 0, coef_rows = 0;
+    for (int s = 0; s < nsub; ++s) {
+        sub[s].blk0 = nblocks;
+        sub[s].coef0 = coef_rows;
+        const int nb = (sub[s].rows + MB - 1) / MB;
+        nblocks += nb;
+        coef_rows += nb * MB;
+    }
+    const int grid1 = nblocks < nsm ? nblocks : nsm;
+
+    double* dsym = (double*)ctx->dsym.ensure(sizeof(double) * (size_t)nsub * NP * KP, &ctx->failed);
+    double* coef = (double*)ctx->coef.ensure(sizeof(double) * 4 * (size_t)coef_rows, &ctx->failed);
+    double* epart = (double*)ctx->epart.ensure(sizeof(double) * grid1, &ctx->failed);
+    if (ctx->failed) return;
+
     const double* planes[4] = {p.ao, p.gx, p.gy, p.gz};
-    for (int i = 0; i < 4; ++i)
-        ok = ok && make_plane_map(&mp[i], planes[i < NPL ? i : 0], ngrid, nao, paired, paired ? VK / 2 : VK);
+    bool ok = make_map(&dp.map_d, dsym, (uint64_t)KP, (uint64_t)nsub * NP, (uint64_t)KP, NT);
+    for (int s = 0; s < nsub; ++s) {
+        ok = ok && make_sub_map(&dp.map_a[s], p.ao, ngrid, nao, split, s, MB);
+        for (int i = 0; i < 4; ++i) ok = ok && make_sub_map(&vp.map_p[s][i], planes[i < NPL ? i : 0], ngrid, nao, split, s, VK);
+    }
     if (!ok) { ctx->failed = true; return; }
+
+    dp.sub[0] = sub[0]; dp.sub[1] = sub[1];
+    dp.nsub = nsub; dp.ngrid = ngrid; dp.nao = nao;
+    dp.xc_mode = p.xc_type == 2 ? 4 : p.xc_type * 2 + (ctx->exact_functionals ? 1 : 0);
+    dp.nblocks = nblocks; dp.ntiles = ntiles; dp.nk = KP / 16; dp.NP = NP;
+    dp.ao = p.ao; dp.gx = p.gx; dp.gy = p.gy; dp.gz = p.gz; dp.w = p.w;
+    dp.coef = coef; dp.exc_part = epart;
+
+    const int lda_half = (NPL == 1) ? 1 : 0;
+    const int tiles = lda_half ? ntiles * (ntiles + 1) / 2 : ntiles * ntiles;
+    const int maxrows = sub[0].rows;
+    int nsl = nsm / (tiles * nsub);
+    if (nsl < 1) nsl = 1;
+    const int max_slices = (maxrows + VK - 1) / VK;
+    if (nsl > max_slices) nsl = max_slices;
+    int rows_per_slice = (maxrows + nsl - 1) / nsl;
+    rows_per_slice = ((rows_per_slice + VK - 1) / VK) * VK;
+    nsl = (maxrows + rows_per_slice - 1) / rows_per_slice;
+    double* vpart = (double*)ctx->vpart.ensure(sizeof(double) * (size_t)nsub * nsl * NP * NP, &ctx->failed);
+    if (ctx->failed) return;
+
+    vp.sub[0] = sub[0]; vp.sub[1] = sub[1];
+    vp.nsub = nsub; vp.ntiles = ntiles; vp.lda_half = lda_half; vp.rows_per_slice = rows_per_slice;
+    vp.slices_per_sub = nsl; vp.NP = NP; vp.coef = coef; vp.vpart = vpart;
 
     using DL = DensitySmem<NF>;
     using VL = VxcSmem<NF, NPL>;
@@ -549,28 +669,14 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, bool paired, int 
     DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, VL::TOTAL));
 
     if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
-    symmetrize_pad_tma_kernel<<<dim3((KP + 127) / 128, NP), 128, 0, st>>>(nao, KP, NP, p.dm, dsym);
-    dk<<<grid1, NTHREADS, DL::TOTAL, st>>>(map_a, map_d, ngrid, nao, paired ? 1 : 0, xc_mode, nblocks, ntiles, KP / 16,
-                                           p.ao, p.gx, p.gy, p.gz, p.w, coef, epart);
+    symmetrize_pad_tma_kernel<<<dim3((KP + 127) / 128, NP * nsub), 128, 0, st>>>(nao, KP, NP, nsub, p.dm, dsym);
+    dk<<<grid1, NTHREADS, DL::TOTAL, st>>>(dp);
     if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
-
-    const int lda_half = (NPL == 1) ? 1 : 0;
-    const int tiles = lda_half ? ntiles * (ntiles + 1) / 2 : ntiles * ntiles;
-    int nslices = nsm / tiles;
-    if (nslices < 1) nslices = 1;
-    const int max_slices = (ngrid + VK - 1) / VK;
-    if (nslices > max_slices) nslices = max_slices;
-    int rows_per_slice = (ngrid + nslices - 1) / nslices;
-    rows_per_slice = ((rows_per_slice + VK - 1) / VK) * VK;
-    nslices = (ngrid + rows_per_slice - 1) / rows_per_slice;
-    double* vpart = (double*)ctx->vpart.ensure(sizeof(double) * (size_t)nslices * NP * NP, &ctx->failed);
-    if (ctx->failed) return;
-    vk<<<dim3(tiles, nslices), NTHREADS, VL::TOTAL, st>>>(mp[0], mp[1], mp[2], mp[3], ngrid, nao, paired ? 1 : 0, ntiles,
-                                                          lda_half, rows_per_slice, NP, coef, vpart);
+    vk<<<dim3(tiles, nsl * nsub), NTHREADS, VL::TOTAL, st>>>(vp);
     if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
     const size_t n2 = (size_t)nao * nao;
-    finalize_tma_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(nao, NP, NT, nslices, lda_half, vpart, p.vxc, grid1,
-                                                                      epart, p.d_exc);
+    finalize_tma_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(nao, NP, NT, nsub, nsl, split ? 1 : 0, lda_half, vpart,
+                                                                      p.vxc, grid1, epart, p.d_exc);
     if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
     ctx->stats.launches = 4;
     ctx->stats.path = PATH_TMA;
@@ -584,33 +690,18 @@ bool tma_compatible(const Problem& p) {
     if (p.nao < 1 || p.ngrid < 1) return false;
     if (!al16(p.ao)) return false;
     if (p.xc_type != 0 && !(al16(p.gx) && al16(p.gy) && al16(p.gz))) return false;
-    if ((p.nao & 1) && (p.ngrid & 1)) return false;  // row pairs need an even number of rows
-    if (p.nao > 128 * 16) return false;               // keep the padded D and partials modest
+    if (p.nao > 128 * 16) return false;  // keep the padded D and the slice partials modest
     return tmapath::encode_fn() != nullptr;
 }
 
 void run_tma(CublasHandleWrapper* ctx, const Problem& p) {
     using namespace tmapath;
-    const int ngrid = p.ngrid, nao = p.nao;
-    const bool paired = (nao & 1) != 0;
-    const int ntiles = (nao + 127) / 128;
-    const int NF = (nao + 32 * ntiles - 1) / (32 * ntiles);  // 1..4
-    const int NT = 32 * NF, NP = ntiles * NT;
-    const int KP = ((nao + 15) / 16) * 16;
+    const int ncols = p.nao + (p.nao & 1);
+    const int ntiles = (ncols + 127) / 128;
+    const int NF = (ncols + 32 * ntiles - 1) / (32 * ntiles);  // 1..4 -> column tile 32 NF
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-    const int nblocks = (ngrid + MB - 1) / MB;
-    const int grid1 = nblocks < nsm ? nblocks : nsm;
-
-    double* dsym = (double*)ctx->dsym.ensure(sizeof(double) * (size_t)NP * KP, &ctx->failed);
-    double* coef = (double*)ctx->coef.ensure(sizeof(double) * 4 * (size_t)nblocks * MB, &ctx->failed);
-    double* epart = (double*)ctx->epart.ensure(sizeof(double) * grid1, &ctx->failed);
-    if (ctx->failed) return;
-    const int xc_mode = p.xc_type == 2 ? 4 : p.xc_type * 2 + (ctx->exact_functionals ? 1 : 0);
-
-#define DFT_LAUNCH(NF_) \
-    (p.xc_type == 0 ? launch<NF_, 1>(ctx, p, paired, ntiles, NP, KP, nsm, dsym, coef, epart, nblocks, grid1, xc_mode) \
-                    : launch<NF_, 4>(ctx, p, paired, ntiles, NP, KP, nsm, dsym, coef, epart, nblocks, grid1, xc_mode))
+#define DFT_LAUNCH(NF_) (p.xc_type == 0 ? launch<NF_, 1>(ctx, p, nsm) : launch<NF_, 4>(ctx, p, nsm))
     switch (NF) {
         case 1: DFT_LAUNCH(1); break;
         case 2: DFT_LAUNCH(2); break;

@@ -191,7 +191,7 @@ def test_tma_path_matches_generic_path_at_scale(engine_lib, functional, ngrid, n
     dm, ao, w, grad = _random_case(rng, ngrid, nao)
     e0, v0, s0 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 1})
     e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 0})
-    assert s0["path"] == 1 and s1["path"] == (2 if (nao % 2 == 0 or ngrid % 2 == 0) else 1)
+    assert s0["path"] == 1 and s1["path"] == 2
     assert abs(e0 - e1) <= E_TOL * max(1.0, abs(e0) * 1e-3)
     np.testing.assert_allclose(v0, v1, rtol=0, atol=V_TOL * max(1.0, np.abs(v0).max() * 1e-3))
 
