@@ -202,7 +202,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
         const int j = 2 * qcol + e;
         ncol[e] = 2 * (j & 3) + (j >> 2);
     }
-    const int ngrid = P.ngrid, nao = P.nao;
+    const int nao = P.nao;
     const double* __restrict__ ao = P.ao;
     const double* __restrict__ gx = P.gx;
     const double* __restrict__ gy = P.gy;
@@ -245,31 +245,49 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             //      the row sums of this column tile are folded into shared memory right away so that
             //      no row accumulator stays live across the k-loop (each red[] entry has one owner lane)
             const int nbase = nt * NT + wn * 8 * NF - shift;
+            // column indices / validity of this lane's 2 NF accumulator columns (same for every row)
+            int ncl[NF][2];
+            bool nok[NF][2];
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = nbase + nf * 8 + ncol[e];
+                    nok[nf][e] = (n >= 0) && (n < nao);
+                    ncl[nf][e] = min(max(n, 0), nao - 1);
+                }
 #pragma unroll
             for (int mf = 0; mf < 8; ++mf) {
                 const int r = wm * 64 + mf * 8 + perm;
                 const int j = blk * MB + r;
+                const bool rok = j < rows;
+                const size_t rowoff = (size_t)((long)gmul * (rok ? j : 0) + gadd) * nao;
+                // all loads of one fragment row are issued back to back (unconditional, clamped
+                // addresses) so that 8 NF x NPL independent requests are in flight per lane
+                double pv[NPL][NF][2];
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const size_t o = rowoff + ncl[nf][e];
+                        pv[0][nf][e] = __ldg(ao + o);
+                        if (NPL == 4) {
+                            pv[1][nf][e] = __ldg(gx + o);
+                            pv[2][nf][e] = __ldg(gy + o);
+                            pv[3][nf][e] = __ldg(gz + o);
+                        }
+                    }
                 double rs[NPL];
 #pragma unroll
                 for (int p = 0; p < NPL; ++p) rs[p] = 0.0;
-                if (j < rows) {
-                    const size_t rowoff = (size_t)((long)gmul * j + gadd) * nao;
 #pragma unroll
-                    for (int nf = 0; nf < NF; ++nf) {
+                for (int nf = 0; nf < NF; ++nf)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int n = nbase + nf * 8 + ncol[e];
-                            if (n < 0 || n >= nao) continue;
-                            const double cv = acc[mf][nf][e];
-                            rs[0] = fma(cv, __ldg(ao + rowoff + n), rs[0]);
-                            if (NPL == 4) {
-                                rs[1] = fma(cv, __ldg(gx + rowoff + n), rs[1]);
-                                rs[2] = fma(cv, __ldg(gy + rowoff + n), rs[2]);
-                                rs[3] = fma(cv, __ldg(gz + rowoff + n), rs[3]);
-                            }
-                        }
+                    for (int e = 0; e < 2; ++e) {
+                        const double cv = (rok && nok[nf][e]) ? acc[mf][nf][e] : 0.0;
+#pragma unroll
+                        for (int p = 0; p < NPL; ++p) rs[p] = fma(cv, pv[p][nf][e], rs[p]);
                     }
-                }
 #pragma unroll
                 for (int p = 0; p < NPL; ++p) {
                     double v = rs[p];
@@ -596,7 +614,7 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     const int ngrid = p.ngrid, nao = p.nao;
     constexpr int NT = 32 * NF;
     const bool split = (nao & 1) != 0;
-    const int nsub = split ? 2 : 1;
+    const int nsub = (split && ngrid >= 2) ? 2 : 1;
     const int ncols = nao + (split ? 1 : 0);            // widest sub-problem
     const int ntiles = (ncols + NT - 1) / NT;
     const int NP = ntiles * NT;

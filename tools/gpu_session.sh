@@ -17,6 +17,11 @@ l=load_library()
 print('DMMA TFLOP/s', l.DFT_MicrobenchDMMA(8192)); print('DFMA TFLOP/s', l.DFT_MicrobenchDFMA(8192))" > $OUT/micro.log 2>&1; echo "micro rc=$?" | tee -a $OUT/summary.txt; cat $OUT/micro.log ;;
     bench:*) W=${what#bench:}; timeout 600 python bench.py --workload $W --steps 5 --warmup 3 > $OUT/bench_$W.json 2> $OUT/bench_$W.err; echo "bench $W rc=$?" | tee -a $OUT/summary.txt; cat $OUT/bench_$W.json; tail -3 $OUT/bench_$W.err ;;
     ref:*)   W=${what#ref:}; timeout 600 python bench.py --impl reference --workload $W --steps 2 --warmup 1 > $OUT/ref_$W.json 2> $OUT/ref_$W.err; echo "ref $W rc=$?" | tee -a $OUT/summary.txt; cat $OUT/ref_$W.json; tail -3 $OUT/ref_$W.err ;;
+    ncu:*)   W=${what#ncu:}; CMD="python bench.py --workload $W --steps 2 --warmup 3 --no-cpu-baseline"
+             timeout 600 $CMD > $OUT/ncu_plain_$W.log 2>&1 && \
+             timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$W.csv $CMD > $OUT/ncu_list_$W.log 2>&1 && \
+             timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'density_tma|vxc_tma|density_kernel|vxc_kernel|eval_kernel' -s 4 -c 2 -o $OUT/prof_$W $CMD > $OUT/ncu_full_$W.log 2>&1
+             echo "ncu $W rc=$?" | tee -a $OUT/summary.txt; tail -3 $OUT/ncu_full_$W.log ;;
     *) echo "unknown step $what" ;;
   esac
 done
