@@ -1,0 +1,53 @@
+"""Grid-sharded multi-rank logic on the CPU (gloo, world_size 2): every rank integrates its slice of
+the grid (here with the oracle standing in for the GPU engine) and the nao x nao partial V_xc plus the
+scalar E_xc are all-reduced -- the same partition (solver.shard_bounds), packing ([V | E]) and reduction
+the engine performs with NCCL on the GPUs (csrc/comm.cu)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, functional, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from quantum_compute_dft_b200 import workload
+    from quantum_compute_dft_b200.solver import shard_bounds
+    hp = workload.host_problem("H2O", scale=0.1, functional=functional)
+    lo, hi = shard_bounds(hp.ngrid, rank, world)
+    ao, grad = O.eval_ao(hp.coords[lo:hi], hp.basis, deriv=1)
+    e, v = O.compute_xc(workload.FUNCTIONAL_TYPE[functional], hp.dm, ao, hp.weights[lo:hi], grad)
+    packed = torch.from_numpy(np.concatenate([O.sym(v).ravel(), [e]]))
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        np.save(os.path.join(out_dir, f"packed_{functional}.npy"), packed.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("functional", ["LDA", "B3LYP"])
+def test_two_rank_grid_sharding_sums_to_whole(oracle, tmp_path, functional):
+    import torch.multiprocessing as mp
+    from quantum_compute_dft_b200 import workload
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, functional, str(tmp_path)), nprocs=2, join=True)
+    packed = np.load(tmp_path / f"packed_{functional}.npy")
+    hp = workload.host_problem("H2O", scale=0.1, functional=functional)
+    ao, grad = oracle.eval_ao(hp.coords, hp.basis, deriv=1)
+    e, v = oracle.compute_xc(workload.FUNCTIONAL_TYPE[functional], hp.dm, ao, hp.weights, grad)
+    nao = hp.nao
+    assert abs(packed[-1] - e) < 1e-10
+    np.testing.assert_allclose(packed[:-1].reshape(nao, nao), oracle.sym(v), rtol=0, atol=1e-11)
