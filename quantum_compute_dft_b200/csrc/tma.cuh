@@ -71,6 +71,13 @@ __device__ __forceinline__ void load_1d(void* smem_dst, const void* gsrc, uint32
                  : "memory");
 }
 
+// L2 prefetch of one box of a tiled tensor (no shared-memory destination, no completion signal)
+__device__ __forceinline__ void prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

@@ -52,10 +52,16 @@ constexpr int MB = 128;                     // grid rows per block (density kern
 constexpr int NCW = 8;                      // consumer warps, 2 (m) x 4 (n)
 constexpr int NCONS = NCW * 32;             // 256 consumer threads = 2 warpgroups
 constexpr int NTHREADS = NCONS + 128;       // + 1 producer warpgroup
-constexpr int REGS_CONSUMER = 232;          // 384*168 = 256*232 + 128*40
+constexpr int REGS_CONSUMER = 232;          // density kernel: 384*168 = 256*232 + 128*40
 constexpr int REGS_PRODUCER = 40;
+constexpr int V_REGS_CONSUMER = 224;        // V kernel (producer warpgroup also builds B): 256*224 + 128*56
+constexpr int V_REGS_PRODUCER = 56;
 constexpr int D_STAGES = 5;                 // density pipeline depth
-constexpr int V_STAGES = 2;                 // V pipeline depth (stages are 5 planes wide)
+constexpr int VP_STAGES = 2;                // V kernel: plane ring (TMA -> builder warps)
+constexpr int VN_STAGES = 3;                // V kernel: Phi column-tile ring (TMA -> MMA warps)
+constexpr int VB_STAGES = 2;                // V kernel: B tile ring (builder warps -> MMA warps)
+constexpr int VB_WARPS = 3;                 // builder warps (warps 8..10); warp 11 drives TMA
+constexpr int D_PREFETCH_LEAD = 8;          // density: k-chunks before the epilogue at which grad tiles are L2-prefetched
 constexpr int VK = 16;                      // grid rows per V chunk
 constexpr int A_TILE_BYTES = MB * 128;      // 128 rows x 16 doubles
 
@@ -70,6 +76,7 @@ struct SubProblem {
 
 struct DensityParams {
     CUtensorMap map_a[2];   // Phi of each sub-problem, box 16 x 128
+    CUtensorMap map_g[2][3];  // grad Phi planes, box 16 x 128 (L2 prefetch of the epilogue tiles only)
     CUtensorMap map_d;      // [2][NP][KP] symmetrised density (plain, shifted), box 16 x NT
     SubProblem sub[2];
     int nsub, ngrid, nao, xc_mode, nblocks, ntiles, nk, NP;
@@ -170,7 +177,16 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                 const int blk = b - P.sub[si].blk0;
                 const int drow0 = P.sub[si].shift * P.NP;
                 for (int nt = 0; nt < ntiles; ++nt) {
+                    const int kpf = nk > D_PREFETCH_LEAD ? nk - D_PREFETCH_LEAD : 0;
                     for (int kc = 0; kc < nk; ++kc, ++it) {
+                        if (NPL == 4 && kc == kpf) {
+                            // the epilogue of this tile gathers grad Phi[blk rows][nt columns] with plain
+                            // loads: pull those tiles into L2 a few chunks ahead (Phi itself is L2-hot, it
+                            // is this block's A operand)
+                            for (int pl = 0; pl < 3; ++pl)
+                                for (int bx = 0; bx < NT / 16; ++bx)
+                                    tma::prefetch_2d(&P.map_g[si][pl], nt * NT + 16 * bx, blk * MB);
+                        }
                         const uint32_t s = it % D_STAGES, ph = (it / D_STAGES) & 1u;
                         tma::mbar_wait(&empty[s], ph ^ 1u);
                         unsigned char* st = sm + s * L::STAGE_BYTES;
@@ -344,15 +360,20 @@ template <int NF, int NPL>
 struct VxcSmem {
     static constexpr int NT = 32 * NF;
     static constexpr int TILE_BYTES = VK * NT * 8;                       // one plane tile: 2NF boxes of 2 KB
-    static constexpr int COEF_OFF = (NPL + 1) * TILE_BYTES;              // 16 x (a,bx,by,bz)
-    static constexpr int STAGE_BYTES = COEF_OFF + 1024;
+    static constexpr int P_STAGE_BYTES = NPL * TILE_BYTES + 1024;        // planes + 16 x (a,bx,by,bz)
+    static constexpr int COEF_OFF = NPL * TILE_BYTES;
+    static constexpr int N_OFF = VP_STAGES * P_STAGE_BYTES;              // Phi column-tile ring
     static constexpr int BPITCH = NT + 4;                                // doubles; (NT+4) mod 16 == 4
-    static constexpr int BS_OFF = V_STAGES * STAGE_BYTES;
-    static constexpr int BS_BYTES = VK * BPITCH * 8;
-    static constexpr int BAR_OFF = BS_OFF + 2 * BS_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 2 * V_STAGES * 8 + 1024;
+    static constexpr int BS_BYTES = ((VK * BPITCH * 8 + 1023) / 1024) * 1024;
+    static constexpr int BS_OFF = N_OFF + VN_STAGES * TILE_BYTES;
+    static constexpr int BAR_OFF = BS_OFF + VB_STAGES * BS_BYTES;
+    static constexpr int NBAR = 2 * (VP_STAGES + VN_STAGES + VB_STAGES);
+    static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 1024;
 };
 
+// Roles (384 threads): warps 0..7 MMA (2 x 4, warp tile 16NF x 8NF), warps 8..10 build the B tile
+// of each chunk from the four plane tiles, warp 11 lane 0 drives TMA.  Three mbarrier rings:
+//   planes  : TMA -> builders          B tile : builders -> MMA          Phi n-tile : TMA -> MMA
 template <int NF, int NPL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vxc_tma_kernel(const __grid_constant__ VxcParams P) {
@@ -361,8 +382,13 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (tma::smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - tma::smem_u32(smem_raw));
-    uint64_t* full = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF);
-    uint64_t* empty = full + V_STAGES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF);
+    uint64_t* full_p = bars;
+    uint64_t* empty_p = full_p + VP_STAGES;
+    uint64_t* full_n = empty_p + VP_STAGES;
+    uint64_t* empty_n = full_n + VN_STAGES;
+    uint64_t* full_b = empty_n + VN_STAGES;
+    uint64_t* empty_b = full_b + VB_STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -378,7 +404,6 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         tm = blockIdx.x / ntiles;
         tn = blockIdx.x % ntiles;
     }
-    const bool diag = (tm == tn);
     const int m0 = tm * NT, n0 = tn * NT;
     // grid slice of this CTA: rows [jbeg, jend) of sub-problem si
     const int si = blockIdx.y / P.slices_per_sub;
@@ -388,42 +413,83 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     const int nchunks = jend > jbeg ? (jend - jbeg + VK - 1) / VK : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < V_STAGES; ++s) {
-            tma::mbar_init(&full[s], 1);
-            tma::mbar_init(&empty[s], NCW);
-        }
+        for (int s = 0; s < VP_STAGES; ++s) { tma::mbar_init(&full_p[s], 1); tma::mbar_init(&empty_p[s], VB_WARPS); }
+        for (int s = 0; s < VN_STAGES; ++s) { tma::mbar_init(&full_n[s], 1); tma::mbar_init(&empty_n[s], NCW); }
+        for (int s = 0; s < VB_STAGES; ++s) { tma::mbar_init(&full_b[s], VB_WARPS); tma::mbar_init(&empty_b[s], NCW); }
         tma::fence_barrier_init();
     }
     __syncthreads();
 
     if (warp >= NCW) {
-        // ===================== producer warpgroup =====================
-        reg_dec<REGS_PRODUCER>();
-        if (warp == NCW && lane == 0) {
-            for (int p = 0; p < NPL; ++p) tma::prefetch_map(&P.map_p[si][p]);
-            const int ntile_loads = NPL + (diag ? 0 : 1);
-            const uint32_t stage_tx = (uint32_t)(ntile_loads * L::TILE_BYTES + VK * 32);
-            const double* coef = P.coef + 4 * (size_t)P.sub[si].coef0;
-            for (int c = 0; c < nchunks; ++c) {
-                const uint32_t s = c % V_STAGES, ph = (c / V_STAGES) & 1u;
-                tma::mbar_wait(&empty[s], ph ^ 1u);
-                unsigned char* st = sm + s * L::STAGE_BYTES;
-                const int j0 = jbeg + c * VK;
-                tma::mbar_arrive_expect_tx(&full[s], stage_tx);
-                for (int p = 0; p < ntile_loads; ++p) {
-                    const CUtensorMap* mp = &P.map_p[si][p < NPL ? p : 0];
-                    const int col0 = (p < NPL) ? m0 : n0;
-                    unsigned char* dst = st + p * L::TILE_BYTES;
-                    for (int b = 0; b < 2 * NF; ++b) tma::load_2d(dst + b * 2048, mp, col0 + 16 * b, j0, &full[s]);
+        reg_dec<V_REGS_PRODUCER>();
+        if (warp == NCW + VB_WARPS) {
+            // ===================== TMA producer =====================
+            if (lane == 0) {
+                for (int p = 0; p < NPL; ++p) tma::prefetch_map(&P.map_p[si][p]);
+                const double* coef = P.coef + 4 * (size_t)P.sub[si].coef0;
+                for (int c = 0; c < nchunks; ++c) {
+                    const int j0 = jbeg + c * VK;
+                    {
+                        const uint32_t s = c % VP_STAGES, ph = (c / VP_STAGES) & 1u;
+                        tma::mbar_wait(&empty_p[s], ph ^ 1u);
+                        unsigned char* st = sm + s * L::P_STAGE_BYTES;
+                        tma::mbar_arrive_expect_tx(&full_p[s], (uint32_t)(NPL * L::TILE_BYTES + VK * 32));
+                        for (int p = 0; p < NPL; ++p)
+                            for (int b = 0; b < 2 * NF; ++b)
+                                tma::load_2d(st + p * L::TILE_BYTES + b * 2048, &P.map_p[si][p], m0 + 16 * b, j0, &full_p[s]);
+                        tma::load_1d(st + L::COEF_OFF, coef + 4 * (size_t)j0, VK * 32, &full_p[s]);
+                    }
+                    {
+                        const uint32_t s = c % VN_STAGES, ph = (c / VN_STAGES) & 1u;
+                        tma::mbar_wait(&empty_n[s], ph ^ 1u);
+                        unsigned char* st = sm + L::N_OFF + s * L::TILE_BYTES;
+                        tma::mbar_arrive_expect_tx(&full_n[s], (uint32_t)L::TILE_BYTES);
+                        for (int b = 0; b < 2 * NF; ++b)
+                            tma::load_2d(st + b * 2048, &P.map_p[si][0], n0 + 16 * b, j0, &full_n[s]);
+                    }
                 }
-                tma::load_1d(st + L::COEF_OFF, coef + 4 * (size_t)j0, VK * 32, &full[s]);
+            }
+            return;
+        }
+        // ===================== builder warps: B = a Phi + bx dxPhi + by dyPhi + bz dzPhi =====================
+        const int btid = tid - NCONS;
+        for (int c = 0; c < nchunks; ++c) {
+            const uint32_t sp = c % VP_STAGES, php = (c / VP_STAGES) & 1u;
+            const uint32_t sb = c % VB_STAGES, phb = (c / VB_STAGES) & 1u;
+            const uint32_t st = base + sp * L::P_STAGE_BYTES;
+            const uint32_t bs = base + L::BS_OFF + sb * L::BS_BYTES;
+            tma::mbar_wait(&full_p[sp], php);
+            tma::mbar_wait(&empty_b[sb], phb ^ 1u);
+            for (int task = btid; task < 256 * NF; task += VB_WARPS * 32) {
+                const int j = task & 7, rb = task >> 3;
+                const int r = rb & 15, b = rb >> 4;
+                const uint32_t off = (uint32_t)(b * 2048 + r * 128 + (((j ^ r) & 7) << 4));
+                const double2 ca = lds_f64x2(st + L::COEF_OFF + r * 32);
+                const double2 v0 = lds_f64x2(st + off);
+                double2 o = make_double2(ca.x * v0.x, ca.x * v0.y);
+                if (NPL == 4) {
+                    const double2 cb = lds_f64x2(st + L::COEF_OFF + r * 32 + 16);
+                    const double2 v1 = lds_f64x2(st + L::TILE_BYTES + off);
+                    const double2 v2 = lds_f64x2(st + 2 * L::TILE_BYTES + off);
+                    const double2 v3 = lds_f64x2(st + 3 * L::TILE_BYTES + off);
+                    o.x = fma(ca.y, v1.x, o.x); o.y = fma(ca.y, v1.y, o.y);
+                    o.x = fma(cb.x, v2.x, o.x); o.y = fma(cb.x, v2.y, o.y);
+                    o.x = fma(cb.y, v3.x, o.x); o.y = fma(cb.y, v3.y, o.y);
+                }
+                const int rho_idx = 8 * (r >> 3) + 4 * (r & 1) + ((r & 7) >> 1);  // MMA order of tile row r
+                sts_f64x2(bs + (uint32_t)((rho_idx * L::BPITCH + b * 16 + 2 * j) * 8), o);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                tma::mbar_arrive(&full_b[sb]);
+                tma::mbar_arrive(&empty_p[sp]);
             }
         }
         return;
     }
 
-    // ===================== consumers: 2 x 4 warps, warp tile (16 NF) x (8 NF) =====================
-    reg_inc<REGS_CONSUMER>();
+    // ===================== MMA warps: 2 x 4, warp tile (16 NF) x (8 NF) =====================
+    reg_inc<V_REGS_CONSUMER>();
     const int wm = warp >> 2, wn = warp & 3;
     const int q = lane >> 2, qcol = lane & 3;
     constexpr int MF = 2 * NF;
@@ -444,39 +510,15 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
             boff[ks][nf] = (uint32_t)((n >> 4) * 2048) + tma::swz128((uint32_t)r, (uint32_t)(n & 15));
         }
     }
-    const uint32_t bs_base = base + L::BS_OFF;
     const uint32_t aoff = (uint32_t)((qcol * L::BPITCH + wm * 16 * NF + q) * 8);
 
     for (int c = 0; c < nchunks; ++c) {
-        const uint32_t s = c % V_STAGES, ph = (c / V_STAGES) & 1u;
-        const uint32_t st = base + s * L::STAGE_BYTES;
-        const uint32_t bs = bs_base + (c & 1) * L::BS_BYTES;
-        tma::mbar_wait(&full[s], ph);
-        // ---- build B rows for this chunk: B = a Phi + bx dxPhi + by dyPhi + bz dzPhi
-#pragma unroll
-        for (int t = 0; t < NF; ++t) {
-            const int task = tid + t * NCONS;
-            const int j = task & 7, rb = task >> 3;
-            const int r = rb & 15, b = rb >> 4;
-            const uint32_t off = (uint32_t)(b * 2048 + r * 128 + (((j ^ r) & 7) << 4));
-            const double2 ca = lds_f64x2(st + L::COEF_OFF + r * 32);
-            const double2 v0 = lds_f64x2(st + off);
-            double2 o = make_double2(ca.x * v0.x, ca.x * v0.y);
-            if (NPL == 4) {
-                const double2 cb = lds_f64x2(st + L::COEF_OFF + r * 32 + 16);
-                const double2 v1 = lds_f64x2(st + L::TILE_BYTES + off);
-                const double2 v2 = lds_f64x2(st + 2 * L::TILE_BYTES + off);
-                const double2 v3 = lds_f64x2(st + 3 * L::TILE_BYTES + off);
-                o.x = fma(ca.y, v1.x, o.x); o.y = fma(ca.y, v1.y, o.y);
-                o.x = fma(cb.x, v2.x, o.x); o.y = fma(cb.x, v2.y, o.y);
-                o.x = fma(cb.y, v3.x, o.x); o.y = fma(cb.y, v3.y, o.y);
-            }
-            const int rho_idx = 8 * (r >> 3) + 4 * (r & 1) + ((r & 7) >> 1);  // MMA order of tile row r
-            sts_f64x2(bs + (uint32_t)((rho_idx * L::BPITCH + b * 16 + 2 * j) * 8), o);
-        }
-        tma::named_bar_sync(1, NCONS);
-        // ---- M += B^T Phi
-        const uint32_t phin = st + (diag ? 0 : NPL * L::TILE_BYTES);
+        const uint32_t sb = c % VB_STAGES, phb = (c / VB_STAGES) & 1u;
+        const uint32_t sn = c % VN_STAGES, phn = (c / VN_STAGES) & 1u;
+        const uint32_t bs = base + L::BS_OFF + sb * L::BS_BYTES;
+        const uint32_t phin = base + L::N_OFF + sn * L::TILE_BYTES;
+        tma::mbar_wait(&full_n[sn], phn);
+        tma::mbar_wait(&full_b[sb], phb);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             double a[MF], bf[NF];
@@ -490,7 +532,10 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
                 for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
         }
         __syncwarp();
-        if (lane == 0) tma::mbar_arrive(&empty[s]);
+        if (lane == 0) {
+            tma::mbar_arrive(&empty_b[sb]);
+            tma::mbar_arrive(&empty_n[sn]);
+        }
     }
     // ---- partial tile out
     const int NP = P.NP;
@@ -651,6 +696,8 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     bool ok = make_map(&dp.map_d, dsym, (uint64_t)KP, (uint64_t)nsub * NP, (uint64_t)KP, NT);
     for (int s = 0; s < nsub; ++s) {
         ok = ok && make_sub_map(&dp.map_a[s], p.ao, ngrid, nao, split, s, MB);
+        for (int i = 0; i < 3; ++i)
+            ok = ok && make_sub_map(&dp.map_g[s][i], NPL == 4 ? planes[i + 1] : p.ao, ngrid, nao, split, s, MB);
         for (int i = 0; i < 4; ++i) ok = ok && make_sub_map(&vp.map_p[s][i], planes[i < NPL ? i : 0], ngrid, nao, split, s, VK);
     }
     if (!ok) { ctx->failed = true; return; }

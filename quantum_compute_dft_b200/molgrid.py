@@ -213,16 +213,21 @@ def overlap_matrix(basis):
 
 
 def synthetic_density(S, nocc, seed=0, lindep=1e-8):
-    """D = 2 C C^T with C = X Q: X the (canonically) orthogonalising transform of S,
-    Q the first nocc columns of the QR of a seeded Gaussian matrix.
-    Symmetric, PSD, tr(D S) = 2 nocc, rho >= 0 everywhere."""
+    """D = 2 C C^T with C = S^{-1/2} Q, Q the first nocc columns of the QR of a seeded Gaussian
+    matrix.  Symmetric, PSD, rho >= 0 everywhere, tr(D S) = 2 nocc.
+    S^{-1/2} is the symmetric (Loewdin) inverse square root U s^-1/2 U^T over the eigenvalues above
+    lindep * s_max: unlike the canonical U s^-1/2 it does not depend on the arbitrary signs /
+    rotations LAPACK gives the eigenvectors, so every host, BLAS thread count and rank builds the
+    same D to rounding."""
     w, U = np.linalg.eigh(S)
+    n = S.shape[0]
     keep = w > lindep * w.max()
-    X = U[:, keep] / np.sqrt(w[keep])
-    m = X.shape[1]
-    nocc = min(nocc, m)
+    X = (U[:, keep] / np.sqrt(w[keep])) @ U[:, keep].T
     rng = np.random.default_rng(seed)
-    Q, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    A = rng.standard_normal((n, n))
+    Q, R = np.linalg.qr(A)
+    Q = Q * np.sign(np.diag(R))          # unique QR (positive diagonal of R)
+    nocc = min(nocc, n)
     C = X @ Q[:, :nocc]
     D = 2.0 * (C @ C.T)
     return 0.5 * (D + D.T)
