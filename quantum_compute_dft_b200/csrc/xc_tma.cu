@@ -54,13 +54,10 @@ constexpr int NCONS = NCW * 32;             // 256 consumer threads = 2 warpgrou
 constexpr int NTHREADS = NCONS + 128;       // + 1 producer warpgroup
 constexpr int REGS_CONSUMER = 232;          // density kernel: 384*168 = 256*232 + 128*40
 constexpr int REGS_PRODUCER = 40;
-constexpr int V_REGS_CONSUMER = 224;        // V kernel (producer warpgroup also builds B): 256*224 + 128*56
-constexpr int V_REGS_PRODUCER = 56;
 constexpr int D_STAGES = 5;                 // density pipeline depth
 constexpr int VP_STAGES = 2;                // V kernel: plane ring (TMA -> builder warps)
 constexpr int VN_STAGES = 3;                // V kernel: Phi column-tile ring (TMA -> MMA warps)
-constexpr int VB_STAGES = 2;                // V kernel: B tile ring (builder warps -> MMA warps)
-constexpr int VB_WARPS = 3;                 // builder warps (warps 8..10); warp 11 drives TMA
+constexpr int VB_STAGES = 2;                // V kernel: B tile double buffer (built by the consumer warps)
 constexpr int D_PREFETCH_LEAD = 8;          // density: k-chunks before the epilogue at which grad tiles are L2-prefetched
 constexpr int VK = 16;                      // grid rows per V chunk
 constexpr int A_TILE_BYTES = MB * 128;      // 128 rows x 16 doubles
@@ -367,13 +364,14 @@ struct VxcSmem {
     static constexpr int BS_BYTES = ((VK * BPITCH * 8 + 1023) / 1024) * 1024;
     static constexpr int BS_OFF = N_OFF + VN_STAGES * TILE_BYTES;
     static constexpr int BAR_OFF = BS_OFF + VB_STAGES * BS_BYTES;
-    static constexpr int NBAR = 2 * (VP_STAGES + VN_STAGES + VB_STAGES);
+    static constexpr int NBAR = 2 * (VP_STAGES + VN_STAGES);
     static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 1024;
 };
 
-// Roles (384 threads): warps 0..7 MMA (2 x 4, warp tile 16NF x 8NF), warps 8..10 build the B tile
-// of each chunk from the four plane tiles, warp 11 lane 0 drives TMA.  Three mbarrier rings:
-//   planes  : TMA -> builders          B tile : builders -> MMA          Phi n-tile : TMA -> MMA
+// Roles (384 threads): warps 0..7 build the B tile of each chunk and run the MMAs (2 x 4, warp tile
+// 16NF x 8NF); warp 8 lane 0 drives TMA.  Two TMA rings with independent lifetimes: the plane ring
+// is released as soon as the B tile is built (so the next chunks' planes stream in during the MMAs),
+// the Phi column-tile ring is released after the MMAs.
 template <int NF, int NPL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vxc_tma_kernel(const __grid_constant__ VxcParams P) {
@@ -387,8 +385,6 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     uint64_t* empty_p = full_p + VP_STAGES;
     uint64_t* full_n = empty_p + VP_STAGES;
     uint64_t* empty_n = full_n + VN_STAGES;
-    uint64_t* full_b = empty_n + VN_STAGES;
-    uint64_t* empty_b = full_b + VB_STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -413,83 +409,45 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     const int nchunks = jend > jbeg ? (jend - jbeg + VK - 1) / VK : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < VP_STAGES; ++s) { tma::mbar_init(&full_p[s], 1); tma::mbar_init(&empty_p[s], VB_WARPS); }
+        for (int s = 0; s < VP_STAGES; ++s) { tma::mbar_init(&full_p[s], 1); tma::mbar_init(&empty_p[s], NCW); }
         for (int s = 0; s < VN_STAGES; ++s) { tma::mbar_init(&full_n[s], 1); tma::mbar_init(&empty_n[s], NCW); }
-        for (int s = 0; s < VB_STAGES; ++s) { tma::mbar_init(&full_b[s], VB_WARPS); tma::mbar_init(&empty_b[s], NCW); }
         tma::fence_barrier_init();
     }
     __syncthreads();
 
     if (warp >= NCW) {
-        reg_dec<V_REGS_PRODUCER>();
-        if (warp == NCW + VB_WARPS) {
-            // ===================== TMA producer =====================
-            if (lane == 0) {
-                for (int p = 0; p < NPL; ++p) tma::prefetch_map(&P.map_p[si][p]);
-                const double* coef = P.coef + 4 * (size_t)P.sub[si].coef0;
-                for (int c = 0; c < nchunks; ++c) {
-                    const int j0 = jbeg + c * VK;
-                    {
-                        const uint32_t s = c % VP_STAGES, ph = (c / VP_STAGES) & 1u;
-                        tma::mbar_wait(&empty_p[s], ph ^ 1u);
-                        unsigned char* st = sm + s * L::P_STAGE_BYTES;
-                        tma::mbar_arrive_expect_tx(&full_p[s], (uint32_t)(NPL * L::TILE_BYTES + VK * 32));
-                        for (int p = 0; p < NPL; ++p)
-                            for (int b = 0; b < 2 * NF; ++b)
-                                tma::load_2d(st + p * L::TILE_BYTES + b * 2048, &P.map_p[si][p], m0 + 16 * b, j0, &full_p[s]);
-                        tma::load_1d(st + L::COEF_OFF, coef + 4 * (size_t)j0, VK * 32, &full_p[s]);
-                    }
-                    {
-                        const uint32_t s = c % VN_STAGES, ph = (c / VN_STAGES) & 1u;
-                        tma::mbar_wait(&empty_n[s], ph ^ 1u);
-                        unsigned char* st = sm + L::N_OFF + s * L::TILE_BYTES;
-                        tma::mbar_arrive_expect_tx(&full_n[s], (uint32_t)L::TILE_BYTES);
+        reg_dec<REGS_PRODUCER>();
+        // ===================== TMA producer =====================
+        if (warp == NCW && lane == 0) {
+            for (int p = 0; p < NPL; ++p) tma::prefetch_map(&P.map_p[si][p]);
+            const double* coef = P.coef + 4 * (size_t)P.sub[si].coef0;
+            for (int c = 0; c < nchunks; ++c) {
+                const int j0 = jbeg + c * VK;
+                {
+                    const uint32_t s = c % VP_STAGES, ph = (c / VP_STAGES) & 1u;
+                    tma::mbar_wait(&empty_p[s], ph ^ 1u);
+                    unsigned char* st = sm + s * L::P_STAGE_BYTES;
+                    tma::mbar_arrive_expect_tx(&full_p[s], (uint32_t)(NPL * L::TILE_BYTES + VK * 32));
+                    for (int p = 0; p < NPL; ++p)
                         for (int b = 0; b < 2 * NF; ++b)
-                            tma::load_2d(st + b * 2048, &P.map_p[si][0], n0 + 16 * b, j0, &full_n[s]);
-                    }
+                            tma::load_2d(st + p * L::TILE_BYTES + b * 2048, &P.map_p[si][p], m0 + 16 * b, j0, &full_p[s]);
+                    tma::load_1d(st + L::COEF_OFF, coef + 4 * (size_t)j0, VK * 32, &full_p[s]);
                 }
-            }
-            return;
-        }
-        // ===================== builder warps: B = a Phi + bx dxPhi + by dyPhi + bz dzPhi =====================
-        const int btid = tid - NCONS;
-        for (int c = 0; c < nchunks; ++c) {
-            const uint32_t sp = c % VP_STAGES, php = (c / VP_STAGES) & 1u;
-            const uint32_t sb = c % VB_STAGES, phb = (c / VB_STAGES) & 1u;
-            const uint32_t st = base + sp * L::P_STAGE_BYTES;
-            const uint32_t bs = base + L::BS_OFF + sb * L::BS_BYTES;
-            tma::mbar_wait(&full_p[sp], php);
-            tma::mbar_wait(&empty_b[sb], phb ^ 1u);
-            for (int task = btid; task < 256 * NF; task += VB_WARPS * 32) {
-                const int j = task & 7, rb = task >> 3;
-                const int r = rb & 15, b = rb >> 4;
-                const uint32_t off = (uint32_t)(b * 2048 + r * 128 + (((j ^ r) & 7) << 4));
-                const double2 ca = lds_f64x2(st + L::COEF_OFF + r * 32);
-                const double2 v0 = lds_f64x2(st + off);
-                double2 o = make_double2(ca.x * v0.x, ca.x * v0.y);
-                if (NPL == 4) {
-                    const double2 cb = lds_f64x2(st + L::COEF_OFF + r * 32 + 16);
-                    const double2 v1 = lds_f64x2(st + L::TILE_BYTES + off);
-                    const double2 v2 = lds_f64x2(st + 2 * L::TILE_BYTES + off);
-                    const double2 v3 = lds_f64x2(st + 3 * L::TILE_BYTES + off);
-                    o.x = fma(ca.y, v1.x, o.x); o.y = fma(ca.y, v1.y, o.y);
-                    o.x = fma(cb.x, v2.x, o.x); o.y = fma(cb.x, v2.y, o.y);
-                    o.x = fma(cb.y, v3.x, o.x); o.y = fma(cb.y, v3.y, o.y);
+                {
+                    const uint32_t s = c % VN_STAGES, ph = (c / VN_STAGES) & 1u;
+                    tma::mbar_wait(&empty_n[s], ph ^ 1u);
+                    unsigned char* st = sm + L::N_OFF + s * L::TILE_BYTES;
+                    tma::mbar_arrive_expect_tx(&full_n[s], (uint32_t)L::TILE_BYTES);
+                    for (int b = 0; b < 2 * NF; ++b)
+                        tma::load_2d(st + b * 2048, &P.map_p[si][0], n0 + 16 * b, j0, &full_n[s]);
                 }
-                const int rho_idx = 8 * (r >> 3) + 4 * (r & 1) + ((r & 7) >> 1);  // MMA order of tile row r
-                sts_f64x2(bs + (uint32_t)((rho_idx * L::BPITCH + b * 16 + 2 * j) * 8), o);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                tma::mbar_arrive(&full_b[sb]);
-                tma::mbar_arrive(&empty_p[sp]);
             }
         }
         return;
     }
 
     // ===================== MMA warps: 2 x 4, warp tile (16 NF) x (8 NF) =====================
-    reg_inc<V_REGS_CONSUMER>();
+    reg_inc<REGS_CONSUMER>();
     const int wm = warp >> 2, wn = warp & 3;
     const int q = lane >> 2, qcol = lane & 3;
     constexpr int MF = 2 * NF;
@@ -513,12 +471,50 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     const uint32_t aoff = (uint32_t)((qcol * L::BPITCH + wm * 16 * NF + q) * 8);
 
     for (int c = 0; c < nchunks; ++c) {
-        const uint32_t sb = c % VB_STAGES, phb = (c / VB_STAGES) & 1u;
+        const uint32_t sp = c % VP_STAGES, php = (c / VP_STAGES) & 1u;
         const uint32_t sn = c % VN_STAGES, phn = (c / VN_STAGES) & 1u;
-        const uint32_t bs = base + L::BS_OFF + sb * L::BS_BYTES;
+        const uint32_t st = base + sp * L::P_STAGE_BYTES;
+        const uint32_t bs = base + L::BS_OFF + (c & 1) * L::BS_BYTES;
         const uint32_t phin = base + L::N_OFF + sn * L::TILE_BYTES;
+        tma::mbar_wait(&full_p[sp], php);
+        // ---- build B rows for this chunk: B = a Phi + bx dxPhi + by dyPhi + bz dzPhi
+        //      (NF tasks of one 16-byte chunk per thread, two at a time to bound register use)
+        constexpr int TB = NF >= 2 ? 2 : 1;
+#pragma unroll
+        for (int t0 = 0; t0 < NF; t0 += TB) {
+            double2 ca[TB], cb[TB], v[TB][NPL];
+            uint32_t dst[TB];
+#pragma unroll
+            for (int u = 0; u < TB; ++u) {
+                const int t = (t0 + u < NF) ? t0 + u : NF - 1;
+                const int task = tid + t * NCONS;
+                const int j = task & 7, rb = task >> 3;
+                const int r = rb & 15, b = rb >> 4;
+                const uint32_t off = (uint32_t)(b * 2048 + r * 128 + (((j ^ r) & 7) << 4));
+                ca[u] = lds_f64x2(st + L::COEF_OFF + r * 32);
+                if (NPL == 4) cb[u] = lds_f64x2(st + L::COEF_OFF + r * 32 + 16);
+#pragma unroll
+                for (int p = 0; p < NPL; ++p) v[u][p] = lds_f64x2(st + p * L::TILE_BYTES + off);
+                const int rho_idx = 8 * (r >> 3) + 4 * (r & 1) + ((r & 7) >> 1);  // MMA order of tile row r
+                dst[u] = bs + (uint32_t)((rho_idx * L::BPITCH + b * 16 + 2 * j) * 8);
+            }
+#pragma unroll
+            for (int u = 0; u < TB; ++u) {
+                if (t0 + u >= NF) continue;
+                double2 o = make_double2(ca[u].x * v[u][0].x, ca[u].x * v[u][0].y);
+                if (NPL == 4) {
+                    o.x = fma(ca[u].y, v[u][1].x, o.x); o.y = fma(ca[u].y, v[u][1].y, o.y);
+                    o.x = fma(cb[u].x, v[u][2].x, o.x); o.y = fma(cb[u].x, v[u][2].y, o.y);
+                    o.x = fma(cb[u].y, v[u][3].x, o.x); o.y = fma(cb[u].y, v[u][3].y, o.y);
+                }
+                sts_f64x2(dst[u], o);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(&empty_p[sp]);  // plane stage is free again
+        tma::named_bar_sync(1, NCONS);
+        // ---- M += B^T Phi
         tma::mbar_wait(&full_n[sn], phn);
-        tma::mbar_wait(&full_b[sb], phb);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             double a[MF], bf[NF];
@@ -532,10 +528,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
                 for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
         }
         __syncwarp();
-        if (lane == 0) {
-            tma::mbar_arrive(&empty_b[sb]);
-            tma::mbar_arrive(&empty_n[sn]);
-        }
+        if (lane == 0) tma::mbar_arrive(&empty_n[sn]);
     }
     // ---- partial tile out
     const int NP = P.NP;
