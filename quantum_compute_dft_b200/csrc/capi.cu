@@ -238,6 +238,7 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "exact_functionals")) { c->exact_functionals = value != 0.0; return 0; }
     if (!strcmp(key, "path")) { c->path = (int)value; return 0; }
     if (!strcmp(key, "timing")) { c->timing = value != 0.0; return 0; }
+    if (!strcmp(key, "density_ctas_per_sm")) { c->density_ctas_per_sm = value == 1.0 ? 1 : 2; return 0; }
     if (!strcmp(key, "deterministic")) { return value != 0.0 ? 0 : 3; }  // reductions are always fixed-order
     return 2;
 }

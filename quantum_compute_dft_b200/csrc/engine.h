@@ -47,6 +47,7 @@ struct CublasHandleWrapper {
     bool exact_functionals = false;
     int path = PATH_AUTO;
     bool timing = true;
+    int density_ctas_per_sm = 2;  // TMA density kernel shape: 2 = two 64-row CTAs per SM, 1 = one 128-row CTA
 
     // workspaces
     DeviceBuffer dsym;     // symmetrised, zero-padded density matrix

@@ -48,19 +48,34 @@
 namespace xc {
 namespace tmapath {
 
-constexpr int MB = 128;                     // grid rows per block (density kernel)
-constexpr int NCW = 8;                      // consumer warps, 2 (m) x 4 (n)
+constexpr int NCW = 8;                      // V kernel consumer warps, 2 (m) x 4 (n)
 constexpr int NCONS = NCW * 32;             // 256 consumer threads = 2 warpgroups
 constexpr int NTHREADS = NCONS + 128;       // + 1 producer warpgroup
-constexpr int REGS_CONSUMER = 232;          // density kernel: 384*168 = 256*232 + 128*40
+constexpr int REGS_CONSUMER = 232;          // 1 CTA/SM of 384 threads: 384*168 = 256*232 + 128*40
 constexpr int REGS_PRODUCER = 40;
-constexpr int D_STAGES = 5;                 // density pipeline depth
+constexpr int REGS_CONSUMER_2CTA = 216;     // 2 CTAs/SM of 256 threads: 256*128 = 128*216 + 128*40
+
+// Density kernel shape, selected by WM (number of 64-row warp rows):
+//   WM = 2: one CTA per SM, 8 consumer warps (2 x 4), 128-row blocks, 384 threads;
+//   WM = 1: two CTAs per SM, 4 consumer warps (1 x 4) each, 64-row blocks, 256 threads -- the two
+//           CTAs drift out of phase, so one CTA's fused epilogue (global gathers, no tensor work)
+//           overlaps the other's k-loop and the DMMA pipe stays busy.
+template <int WM>
+struct DShape {
+    static constexpr int MB = 64 * WM;            // grid rows per block
+    static constexpr int NCW = 4 * WM;            // consumer warps
+    static constexpr int NCONS = NCW * 32;
+    static constexpr int NTHREADS = NCONS + 128;  // + producer warpgroup
+    static constexpr int CTAS_PER_SM = WM == 1 ? 2 : 1;
+    static constexpr int REGS_CONS = WM == 1 ? REGS_CONSUMER_2CTA : REGS_CONSUMER;
+    static constexpr int STAGES = WM == 1 ? 4 : 5;
+    static constexpr int A_TILE_BYTES = MB * 128;  // MB rows x 16 doubles
+};
 constexpr int VP_STAGES = 2;                // V kernel: plane ring (TMA -> builder warps)
 constexpr int VN_STAGES = 3;                // V kernel: Phi column-tile ring (TMA -> MMA warps)
 constexpr int VB_STAGES = 2;                // V kernel: B tile double buffer (built by the consumer warps)
 constexpr int D_PREFETCH_LEAD = 8;          // density: k-chunks before the epilogue at which grad tiles are L2-prefetched
 constexpr int VK = 16;                      // grid rows per V chunk
-constexpr int A_TILE_BYTES = MB * 128;      // 128 rows x 16 doubles
 
 struct SubProblem {
     int rows;    // rows of this sub-problem
@@ -125,22 +140,26 @@ __device__ __forceinline__ xcfun::PointCoef eval_mode(int mode, double rho, doub
 // ------------------------------------------------------------------------------------------------
 // density kernel
 // ------------------------------------------------------------------------------------------------
-template <int NF>
+template <int NF, int WM>
 struct DensitySmem {
+    using S = DShape<WM>;
     static constexpr int NT = 32 * NF;
     static constexpr int B_TILE_BYTES = NT * 128;
-    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int RED_OFF = D_STAGES * STAGE_BYTES;            // double red[128][4][4]
-    static constexpr int BAR_OFF = RED_OFF + MB * 4 * 4 * 8;          // full[D_STAGES], empty[D_STAGES]
-    static constexpr int ESUM_OFF = BAR_OFF + 2 * D_STAGES * 8;
-    static constexpr int TOTAL = ESUM_OFF + 8 * 8 + 1024;             // + alignment slack
+    static constexpr int STAGE_BYTES = S::A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int RED_OFF = S::STAGES * STAGE_BYTES;             // double red[MB][4][4]
+    static constexpr int BAR_OFF = RED_OFF + S::MB * 4 * 4 * 8;         // full[STAGES], empty[STAGES]
+    static constexpr int ESUM_OFF = BAR_OFF + 2 * S::STAGES * 8;
+    static constexpr int TOTAL = ESUM_OFF + 8 * 8 + 1024;               // + alignment slack
 };
 
-template <int NF, int NPL>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int NF, int NPL, int WM>
+__global__ void __launch_bounds__(DShape<WM>::NTHREADS, DShape<WM>::CTAS_PER_SM)
 density_tma_kernel(const __grid_constant__ DensityParams P) {
-    using L = DensitySmem<NF>;
+    using L = DensitySmem<NF, WM>;
+    using S = DShape<WM>;
     constexpr int NT = L::NT;
+    constexpr int MB = S::MB, NCW = S::NCW, NCONS = S::NCONS, D_STAGES = S::STAGES;
+    constexpr int A_TILE_BYTES = S::A_TILE_BYTES;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (tma::smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - tma::smem_u32(smem_raw));
@@ -198,8 +217,8 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
     }
 
     // ===================== consumers: 8 warps, warp tile 64 x (8 NF) =====================
-    reg_inc<REGS_CONSUMER>();
-    const int wm = warp >> 2, wn = warp & 3;
+    reg_inc<S::REGS_CONS>();
+    const int wm = warp >> 2, wn = warp & 3;  // wm in [0, WM)
     const int q = lane >> 2, qcol = lane & 3;
     const int perm = 2 * (q & 3) + (q >> 2);  // fragment row -> tile row: conflict-free with SWIZZLE_128B
     // per-lane byte offsets inside a 128-byte-row tile for k-step ks: chunk = (2ks + qcol/2) ^ perm
@@ -341,13 +360,17 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
         tma::named_bar_sync(1, NCONS);
     }
     // ---- per-CTA E_xc partial (fixed order)
-    if (warp < 4) {
+    if (warp < MB / 32) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) e_acc += __shfl_xor_sync(0xffffffffu, e_acc, o);
         if (lane == 0) esum[warp] = e_acc;
     }
     tma::named_bar_sync(1, NCONS);
-    if (tid == 0) P.exc_part[blockIdx.x] = (esum[0] + esum[1]) + (esum[2] + esum[3]);
+    if (tid == 0) {
+        double e = esum[0] + esum[1];
+        if (MB / 32 == 4) e += esum[2] + esum[3];
+        P.exc_part[blockIdx.x] = e;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -470,65 +493,97 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     }
     const uint32_t aoff = (uint32_t)((qcol * L::BPITCH + wm * 16 * NF + q) * 8);
 
+    // ---- B-tile builder, software-pipelined under the MMAs of the previous chunk.
+    // B = a Phi + bx dxPhi + by dyPhi + bz dzPhi for one chunk of 16 grid points: 256 NF tasks of one
+    // 16-byte chunk each, NF per thread, handled in batches of TB = 2 (loads first, math + store later
+    // so that the shared-memory latency hides behind 32 DMMAs).
+    constexpr int TB = NF >= 2 ? 2 : 1;
+    constexpr int NBATCH = (NF + TB - 1) / TB;  // 1 or 2
+    double2 bca[TB], bcb[TB], bv[TB][NPL];
+    uint32_t bdst[TB];
+    auto build_load = [&](int batch, uint32_t st, uint32_t bs) {
+#pragma unroll
+        for (int u = 0; u < TB; ++u) {
+            const int t = (batch * TB + u < NF) ? batch * TB + u : NF - 1;
+            const int task = tid + t * NCONS;
+            const int j = task & 7, rb = task >> 3;
+            const int r = rb & 15, b = rb >> 4;
+            const uint32_t off = (uint32_t)(b * 2048 + r * 128 + (((j ^ r) & 7) << 4));
+            bca[u] = lds_f64x2(st + L::COEF_OFF + r * 32);
+            if (NPL == 4) bcb[u] = lds_f64x2(st + L::COEF_OFF + r * 32 + 16);
+#pragma unroll
+            for (int p = 0; p < NPL; ++p) bv[u][p] = lds_f64x2(st + p * L::TILE_BYTES + off);
+            const int rho_idx = 8 * (r >> 3) + 4 * (r & 1) + ((r & 7) >> 1);  // MMA order of tile row r
+            bdst[u] = bs + (uint32_t)((rho_idx * L::BPITCH + b * 16 + 2 * j) * 8);
+        }
+    };
+    auto build_store = [&](int batch) {
+#pragma unroll
+        for (int u = 0; u < TB; ++u) {
+            if (batch * TB + u >= NF) continue;
+            double2 o = make_double2(bca[u].x * bv[u][0].x, bca[u].x * bv[u][0].y);
+            if (NPL == 4) {
+                o.x = fma(bca[u].y, bv[u][1].x, o.x); o.y = fma(bca[u].y, bv[u][1].y, o.y);
+                o.x = fma(bcb[u].x, bv[u][2].x, o.x); o.y = fma(bcb[u].x, bv[u][2].y, o.y);
+                o.x = fma(bcb[u].y, bv[u][3].x, o.x); o.y = fma(bcb[u].y, bv[u][3].y, o.y);
+            }
+            sts_f64x2(bdst[u], o);
+        }
+    };
+    auto mma_step = [&](int ks, uint32_t bs, uint32_t phin) {
+        double a[MF], bf[NF];
+#pragma unroll
+        for (int mf = 0; mf < MF; ++mf) a[mf] = lds_f64(bs + aoff + (uint32_t)((4 * ks * L::BPITCH + mf * 8) * 8));
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) bf[nf] = lds_f64(phin + boff[ks][nf]);
+#pragma unroll
+        for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
+    };
+
+    // prologue: B tile of chunk 0
+    if (nchunks > 0) {
+        tma::mbar_wait(&full_p[0], 0);
+#pragma unroll
+        for (int bt = 0; bt < NBATCH; ++bt) {
+            build_load(bt, base, base + L::BS_OFF);
+            build_store(bt);
+        }
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(&empty_p[0]);
+        tma::named_bar_sync(1, NCONS);
+    }
     for (int c = 0; c < nchunks; ++c) {
-        const uint32_t sp = c % VP_STAGES, php = (c / VP_STAGES) & 1u;
         const uint32_t sn = c % VN_STAGES, phn = (c / VN_STAGES) & 1u;
-        const uint32_t st = base + sp * L::P_STAGE_BYTES;
         const uint32_t bs = base + L::BS_OFF + (c & 1) * L::BS_BYTES;
         const uint32_t phin = base + L::N_OFF + sn * L::TILE_BYTES;
-        tma::mbar_wait(&full_p[sp], php);
-        // ---- build B rows for this chunk: B = a Phi + bx dxPhi + by dyPhi + bz dzPhi
-        //      (NF tasks of one 16-byte chunk per thread, two at a time to bound register use)
-        constexpr int TB = NF >= 2 ? 2 : 1;
-#pragma unroll
-        for (int t0 = 0; t0 < NF; t0 += TB) {
-            double2 ca[TB], cb[TB], v[TB][NPL];
-            uint32_t dst[TB];
-#pragma unroll
-            for (int u = 0; u < TB; ++u) {
-                const int t = (t0 + u < NF) ? t0 + u : NF - 1;
-                const int task = tid + t * NCONS;
-                const int j = task & 7, rb = task >> 3;
-                const int r = rb & 15, b = rb >> 4;
-                const uint32_t off = (uint32_t)(b * 2048 + r * 128 + (((j ^ r) & 7) << 4));
-                ca[u] = lds_f64x2(st + L::COEF_OFF + r * 32);
-                if (NPL == 4) cb[u] = lds_f64x2(st + L::COEF_OFF + r * 32 + 16);
-#pragma unroll
-                for (int p = 0; p < NPL; ++p) v[u][p] = lds_f64x2(st + p * L::TILE_BYTES + off);
-                const int rho_idx = 8 * (r >> 3) + 4 * (r & 1) + ((r & 7) >> 1);  // MMA order of tile row r
-                dst[u] = bs + (uint32_t)((rho_idx * L::BPITCH + b * 16 + 2 * j) * 8);
-            }
-#pragma unroll
-            for (int u = 0; u < TB; ++u) {
-                if (t0 + u >= NF) continue;
-                double2 o = make_double2(ca[u].x * v[u][0].x, ca[u].x * v[u][0].y);
-                if (NPL == 4) {
-                    o.x = fma(ca[u].y, v[u][1].x, o.x); o.y = fma(ca[u].y, v[u][1].y, o.y);
-                    o.x = fma(cb[u].x, v[u][2].x, o.x); o.y = fma(cb[u].x, v[u][2].y, o.y);
-                    o.x = fma(cb[u].y, v[u][3].x, o.x); o.y = fma(cb[u].y, v[u][3].y, o.y);
-                }
-                sts_f64x2(dst[u], o);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) tma::mbar_arrive(&empty_p[sp]);  // plane stage is free again
-        tma::named_bar_sync(1, NCONS);
-        // ---- M += B^T Phi
+        const bool has_next = c + 1 < nchunks;
+        const uint32_t sp1 = (c + 1) % VP_STAGES, php1 = ((c + 1) / VP_STAGES) & 1u;
+        const uint32_t st1 = base + sp1 * L::P_STAGE_BYTES;
+        const uint32_t bs1 = base + L::BS_OFF + ((c + 1) & 1) * L::BS_BYTES;
         tma::mbar_wait(&full_n[sn], phn);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            double a[MF], bf[NF];
-#pragma unroll
-            for (int mf = 0; mf < MF; ++mf) a[mf] = lds_f64(bs + aoff + (uint32_t)((4 * ks * L::BPITCH + mf * 8) * 8));
-#pragma unroll
-            for (int nf = 0; nf < NF; ++nf) bf[nf] = lds_f64(phin + boff[ks][nf]);
-#pragma unroll
-            for (int mf = 0; mf < MF; ++mf)
-#pragma unroll
-                for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
+        if (has_next) {
+            tma::mbar_wait(&full_p[sp1], php1);
+            build_load(0, st1, bs1);
         }
+        mma_step(0, bs, phin);
+        if (has_next) {
+            build_store(0);
+            if (NBATCH > 1) build_load(1, st1, bs1);
+        }
+        mma_step(1, bs, phin);
+        if (has_next) {
+            if (NBATCH > 1) build_store(1);
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(&empty_p[sp1]);  // plane stage of chunk c+1 is free again
+        }
+        mma_step(2, bs, phin);
+        mma_step(3, bs, phin);
         __syncwarp();
         if (lane == 0) tma::mbar_arrive(&empty_n[sn]);
+        // B tile of chunk c+1 complete, and everyone is done reading the B tile of chunk c
+        tma::named_bar_sync(1, NCONS);
     }
     // ---- partial tile out
     const int NP = P.NP;
@@ -646,8 +701,10 @@ static bool make_sub_map(CUtensorMap* m, const double* ptr, int ngrid, int nao, 
     return make_map(m, ptr + (nao - 1), (uint64_t)nao + 1, (uint64_t)ngrid / 2, 2ull * nao, box_rows);
 }
 
-template <int NF, int NPL>
+template <int NF, int NPL, int WM>
 static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
+    using DS = DShape<WM>;
+    constexpr int MB = DS::MB;
     cudaStream_t st = ctx->stream;
     const int ngrid = p.ngrid, nao = p.nao;
     constexpr int NT = 32 * NF;
@@ -678,7 +735,7 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
         nblocks += nb;
         coef_rows += nb * MB;
     }
-    const int grid1 = nblocks < nsm ? nblocks : nsm;
+    const int grid1 = nblocks < nsm * DS::CTAS_PER_SM ? nblocks : nsm * DS::CTAS_PER_SM;
 
     double* dsym = (double*)ctx->dsym.ensure(sizeof(double) * (size_t)nsub * NP * KP, &ctx->failed);
     double* coef = (double*)ctx->coef.ensure(sizeof(double) * 4 * (size_t)coef_rows, &ctx->failed);
@@ -719,16 +776,16 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     vp.nsub = nsub; vp.ntiles = ntiles; vp.lda_half = lda_half; vp.rows_per_slice = rows_per_slice;
     vp.slices_per_sub = nsl; vp.NP = NP; vp.coef = coef; vp.vpart = vpart;
 
-    using DL = DensitySmem<NF>;
+    using DL = DensitySmem<NF, WM>;
     using VL = VxcSmem<NF, NPL>;
-    auto dk = density_tma_kernel<NF, NPL>;
+    auto dk = density_tma_kernel<NF, NPL, WM>;
     auto vk = vxc_tma_kernel<NF, NPL>;
     DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(dk, cudaFuncAttributeMaxDynamicSharedMemorySize, DL::TOTAL));
     DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, VL::TOTAL));
 
     if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
     symmetrize_pad_tma_kernel<<<dim3((KP + 127) / 128, NP * nsub), 128, 0, st>>>(nao, KP, NP, nsub, p.dm, dsym);
-    dk<<<grid1, NTHREADS, DL::TOTAL, st>>>(dp);
+    dk<<<grid1, DS::NTHREADS, DL::TOTAL, st>>>(dp);
     if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
     vk<<<dim3(tiles, nsl * nsub), NTHREADS, VL::TOTAL, st>>>(vp);
     if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
@@ -759,7 +816,12 @@ void run_tma(CublasHandleWrapper* ctx, const Problem& p) {
     const int NF = (ncols + 32 * ntiles - 1) / (32 * ntiles);  // 1..4 -> column tile 32 NF
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-#define DFT_LAUNCH(NF_) (p.xc_type == 0 ? launch<NF_, 1>(ctx, p, nsm) : launch<NF_, 4>(ctx, p, nsm))
+    const bool two_ctas = ctx->density_ctas_per_sm != 1;
+#define DFT_LAUNCH(NF_)                                                                                    \
+    do {                                                                                                   \
+        if (two_ctas) { if (p.xc_type == 0) launch<NF_, 1, 1>(ctx, p, nsm); else launch<NF_, 4, 1>(ctx, p, nsm); } \
+        else { if (p.xc_type == 0) launch<NF_, 1, 2>(ctx, p, nsm); else launch<NF_, 4, 2>(ctx, p, nsm); }          \
+    } while (0)
     switch (NF) {
         case 1: DFT_LAUNCH(1); break;
         case 2: DFT_LAUNCH(2); break;

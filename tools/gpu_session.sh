@@ -16,6 +16,7 @@ from quantum_compute_dft_b200.solver import load_library
 l=load_library()
 print('DMMA TFLOP/s', l.DFT_MicrobenchDMMA(8192)); print('DFMA TFLOP/s', l.DFT_MicrobenchDFMA(8192))" > $OUT/micro.log 2>&1; echo "micro rc=$?" | tee -a $OUT/summary.txt; cat $OUT/micro.log ;;
     bench:*) W=${what#bench:}; timeout 600 python bench.py --workload $W --steps 5 --warmup 3 > $OUT/bench_$W.json 2> $OUT/bench_$W.err; echo "bench $W rc=$?" | tee -a $OUT/summary.txt; cat $OUT/bench_$W.json; tail -3 $OUT/bench_$W.err ;;
+    benchx:*) A=${what#benchx:}; W=${A%%:*}; X=${A#*:}; timeout 600 python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline $X > $OUT/benchx_${W}_$(echo $X | tr -d ' -').json 2> $OUT/benchx_$W.err; echo "benchx $W [$X] rc=$?" | tee -a $OUT/summary.txt; tail -1 $OUT/benchx_${W}_$(echo $X | tr -d ' -').json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['config']['workload'], 'ms', d['ms_per_step'], 'dens', d['roofline']['density_ms'], 'vxc', d['roofline']['vxc_ms'])" ;;
     ref:*)   W=${what#ref:}; timeout 600 python bench.py --impl reference --workload $W --steps 2 --warmup 1 > $OUT/ref_$W.json 2> $OUT/ref_$W.err; echo "ref $W rc=$?" | tee -a $OUT/summary.txt; cat $OUT/ref_$W.json; tail -3 $OUT/ref_$W.err ;;
     ncu:*)   W=${what#ncu:}; CMD="python bench.py --workload $W --steps 2 --warmup 3 --no-cpu-baseline"
              timeout 600 $CMD > $OUT/ncu_plain_$W.log 2>&1 && \
