@@ -49,7 +49,7 @@ int DFT_CommDestroy(XCSolver* solver);
 //       that are the exact derivatives of the energies, i.e. libxc/PySCF numint)
 //       "path" 0 auto | 1 generic (any alignment) | 2 TMA-fed
 //       "deterministic" 0|1 (default 1: fixed-order reductions, bit-reproducible results)
-//       "density_ctas_per_sm" 1|2 (tuning: shape of the TMA density kernel, default 2)
+//       "density_ctas_per_sm" 1|2 (tuning: shape of the TMA density kernel, default 1; 2 is experimental)
 //       "timing" 0|1 (record the per-kernel CUDA events behind DFT_GetStat, default 1)
 int DFT_SetOption(XCSolver* solver, const char* key, double value);
 // keys: "density_ms", "vxc_ms", "reduce_ms", "total_ms" (CUDA-event times of the last

@@ -16,7 +16,7 @@ OBJ = os.path.join(HERE, "_obj")
 OUT = os.path.join(HERE, "weights", "dft.so")
 SOURCES = ["capi.cu", "xc_generic.cu", "xc_tma.cu", "ao_eval.cu", "linalg.cu", "microbench.cu", "comm.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC"] + os.environ.get("DFT_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _deps_mtime():

@@ -238,6 +238,7 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "exact_functionals")) { c->exact_functionals = value != 0.0; return 0; }
     if (!strcmp(key, "path")) { c->path = (int)value; return 0; }
     if (!strcmp(key, "timing")) { c->timing = value != 0.0; return 0; }
+    if (!strcmp(key, "l2_prefetch")) { c->l2_prefetch = value != 0.0; return 0; }
     if (!strcmp(key, "density_ctas_per_sm")) { c->density_ctas_per_sm = value == 1.0 ? 1 : 2; return 0; }
     if (!strcmp(key, "deterministic")) { return value != 0.0 ? 0 : 3; }  // reductions are always fixed-order
     return 2;
@@ -255,6 +256,18 @@ double DFT_GetStat(XCSolver* solver, const char* key) {
     if (!strcmp(key, "workspace_bytes")) return (double)c->workspace_bytes();
     if (!strcmp(key, "nranks")) return c->nranks;
     return -1.0;
+}
+
+// Debug aid (not part of the documented surface): copy an engine workspace to the host.
+int DFT_DebugRead(XCSolver* solver, const char* what, void* dst, unsigned long long nbytes) {
+    if (!solver || !what || !dst) return 1;
+    CublasHandleWrapper* c = solver->context();
+    DeviceBuffer* b = !strcmp(what, "coef") ? &c->coef : !strcmp(what, "epart") ? &c->epart
+                    : !strcmp(what, "dsym") ? &c->dsym : !strcmp(what, "vpart") ? &c->vpart : nullptr;
+    if (!b || !b->ptr) return 2;
+    if (nbytes > b->capacity) nbytes = b->capacity;
+    cudaStreamSynchronize(c->stream);
+    return cudaMemcpy(dst, b->ptr, nbytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 3;
 }
 
 const char* DFT_B200_Version(void) { return "quantum_compute_dft_b200 0.1 (sm_100a)"; }

@@ -47,7 +47,8 @@ struct CublasHandleWrapper {
     bool exact_functionals = false;
     int path = PATH_AUTO;
     bool timing = true;
-    int density_ctas_per_sm = 2;  // TMA density kernel shape: 2 = two 64-row CTAs per SM, 1 = one 128-row CTA
+    bool l2_prefetch = true;       // TMA density kernel: L2-prefetch the epilogue's grad tiles
+    int density_ctas_per_sm = 1;  // TMA density kernel shape: 1 = one 128-row CTA per SM; 2 = two 64-row CTAs (experimental, racy)
 
     // workspaces
     DeviceBuffer dsym;     // symmetrised, zero-padded density matrix

@@ -53,7 +53,11 @@ constexpr int NCONS = NCW * 32;             // 256 consumer threads = 2 warpgrou
 constexpr int NTHREADS = NCONS + 128;       // + 1 producer warpgroup
 constexpr int REGS_CONSUMER = 232;          // 1 CTA/SM of 384 threads: 384*168 = 256*232 + 128*40
 constexpr int REGS_PRODUCER = 40;
+#ifdef DFT_DEBUG_REGS2
+constexpr int REGS_CONSUMER_2CTA = DFT_DEBUG_REGS2;
+#else
 constexpr int REGS_CONSUMER_2CTA = 216;     // 2 CTAs/SM of 256 threads: 256*128 = 128*216 + 128*40
+#endif
 
 // Density kernel shape, selected by WM (number of 64-row warp rows):
 //   WM = 2: one CTA per SM, 8 consumer warps (2 x 4), 128-row blocks, 384 threads;
@@ -66,8 +70,13 @@ struct DShape {
     static constexpr int NCW = 4 * WM;            // consumer warps
     static constexpr int NCONS = NCW * 32;
     static constexpr int NTHREADS = NCONS + 128;  // + producer warpgroup
+#ifdef DFT_DEBUG_WM1_SINGLE   // diagnostic build: 64-row shape but one CTA per SM
+    static constexpr int CTAS_PER_SM = 1;
+    static constexpr int REGS_CONS = WM == 1 ? DFT_DEBUG_WM1_SINGLE : REGS_CONSUMER;
+#else
     static constexpr int CTAS_PER_SM = WM == 1 ? 2 : 1;
     static constexpr int REGS_CONS = WM == 1 ? REGS_CONSUMER_2CTA : REGS_CONSUMER;
+#endif
     static constexpr int STAGES = WM == 1 ? 4 : 5;
     static constexpr int A_TILE_BYTES = MB * 128;  // MB rows x 16 doubles
 };
@@ -91,7 +100,7 @@ struct DensityParams {
     CUtensorMap map_g[2][3];  // grad Phi planes, box 16 x 128 (L2 prefetch of the epilogue tiles only)
     CUtensorMap map_d;      // [2][NP][KP] symmetrised density (plain, shifted), box 16 x NT
     SubProblem sub[2];
-    int nsub, ngrid, nao, xc_mode, nblocks, ntiles, nk, NP;
+    int nsub, ngrid, nao, xc_mode, nblocks, ntiles, nk, NP, l2_prefetch;
     const double *ao, *gx, *gy, *gz, *w;
     double* coef;
     double* exc_part;
@@ -120,11 +129,15 @@ __device__ __forceinline__ void sts_f64x2(uint32_t addr, double2 v) {
 }
 template <int N>
 __device__ __forceinline__ void reg_inc() {
+#ifndef DFT_DEBUG_NO_SETMAXNREG
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+#endif
 }
 template <int N>
 __device__ __forceinline__ void reg_dec() {
+#ifndef DFT_DEBUG_NO_SETMAXNREG
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+#endif
 }
 
 __device__ __forceinline__ xcfun::PointCoef eval_mode(int mode, double rho, double gx, double gy, double gz, double w) {
@@ -195,7 +208,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                 for (int nt = 0; nt < ntiles; ++nt) {
                     const int kpf = nk > D_PREFETCH_LEAD ? nk - D_PREFETCH_LEAD : 0;
                     for (int kc = 0; kc < nk; ++kc, ++it) {
-                        if (NPL == 4 && kc == kpf) {
+                        if (NPL == 4 && kc == kpf && P.l2_prefetch) {
                             // the epilogue of this tile gathers grad Phi[blk rows][nt columns] with plain
                             // loads: pull those tiles into L2 a few chunks ahead (Phi itself is L2-hot, it
                             // is this block's A operand)
@@ -213,6 +226,11 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                 }
             }
         }
+        // Park the whole producer warpgroup until the consumers are done instead of exiting: warps
+        // that exit right after setmaxnreg.dec hand their registers back to the SM while a co-resident
+        // CTA is still re-allocating, which corrupted consumer registers with two CTAs per SM.
+        __syncwarp();
+        tma::named_bar_sync(2, S::NTHREADS);
         return;
     }
 
@@ -371,6 +389,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
         if (MB / 32 == 4) e += esum[2] + esum[3];
         P.exc_part[blockIdx.x] = e;
     }
+    tma::named_bar_sync(2, S::NTHREADS);  // releases the parked producer warpgroup
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -755,7 +774,7 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     dp.sub[0] = sub[0]; dp.sub[1] = sub[1];
     dp.nsub = nsub; dp.ngrid = ngrid; dp.nao = nao;
     dp.xc_mode = p.xc_type == 2 ? 4 : p.xc_type * 2 + (ctx->exact_functionals ? 1 : 0);
-    dp.nblocks = nblocks; dp.ntiles = ntiles; dp.nk = KP / 16; dp.NP = NP;
+    dp.nblocks = nblocks; dp.ntiles = ntiles; dp.nk = KP / 16; dp.NP = NP; dp.l2_prefetch = ctx->l2_prefetch ? 1 : 0;
     dp.ao = p.ao; dp.gx = p.gx; dp.gy = p.gy; dp.gz = p.gz; dp.w = p.w;
     dp.coef = coef; dp.exc_part = epart;
 

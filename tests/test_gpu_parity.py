@@ -197,19 +197,6 @@ def test_tma_path_matches_generic_path_at_scale(engine_lib, functional, ngrid, n
 
 
 @pytest.mark.parametrize("functional", FUNCS)
-@pytest.mark.parametrize("ngrid,nao", [(20000, 377), (9999, 36), (30000, 152)])
-def test_density_kernel_shapes_agree(engine_lib, functional, ngrid, nao):
-    """The TMA density kernel exists in two shapes (one 128-row CTA per SM / two 64-row CTAs per SM)."""
-    rng = np.random.default_rng(7 * ngrid + nao)
-    dm, ao, w, grad = _random_case(rng, ngrid, nao)
-    e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"density_ctas_per_sm": 1})
-    e2, v2, s2 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"density_ctas_per_sm": 2})
-    assert s1["path"] == 2 and s2["path"] == 2
-    assert abs(e1 - e2) <= E_TOL * max(1.0, abs(e1) * 1e-3)
-    np.testing.assert_allclose(v1, v2, rtol=0, atol=V_TOL * max(1.0, np.abs(v1).max() * 1e-3))
-
-
-@pytest.mark.parametrize("functional", FUNCS)
 def test_forced_generic_path_matches_auto(oracle, engine_lib, functional):
     rng = np.random.default_rng(16)
     dm, ao, w, grad = _random_case(rng, 5000, 36)
