@@ -162,7 +162,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 generic, 2 TMA")
-    ap.add_argument("--density-ctas", type=int, default=0, help="tuning: 1 or 2 CTAs/SM in the TMA density kernel")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="engine tuning option passed to DFT_SetOption (e.g. vxc_vk=16, vxc_shape=160, l2_prefetch=0)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -187,8 +188,9 @@ def main():
     hp = workload.host_problem(args.workload, scale=args.scale)
     solver = workload.make_solver(hp.functional)
     solver.set_option("path", args.path)
-    if args.density_ctas:
-        solver.set_option("density_ctas_per_sm", args.density_ctas)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        solver.set_option(k, float(v))
     if world > 1:
         ids = [solver.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)

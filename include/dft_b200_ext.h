@@ -49,7 +49,10 @@ int DFT_CommDestroy(XCSolver* solver);
 //       that are the exact derivatives of the energies, i.e. libxc/PySCF numint)
 //       "path" 0 auto | 1 generic (any alignment) | 2 TMA-fed
 //       "deterministic" 0|1 (default 1: fixed-order reductions, bit-reproducible results)
-//       "density_ctas_per_sm" 1|2 (tuning: shape of the TMA density kernel, default 1; 2 is experimental)
+//       "vxc_shape" 0|64|128|160 (tuning: output tile of the TMA V kernel; 0 = chosen from nao)
+//       "vxc_vk" 8|16 (tuning: grid rows per ring stage of the 128 x 128 V kernel)
+//       "tma_3d" 0|1 (tuning: 3-D tensor maps in the V kernel, one TMA load per plane and stage; default 1)
+//       "l2_prefetch" 0|1 (tuning: L2 prefetch of the density kernel's epilogue pieces, default 0)
 //       "timing" 0|1 (record the per-kernel CUDA events behind DFT_GetStat, default 1)
 int DFT_SetOption(XCSolver* solver, const char* key, double value);
 // keys: "density_ms", "vxc_ms", "reduce_ms", "total_ms" (CUDA-event times of the last

@@ -28,37 +28,43 @@ def _deps_mtime():
     return m
 
 
-def _compile(src, verbose):
-    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+def _compile(src, verbose, extra=(), tag=""):
+    obj = os.path.join(OBJ, src.replace(".cu", tag + ".o"))
     spath = os.path.join(CSRC, src)
     if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(spath), _deps_mtime()):
         return obj, ""
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", spath, "-o", obj]
+    cmd = ["nvcc"] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", spath, "-o", obj]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}")
     return obj, r.stdout
 
 
-def build(verbose=False, force=False):
+def build(verbose=False, force=False, extra=(), tag=""):
+    """Build weights/dft.so; `extra` nvcc flags with a non-empty `tag` build a diagnostic variant
+    weights/dft<tag>.so beside it (e.g. extra=["-DDFT_PHASE_TIMING"], tag="_timing")."""
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    out = OUT.replace(".so", tag + ".so")
     if force:
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
     with ThreadPoolExecutor(max_workers=8) as ex:
-        res = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
+        res = list(ex.map(lambda s: _compile(s, verbose, extra, tag), SOURCES))
     objs = [o for o, _ in res]
     log = "".join(l for _, l in res)
-    if (not os.path.exists(OUT)) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
-        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-ldl"]
+    if (not os.path.exists(out)) or any(os.path.getmtime(o) > os.path.getmtime(out) for o in objs):
+        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-ldl"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}")
     if verbose:
         print(log)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    if "--timing" in sys.argv:
+        print(build(verbose="-v" in sys.argv, extra=["-DDFT_PHASE_TIMING"], tag="_timing"))
+    else:
+        print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

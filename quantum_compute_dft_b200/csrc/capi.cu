@@ -239,7 +239,9 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "path")) { c->path = (int)value; return 0; }
     if (!strcmp(key, "timing")) { c->timing = value != 0.0; return 0; }
     if (!strcmp(key, "l2_prefetch")) { c->l2_prefetch = value != 0.0; return 0; }
-    if (!strcmp(key, "density_ctas_per_sm")) { c->density_ctas_per_sm = value == 1.0 ? 1 : 2; return 0; }
+    if (!strcmp(key, "tma_3d")) { c->tma_3d = value != 0.0; return 0; }
+    if (!strcmp(key, "vxc_shape")) { const int v = (int)value; if (v != 0 && v != 64 && v != 128 && v != 160) return 3; c->vxc_shape = v; return 0; }
+    if (!strcmp(key, "vxc_vk")) { c->vxc_vk = value == 16.0 ? 16 : 8; return 0; }
     if (!strcmp(key, "deterministic")) { return value != 0.0 ? 0 : 3; }  // reductions are always fixed-order
     return 2;
 }
@@ -263,7 +265,8 @@ int DFT_DebugRead(XCSolver* solver, const char* what, void* dst, unsigned long l
     if (!solver || !what || !dst) return 1;
     CublasHandleWrapper* c = solver->context();
     DeviceBuffer* b = !strcmp(what, "coef") ? &c->coef : !strcmp(what, "epart") ? &c->epart
-                    : !strcmp(what, "dsym") ? &c->dsym : !strcmp(what, "vpart") ? &c->vpart : nullptr;
+                    : !strcmp(what, "dsym") ? &c->dsym : !strcmp(what, "vpart") ? &c->vpart
+                    : !strcmp(what, "scratch") ? &c->scratch : nullptr;
     if (!b || !b->ptr) return 2;
     if (nbytes > b->capacity) nbytes = b->capacity;
     cudaStreamSynchronize(c->stream);

@@ -47,8 +47,10 @@ struct CublasHandleWrapper {
     bool exact_functionals = false;
     int path = PATH_AUTO;
     bool timing = true;
-    bool l2_prefetch = true;       // TMA density kernel: L2-prefetch the epilogue's grad tiles
-    int density_ctas_per_sm = 1;  // TMA density kernel shape: 1 = one 128-row CTA per SM; 2 = two 64-row CTAs (experimental, racy)
+    bool l2_prefetch = false;      // TMA density kernel: L2-prefetch the epilogue's grad tiles
+    bool tma_3d = true;            // TMA V kernel: one 3-D TMA load per plane and stage instead of one per 16-column block
+    int vxc_shape = 0;             // TMA V kernel output tile: 0 = auto, 64 | 128 | 160 (= 160 x 80)
+    int vxc_vk = 16;               // TMA V kernel, 128 x 128 tile: grid rows per ring stage (8: 5 stages, 16: 2 stages)
 
     // workspaces
     DeviceBuffer dsym;     // symmetrised, zero-padded density matrix

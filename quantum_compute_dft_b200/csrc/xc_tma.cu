@@ -1,27 +1,33 @@
 // xc_tma.cu -- the fast XC path: TMA-fed, mbarrier-pipelined FP64 tensor-core (DMMA) kernels.
 //
-// Two persistent, warp-specialised kernels per XC build.  One CTA per SM, 384 threads: two consumer
-// warpgroups (8 warps in a 2 x 4 grid, warp tile 64 x 32 at the widest) and one producer warpgroup
-// whose first lane drives TMA; `setmaxnreg` moves registers from the producer to the consumers
-// (40 / 232 per thread) so that 64 x 32 FP64 accumulator tiles fit without spills.
+// Two persistent-style, warp-specialised kernels per XC build.  One CTA per SM, 384 threads: two
+// consumer warpgroups (8 warps) and one producer warpgroup whose first lane drives TMA;
+// `setmaxnreg` moves registers from the producer to the consumers (40 / 232 per thread) so that
+// 64 x 40 FP64 accumulator tiles fit without spills.  Neither kernel has a CTA-wide barrier in its
+// main loop: everything a consumer warp touches arrives through one TMA ring (full/empty
+// mbarriers), so the DMMA pipe never drains between tiles.
 //
-//   density_tma_kernel   subsystem (b)+(c): for each block of 128 grid points
-//        C = Phi_blk . Dsym                      DMMA tiles, operands streamed by TMA (SWIZZLE_128B)
-//        rho = rowsum(C o Phi), grad rho = 2 rowsum(C o dPhi)   fused epilogue, C never stored
+//   density_tma_kernel   subsystem (b)+(c): for each block of 128 grid points and column tile nt
+//        C = Phi_blk . Dsym[:, nt]                DMMA, operands streamed by TMA (SWIZZLE_128B)
+//        rho += rowsum(C o Phi), grad rho += 2 rowsum(C o dPhi)
+//                                                 the Phi / dPhi tiles of the row-dots come through
+//                                                 the SAME ring as 32 KB "pieces" right behind the
+//                                                 k-chunks (no global gathers, no exposed latency)
 //        pointwise functional once per point -> (a, b) coefficients + E_xc partial
 //     replaces get_rho_kernel / get_rho_sigma_kernel_planar (dft_solver.cu:294-307, :346-380), both
 //     passes of the *_fused_kernel's (:309-513) and reduce_sum_kernel (:285-292).
 //
 //   vxc_tma_kernel       subsystem (d): for each (output tile, grid slice)
-//        B = a o Phi + b . grad Phi               built on the fly in shared memory (no (ngrid,nao) B
-//        M += B^T Phi                              matrix in HBM), DMMA tiles, split over grid slices
+//        M += B^T Phi,  B = a o Phi + b . grad Phi
+//     B never exists in memory: each warp combines the four plane tiles with the point's
+//     coefficients directly into its DMMA A fragments (4 shared loads + 4 FP64 ops per fragment).
 //     replaces the B matrix (:577,:613,:655) and cublasDgemm (:580,:616,:663).
 //
 //   finalize_tma_kernel  out = M + M^T over slices in a fixed order (replaces :515-527) + E_xc.
 //
-// Shared-memory operand tiles are written by TMA with the 128-byte swizzle; fragment rows (density
-// kernel) or reduction rows (V kernel) are permuted so that every 64-bit fragment load is
-// bank-conflict free ("swizzle and fragment permutation").
+// Shared-memory tiles are written by TMA with the 128-byte swizzle; fragment rows (density kernel)
+// or reduction rows (V kernel) are permuted so that every 64-bit fragment load -- including the
+// epilogue's -- is bank-conflict free (tools/check_smem_maps.py proves the maps on the host).
 //
 // Odd nao.  The caller's AO rows are 8*nao bytes apart; TMA needs 16-byte aligned rows and box
 // starts.  For odd nao only every second row is aligned, so the grid is split into two
@@ -48,43 +54,12 @@
 namespace xc {
 namespace tmapath {
 
-constexpr int NCW = 8;                      // V kernel consumer warps, 2 (m) x 4 (n)
+constexpr int NCW = 8;                      // consumer warps
 constexpr int NCONS = NCW * 32;             // 256 consumer threads = 2 warpgroups
 constexpr int NTHREADS = NCONS + 128;       // + 1 producer warpgroup
-constexpr int REGS_CONSUMER = 232;          // 1 CTA/SM of 384 threads: 384*168 = 256*232 + 128*40
+constexpr int REGS_CONSUMER = 232;          // 384 threads x 168 = 256 x 232 + 128 x 40
 constexpr int REGS_PRODUCER = 40;
-#ifdef DFT_DEBUG_REGS2
-constexpr int REGS_CONSUMER_2CTA = DFT_DEBUG_REGS2;
-#else
-constexpr int REGS_CONSUMER_2CTA = 216;     // 2 CTAs/SM of 256 threads: 256*128 = 128*216 + 128*40
-#endif
-
-// Density kernel shape, selected by WM (number of 64-row warp rows):
-//   WM = 2: one CTA per SM, 8 consumer warps (2 x 4), 128-row blocks, 384 threads;
-//   WM = 1: two CTAs per SM, 4 consumer warps (1 x 4) each, 64-row blocks, 256 threads -- the two
-//           CTAs drift out of phase, so one CTA's fused epilogue (global gathers, no tensor work)
-//           overlaps the other's k-loop and the DMMA pipe stays busy.
-template <int WM>
-struct DShape {
-    static constexpr int MB = 64 * WM;            // grid rows per block
-    static constexpr int NCW = 4 * WM;            // consumer warps
-    static constexpr int NCONS = NCW * 32;
-    static constexpr int NTHREADS = NCONS + 128;  // + producer warpgroup
-#ifdef DFT_DEBUG_WM1_SINGLE   // diagnostic build: 64-row shape but one CTA per SM
-    static constexpr int CTAS_PER_SM = 1;
-    static constexpr int REGS_CONS = WM == 1 ? DFT_DEBUG_WM1_SINGLE : REGS_CONSUMER;
-#else
-    static constexpr int CTAS_PER_SM = WM == 1 ? 2 : 1;
-    static constexpr int REGS_CONS = WM == 1 ? REGS_CONSUMER_2CTA : REGS_CONSUMER;
-#endif
-    static constexpr int STAGES = WM == 1 ? 4 : 5;
-    static constexpr int A_TILE_BYTES = MB * 128;  // MB rows x 16 doubles
-};
-constexpr int VP_STAGES = 2;                // V kernel: plane ring (TMA -> builder warps)
-constexpr int VN_STAGES = 3;                // V kernel: Phi column-tile ring (TMA -> MMA warps)
-constexpr int VB_STAGES = 2;                // V kernel: B tile double buffer (built by the consumer warps)
-constexpr int D_PREFETCH_LEAD = 8;          // density: k-chunks before the epilogue at which grad tiles are L2-prefetched
-constexpr int VK = 16;                      // grid rows per V chunk
+constexpr int MB = 128;                     // grid rows per density block
 
 struct SubProblem {
     int rows;    // rows of this sub-problem
@@ -96,22 +71,35 @@ struct SubProblem {
 };
 
 struct DensityParams {
-    CUtensorMap map_a[2];   // Phi of each sub-problem, box 16 x 128
-    CUtensorMap map_g[2][3];  // grad Phi planes, box 16 x 128 (L2 prefetch of the epilogue tiles only)
-    CUtensorMap map_d;      // [2][NP][KP] symmetrised density (plain, shifted), box 16 x NT
+    CUtensorMap map_a[2];     // Phi of each sub-problem, box 16 x 128 (k-loop A operand, LDA pieces)
+    CUtensorMap map_e[2][4];  // the four planes, box 16 x 64 (GGA epilogue pieces)
+    CUtensorMap map_d;        // [2][NP][KP] symmetrised density (plain, shifted), box 16 x NT
     SubProblem sub[2];
-    int nsub, ngrid, nao, xc_mode, nblocks, ntiles, nk, NP, l2_prefetch;
-    const double *ao, *gx, *gy, *gz, *w;
+    int nsub, xc_mode, nblocks, ntiles, nk, NP, l2_prefetch;
+    const double* w;
     double* coef;
     double* exc_part;
+    long long* phase;  // DFT_PHASE_TIMING builds: [CTA][warp][4] cycles in {k-loop, piece wait, piece math, block tail}
 };
 
+// V kernel operand maps.  A plane is also described as a 3-D tensor {16 columns, rows, 16-column
+// blocks} over its WHOLE 16-column blocks, so that one TMA instruction brings all the blocks of a tile
+// (box {16, VK, tile/16}) in the [block][row][16] layout the fragment loads expect; the partial last
+// block (nao mod 16 columns, zero-filled past the end) still comes through the 2-D map.
 struct VxcParams {
-    CUtensorMap map_p[2][4];  // planes of each sub-problem, box 16 x 16
+    CUtensorMap m3[2][4];    // M side: box {16, VK, MT / 16}
+    CUtensorMap m3l[2][4];   // M side, last (partial) tile: box {16, VK, whole blocks in that tile}
+    CUtensorMap n3[2];       // N side (Phi): box {16, VK, NT / 16}
+    CUtensorMap n3l[2];
+    CUtensorMap p2[2][4];    // 2-D, box 16 x VK
     SubProblem sub[2];
-    int nsub, ntiles, lda_half, rows_per_slice, slices_per_sub, NP;
+    int nfull[2];            // whole 16-column blocks of each sub-problem
+    int rem[2];              // columns in the partial block (0: none)
+    int use3d;
+    int nsub, tiles_m, tiles_n, lda_half, rows_per_slice, slices_per_sub, ldv, mpv;
     const double* coef;
     double* vpart;
+    long long* phase;  // DFT_PHASE_TIMING builds: [CTA][9 warps][4] cycles {wait, work, tail, total}
 };
 
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
@@ -124,20 +112,13 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sts_f64x2(uint32_t addr, double2 v) {
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
-}
 template <int N>
 __device__ __forceinline__ void reg_inc() {
-#ifndef DFT_DEBUG_NO_SETMAXNREG
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
-#endif
 }
 template <int N>
 __device__ __forceinline__ void reg_dec() {
-#ifndef DFT_DEBUG_NO_SETMAXNREG
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
-#endif
 }
 
 __device__ __forceinline__ xcfun::PointCoef eval_mode(int mode, double rho, double gx, double gy, double gz, double w) {
@@ -153,37 +134,59 @@ __device__ __forceinline__ xcfun::PointCoef eval_mode(int mode, double rho, doub
 // ------------------------------------------------------------------------------------------------
 // density kernel
 // ------------------------------------------------------------------------------------------------
-template <int NF, int WM>
+// Ring contents per (block, column tile): nk k-chunks {A: Phi[128 rows][16 k], D: Dsym[NT cols][16 k]}
+// followed by the tile's epilogue pieces.  A GGA piece is {Phi, dxPhi, dyPhi, dzPhi}[64 rows][16 cols]
+// (4 boxes of 8 KB); an LDA piece is Phi[128 rows][16 cols].  Every warp waits for and releases every
+// stage; only the two (GGA) or four (LDA) warps whose accumulator columns fall into a piece read it.
+//
+// Consumer warps form a 4 (rows) x 2 (columns) grid, warp tile 32 x (8 NF2): a lane then owns 4
+// fragment rows, and its partial row sums rs[4][NPL] stay in registers for the WHOLE block (all
+// column tiles, all pieces).  A piece costs its owners 64 shared loads + 64 FMAs in 16 independent
+// chains; the cross-lane reduction happens once per block.
+template <int NF2, int NPL>
 struct DensitySmem {
-    using S = DShape<WM>;
-    static constexpr int NT = 32 * NF;
-    static constexpr int B_TILE_BYTES = NT * 128;
-    static constexpr int STAGE_BYTES = S::A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int RED_OFF = S::STAGES * STAGE_BYTES;             // double red[MB][4][4]
-    static constexpr int BAR_OFF = RED_OFF + S::MB * 4 * 4 * 8;         // full[STAGES], empty[STAGES]
-    static constexpr int ESUM_OFF = BAR_OFF + 2 * S::STAGES * 8;
-    static constexpr int TOTAL = ESUM_OFF + 8 * 8 + 1024;               // + alignment slack
+    static_assert(NF2 % 2 == 0, "a warp's columns are whole 16-column groups");
+    static constexpr int NT = 16 * NF2;
+    static constexpr int A_BYTES = MB * 128;
+    static constexpr int D_BYTES = NT * 128;
+    static constexpr int K_BYTES = A_BYTES + D_BYTES;
+    static constexpr int PLANE_BYTES = 64 * 128;                          // one plane of a GGA piece
+    static constexpr int PIECE_BYTES = NPL == 4 ? 4 * PLANE_BYTES : MB * 128;
+    static constexpr int STAGE_BYTES = K_BYTES > PIECE_BYTES ? K_BYTES : PIECE_BYTES;
+    static constexpr int FIXED_BYTES = 2 * MB * 4 * 8 + 256 + 1024;       // red[], barriers, E partials, alignment slack
+    static constexpr int STAGES = (232448 - FIXED_BYTES) / STAGE_BYTES < 6 ? (232448 - FIXED_BYTES) / STAGE_BYTES : 6;
+    static constexpr int NCG = NT / 16;                                   // 16-column groups per tile (= NF2)
+    static constexpr int NPIECES = (NPL == 4 ? 2 : 1) * NCG;
+    static constexpr int RED_OFF = STAGES * STAGE_BYTES;                  // double red[2 wn][128][4]
+    static constexpr int BAR_OFF = RED_OFF + 2 * MB * 4 * 8;              // full[STAGES], empty[STAGES]
+    static constexpr int ESUM_OFF = BAR_OFF + 2 * STAGES * 8;
+    static constexpr int TOTAL = ESUM_OFF + 8 * 8 + 1024;                 // + alignment slack
+    static_assert(TOTAL <= 232448, "shared memory");
+
+    // piece pc -> (row half h, column group cg); consecutive pieces go to different warps
+    __host__ __device__ static constexpr int piece_half(int pc) { return NPL == 4 ? (pc & 1) : 0; }
+    __host__ __device__ static constexpr int piece_cg(int pc) {
+        const int i = NPL == 4 ? (pc >> 1) : pc;
+        return (i & 1) * (NCG / 2) + (i >> 1);
+    }
 };
 
-template <int NF, int NPL, int WM>
-__global__ void __launch_bounds__(DShape<WM>::NTHREADS, DShape<WM>::CTAS_PER_SM)
+template <int NF2, int NPL>
+__global__ void __launch_bounds__(NTHREADS, 1)
 density_tma_kernel(const __grid_constant__ DensityParams P) {
-    using L = DensitySmem<NF, WM>;
-    using S = DShape<WM>;
+    using L = DensitySmem<NF2, NPL>;
     constexpr int NT = L::NT;
-    constexpr int MB = S::MB, NCW = S::NCW, NCONS = S::NCONS, D_STAGES = S::STAGES;
-    constexpr int A_TILE_BYTES = S::A_TILE_BYTES;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (tma::smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - tma::smem_u32(smem_raw));
     uint64_t* full = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF);
-    uint64_t* empty = full + D_STAGES;
+    uint64_t* empty = full + L::STAGES;
     double* red = reinterpret_cast<double*>(sm + L::RED_OFF);
     double* esum = reinterpret_cast<double*>(sm + L::ESUM_OFF);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int s = 0; s < D_STAGES; ++s) {
+        for (int s = 0; s < L::STAGES; ++s) {
             tma::mbar_init(&full[s], 1);
             tma::mbar_init(&empty[s], NCW);
         }
@@ -200,154 +203,186 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             tma::prefetch_map(&P.map_a[0]);
             if (P.nsub > 1) tma::prefetch_map(&P.map_a[1]);
             tma::prefetch_map(&P.map_d);
+            constexpr int NPF = NPL == 4 ? 3 * L::NPIECES : 0;  // gradient boxes of one tile's pieces
             uint32_t it = 0;
             for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
                 const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
                 const int blk = b - P.sub[si].blk0;
                 const int drow0 = P.sub[si].shift * P.NP;
                 for (int nt = 0; nt < ntiles; ++nt) {
-                    const int kpf = nk > D_PREFETCH_LEAD ? nk - D_PREFETCH_LEAD : 0;
                     for (int kc = 0; kc < nk; ++kc, ++it) {
-                        if (NPL == 4 && kc == kpf && P.l2_prefetch) {
-                            // the epilogue of this tile gathers grad Phi[blk rows][nt columns] with plain
-                            // loads: pull those tiles into L2 a few chunks ahead (Phi itself is L2-hot, it
-                            // is this block's A operand)
-                            for (int pl = 0; pl < 3; ++pl)
-                                for (int bx = 0; bx < NT / 16; ++bx)
-                                    tma::prefetch_2d(&P.map_g[si][pl], nt * NT + 16 * bx, blk * MB);
+                        if (NPL == 4 && P.l2_prefetch) {
+                            // optional: pull the gradient boxes of this tile's pieces into L2 while the
+                            // k-loop runs, spread evenly over its chunks
+                            const int lo = (kc * NPF) / nk, hi = ((kc + 1) * NPF) / nk;
+                            for (int x = lo; x < hi; ++x) {
+                                const int pc = x / 3, pl = 1 + x % 3;
+                                tma::prefetch_2d(&P.map_e[si][pl], nt * NT + 16 * L::piece_cg(pc),
+                                                 blk * MB + 64 * L::piece_half(pc));
+                            }
                         }
-                        const uint32_t s = it % D_STAGES, ph = (it / D_STAGES) & 1u;
+                        const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
                         tma::mbar_wait(&empty[s], ph ^ 1u);
                         unsigned char* st = sm + s * L::STAGE_BYTES;
-                        tma::mbar_arrive_expect_tx(&full[s], L::STAGE_BYTES);
+                        tma::mbar_arrive_expect_tx(&full[s], L::K_BYTES);
                         tma::load_2d(st, &P.map_a[si], kc * 16, blk * MB, &full[s]);
-                        tma::load_2d(st + A_TILE_BYTES, &P.map_d, kc * 16, drow0 + nt * NT, &full[s]);
+                        tma::load_2d(st + L::A_BYTES, &P.map_d, kc * 16, drow0 + nt * NT, &full[s]);
+                    }
+                    for (int pc = 0; pc < L::NPIECES; ++pc, ++it) {
+                        const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
+                        tma::mbar_wait(&empty[s], ph ^ 1u);
+                        unsigned char* st = sm + s * L::STAGE_BYTES;
+                        tma::mbar_arrive_expect_tx(&full[s], L::PIECE_BYTES);
+                        const int c0 = nt * NT + 16 * L::piece_cg(pc);
+                        if (NPL == 4) {
+                            const int r0 = blk * MB + 64 * L::piece_half(pc);
+                            for (int p = 0; p < 4; ++p)
+                                tma::load_2d(st + p * L::PLANE_BYTES, &P.map_e[si][p], c0, r0, &full[s]);
+                        } else {
+                            tma::load_2d(st, &P.map_a[si], c0, blk * MB, &full[s]);
+                        }
                     }
                 }
             }
         }
-        // Park the whole producer warpgroup until the consumers are done instead of exiting: warps
-        // that exit right after setmaxnreg.dec hand their registers back to the SM while a co-resident
-        // CTA is still re-allocating, which corrupted consumer registers with two CTAs per SM.
-        __syncwarp();
-        tma::named_bar_sync(2, S::NTHREADS);
         return;
     }
 
-    // ===================== consumers: 8 warps, warp tile 64 x (8 NF) =====================
-    reg_inc<S::REGS_CONS>();
-    const int wm = warp >> 2, wn = warp & 3;  // wm in [0, WM)
+    // ===================== consumers: 8 warps (4 x 2), warp tile 32 x (8 NF2) =====================
+    reg_inc<REGS_CONSUMER>();
+    const int wm = warp >> 1, wn = warp & 1;
     const int q = lane >> 2, qcol = lane & 3;
-    const int perm = 2 * (q & 3) + (q >> 2);  // fragment row -> tile row: conflict-free with SWIZZLE_128B
-    // per-lane byte offsets inside a 128-byte-row tile for k-step ks: chunk = (2ks + qcol/2) ^ perm
-    uint32_t koff[4];
+    // fragment row -> tile row.  A side: {0,3,4,7 | 1,2,5,6}; B side: {0,2,4,6 | 1,3,5,7}.  Both make
+    // the k-loop loads conflict-free under SWIZZLE_128B, and together they make the epilogue loads
+    // conflict-free as well (tools/check_smem_maps.py).
+    const int rho = (0x65217430u >> (4 * q)) & 7;
+    const int perm = 2 * (q & 3) + (q >> 2);
+    uint32_t koff_a[4], koff_b[4];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) koff[ks] = ((((2 * ks + (qcol >> 1)) ^ perm) & 7) << 4) + ((qcol & 1) << 3);
-    const uint32_t a_row = (uint32_t)(wm * 64 + perm) * 128u;
-    const uint32_t b_row = (uint32_t)(wn * 8 * NF + perm) * 128u;
-    // accumulator column j = 2 qcol + e of an n-fragment is tile column perm_j(j)
-    int ncol[2];
+    for (int ks = 0; ks < 4; ++ks) {
+        koff_a[ks] = ((((2 * ks + (qcol >> 1)) ^ rho) & 7) << 4) + ((qcol & 1) << 3);
+        koff_b[ks] = ((((2 * ks + (qcol >> 1)) ^ perm) & 7) << 4) + ((qcol & 1) << 3);
+    }
+    const uint32_t a_row = (uint32_t)(wm * 32 + rho) * 128u;
+    const uint32_t b_row = (uint32_t)(wn * 8 * NF2 + perm) * 128u;
+    // accumulator column j = 2 qcol + e of an n-fragment is tile column 2 (j & 3) + (j >> 2); eoff[e][s]
+    // is the byte offset of that column in a piece row for the fragment in the lower (s = 0) / upper
+    // (s = 1) 8 columns of the 16-column group
+    uint32_t eoff[2][2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
         const int j = 2 * qcol + e;
-        ncol[e] = 2 * (j & 3) + (j >> 2);
+        const int nc = 2 * (j & 3) + (j >> 2);
+#pragma unroll
+        for (int sx = 0; sx < 2; ++sx)
+            eoff[e][sx] = (uint32_t)(rho * 128 + ((((4 * sx + (nc >> 1)) ^ rho) & 7) << 4) + ((nc & 1) << 3));
     }
-    const int nao = P.nao;
-    const double* __restrict__ ao = P.ao;
-    const double* __restrict__ gx = P.gx;
-    const double* __restrict__ gy = P.gy;
-    const double* __restrict__ gz = P.gz;
+    // this warp's rows inside a piece: GGA pieces hold one 64-row half, LDA pieces all 128 rows
+    const int prow0 = NPL == 4 ? (wm & 1) * 32 : wm * 32;
+    // red[wn][row][plane]: slot (row of fragment row q of fragment mf, plane qcol) is this lane's alone
+    double* red_mine = red + ((wn * MB + wm * 32 + rho) * 4 + qcol);  // + 32 doubles per fragment mf
 
     double e_acc = 0.0;
     uint32_t it = 0;
+#ifdef DFT_PHASE_TIMING
+    long long t_k = 0, t_w = 0, t_m = 0, t_t = 0, t0 = clock64(), t1;
+#define PHASE_MARK(acc_) do { t1 = clock64(); acc_ += t1 - t0; t0 = t1; } while (0)
+#else
+#define PHASE_MARK(acc_) do { } while (0)
+#endif
     for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
         const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
         const int blk = b - P.sub[si].blk0;
-        const int rows = P.sub[si].rows, gmul = P.sub[si].gmul, gadd = P.sub[si].gadd, shift = P.sub[si].shift;
+        double rs[4][NPL];  // per-lane partial row sums of the whole block
+#pragma unroll
+        for (int mf = 0; mf < 4; ++mf)
+#pragma unroll
+            for (int p = 0; p < NPL; ++p) rs[mf][p] = 0.0;
+
         for (int nt = 0; nt < ntiles; ++nt) {
-            double acc[8][NF][2];
+            double acc[4][NF2][2];
 #pragma unroll
-            for (int mf = 0; mf < 8; ++mf)
+            for (int mf = 0; mf < 4; ++mf)
 #pragma unroll
-                for (int nf = 0; nf < NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+                for (int nf = 0; nf < NF2; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
 
             for (int kc = 0; kc < nk; ++kc, ++it) {
-                const uint32_t s = it % D_STAGES, ph = (it / D_STAGES) & 1u;
+                const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
                 tma::mbar_wait(&full[s], ph);
                 const uint32_t a_base = base + s * L::STAGE_BYTES + a_row;
-                const uint32_t b_base = base + s * L::STAGE_BYTES + A_TILE_BYTES + b_row;
+                const uint32_t b_base = base + s * L::STAGE_BYTES + L::A_BYTES + b_row;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    double a[8], bf[NF];
+                    double a[4], bf[NF2];
 #pragma unroll
-                    for (int mf = 0; mf < 8; ++mf) a[mf] = lds_f64(a_base + mf * 1024 + koff[ks]);
+                    for (int mf = 0; mf < 4; ++mf) a[mf] = lds_f64(a_base + mf * 1024 + koff_a[ks]);
 #pragma unroll
-                    for (int nf = 0; nf < NF; ++nf) bf[nf] = lds_f64(b_base + nf * 1024 + koff[ks]);
+                    for (int nf = 0; nf < NF2; ++nf) bf[nf] = lds_f64(b_base + nf * 1024 + koff_b[ks]);
 #pragma unroll
-                    for (int mf = 0; mf < 8; ++mf)
+                    for (int mf = 0; mf < 4; ++mf)
 #pragma unroll
-                        for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
+                        for (int nf = 0; nf < NF2; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
                 }
                 __syncwarp();
                 if (lane == 0) tma::mbar_arrive(&empty[s]);
             }
-            // ---- fused epilogue: row-dots of C with Phi and grad Phi (global loads, L2-hot for Phi);
-            //      the row sums of this column tile are folded into shared memory right away so that
-            //      no row accumulator stays live across the k-loop (each red[] entry has one owner lane)
-            const int nbase = nt * NT + wn * 8 * NF - shift;
-            // column indices / validity of this lane's 2 NF accumulator columns (same for every row)
-            int ncl[NF][2];
-            bool nok[NF][2];
+            PHASE_MARK(t_k);
+            // ---- epilogue: row-dots of C with the plane tiles, straight from the ring
+            for (int pc = 0; pc < L::NPIECES; ++pc, ++it) {
+                const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
+                tma::mbar_wait(&full[s], ph);
+                PHASE_MARK(t_w);
+                const int cg = L::piece_cg(pc);
+                if ((NPL == 1 || (wm >> 1) == L::piece_half(pc)) && cg / (NF2 / 2) == wn) {
+                    // plain shared-memory loads (not asm volatile): the compiler batches them freely
+                    const unsigned char* pbase = sm + s * L::STAGE_BYTES + prow0 * 128;
+                    const int nfp = cg % (NF2 / 2);
 #pragma unroll
-            for (int nf = 0; nf < NF; ++nf)
+                    for (int np = 0; np < NF2 / 2; ++np) {
+                        if (np == nfp) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int n = nbase + nf * 8 + ncol[e];
-                    nok[nf][e] = (n >= 0) && (n < nao);
-                    ncl[nf][e] = min(max(n, 0), nao - 1);
-                }
+                            for (int sx = 0; sx < 2; ++sx)
 #pragma unroll
-            for (int mf = 0; mf < 8; ++mf) {
-                const int r = wm * 64 + mf * 8 + perm;
-                const int j = blk * MB + r;
-                const bool rok = j < rows;
-                const size_t rowoff = (size_t)((long)gmul * (rok ? j : 0) + gadd) * nao;
-                // all loads of one fragment row are issued back to back (unconditional, clamped
-                // addresses) so that 8 NF x NPL independent requests are in flight per lane
-                double pv[NPL][NF][2];
+                                for (int e = 0; e < 2; ++e)
 #pragma unroll
-                for (int nf = 0; nf < NF; ++nf)
+                                    for (int mf = 0; mf < 4; ++mf) {
+                                        const double cv = acc[mf][2 * np + sx][e];
+                                        const unsigned char* ad = pbase + mf * 1024 + eoff[e][sx];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const size_t o = rowoff + ncl[nf][e];
-                        pv[0][nf][e] = __ldg(ao + o);
-                        if (NPL == 4) {
-                            pv[1][nf][e] = __ldg(gx + o);
-                            pv[2][nf][e] = __ldg(gy + o);
-                            pv[3][nf][e] = __ldg(gz + o);
+                                        for (int p = 0; p < NPL; ++p)
+                                            rs[mf][p] = fma(cv, *reinterpret_cast<const double*>(ad + p * L::PLANE_BYTES),
+                                                            rs[mf][p]);
+                                    }
                         }
                     }
-                double rs[NPL];
-#pragma unroll
-                for (int p = 0; p < NPL; ++p) rs[p] = 0.0;
-#pragma unroll
-                for (int nf = 0; nf < NF; ++nf)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const double cv = (rok && nok[nf][e]) ? acc[mf][nf][e] : 0.0;
-#pragma unroll
-                        for (int p = 0; p < NPL; ++p) rs[p] = fma(cv, pv[p][nf][e], rs[p]);
-                    }
-#pragma unroll
-                for (int p = 0; p < NPL; ++p) {
-                    double v = rs[p];
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    if (qcol == 0) {
-                        double* dst = red + (r * 4 + wn) * 4 + p;
-                        *dst = (nt == 0) ? v : *dst + v;
-                    }
                 }
+                __syncwarp();
+                if (lane == 0) tma::mbar_arrive(&empty[s]);
+                PHASE_MARK(t_m);
+            }
+        }
+        // ---- once per block: reduce the partial row sums over the 4 lanes of a fragment row.
+        // GGA: transpose-reduce (3 shuffles per row) after which lane qcol holds plane qcol.
+        if (NPL == 4) {
+            const bool b0 = (qcol & 1) != 0, b1 = (qcol & 2) != 0;
+#pragma unroll
+            for (int mf = 0; mf < 4; ++mf) {
+                // round 1 (lane ^ 1): keep planes {b0, 2 + b0}, hand over the other two
+                const double k0 = b0 ? rs[mf][1] : rs[mf][0], g0v = b0 ? rs[mf][0] : rs[mf][1];
+                const double k1 = b0 ? rs[mf][NPL - 1] : rs[mf][NPL / 2], g1v = b0 ? rs[mf][NPL / 2] : rs[mf][NPL - 1];
+                const double s0 = k0 + __shfl_xor_sync(0xffffffffu, g0v, 1);
+                const double s1 = k1 + __shfl_xor_sync(0xffffffffu, g1v, 1);
+                // round 2 (lane ^ 2): keep plane 2 b1 + b0 = qcol
+                const double k = b1 ? s1 : s0, g = b1 ? s0 : s1;
+                red_mine[mf * 32] = k + __shfl_xor_sync(0xffffffffu, g, 2);
+            }
+        } else {
+#pragma unroll
+            for (int mf = 0; mf < 4; ++mf) {
+                double v = rs[mf][0];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                red_mine[mf * 32] = qcol == 0 ? v : 0.0;
             }
         }
         tma::named_bar_sync(1, NCONS);
@@ -355,17 +390,17 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             const int r = tid;
             const int j = blk * MB + r;
             double2 c01 = make_double2(0.0, 0.0), c23 = make_double2(0.0, 0.0);
-            if (j < rows) {
-                const long g = (long)gmul * j + gadd;
-                const double* rr = red + r * 16;
-                const double rho = (rr[0] + rr[4]) + (rr[8] + rr[12]);
+            if (j < P.sub[si].rows) {
+                const long g = (long)P.sub[si].gmul * j + P.sub[si].gadd;
+                const double* rr = red + r * 4;  // + 4 MB doubles for wn = 1
+                const double rhov = rr[0] + rr[4 * MB];
                 double dx = 0.0, dy = 0.0, dz = 0.0;
                 if (NPL == 4) {
-                    dx = 2.0 * ((rr[1] + rr[5]) + (rr[9] + rr[13]));
-                    dy = 2.0 * ((rr[2] + rr[6]) + (rr[10] + rr[14]));
-                    dz = 2.0 * ((rr[3] + rr[7]) + (rr[11] + rr[15]));
+                    dx = 2.0 * (rr[1] + rr[4 * MB + 1]);
+                    dy = 2.0 * (rr[2] + rr[4 * MB + 2]);
+                    dz = 2.0 * (rr[3] + rr[4 * MB + 3]);
                 }
-                const xcfun::PointCoef pc = eval_mode(P.xc_mode, rho, dx, dy, dz, __ldg(P.w + g));
+                const xcfun::PointCoef pc = eval_mode(P.xc_mode, rhov, dx, dy, dz, __ldg(P.w + g));
                 c01 = make_double2(pc.a, pc.bx);
                 c23 = make_double2(pc.by, pc.bz);
                 e_acc += pc.exc;
@@ -376,7 +411,14 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             cp[1] = c23;
         }
         tma::named_bar_sync(1, NCONS);
+        PHASE_MARK(t_t);
     }
+#ifdef DFT_PHASE_TIMING
+    if (lane == 0 && P.phase) {
+        long long* o = P.phase + ((size_t)blockIdx.x * NCW + warp) * 4;
+        o[0] = t_k; o[1] = t_w; o[2] = t_m; o[3] = t_t;
+    }
+#endif
     // ---- per-CTA E_xc partial (fixed order)
     if (warp < MB / 32) {
 #pragma unroll
@@ -384,65 +426,58 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
         if (lane == 0) esum[warp] = e_acc;
     }
     tma::named_bar_sync(1, NCONS);
-    if (tid == 0) {
-        double e = esum[0] + esum[1];
-        if (MB / 32 == 4) e += esum[2] + esum[3];
-        P.exc_part[blockIdx.x] = e;
-    }
-    tma::named_bar_sync(2, S::NTHREADS);  // releases the parked producer warpgroup
+    if (tid == 0) P.exc_part[blockIdx.x] = (esum[0] + esum[1]) + (esum[2] + esum[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
 // V kernel
 // ------------------------------------------------------------------------------------------------
-template <int NF, int NPL>
-struct VxcSmem {
-    static constexpr int NT = 32 * NF;
-    static constexpr int TILE_BYTES = VK * NT * 8;                       // one plane tile: 2NF boxes of 2 KB
-    static constexpr int P_STAGE_BYTES = NPL * TILE_BYTES + 1024;        // planes + 16 x (a,bx,by,bz)
-    static constexpr int COEF_OFF = NPL * TILE_BYTES;
-    static constexpr int N_OFF = VP_STAGES * P_STAGE_BYTES;              // Phi column-tile ring
-    static constexpr int BPITCH = NT + 4;                                // doubles; (NT+4) mod 16 == 4
-    static constexpr int BS_BYTES = ((VK * BPITCH * 8 + 1023) / 1024) * 1024;
-    static constexpr int BS_OFF = N_OFF + VN_STAGES * TILE_BYTES;
-    static constexpr int BAR_OFF = BS_OFF + VB_STAGES * BS_BYTES;
-    static constexpr int NBAR = 2 * (VP_STAGES + VN_STAGES);
-    static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 1024;
+// Output tile MT x NT_ = (WM MF 8) x (WN NFN 8), consumer warps WM x WN, warp tile (8 MF) x (8 NFN).
+// One ring stage holds VK grid rows: the NPL plane tiles of the MT columns, the Phi tile of the NT_
+// columns and the VK coefficient rows.
+template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES>
+struct VxcCfg {
+    static_assert(WM * WN == NCW, "8 consumer warps");
+    static constexpr int MT = WM * MF * 8;
+    static constexpr int NT_ = WN * NFN * 8;
+    static_assert(MT % 16 == 0 && NT_ % 16 == 0, "tiles are whole 16-column boxes");
+    static constexpr int KS = VK / 4;
+    static constexpr int BOXB = VK * 128;                                // one 16-column box
+    static constexpr int PLANE_BYTES = (MT / 16) * BOXB;
+    static constexpr int N_OFF = NPL * PLANE_BYTES;
+    static constexpr int COEF_OFF = N_OFF + (NT_ / 16) * BOXB;
+    static constexpr int TX_BYTES = COEF_OFF + VK * 32;
+    static constexpr int STAGE_BYTES = ((TX_BYTES + 1023) / 1024) * 1024;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 2 * STAGES * 8 + 1024;
+    static_assert(TOTAL <= 232448, "shared memory");
 };
 
-// Roles (384 threads): warps 0..7 build the B tile of each chunk and run the MMAs (2 x 4, warp tile
-// 16NF x 8NF); warp 8 lane 0 drives TMA.  Two TMA rings with independent lifetimes: the plane ring
-// is released as soon as the B tile is built (so the next chunks' planes stream in during the MMAs),
-// the Phi column-tile ring is released after the MMAs.
-template <int NF, int NPL>
+template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vxc_tma_kernel(const __grid_constant__ VxcParams P) {
-    using L = VxcSmem<NF, NPL>;
-    constexpr int NT = L::NT;
+    using L = VxcCfg<MF, NFN, WM, WN, NPL, VK, STAGES>;
+    constexpr int KS = L::KS;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (tma::smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - tma::smem_u32(smem_raw));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF);
-    uint64_t* full_p = bars;
-    uint64_t* empty_p = full_p + VP_STAGES;
-    uint64_t* full_n = empty_p + VP_STAGES;
-    uint64_t* empty_n = full_n + VN_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF);
+    uint64_t* empty = full + STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // output tile of this CTA
-    const int ntiles = P.ntiles;
     int tm, tn;
-    if (P.lda_half) {  // upper-triangular tile pairs, row-major
+    if (P.lda_half) {  // upper-triangular tile pairs, row-major (square tiles only)
         int t = blockIdx.x;
         tm = 0;
-        while (t >= ntiles - tm) { t -= ntiles - tm; ++tm; }
+        while (t >= P.tiles_n - tm) { t -= P.tiles_n - tm; ++tm; }
         tn = tm + t;
     } else {
-        tm = blockIdx.x / ntiles;
-        tn = blockIdx.x % ntiles;
+        tm = blockIdx.x / P.tiles_n;
+        tn = blockIdx.x % P.tiles_n;
     }
-    const int m0 = tm * NT, n0 = tn * NT;
+    const int m0 = tm * L::MT, n0 = tn * L::NT_;
     // grid slice of this CTA: rows [jbeg, jend) of sub-problem si
     const int si = blockIdx.y / P.slices_per_sub;
     const int sl = blockIdx.y % P.slices_per_sub;
@@ -451,178 +486,178 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     const int nchunks = jend > jbeg ? (jend - jbeg + VK - 1) / VK : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < VP_STAGES; ++s) { tma::mbar_init(&full_p[s], 1); tma::mbar_init(&empty_p[s], NCW); }
-        for (int s = 0; s < VN_STAGES; ++s) { tma::mbar_init(&full_n[s], 1); tma::mbar_init(&empty_n[s], NCW); }
+        for (int s = 0; s < STAGES; ++s) {
+            tma::mbar_init(&full[s], 1);
+            tma::mbar_init(&empty[s], NCW);
+        }
         tma::fence_barrier_init();
     }
+    // 16-column blocks past the edge of the matrix are never written by TMA: clear the ring once
+    for (int o = tid * 16; o < STAGES * L::STAGE_BYTES; o += NTHREADS * 16)
+        *reinterpret_cast<double2*>(sm + o) = make_double2(0.0, 0.0);
+    tma::fence_proxy_async();
     __syncthreads();
 
     if (warp >= NCW) {
         reg_dec<REGS_PRODUCER>();
         // ===================== TMA producer =====================
         if (warp == NCW && lane == 0) {
-            for (int p = 0; p < NPL; ++p) tma::prefetch_map(&P.map_p[si][p]);
             const double* coef = P.coef + 4 * (size_t)P.sub[si].coef0;
+            // blocks of this CTA's M / N tile: fbm / fbn whole ones (one 3-D load), then possibly the partial one
+            const int nfull = P.nfull[si], rem = P.rem[si];
+            constexpr int NBM = L::MT / 16, NBN = L::NT_ / 16;
+            const int bm0 = m0 / 16, bn0 = n0 / 16;
+            const int fbm = min(max(nfull - bm0, 0), NBM), fbn = min(max(nfull - bn0, 0), NBN);
+            const bool pm = rem > 0 && nfull >= bm0 && nfull - bm0 < NBM;
+            const bool pn = rem > 0 && nfull >= bn0 && nfull - bn0 < NBN;
+            const uint32_t tx = (uint32_t)(NPL * (fbm + (pm ? 1 : 0)) * L::BOXB + (fbn + (pn ? 1 : 0)) * L::BOXB + VK * 32);
+#ifdef DFT_PHASE_TIMING
+            long long t_w = 0, t_c = 0, t_start = clock64(), t0 = t_start, t1;
+#endif
             for (int c = 0; c < nchunks; ++c) {
                 const int j0 = jbeg + c * VK;
-                {
-                    const uint32_t s = c % VP_STAGES, ph = (c / VP_STAGES) & 1u;
-                    tma::mbar_wait(&empty_p[s], ph ^ 1u);
-                    unsigned char* st = sm + s * L::P_STAGE_BYTES;
-                    tma::mbar_arrive_expect_tx(&full_p[s], (uint32_t)(NPL * L::TILE_BYTES + VK * 32));
-                    for (int p = 0; p < NPL; ++p)
-                        for (int b = 0; b < 2 * NF; ++b)
-                            tma::load_2d(st + p * L::TILE_BYTES + b * 2048, &P.map_p[si][p], m0 + 16 * b, j0, &full_p[s]);
-                    tma::load_1d(st + L::COEF_OFF, coef + 4 * (size_t)j0, VK * 32, &full_p[s]);
+                const uint32_t s = c % STAGES, ph = (c / STAGES) & 1u;
+#ifdef DFT_PHASE_TIMING
+                t1 = clock64(); t_c += t1 - t0; t0 = t1;
+#endif
+                tma::mbar_wait(&empty[s], ph ^ 1u);
+#ifdef DFT_PHASE_TIMING
+                t1 = clock64(); t_w += t1 - t0; t0 = t1;
+#endif
+                unsigned char* st = sm + s * L::STAGE_BYTES;
+                tma::mbar_arrive_expect_tx(&full[s], tx);
+                for (int p = 0; p < NPL; ++p) {
+                    unsigned char* dst = st + p * L::PLANE_BYTES;
+                    if (P.use3d) {
+                        if (fbm == NBM) tma::load_3d(dst, &P.m3[si][p], 0, j0, bm0, &full[s]);
+                        else if (fbm > 0) tma::load_3d(dst, &P.m3l[si][p], 0, j0, bm0, &full[s]);
+                    } else {
+                        for (int b = 0; b < fbm; ++b) tma::load_2d(dst + b * L::BOXB, &P.p2[si][p], m0 + 16 * b, j0, &full[s]);
+                    }
+                    if (pm) tma::load_2d(dst + fbm * L::BOXB, &P.p2[si][p], m0 + 16 * fbm, j0, &full[s]);
                 }
                 {
-                    const uint32_t s = c % VN_STAGES, ph = (c / VN_STAGES) & 1u;
-                    tma::mbar_wait(&empty_n[s], ph ^ 1u);
-                    unsigned char* st = sm + L::N_OFF + s * L::TILE_BYTES;
-                    tma::mbar_arrive_expect_tx(&full_n[s], (uint32_t)L::TILE_BYTES);
-                    for (int b = 0; b < 2 * NF; ++b)
-                        tma::load_2d(st + b * 2048, &P.map_p[si][0], n0 + 16 * b, j0, &full_n[s]);
+                    unsigned char* dst = st + L::N_OFF;
+                    if (P.use3d) {
+                        if (fbn == NBN) tma::load_3d(dst, &P.n3[si], 0, j0, bn0, &full[s]);
+                        else if (fbn > 0) tma::load_3d(dst, &P.n3l[si], 0, j0, bn0, &full[s]);
+                    } else {
+                        for (int b = 0; b < fbn; ++b) tma::load_2d(dst + b * L::BOXB, &P.p2[si][0], n0 + 16 * b, j0, &full[s]);
+                    }
+                    if (pn) tma::load_2d(dst + fbn * L::BOXB, &P.p2[si][0], n0 + 16 * fbn, j0, &full[s]);
                 }
+                tma::load_1d(st + L::COEF_OFF, coef + 4 * (size_t)j0, VK * 32, &full[s]);
             }
+#ifdef DFT_PHASE_TIMING
+            if (P.phase) {
+                long long* o = P.phase + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (NCW + 1) + NCW) * 4;
+                t1 = clock64();
+                o[0] = t_w; o[1] = t_c + (t1 - t0); o[2] = 0; o[3] = t1 - t_start;
+            }
+#endif
         }
         return;
     }
 
-    // ===================== MMA warps: 2 x 4, warp tile (16 NF) x (8 NF) =====================
+    // ===================== MMA warps =====================
     reg_inc<REGS_CONSUMER>();
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp / WN, wn = warp % WN;
     const int q = lane >> 2, qcol = lane & 3;
-    constexpr int MF = 2 * NF;
-    double acc[MF][NF][2];
+    double acc[MF][NFN][2];
 #pragma unroll
     for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
-        for (int nf = 0; nf < NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+        for (int nf = 0; nf < NFN; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
 
-    // B-fragment (Phi n-tile) addressing: reduction row of k-step ks is 8(ks/2) + 2 qcol + (ks&1)
-    uint32_t boff[4][NF];
+    // Fragment addressing.  A DMMA k-step ks contracts 4 grid rows; lane (q, qcol) supplies row
+    // krow(ks, qcol) -- rows {0,2,4,6} / {1,3,5,7} of an 8-row group, so that with the 128-byte swizzle
+    // the 16 lanes of a load phase hit 16 distinct bank pairs -- and column (8-column group G) * 8 + q.
+    // Group G lives in box G/2 at columns 8 (G & 1) + q, whose swizzled offset is c0 ^ ((G & 1) << 6).
+    const int ga0 = wm * MF, gb0 = wn * NFN;  // first 8-column group of this warp in the M / N tile
+    uint32_t a_even[KS], a_odd[KS], b_even[KS], b_odd[KS], c_off[KS];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-        const int r = 8 * (ks >> 1) + 2 * qcol + (ks & 1);
-#pragma unroll
-        for (int nf = 0; nf < NF; ++nf) {
-            const int n = wn * 8 * NF + nf * 8 + q;
-            boff[ks][nf] = (uint32_t)((n >> 4) * 2048) + tma::swz128((uint32_t)r, (uint32_t)(n & 15));
-        }
+    for (int ks = 0; ks < KS; ++ks) {
+        const int row = (VK == 16 ? 8 * (ks >> 1) : 0) + 2 * qcol + (ks & 1);
+        const uint32_t c0 = (uint32_t)(row * 128 + ((((q >> 1) ^ row) & 7) << 4) + ((q & 1) << 3));
+        const uint32_t pa = (uint32_t)(ga0 & 1), pb = (uint32_t)(gb0 & 1);
+        a_even[ks] = (uint32_t)((ga0 >> 1) * L::BOXB) + (c0 ^ (pa << 6));
+        a_odd[ks] = (uint32_t)(((ga0 >> 1) + (int)pa) * L::BOXB) + (c0 ^ ((pa ^ 1u) << 6));
+        b_even[ks] = (uint32_t)(L::N_OFF + (gb0 >> 1) * L::BOXB) + (c0 ^ (pb << 6));
+        b_odd[ks] = (uint32_t)(L::N_OFF + ((gb0 >> 1) + (int)pb) * L::BOXB) + (c0 ^ ((pb ^ 1u) << 6));
+        c_off[ks] = (uint32_t)(L::COEF_OFF + row * 32);
     }
-    const uint32_t aoff = (uint32_t)((qcol * L::BPITCH + wm * 16 * NF + q) * 8);
 
-    // ---- B-tile builder, software-pipelined under the MMAs of the previous chunk.
-    // B = a Phi + bx dxPhi + by dyPhi + bz dzPhi for one chunk of 16 grid points: 256 NF tasks of one
-    // 16-byte chunk each, NF per thread, handled in batches of TB = 2 (loads first, math + store later
-    // so that the shared-memory latency hides behind 32 DMMAs).
-    constexpr int TB = NF >= 2 ? 2 : 1;
-    constexpr int NBATCH = (NF + TB - 1) / TB;  // 1 or 2
-    double2 bca[TB], bcb[TB], bv[TB][NPL];
-    uint32_t bdst[TB];
-    auto build_load = [&](int batch, uint32_t st, uint32_t bs) {
-#pragma unroll
-        for (int u = 0; u < TB; ++u) {
-            const int t = (batch * TB + u < NF) ? batch * TB + u : NF - 1;
-            const int task = tid + t * NCONS;
-            const int j = task & 7, rb = task >> 3;
-            const int r = rb & 15, b = rb >> 4;
-            const uint32_t off = (uint32_t)(b * 2048 + r * 128 + (((j ^ r) & 7) << 4));
-            bca[u] = lds_f64x2(st + L::COEF_OFF + r * 32);
-            if (NPL == 4) bcb[u] = lds_f64x2(st + L::COEF_OFF + r * 32 + 16);
-#pragma unroll
-            for (int p = 0; p < NPL; ++p) bv[u][p] = lds_f64x2(st + p * L::TILE_BYTES + off);
-            const int rho_idx = 8 * (r >> 3) + 4 * (r & 1) + ((r & 7) >> 1);  // MMA order of tile row r
-            bdst[u] = bs + (uint32_t)((rho_idx * L::BPITCH + b * 16 + 2 * j) * 8);
-        }
-    };
-    auto build_store = [&](int batch) {
-#pragma unroll
-        for (int u = 0; u < TB; ++u) {
-            if (batch * TB + u >= NF) continue;
-            double2 o = make_double2(bca[u].x * bv[u][0].x, bca[u].x * bv[u][0].y);
-            if (NPL == 4) {
-                o.x = fma(bca[u].y, bv[u][1].x, o.x); o.y = fma(bca[u].y, bv[u][1].y, o.y);
-                o.x = fma(bcb[u].x, bv[u][2].x, o.x); o.y = fma(bcb[u].x, bv[u][2].y, o.y);
-                o.x = fma(bcb[u].y, bv[u][3].x, o.x); o.y = fma(bcb[u].y, bv[u][3].y, o.y);
-            }
-            sts_f64x2(bdst[u], o);
-        }
-    };
-    auto mma_step = [&](int ks, uint32_t bs, uint32_t phin) {
-        double a[MF], bf[NF];
-#pragma unroll
-        for (int mf = 0; mf < MF; ++mf) a[mf] = lds_f64(bs + aoff + (uint32_t)((4 * ks * L::BPITCH + mf * 8) * 8));
-#pragma unroll
-        for (int nf = 0; nf < NF; ++nf) bf[nf] = lds_f64(phin + boff[ks][nf]);
-#pragma unroll
-        for (int mf = 0; mf < MF; ++mf)
-#pragma unroll
-            for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
-    };
-
-    // prologue: B tile of chunk 0
-    if (nchunks > 0) {
-        tma::mbar_wait(&full_p[0], 0);
-#pragma unroll
-        for (int bt = 0; bt < NBATCH; ++bt) {
-            build_load(bt, base, base + L::BS_OFF);
-            build_store(bt);
-        }
-        __syncwarp();
-        if (lane == 0) tma::mbar_arrive(&empty_p[0]);
-        tma::named_bar_sync(1, NCONS);
-    }
+#ifdef DFT_PHASE_TIMING
+    long long t_w = 0, t_c = 0, t_start = clock64(), t0 = t_start, t1;
+#endif
+    // (ptxas software-pipelines the k-steps of a stage by itself: the fragment loads of k-step ks+1 are
+    // interleaved with the DMMAs of k-step ks.  Pipelining by hand across stages costs registers and spills.)
     for (int c = 0; c < nchunks; ++c) {
-        const uint32_t sn = c % VN_STAGES, phn = (c / VN_STAGES) & 1u;
-        const uint32_t bs = base + L::BS_OFF + (c & 1) * L::BS_BYTES;
-        const uint32_t phin = base + L::N_OFF + sn * L::TILE_BYTES;
-        const bool has_next = c + 1 < nchunks;
-        const uint32_t sp1 = (c + 1) % VP_STAGES, php1 = ((c + 1) / VP_STAGES) & 1u;
-        const uint32_t st1 = base + sp1 * L::P_STAGE_BYTES;
-        const uint32_t bs1 = base + L::BS_OFF + ((c + 1) & 1) * L::BS_BYTES;
-        tma::mbar_wait(&full_n[sn], phn);
-        if (has_next) {
-            tma::mbar_wait(&full_p[sp1], php1);
-            build_load(0, st1, bs1);
+        const uint32_t s = c % STAGES, ph = (c / STAGES) & 1u;
+        tma::mbar_wait(&full[s], ph);
+#ifdef DFT_PHASE_TIMING
+        t1 = clock64(); t_w += t1 - t0; t0 = t1;
+#endif
+        const uint32_t sb = base + s * L::STAGE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            // A fragments: B[k][m] = a Phi + bx dxPhi + by dyPhi + bz dzPhi, built in registers
+            const double2 ca = lds_f64x2(sb + c_off[ks]);
+            double2 cb = make_double2(0.0, 0.0);
+            if (NPL == 4) cb = lds_f64x2(sb + c_off[ks] + 16);
+            double a[MF], bf[NFN];
+#pragma unroll
+            for (int mf = 0; mf < MF; ++mf) {
+                const uint32_t ad = sb + ((mf & 1) ? a_odd[ks] + (uint32_t)(((mf - 1) / 2) * L::BOXB)
+                                                    : a_even[ks] + (uint32_t)((mf / 2) * L::BOXB));
+                double v = ca.x * lds_f64(ad);
+                if (NPL == 4) {
+                    v = fma(ca.y, lds_f64(ad + L::PLANE_BYTES), v);
+                    v = fma(cb.x, lds_f64(ad + 2 * L::PLANE_BYTES), v);
+                    v = fma(cb.y, lds_f64(ad + 3 * L::PLANE_BYTES), v);
+                }
+                a[mf] = v;
+            }
+#pragma unroll
+            for (int nf = 0; nf < NFN; ++nf)
+                bf[nf] = lds_f64(sb + ((nf & 1) ? b_odd[ks] + (uint32_t)(((nf - 1) / 2) * L::BOXB)
+                                                : b_even[ks] + (uint32_t)((nf / 2) * L::BOXB)));
+#pragma unroll
+            for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+                for (int nf = 0; nf < NFN; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
         }
-        mma_step(0, bs, phin);
-        if (has_next) {
-            build_store(0);
-            if (NBATCH > 1) build_load(1, st1, bs1);
-        }
-        mma_step(1, bs, phin);
-        if (has_next) {
-            if (NBATCH > 1) build_store(1);
-            __syncwarp();
-            if (lane == 0) tma::mbar_arrive(&empty_p[sp1]);  // plane stage of chunk c+1 is free again
-        }
-        mma_step(2, bs, phin);
-        mma_step(3, bs, phin);
         __syncwarp();
-        if (lane == 0) tma::mbar_arrive(&empty_n[sn]);
-        // B tile of chunk c+1 complete, and everyone is done reading the B tile of chunk c
-        tma::named_bar_sync(1, NCONS);
+        if (lane == 0) tma::mbar_arrive(&empty[s]);
+#ifdef DFT_PHASE_TIMING
+        t1 = clock64(); t_c += t1 - t0; t0 = t1;
+#endif
     }
     // ---- partial tile out
-    const int NP = P.NP;
-    double* out = P.vpart + (size_t)blockIdx.y * NP * NP;
+    double* out = P.vpart + (size_t)blockIdx.y * P.mpv * P.ldv;
 #pragma unroll
     for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
-        for (int nf = 0; nf < NF; ++nf) {
-            const int r = m0 + wm * 16 * NF + mf * 8 + q;
-            const int cc = n0 + wn * 8 * NF + nf * 8 + 2 * qcol;
-            *reinterpret_cast<double2*>(out + (size_t)r * NP + cc) = make_double2(acc[mf][nf][0], acc[mf][nf][1]);
+        for (int nf = 0; nf < NFN; ++nf) {
+            const int r = m0 + (ga0 + mf) * 8 + q;
+            const int cc = n0 + (gb0 + nf) * 8 + 2 * qcol;
+            *reinterpret_cast<double2*>(out + (size_t)r * P.ldv + cc) = make_double2(acc[mf][nf][0], acc[mf][nf][1]);
         }
+#ifdef DFT_PHASE_TIMING
+    if (lane == 0 && P.phase) {
+        long long* o = P.phase + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (NCW + 1) + warp) * 4;
+        t1 = clock64();
+        o[0] = t_w; o[1] = t_c; o[2] = t1 - t0; o[3] = t1 - t_start;
+    }
+#endif
 }
 
 // out[i][j] = sum over slices of T(i+s, j+s) + T(j+s, i+s), s = column shift of the slice's
 // sub-problem; T = M where the tile was computed (lda_half: the mirror tile otherwise).
 // Fixed summation order -> bit-reproducible and exactly symmetric.
-__global__ void finalize_tma_kernel(int nao, int NP, int NT, int nsub, int slices_per_sub, int shift1, int lda_half,
-                                    const double* __restrict__ vpart, double* __restrict__ vxc, int nepart,
-                                    const double* __restrict__ epart, double* __restrict__ d_exc) {
+__global__ void finalize_tma_kernel(int nao, int ldv, int mpv, int NT, int nsub, int slices_per_sub, int shift1,
+                                    int lda_half, const double* __restrict__ vpart, double* __restrict__ vxc,
+                                    int nepart, const double* __restrict__ epart, double* __restrict__ d_exc) {
     const size_t n2 = (size_t)nao * nao;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < n2) {
@@ -631,13 +666,13 @@ __global__ void finalize_tma_kernel(int nao, int NP, int NT, int nsub, int slice
         for (int su = 0; su < nsub; ++su) {
             const int sh = su ? shift1 : 0;
             const int i = i0 + sh, j = j0 + sh;
-            size_t o1 = (size_t)i * NP + j, o2 = (size_t)j * NP + i;
+            size_t o1 = (size_t)i * ldv + j, o2 = (size_t)j * ldv + i;
             if (lda_half) {
                 if (i / NT > j / NT) o1 = o2;
                 else if (j / NT > i / NT) o2 = o1;
             }
             for (int sl = 0; sl < slices_per_sub; ++sl) {
-                const double* p = vpart + (size_t)(su * slices_per_sub + sl) * NP * NP;
+                const double* p = vpart + (size_t)(su * slices_per_sub + sl) * mpv * ldv;
                 s += p[o1] + p[o2];
             }
         }
@@ -713,105 +748,220 @@ static bool make_map(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t ro
     return true;
 }
 
+// 3-D f64 map {16 columns, rows, nblk 16-column blocks} over the whole blocks of a row-major array
+// (strides: row pitch, 128 bytes), box {16, box_rows, box_blks}, 128-byte swizzle.
+static bool make_map3(CUtensorMap* m, const void* ptr, uint64_t nblk, uint64_t rows, uint64_t pitch_elems,
+                      uint32_t box_rows, uint32_t box_blks) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdim[3] = {16, rows, nblk};
+    cuuint64_t gstride[2] = {pitch_elems * 8, 128};
+    cuuint32_t box[3] = {16, box_rows, box_blks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // Tensor map of plane `ptr` for sub-problem (parity) si of an (ngrid x nao) array: see file header.
 static bool make_sub_map(CUtensorMap* m, const double* ptr, int ngrid, int nao, bool split, int si, uint32_t box_rows) {
     if (!split) return make_map(m, ptr, (uint64_t)nao, (uint64_t)ngrid, (uint64_t)nao, box_rows);
     if (si == 0) return make_map(m, ptr, (uint64_t)nao, (uint64_t)(ngrid + 1) / 2, 2ull * nao, box_rows);
     return make_map(m, ptr + (nao - 1), (uint64_t)nao + 1, (uint64_t)ngrid / 2, 2ull * nao, box_rows);
 }
+static bool make_sub_map3(CUtensorMap* m, const double* ptr, int ngrid, int nao, bool split, int si, uint32_t box_rows,
+                          uint32_t box_blks) {
+    if (!split) return make_map3(m, ptr, (uint64_t)nao / 16, (uint64_t)ngrid, (uint64_t)nao, box_rows, box_blks);
+    if (si == 0) return make_map3(m, ptr, (uint64_t)nao / 16, (uint64_t)(ngrid + 1) / 2, 2ull * nao, box_rows, box_blks);
+    return make_map3(m, ptr + (nao - 1), ((uint64_t)nao + 1) / 16, (uint64_t)ngrid / 2, 2ull * nao, box_rows, box_blks);
+}
 
-template <int NF, int NPL, int WM>
-static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
-    using DS = DShape<WM>;
-    constexpr int MB = DS::MB;
+struct Geometry {
+    bool split;
+    int nsub, ncols;
+    SubProblem sub[2];
+    int nblocks, coef_rows;
+};
+
+static Geometry make_geometry(int ngrid, int nao) {
+    Geometry g;
+    memset(&g, 0, sizeof(g));
+    g.split = (nao & 1) != 0;
+    g.nsub = (g.split && ngrid >= 2) ? 2 : 1;
+    g.ncols = nao + (g.split ? 1 : 0);  // widest sub-problem
+    if (!g.split) {
+        g.sub[0] = SubProblem{ngrid, 1, 0, 0, 0, 0};
+    } else {
+        g.sub[0] = SubProblem{(ngrid + 1) / 2, 2, 0, 0, 0, 0};
+        g.sub[1] = SubProblem{ngrid / 2, 2, 1, 1, 0, 0};
+    }
+    for (int s = 0; s < g.nsub; ++s) {
+        g.sub[s].blk0 = g.nblocks;
+        g.sub[s].coef0 = g.coef_rows;
+        const int nb = (g.sub[s].rows + MB - 1) / MB;
+        g.nblocks += nb;
+        g.coef_rows += nb * MB;
+    }
+    return g;
+}
+
+// ---- density launch: column tile 16 NF2
+template <int NF2, int NPL>
+static void launch_density(CublasHandleWrapper* ctx, const Problem& p, const Geometry& g, int nsm, double* coef,
+                           double** epart_out, int* nepart_out) {
+    using DL = DensitySmem<NF2, NPL>;
+    constexpr int NT = DL::NT;
     cudaStream_t st = ctx->stream;
     const int ngrid = p.ngrid, nao = p.nao;
-    constexpr int NT = 32 * NF;
-    const bool split = (nao & 1) != 0;
-    const int nsub = (split && ngrid >= 2) ? 2 : 1;
-    const int ncols = nao + (split ? 1 : 0);            // widest sub-problem
-    const int ntiles = (ncols + NT - 1) / NT;
+    const int ntiles = (g.ncols + NT - 1) / NT;
     const int NP = ntiles * NT;
-    const int KP = ((ncols + 15) / 16) * 16;
+    const int KP = ((g.ncols + 15) / 16) * 16;
+    const int grid1 = g.nblocks < nsm ? g.nblocks : nsm;
 
-    DensityParams dp;
-    VxcParams vp;
-    memset(&dp, 0, sizeof(dp));
-    memset(&vp, 0, sizeof(vp));
-    SubProblem sub[2];
-    memset(sub, 0, sizeof(sub));
-    if (!split) {
-        sub[0] = SubProblem{ngrid, 1, 0, 0, 0, 0};
-    } else {
-        sub[0] = SubProblem{(ngrid + 1) / 2, 2, 0, 0, 0, 0};
-        sub[1] = SubProblem{ngrid / 2, 2, 1, 1, 0, 0};
-    }
-    int nblocks = 0, coef_rows = 0;
-    for (int s = 0; s < nsub; ++s) {
-        sub[s].blk0 = nblocks;
-        sub[s].coef0 = coef_rows;
-        const int nb = (sub[s].rows + MB - 1) / MB;
-        nblocks += nb;
-        coef_rows += nb * MB;
-    }
-    const int grid1 = nblocks < nsm * DS::CTAS_PER_SM ? nblocks : nsm * DS::CTAS_PER_SM;
-
-    double* dsym = (double*)ctx->dsym.ensure(sizeof(double) * (size_t)nsub * NP * KP, &ctx->failed);
-    double* coef = (double*)ctx->coef.ensure(sizeof(double) * 4 * (size_t)coef_rows, &ctx->failed);
+    double* dsym = (double*)ctx->dsym.ensure(sizeof(double) * (size_t)g.nsub * NP * KP, &ctx->failed);
     double* epart = (double*)ctx->epart.ensure(sizeof(double) * grid1, &ctx->failed);
     if (ctx->failed) return;
 
+    DensityParams dp;
+    memset(&dp, 0, sizeof(dp));
     const double* planes[4] = {p.ao, p.gx, p.gy, p.gz};
-    bool ok = make_map(&dp.map_d, dsym, (uint64_t)KP, (uint64_t)nsub * NP, (uint64_t)KP, NT);
-    for (int s = 0; s < nsub; ++s) {
-        ok = ok && make_sub_map(&dp.map_a[s], p.ao, ngrid, nao, split, s, MB);
-        for (int i = 0; i < 3; ++i)
-            ok = ok && make_sub_map(&dp.map_g[s][i], NPL == 4 ? planes[i + 1] : p.ao, ngrid, nao, split, s, MB);
-        for (int i = 0; i < 4; ++i) ok = ok && make_sub_map(&vp.map_p[s][i], planes[i < NPL ? i : 0], ngrid, nao, split, s, VK);
+    bool ok = make_map(&dp.map_d, dsym, (uint64_t)KP, (uint64_t)g.nsub * NP, (uint64_t)KP, NT);
+    for (int s = 0; s < g.nsub; ++s) {
+        ok = ok && make_sub_map(&dp.map_a[s], p.ao, ngrid, nao, g.split, s, MB);
+        for (int i = 0; i < 4; ++i)
+            ok = ok && make_sub_map(&dp.map_e[s][i], planes[i < NPL ? i : 0], ngrid, nao, g.split, s, 64);
     }
     if (!ok) { ctx->failed = true; return; }
-
-    dp.sub[0] = sub[0]; dp.sub[1] = sub[1];
-    dp.nsub = nsub; dp.ngrid = ngrid; dp.nao = nao;
+    dp.sub[0] = g.sub[0]; dp.sub[1] = g.sub[1];
+    dp.nsub = g.nsub;
     dp.xc_mode = p.xc_type == 2 ? 4 : p.xc_type * 2 + (ctx->exact_functionals ? 1 : 0);
-    dp.nblocks = nblocks; dp.ntiles = ntiles; dp.nk = KP / 16; dp.NP = NP; dp.l2_prefetch = ctx->l2_prefetch ? 1 : 0;
-    dp.ao = p.ao; dp.gx = p.gx; dp.gy = p.gy; dp.gz = p.gz; dp.w = p.w;
-    dp.coef = coef; dp.exc_part = epart;
+    dp.nblocks = g.nblocks; dp.ntiles = ntiles; dp.nk = KP / 16; dp.NP = NP;
+    dp.l2_prefetch = ctx->l2_prefetch ? 1 : 0;
+    dp.w = p.w; dp.coef = coef; dp.exc_part = epart;
+#ifdef DFT_PHASE_TIMING
+    dp.phase = (long long*)ctx->scratch.ensure(sizeof(long long) * (8192 + 160 * 9 * 4), &ctx->failed);
+#endif
 
-    const int lda_half = (NPL == 1) ? 1 : 0;
-    const int tiles = lda_half ? ntiles * (ntiles + 1) / 2 : ntiles * ntiles;
-    const int maxrows = sub[0].rows;
-    int nsl = nsm / (tiles * nsub);
+    auto dk = density_tma_kernel<NF2, NPL>;
+    DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(dk, cudaFuncAttributeMaxDynamicSharedMemorySize, DL::TOTAL));
+    symmetrize_pad_tma_kernel<<<dim3((KP + 127) / 128, NP * g.nsub), 128, 0, st>>>(nao, KP, NP, g.nsub, p.dm, dsym);
+    dk<<<grid1, NTHREADS, DL::TOTAL, st>>>(dp);
+    *epart_out = epart;
+    *nepart_out = grid1;
+}
+
+// ---- V launch: output tile (WM MF 8) x (WN NFN 8)
+template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES>
+static void launch_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry& g, int nsm, const double* coef,
+                       const double* epart, int nepart) {
+    using VL = VxcCfg<MF, NFN, WM, WN, NPL, VK, STAGES>;
+    cudaStream_t st = ctx->stream;
+    const int ngrid = p.ngrid, nao = p.nao;
+    const int tiles_m = (g.ncols + VL::MT - 1) / VL::MT, tiles_n = (g.ncols + VL::NT_ - 1) / VL::NT_;
+    const int lda_half = (NPL == 1 && VL::MT == VL::NT_) ? 1 : 0;
+    const int tiles = lda_half ? tiles_n * (tiles_n + 1) / 2 : tiles_m * tiles_n;
+    const int mpv = tiles_m * VL::MT, ldv = tiles_n * VL::NT_;
+
+    const int maxrows = g.sub[0].rows;
+    int nsl = nsm / (tiles * g.nsub);
     if (nsl < 1) nsl = 1;
     const int max_slices = (maxrows + VK - 1) / VK;
     if (nsl > max_slices) nsl = max_slices;
     int rows_per_slice = (maxrows + nsl - 1) / nsl;
     rows_per_slice = ((rows_per_slice + VK - 1) / VK) * VK;
     nsl = (maxrows + rows_per_slice - 1) / rows_per_slice;
-    double* vpart = (double*)ctx->vpart.ensure(sizeof(double) * (size_t)nsub * nsl * NP * NP, &ctx->failed);
+    double* vpart = (double*)ctx->vpart.ensure(sizeof(double) * (size_t)g.nsub * nsl * mpv * ldv, &ctx->failed);
     if (ctx->failed) return;
 
-    vp.sub[0] = sub[0]; vp.sub[1] = sub[1];
-    vp.nsub = nsub; vp.ntiles = ntiles; vp.lda_half = lda_half; vp.rows_per_slice = rows_per_slice;
-    vp.slices_per_sub = nsl; vp.NP = NP; vp.coef = coef; vp.vpart = vpart;
+    VxcParams vp;
+    memset(&vp, 0, sizeof(vp));
+    const double* planes[4] = {p.ao, p.gx, p.gy, p.gz};
+    bool ok = true, ok3 = ctx->tma_3d;
+    for (int s = 0; s < g.nsub; ++s) {
+        const int cols = g.split ? (s == 0 ? nao : nao + 1) : nao;
+        vp.nfull[s] = cols / 16;
+        vp.rem[s] = cols % 16;
+        // whole blocks in the last M / N tile of this sub-problem (where that tile is partial)
+        const int lm = vp.nfull[s] - (tiles_m - 1) * (VL::MT / 16), ln = vp.nfull[s] - (tiles_n - 1) * (VL::NT_ / 16);
+        for (int i = 0; i < 4; ++i) {
+            const double* pl = planes[i < NPL ? i : 0];
+            ok = ok && make_sub_map(&vp.p2[s][i], pl, ngrid, nao, g.split, s, VK);
+            if (ok3 && vp.nfull[s] > 0) {
+                ok3 = ok3 && make_sub_map3(&vp.m3[s][i], pl, ngrid, nao, g.split, s, VK, VL::MT / 16);
+                if (lm > 0 && lm < VL::MT / 16) ok3 = ok3 && make_sub_map3(&vp.m3l[s][i], pl, ngrid, nao, g.split, s, VK, lm);
+            }
+        }
+        if (ok3 && vp.nfull[s] > 0) {
+            ok3 = ok3 && make_sub_map3(&vp.n3[s], p.ao, ngrid, nao, g.split, s, VK, VL::NT_ / 16);
+            if (ln > 0 && ln < VL::NT_ / 16) ok3 = ok3 && make_sub_map3(&vp.n3l[s], p.ao, ngrid, nao, g.split, s, VK, ln);
+        }
+    }
+    if (!ok) { ctx->failed = true; return; }
+    vp.use3d = ok3 ? 1 : 0;  // (a driver that rejects the 3-D form leaves the per-block 2-D loads)
+    vp.sub[0] = g.sub[0]; vp.sub[1] = g.sub[1];
+    vp.nsub = g.nsub; vp.tiles_m = tiles_m; vp.tiles_n = tiles_n; vp.lda_half = lda_half;
+    vp.rows_per_slice = rows_per_slice; vp.slices_per_sub = nsl; vp.ldv = ldv; vp.mpv = mpv;
+    vp.coef = coef; vp.vpart = vpart;
+#ifdef DFT_PHASE_TIMING
+    {   // the density kernel's phase record occupies the first 148*8*4 entries of `scratch`
+        long long* ph = (long long*)ctx->scratch.ensure(sizeof(long long) * (8192 + (size_t)tiles * nsl * g.nsub * (NCW + 1) * 4), &ctx->failed);
+        vp.phase = ph ? ph + 8192 : nullptr;
+    }
+#endif
 
-    using DL = DensitySmem<NF, WM>;
-    using VL = VxcSmem<NF, NPL>;
-    auto dk = density_tma_kernel<NF, NPL, WM>;
-    auto vk = vxc_tma_kernel<NF, NPL>;
-    DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(dk, cudaFuncAttributeMaxDynamicSharedMemorySize, DL::TOTAL));
+    auto vk = vxc_tma_kernel<MF, NFN, WM, WN, NPL, VK, STAGES>;
     DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, VL::TOTAL));
-
-    if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
-    symmetrize_pad_tma_kernel<<<dim3((KP + 127) / 128, NP * nsub), 128, 0, st>>>(nao, KP, NP, nsub, p.dm, dsym);
-    dk<<<grid1, DS::NTHREADS, DL::TOTAL, st>>>(dp);
-    if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
-    vk<<<dim3(tiles, nsl * nsub), NTHREADS, VL::TOTAL, st>>>(vp);
+    vk<<<dim3(tiles, nsl * g.nsub), NTHREADS, VL::TOTAL, st>>>(vp);
     if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
     const size_t n2 = (size_t)nao * nao;
-    finalize_tma_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(nao, NP, NT, nsub, nsl, split ? 1 : 0, lda_half, vpart,
-                                                                      p.vxc, grid1, epart, p.d_exc);
+    finalize_tma_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(nao, ldv, mpv, VL::NT_, g.nsub, nsl, g.split ? 1 : 0,
+                                                                      lda_half, vpart, p.vxc, nepart, epart, p.d_exc);
     if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
+}
+
+template <int NPL>
+static void launch_all(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
+    const Geometry g = make_geometry(p.ngrid, p.nao);
+    double* coef = (double*)ctx->coef.ensure(sizeof(double) * 4 * (size_t)g.coef_rows, &ctx->failed);
+    if (ctx->failed) return;
+    cudaStream_t st = ctx->stream;
+
+    // density column tile: the NF in 1..5 with the least padded width, larger tiles on ties
+    int best_nf = 1, best_np = 1 << 30;
+    for (int nf = 1; nf <= 5; ++nf) {
+        const int nt = 32 * nf, np = ((g.ncols + nt - 1) / nt) * nt;
+        if (np <= best_np) { best_np = np; best_nf = nf; }
+    }
+    double* epart = nullptr;
+    int nepart = 0;
+    if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
+    switch (best_nf) {
+        case 1: launch_density<2, NPL>(ctx, p, g, nsm, coef, &epart, &nepart); break;
+        case 2: launch_density<4, NPL>(ctx, p, g, nsm, coef, &epart, &nepart); break;
+        case 3: launch_density<6, NPL>(ctx, p, g, nsm, coef, &epart, &nepart); break;
+        case 4: launch_density<8, NPL>(ctx, p, g, nsm, coef, &epart, &nepart); break;
+        default: launch_density<10, NPL>(ctx, p, g, nsm, coef, &epart, &nepart); break;
+    }
+    if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
+    if (ctx->failed) return;
+
+    // V output tile: 64 x 64 for narrow matrices, else the cheaper of 128 x 128 and 160 x 80
+    // (the latter pays ~15 % more shared-memory and FP64 work per flop)
+    const int n = g.ncols;
+    auto pad = [](int x, int t) { return ((x + t - 1) / t) * t; };
+    const double cost128 = (double)pad(n, 128) * pad(n, 128);
+    const double cost160 = 1.15 * (double)pad(n, 160) * pad(n, 80);
+    int shape = ctx->vxc_shape;
+    if (shape == 0) shape = n <= 64 ? 64 : (cost160 < cost128 ? 160 : 128);
+    if (shape == 64) {
+        launch_vxc<1, 8, 8, 1, NPL, 16, 4>(ctx, p, g, nsm, coef, epart, nepart);
+    } else if (shape == 160) {
+        launch_vxc<5, 5, 4, 2, NPL, 16, 2>(ctx, p, g, nsm, coef, epart, nepart);
+    } else {
+        if (ctx->vxc_vk == 16) launch_vxc<2, 16, 8, 1, NPL, 16, 2>(ctx, p, g, nsm, coef, epart, nepart);
+        else launch_vxc<2, 16, 8, 1, NPL, 8, 5>(ctx, p, g, nsm, coef, epart, nepart);
+    }
     ctx->stats.launches = 4;
     ctx->stats.path = PATH_TMA;
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
@@ -829,25 +979,10 @@ bool tma_compatible(const Problem& p) {
 }
 
 void run_tma(CublasHandleWrapper* ctx, const Problem& p) {
-    using namespace tmapath;
-    const int ncols = p.nao + (p.nao & 1);
-    const int ntiles = (ncols + 127) / 128;
-    const int NF = (ncols + 32 * ntiles - 1) / (32 * ntiles);  // 1..4 -> column tile 32 NF
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-    const bool two_ctas = ctx->density_ctas_per_sm != 1;
-#define DFT_LAUNCH(NF_)                                                                                    \
-    do {                                                                                                   \
-        if (two_ctas) { if (p.xc_type == 0) launch<NF_, 1, 1>(ctx, p, nsm); else launch<NF_, 4, 1>(ctx, p, nsm); } \
-        else { if (p.xc_type == 0) launch<NF_, 1, 2>(ctx, p, nsm); else launch<NF_, 4, 2>(ctx, p, nsm); }          \
-    } while (0)
-    switch (NF) {
-        case 1: DFT_LAUNCH(1); break;
-        case 2: DFT_LAUNCH(2); break;
-        case 3: DFT_LAUNCH(3); break;
-        default: DFT_LAUNCH(4); break;
-    }
-#undef DFT_LAUNCH
+    if (p.xc_type == 0) tmapath::launch_all<1>(ctx, p, nsm);
+    else tmapath::launch_all<4>(ctx, p, nsm);
 }
 
 }  // namespace xc

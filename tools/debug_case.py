@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Debug helper: compare generic / TMA (both density shapes) on one random case."""
+"""Debug helper: compare the generic path with the TMA path (all V tile shapes) on one random case.
+Usage: python tools/debug_case.py <LDA|GGA|B3LYP> <ngrid> <nao> [seed]"""
 import sys
 import numpy as np
 sys.path.insert(0, ".")
@@ -12,10 +13,10 @@ seed = int(sys.argv[4]) if len(sys.argv) > 4 else ngrid + nao
 rng = np.random.default_rng(seed)
 dm, ao, w, grad = _random_case(rng, ngrid, nao)
 res = {}
-for name, opt in (("generic", {"path": 1}), ("tma1", {"density_ctas_per_sm": 1}), ("tma2", {"density_ctas_per_sm": 2}),
-                  ("tma2b", {"density_ctas_per_sm": 2}), ("tma2np", {"density_ctas_per_sm": 2, "l2_prefetch": 0})):
+variants = (("generic", {"path": 1}), ("tma", {}), ("tma-again", {}), ("vk16", {"vxc_vk": 16}), ("v64", {"vxc_shape": 64}),
+            ("v128", {"vxc_shape": 128}), ("v160", {"vxc_shape": 160}), ("pf", {"l2_prefetch": 1}), ("no3d", {"tma_3d": 0}))
+for name, opt in variants:
     e, v, s = _run_engine(DEFAULT_LIB, fn, dm, ao, w, grad, opt)
     res[name] = (e, v)
-    print(f"{name:8s} path {int(s['path'])} E = {e!r}  |V|max = {np.abs(v).max():.6e}")
-for k in ("tma1", "tma2", "tma2b", "tma2np"):
-    print(k, "dE", res[k][0] - res["generic"][0], "dV", np.abs(res[k][1] - res["generic"][1]).max())
+    print(f"{name:10s} path {int(s['path'])} E = {e!r}  |V|max = {np.abs(v).max():.6e}  "
+          f"dE {e - res['generic'][0]:.3e} dV {np.abs(v - res['generic'][1]).max():.3e}", flush=True)

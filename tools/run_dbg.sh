@@ -1,1 +1,6 @@
-for a in "GGA 20000 378" "GGA 20000 255" "GGA 40000 377" "B3LYP 30000 377"; do echo "== $a"; timeout 120 python tools/debug_coef.py $a 2>&1 | grep -E "^E|rows differing"; done
+#!/bin/bash
+# debugging session on the GPU box: a few random cases through every TMA variant
+mkdir -p gpurun_out/dbg
+for a in "GGA 3000 36" "LDA 3000 36" "GGA 20000 152" "B3LYP 20000 377" "LDA 20000 377" "GGA 20001 64" "GGA 10000 255" "B3LYP 5000 7" "GGA 30000 300"; do
+  echo "== $a"; timeout 120 python tools/debug_case.py $a 2>&1 | tail -10
+done 2>&1 | tee gpurun_out/dbg/dbg.log
