@@ -57,7 +57,8 @@ int DFT_CommDestroy(XCSolver* solver);
 int DFT_SetOption(XCSolver* solver, const char* key, double value);
 // keys: "density_ms", "vxc_ms", "reduce_ms", "total_ms" (CUDA-event times of the last
 //       DFT_ComputeXC on the engine's stream), "launches" (kernels launched by the last call),
-//       "path" (path actually taken), "workspace_bytes".
+//       "path" (path actually taken), "workspace_bytes", "plans_built" (TMA launch plans encoded so
+//       far: a steady SCF loop over the same arrays builds exactly one).
 double DFT_GetStat(XCSolver* solver, const char* key);
 
 // ---- convenience for callers that keep V_xc/E_xc on the device (no host sync) --------------

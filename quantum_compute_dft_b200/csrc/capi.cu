@@ -46,6 +46,7 @@ CublasHandleWrapper::CublasHandleWrapper() {
 
 CublasHandleWrapper::~CublasHandleWrapper() {
     if (stream) cudaStreamSynchronize(stream);
+    xc::free_tma_plan(this);
     dsym.release(); coef.release(); epart.release(); vpart.release(); result.release(); scratch.release();
     if (h_scalar) cudaFreeHost(h_scalar);
     for (auto& e : ev)
@@ -109,7 +110,7 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
     if (ngrid == 0) {
         cudaMemsetAsync(p.vxc, 0, sizeof(double) * n2, ctx->stream);
         cudaMemsetAsync(p.d_exc, 0, sizeof(double), ctx->stream);
-        ctx->stats = XcStats();
+        { const int pb = ctx->stats.plans_built; ctx->stats = XcStats(); ctx->stats.plans_built = pb; }
     } else {
         bool use_tma = false;
         if (ctx->path == PATH_TMA) use_tma = xc::tma_compatible(p);
@@ -254,6 +255,7 @@ double DFT_GetStat(XCSolver* solver, const char* key) {
     if (!strcmp(key, "reduce_ms")) return c->stats.reduce_ms;
     if (!strcmp(key, "total_ms")) return c->stats.total_ms;
     if (!strcmp(key, "launches")) return c->stats.launches;
+    if (!strcmp(key, "plans_built")) return c->stats.plans_built;
     if (!strcmp(key, "path")) return c->stats.path;
     if (!strcmp(key, "workspace_bytes")) return (double)c->workspace_bytes();
     if (!strcmp(key, "nranks")) return c->nranks;

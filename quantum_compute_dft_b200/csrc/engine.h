@@ -35,6 +35,7 @@ struct XcStats {
     float density_ms = 0.f, vxc_ms = 0.f, reduce_ms = 0.f, total_ms = 0.f;
     int launches = 0;
     int path = 0;
+    int plans_built = 0;  // TMA path: launch plans (tensor maps, geometry) encoded so far; a steady SCF loop builds one
 };
 
 struct CublasHandleWrapper {
@@ -60,6 +61,8 @@ struct CublasHandleWrapper {
     DeviceBuffer result;   // packed [V_xc (nao*nao) | E_xc] for the all-reduce / async E
     DeviceBuffer scratch;  // repacked AO planes etc.
     double* h_scalar = nullptr;  // pinned
+    void* tma_plan = nullptr;    // cached launch plan of the TMA path (xc_tma.cu)
+    int num_sms = 0;
 
     // multi-GPU (NCCL loaded lazily; see comm.cu)
     void* nccl_comm = nullptr;
@@ -93,6 +96,7 @@ void run_generic(CublasHandleWrapper* ctx, const Problem& p);
 // TMA-fed path: xc_tma.cu.  Returns false when the inputs are not TMA-compatible.
 bool tma_compatible(const Problem& p);
 void run_tma(CublasHandleWrapper* ctx, const Problem& p);
+void free_tma_plan(CublasHandleWrapper* ctx);
 
 // all-reduce of [V | E] over the communicator (comm.cu); no-op when nranks == 1
 int allreduce_result(CublasHandleWrapper* ctx, double* d_packed, size_t count);

@@ -806,13 +806,36 @@ static Geometry make_geometry(int ngrid, int nao) {
     return g;
 }
 
-// ---- density launch: column tile 16 NF2
+// ---- launch plan -------------------------------------------------------------------------------
+// Everything a call needs besides the data itself: geometry, ~40 encoded tensor maps, kernel
+// instances and launch shapes.  An SCF loop calls with the same arrays every iteration
+// (dft.py:155-176 keeps the AO planes resident), so the plan of the previous call is kept in the
+// engine context and reused when pointers, shapes and options are unchanged; tensor maps only hold
+// addresses, so a plan stays valid when the caller rewrites the CONTENTS of its arrays.
+struct PlanKey {
+    Problem prob;
+    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk;
+    const void *dsym, *coef, *epart, *vpart;  // engine workspaces (grow-only: may move when they grow)
+};
+
+struct Plan {
+    bool valid = false;
+    PlanKey key;
+    DensityParams dp;
+    VxcParams vp;
+    const void* dfunc = nullptr;
+    const void* vfunc = nullptr;
+    int dgrid = 0, dsmem = 0, vsmem = 0;
+    dim3 vgrid;
+    // symmetrize_pad / finalize arguments
+    int KP = 0, NP = 0, nsub = 0, ldv = 0, mpv = 0, fin_nt = 0, nsl = 0, shift1 = 0, lda_half = 0;
+    double *dsym = nullptr, *epart = nullptr, *vpart = nullptr;
+};
+
 template <int NF2, int NPL>
-static void launch_density(CublasHandleWrapper* ctx, const Problem& p, const Geometry& g, int nsm, double* coef,
-                           double** epart_out, int* nepart_out) {
+static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geometry& g, int nsm, double* coef, Plan& pl) {
     using DL = DensitySmem<NF2, NPL>;
     constexpr int NT = DL::NT;
-    cudaStream_t st = ctx->stream;
     const int ngrid = p.ngrid, nao = p.nao;
     const int ntiles = (g.ncols + NT - 1) / NT;
     const int NP = ntiles * NT;
@@ -823,7 +846,7 @@ static void launch_density(CublasHandleWrapper* ctx, const Problem& p, const Geo
     double* epart = (double*)ctx->epart.ensure(sizeof(double) * grid1, &ctx->failed);
     if (ctx->failed) return;
 
-    DensityParams dp;
+    DensityParams& dp = pl.dp;
     memset(&dp, 0, sizeof(dp));
     const double* planes[4] = {p.ao, p.gx, p.gy, p.gz};
     bool ok = make_map(&dp.map_d, dsym, (uint64_t)KP, (uint64_t)g.nsub * NP, (uint64_t)KP, NT);
@@ -845,18 +868,15 @@ static void launch_density(CublasHandleWrapper* ctx, const Problem& p, const Geo
 
     auto dk = density_tma_kernel<NF2, NPL>;
     DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(dk, cudaFuncAttributeMaxDynamicSharedMemorySize, DL::TOTAL));
-    symmetrize_pad_tma_kernel<<<dim3((KP + 127) / 128, NP * g.nsub), 128, 0, st>>>(nao, KP, NP, g.nsub, p.dm, dsym);
-    dk<<<grid1, NTHREADS, DL::TOTAL, st>>>(dp);
-    *epart_out = epart;
-    *nepart_out = grid1;
+    pl.dfunc = reinterpret_cast<const void*>(dk);
+    pl.dgrid = grid1; pl.dsmem = DL::TOTAL;
+    pl.KP = KP; pl.NP = NP; pl.nsub = g.nsub; pl.dsym = dsym; pl.epart = epart;
 }
 
-// ---- V launch: output tile (WM MF 8) x (WN NFN 8)
+// ---- V plan: output tile (WM MF 8) x (WN NFN 8)
 template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES>
-static void launch_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry& g, int nsm, const double* coef,
-                       const double* epart, int nepart) {
+static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry& g, int nsm, const double* coef, Plan& pl) {
     using VL = VxcCfg<MF, NFN, WM, WN, NPL, VK, STAGES>;
-    cudaStream_t st = ctx->stream;
     const int ngrid = p.ngrid, nao = p.nao;
     const int tiles_m = (g.ncols + VL::MT - 1) / VL::MT, tiles_n = (g.ncols + VL::NT_ - 1) / VL::NT_;
     const int lda_half = (NPL == 1 && VL::MT == VL::NT_) ? 1 : 0;
@@ -874,7 +894,7 @@ static void launch_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometr
     double* vpart = (double*)ctx->vpart.ensure(sizeof(double) * (size_t)g.nsub * nsl * mpv * ldv, &ctx->failed);
     if (ctx->failed) return;
 
-    VxcParams vp;
+    VxcParams& vp = pl.vp;
     memset(&vp, 0, sizeof(vp));
     const double* planes[4] = {p.ao, p.gx, p.gy, p.gz};
     bool ok = true, ok3 = ctx->tma_3d;
@@ -885,11 +905,11 @@ static void launch_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometr
         // whole blocks in the last M / N tile of this sub-problem (where that tile is partial)
         const int lm = vp.nfull[s] - (tiles_m - 1) * (VL::MT / 16), ln = vp.nfull[s] - (tiles_n - 1) * (VL::NT_ / 16);
         for (int i = 0; i < 4; ++i) {
-            const double* pl = planes[i < NPL ? i : 0];
-            ok = ok && make_sub_map(&vp.p2[s][i], pl, ngrid, nao, g.split, s, VK);
+            const double* plane = planes[i < NPL ? i : 0];
+            ok = ok && make_sub_map(&vp.p2[s][i], plane, ngrid, nao, g.split, s, VK);
             if (ok3 && vp.nfull[s] > 0) {
-                ok3 = ok3 && make_sub_map3(&vp.m3[s][i], pl, ngrid, nao, g.split, s, VK, VL::MT / 16);
-                if (lm > 0 && lm < VL::MT / 16) ok3 = ok3 && make_sub_map3(&vp.m3l[s][i], pl, ngrid, nao, g.split, s, VK, lm);
+                ok3 = ok3 && make_sub_map3(&vp.m3[s][i], plane, ngrid, nao, g.split, s, VK, VL::MT / 16);
+                if (lm > 0 && lm < VL::MT / 16) ok3 = ok3 && make_sub_map3(&vp.m3l[s][i], plane, ngrid, nao, g.split, s, VK, lm);
             }
         }
         if (ok3 && vp.nfull[s] > 0) {
@@ -912,20 +932,17 @@ static void launch_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometr
 
     auto vk = vxc_tma_kernel<MF, NFN, WM, WN, NPL, VK, STAGES>;
     DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, VL::TOTAL));
-    vk<<<dim3(tiles, nsl * g.nsub), NTHREADS, VL::TOTAL, st>>>(vp);
-    if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
-    const size_t n2 = (size_t)nao * nao;
-    finalize_tma_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(nao, ldv, mpv, VL::NT_, g.nsub, nsl, g.split ? 1 : 0,
-                                                                      lda_half, vpart, p.vxc, nepart, epart, p.d_exc);
-    if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
+    pl.vfunc = reinterpret_cast<const void*>(vk);
+    pl.vgrid = dim3(tiles, nsl * g.nsub); pl.vsmem = VL::TOTAL;
+    pl.ldv = ldv; pl.mpv = mpv; pl.fin_nt = VL::NT_; pl.nsl = nsl; pl.shift1 = g.split ? 1 : 0; pl.lda_half = lda_half;
+    pl.vpart = vpart;
 }
 
 template <int NPL>
-static void launch_all(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
+static void build_plan(CublasHandleWrapper* ctx, const Problem& p, int nsm, Plan& pl) {
     const Geometry g = make_geometry(p.ngrid, p.nao);
     double* coef = (double*)ctx->coef.ensure(sizeof(double) * 4 * (size_t)g.coef_rows, &ctx->failed);
     if (ctx->failed) return;
-    cudaStream_t st = ctx->stream;
 
     // density column tile: the NF in 1..5 with the least padded width, larger tiles on ties
     int best_nf = 1, best_np = 1 << 30;
@@ -933,17 +950,13 @@ static void launch_all(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
         const int nt = 32 * nf, np = ((g.ncols + nt - 1) / nt) * nt;
         if (np <= best_np) { best_np = np; best_nf = nf; }
     }
-    double* epart = nullptr;
-    int nepart = 0;
-    if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
     switch (best_nf) {
-        case 1: launch_density<2, NPL>(ctx, p, g, nsm, coef, &epart, &nepart); break;
-        case 2: launch_density<4, NPL>(ctx, p, g, nsm, coef, &epart, &nepart); break;
-        case 3: launch_density<6, NPL>(ctx, p, g, nsm, coef, &epart, &nepart); break;
-        case 4: launch_density<8, NPL>(ctx, p, g, nsm, coef, &epart, &nepart); break;
-        default: launch_density<10, NPL>(ctx, p, g, nsm, coef, &epart, &nepart); break;
+        case 1: plan_density<2, NPL>(ctx, p, g, nsm, coef, pl); break;
+        case 2: plan_density<4, NPL>(ctx, p, g, nsm, coef, pl); break;
+        case 3: plan_density<6, NPL>(ctx, p, g, nsm, coef, pl); break;
+        case 4: plan_density<8, NPL>(ctx, p, g, nsm, coef, pl); break;
+        default: plan_density<10, NPL>(ctx, p, g, nsm, coef, pl); break;
     }
-    if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
     if (ctx->failed) return;
 
     // V output tile: 64 x 64 for narrow matrices, else the cheaper of 128 x 128 and 160 x 80
@@ -955,13 +968,42 @@ static void launch_all(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     int shape = ctx->vxc_shape;
     if (shape == 0) shape = n <= 64 ? 64 : (cost160 < cost128 ? 160 : 128);
     if (shape == 64) {
-        launch_vxc<1, 8, 8, 1, NPL, 16, 4>(ctx, p, g, nsm, coef, epart, nepart);
+        plan_vxc<1, 8, 8, 1, NPL, 16, 4>(ctx, p, g, nsm, coef, pl);
     } else if (shape == 160) {
-        launch_vxc<5, 5, 4, 2, NPL, 16, 2>(ctx, p, g, nsm, coef, epart, nepart);
+        plan_vxc<5, 5, 4, 2, NPL, 16, 2>(ctx, p, g, nsm, coef, pl);
     } else {
-        if (ctx->vxc_vk == 16) launch_vxc<2, 16, 8, 1, NPL, 16, 2>(ctx, p, g, nsm, coef, epart, nepart);
-        else launch_vxc<2, 16, 8, 1, NPL, 8, 5>(ctx, p, g, nsm, coef, epart, nepart);
+        if (ctx->vxc_vk == 16) plan_vxc<2, 16, 8, 1, NPL, 16, 2>(ctx, p, g, nsm, coef, pl);
+        else plan_vxc<2, 16, 8, 1, NPL, 8, 5>(ctx, p, g, nsm, coef, pl);
     }
+}
+
+static PlanKey make_key(const CublasHandleWrapper* ctx, const Problem& p) {
+    PlanKey k;
+    memset(&k, 0, sizeof(k));  // (padding bytes too: keys are compared with memcmp)
+    k.prob.xc_type = p.xc_type; k.prob.ngrid = p.ngrid; k.prob.nao = p.nao;
+    k.prob.dm = p.dm; k.prob.ao = p.ao; k.prob.gx = p.gx; k.prob.gy = p.gy; k.prob.gz = p.gz; k.prob.w = p.w;
+    k.prob.vxc = p.vxc; k.prob.d_exc = p.d_exc;
+    k.exact = ctx->exact_functionals; k.l2_prefetch = ctx->l2_prefetch; k.tma_3d = ctx->tma_3d;
+    k.vxc_shape = ctx->vxc_shape; k.vxc_vk = ctx->vxc_vk;
+    k.dsym = ctx->dsym.ptr; k.coef = ctx->coef.ptr; k.epart = ctx->epart.ptr; k.vpart = ctx->vpart.ptr;
+    return k;
+}
+
+static void run_plan(CublasHandleWrapper* ctx, const Problem& p, Plan& pl) {
+    cudaStream_t st = ctx->stream;
+    if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
+    symmetrize_pad_tma_kernel<<<dim3((pl.KP + 127) / 128, pl.NP * pl.nsub), 128, 0, st>>>(p.nao, pl.KP, pl.NP, pl.nsub, p.dm,
+                                                                                         pl.dsym);
+    void* dargs[1] = {&pl.dp};
+    DFT_CUDA_CHECK(ctx, cudaLaunchKernel(pl.dfunc, dim3(pl.dgrid), dim3(NTHREADS), dargs, (size_t)pl.dsmem, st));
+    if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
+    void* vargs[1] = {&pl.vp};
+    DFT_CUDA_CHECK(ctx, cudaLaunchKernel(pl.vfunc, pl.vgrid, dim3(NTHREADS), vargs, (size_t)pl.vsmem, st));
+    if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
+    const size_t n2 = (size_t)p.nao * p.nao;
+    finalize_tma_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(p.nao, pl.ldv, pl.mpv, pl.fin_nt, pl.nsub, pl.nsl, pl.shift1,
+                                                                      pl.lda_half, pl.vpart, p.vxc, pl.dgrid, pl.epart, p.d_exc);
+    if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
     ctx->stats.launches = 4;
     ctx->stats.path = PATH_TMA;
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
@@ -979,10 +1021,26 @@ bool tma_compatible(const Problem& p) {
 }
 
 void run_tma(CublasHandleWrapper* ctx, const Problem& p) {
-    int nsm = 148;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-    if (p.xc_type == 0) tmapath::launch_all<1>(ctx, p, nsm);
-    else tmapath::launch_all<4>(ctx, p, nsm);
+    using namespace tmapath;
+    if (!ctx->tma_plan) ctx->tma_plan = new Plan();
+    Plan& pl = *static_cast<Plan*>(ctx->tma_plan);
+    PlanKey key = make_key(ctx, p);
+    if (!pl.valid || memcmp(&key, &pl.key, sizeof(key)) != 0) {
+        pl.valid = false;
+        if (ctx->num_sms <= 0) cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        if (p.xc_type == 0) build_plan<1>(ctx, p, ctx->num_sms, pl);
+        else build_plan<4>(ctx, p, ctx->num_sms, pl);
+        if (ctx->failed) return;
+        pl.key = make_key(ctx, p);  // (workspaces may have grown while planning)
+        pl.valid = true;
+        ctx->stats.plans_built++;
+    }
+    run_plan(ctx, p, pl);
+}
+
+void free_tma_plan(CublasHandleWrapper* ctx) {
+    delete static_cast<tmapath::Plan*>(ctx->tma_plan);
+    ctx->tma_plan = nullptr;
 }
 
 }  // namespace xc

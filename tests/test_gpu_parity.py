@@ -197,6 +197,62 @@ def test_tma_path_matches_generic_path_at_scale(engine_lib, functional, ngrid, n
 
 
 @pytest.mark.parametrize("functional", FUNCS)
+@pytest.mark.parametrize("ngrid,nao", [(20000, 152), (12001, 64), (9000, 377), (6000, 255), (3000, 36), (2500, 7)])
+def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
+    """Every tuning variant of the TMA path (V output tile 64/128/160x80, 8 or 16 rows per ring stage, 3-D or
+    per-block 2-D tensor maps, L2 prefetch) computes the same result as the generic path."""
+    rng = np.random.default_rng(3 * ngrid + nao)
+    dm, ao, w, grad = _random_case(rng, ngrid, nao)
+    e0, v0, s0 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 1})
+    assert s0["path"] == 1
+    for opt in ({"vxc_shape": 64}, {"vxc_shape": 128, "vxc_vk": 8}, {"vxc_shape": 128, "vxc_vk": 16}, {"vxc_shape": 160},
+                {"tma_3d": 0}, {"l2_prefetch": 1}):
+        e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
+        assert s1["path"] == 2, opt
+        assert abs(e0 - e1) <= E_TOL * max(1.0, abs(e0) * 1e-3), opt
+        np.testing.assert_allclose(v0, v1, rtol=0, atol=V_TOL * max(1.0, np.abs(v0).max() * 1e-3), err_msg=str(opt))
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+def test_launch_plan_reuse(oracle, engine_lib, functional):
+    """An SCF loop calls with the same device arrays every iteration: the TMA launch plan (tensor maps,
+    geometry) is built once and reused; it caches addresses only, so new CONTENTS behind the same pointers are
+    seen, and new pointers / shapes / options build a new plan."""
+    from quantum_compute_dft_b200.cuda_rt import DeviceArray
+    from quantum_compute_dft_b200.solver import DFTSolverWrapper
+    rng = np.random.default_rng(21)
+    ngrid, nao = 6000, 36
+    dm, ao, w, grad = _random_case(rng, ngrid, nao)
+    dm2 = 0.5 * dm + 0.1 * np.eye(nao)
+    s = DFTSolverWrapper(engine_lib, functional)
+    d_dm, d_ao, d_w = DeviceArray.from_host(dm), DeviceArray.from_host(ao), DeviceArray.from_host(w)
+    d_g = DeviceArray.from_host(grad) if functional != "LDA" else None
+    d_v = DeviceArray((nao, nao), zero=True)
+    e1 = s.compute_xc(ngrid, nao, d_dm, d_ao, d_w, d_v, d_g); v1 = d_v.get()
+    e2 = s.compute_xc(ngrid, nao, d_dm, d_ao, d_w, d_v, d_g); v2 = d_v.get()
+    assert s.stat("path") == 2 and s.stat("plans_built") == 1
+    assert e1 == e2
+    np.testing.assert_array_equal(v1, v2)
+    # same pointers, new density matrix (what dft.py:200 does every iteration)
+    d_dm.set(dm2)
+    e3 = s.compute_xc(ngrid, nao, d_dm, d_ao, d_w, d_v, d_g); v3 = d_v.get()
+    assert s.stat("plans_built") == 1
+    e_o, v_o = oracle.compute_xc(XC[functional], dm2, ao, w, grad, mode=0)
+    assert abs(e3 - e_o) <= E_TOL
+    np.testing.assert_allclose(0.5 * (v3 + v3.T), oracle.sym(v_o), rtol=0, atol=V_TOL)
+    # fewer grid points through the same solver: new plan, right answer
+    h = 3000
+    e4 = s.compute_xc(h, nao, d_dm, d_ao, d_w, d_v, d_g if functional == "LDA" else DeviceArray.from_host(np.ascontiguousarray(grad[:, :h])))
+    assert s.stat("plans_built") == 2
+    e_o4, _ = oracle.compute_xc(XC[functional], dm2, ao[:h], w[:h], np.ascontiguousarray(grad[:, :h]), mode=0)
+    assert abs(e4 - e_o4) <= E_TOL
+    # an option that changes the kernels invalidates the plan
+    s.set_option("vxc_shape", 128)
+    e5 = s.compute_xc(ngrid, nao, d_dm, d_ao, d_w, d_v, d_g)
+    assert s.stat("plans_built") == 3 and abs(e5 - e3) <= E_TOL
+
+
+@pytest.mark.parametrize("functional", FUNCS)
 def test_forced_generic_path_matches_auto(oracle, engine_lib, functional):
     rng = np.random.default_rng(16)
     dm, ao, w, grad = _random_case(rng, 5000, 36)
