@@ -71,6 +71,25 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback of B200_PROFILING.md (of fallback)"
 
 
+def ncu_traffic(workload_key, kernel_key, world):
+    """DRAM bytes per launch of a kernel from the committed ncu capture of the same command line
+    (profiles/*_ncu_summary.json, written by tools/ncu_summary.py).  Captured at 1 GPU: null otherwise."""
+    if world != 1:
+        return None, None
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        for f in sorted(os.listdir(pdir)):
+            if f.endswith("_ncu_summary.json"):
+                db = json.load(open(os.path.join(pdir, f)))
+                k = db.get(workload_key, {}).get(kernel_key)
+                if k:
+                    best = (k.get("dram_bytes"), f"profiles/{f} ({k.get('source')})")
+    except Exception:
+        return None, None
+    return best if best else (None, None)
+
+
 def cpu_port_baseline(hp, sample_points):
     """PySCF-numint-shaped CPU port (oracle/numint_port.py) on a bounded sample of the same workload."""
     from oracle import numint_port, oracle as O
@@ -283,8 +302,10 @@ def main():
             dmma_peak = solver.lib.DFT_MicrobenchDMMA(4096)
             dfma_peak = solver.lib.DFT_MicrobenchDFMA(4096)
             achieved = 0.5 * flops_local / (dom_ms * 1e-3) / 1e12
+            traffic, traffic_src = ncu_traffic(args.workload, dom.split("_")[0], world)
             roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
-                        "frac": achieved / dmma_peak if dmma_peak > 0 else None, "traffic": None,
+                        "frac": achieved / dmma_peak if dmma_peak > 0 else None, "traffic": traffic,
+                        "traffic_source": traffic_src,
                         "peak_source": "DFT_MicrobenchDMMA measured in this run (register-resident mma.sync m8n8k4 f64 "
                                        "-> DMMA); MEASURED_PEAKS.json has no FP64 entry; nominal 37-40 TFLOP/s",
                         "dfma_peak_tflops": dfma_peak,
