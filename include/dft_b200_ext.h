@@ -51,12 +51,14 @@ int DFT_CommDestroy(XCSolver* solver);
 //       "deterministic" 0|1 (default 1: fixed-order reductions, bit-reproducible results)
 //       "vxc_shape" 0|64|128|160 (tuning: output tile of the TMA V kernel; 0 = chosen from nao)
 //       "vxc_vk" 8|16 (tuning: grid rows per ring stage of the 128 x 128 V kernel)
+//       "ao_shape" 0|16|32 (tuning: grid points per block of DFT_EvalAO; 0 = chosen from the basis size)
 //       "tma_3d" 0|1 (tuning: 3-D tensor maps in the V kernel, one TMA load per plane and stage; default 1)
 //       "l2_prefetch" 0|1 (tuning: L2 prefetch of the density kernel's epilogue pieces, default 0)
 //       "timing" 0|1 (record the per-kernel CUDA events behind DFT_GetStat, default 1)
 int DFT_SetOption(XCSolver* solver, const char* key, double value);
 // keys: "density_ms", "vxc_ms", "reduce_ms", "total_ms" (CUDA-event times of the last
 //       DFT_ComputeXC on the engine's stream), "launches" (kernels launched by the last call),
+//       "ao_ms" (kernel time of the last DFT_EvalAO),
 //       "path" (path actually taken), "workspace_bytes", "plans_built" (TMA launch plans encoded so
 //       far: a steady SCF loop over the same arrays builds exactly one).
 double DFT_GetStat(XCSolver* solver, const char* key);

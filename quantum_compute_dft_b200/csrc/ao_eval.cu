@@ -5,17 +5,27 @@
 // Output layouts are exactly what DFT_ComputeXC consumes: ao (ngrid,nao) and the planar
 // gradient (3,ngrid,nao).
 //
-// Design (HBM-bound: 8*ngrid*nao*P bytes written, P = 1 or 4):
-//   * shell tables (centres, exponents, contraction coefficients) are staged once per CTA in
-//     shared memory;
-//   * one warp owns one grid point at a time: lanes evaluate different shells into a per-warp
-//     shared-memory row (all P planes), then the warp streams the finished rows out with fully
-//     coalesced stores (consecutive lanes -> consecutive AOs of the same point);
-//   * primitives with exp*r^2 > cutoff are skipped (PySCF-like screening) which removes most of
-//     the exp() work for core functions far from their atom and produces exact zeros that later
-//     block screening can exploit.
+// Design (HBM-bound by nature: 8*ngrid*nao*P bytes written, P = 1 or 4).  Earlier versions (one warp
+// per point, lanes over shells, a staged row per point) were bound by shared-memory bank conflicts and
+// then by instruction issue (ncu: 2500 warp instructions per point, exp() only 10 % of them).  This
+// one minimises instructions per output value:
+//   * shells on the same centre with the same exponents (the s and p parts of an STO-3G "sp" shell)
+//     form one GROUP whose exponentials are evaluated once -- 1/3 fewer exp() than shell by shell;
+//   * all tables are structure-of-arrays in shared memory, staged once per CTA;
+//   * a CTA takes blocks of 16 consecutive grid points (two or three CTAs per SM overlap each other's
+//     phases);
+//   * phase 1, lanes over POINTS: a half-warp evaluates one group for the 16 points -- the group's data
+//     is uniform over the half-warp (broadcast loads), neighbouring points agree on which primitives
+//     fall beyond the cutoff (AO screening without divergence or compaction; a primitive is dropped
+//     when exp*r^2 > cutoff exactly as in the CPU statement) -- and stores the radial sums
+//     (e0, e1) = sum c (1, -2a) exp(-a r^2) of each member shell in a [point][shell] array whose
+//     point pitch is odd in 16-byte units (conflict-free both ways);
+//   * phase 2, lanes over AOs: a warp takes one point, lane i combines its shell's (e0, e1) with the
+//     distance vector and writes the value and the three gradient components STRAIGHT to global memory:
+//     consecutive lanes -> consecutive AOs, 256 contiguous bytes per warp store, no staging row.
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "../../include/dft_b200_ext.h"
 #include "engine.h"
@@ -23,86 +33,168 @@
 namespace xc {
 namespace ao {
 
+constexpr int MAXP = 4;       // primitives per group evaluated from registers (more: recomputed per member)
+// Block shapes (grid points per block G, warps per CTA NW): 32 points x 16 warps when at least two such
+// CTAs fit in an SM's shared memory, 16 points x 8 warps otherwise.
+
+// exp(t) for t in [-700, 0] (here t = -a r^2 >= -cutoff): Cody-Waite reduction t = n ln2 + r, |r| <= ln2/2,
+// Taylor polynomial to r^13 (truncation 4e-18), scaling by 2^n through the exponent field.  About 1 ulp;
+// half the instructions of the general-purpose exp(), which this kernel's phase 1 is made of.
+__device__ __forceinline__ double exp_neg(double t) {
+#ifdef DFT_AO_LIBM_EXP
+    return exp(t);
+#else
+    const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
+    const double u = fma(t, 1.4426950408889634074, SHIFT);
+    const int n = __double2loint(u);
+    const double nf = u - SHIFT;
+    double r = fma(nf, -6.93147180369123816490e-01, t);
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821614599e-10;            // 1/13!
+    p = fma(p, r, 2.0876756987868098979e-09);        // 1/12!
+    p = fma(p, r, 2.5052108385441718775e-08);        // 1/11!
+    p = fma(p, r, 2.7557319223985890653e-07);        // 1/10!
+    p = fma(p, r, 2.7557319223985892511e-06);        // 1/9!
+    p = fma(p, r, 2.4801587301587301566e-05);        // 1/8!
+    p = fma(p, r, 1.9841269841269841253e-04);        // 1/7!
+    p = fma(p, r, 1.3888888888888889419e-03);        // 1/6!
+    p = fma(p, r, 8.3333333333333332177e-03);        // 1/5!
+    p = fma(p, r, 4.1666666666666664354e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666665741e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+#endif
+}
+
+// Device tables, one block of memory (offsets in bytes from the start; all 8-byte aligned)
 struct Tables {
-    const double* shell_xyz;
-    const double* prim_exp;
-    const double* prim_coef;
-    const int* shell_meta;  // [nshell][4] = l, ao_off, prim_off, nprim
+    const unsigned char* base;
+    size_t bytes;
+    int ngroup, nshell, nmember, nexp, ncoef, nao;
+    // doubles: gx gy gz gamin [ngroup] | sx sy sz [nshell] | exps [nexp] | coefs [ncoef]
+    // ints:    gprim gnprim gmem gnmem [ngroup] | mshell mcoef [nmember] | ao_shell ao_comp [nao]
+    size_t o_gx, o_gy, o_gz, o_gamin, o_sx, o_sy, o_sz, o_exp, o_coef;
+    size_t o_gprim, o_gnprim, o_gmem, o_gnmem, o_mshell, o_mcoef, o_aoshell, o_aocomp;
 };
 
-template <bool DERIV>
-__global__ void __launch_bounds__(512)
-eval_kernel(int ngrid, const double* __restrict__ coords, Tables t, int nshell, int nprim, int nao,
-            double cutoff, double* __restrict__ ao, double* __restrict__ gout) {
+template <bool DERIV, int G, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
+eval_kernel(int ngrid, const double* __restrict__ coords, Tables t, int epitch, double cutoff, double* __restrict__ ao,
+            double* __restrict__ gout) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int P = DERIV ? 4 : 1;
-    double* s_xyz = reinterpret_cast<double*>(smem_raw);
-    double* s_exp = s_xyz + 3 * nshell;
-    double* s_coef = s_exp + nprim;
-    double* s_rows = s_coef + nprim;  // [nwarps][P][nao]
-    const int nwarps = blockDim.x >> 5;
-    int* s_meta = reinterpret_cast<int*>(s_rows + (size_t)nwarps * P * nao);
-
-    for (int i = threadIdx.x; i < 3 * nshell; i += blockDim.x) s_xyz[i] = t.shell_xyz[i];
-    for (int i = threadIdx.x; i < nprim; i += blockDim.x) {
-        s_exp[i] = t.prim_exp[i];
-        s_coef[i] = t.prim_coef[i];
+    {   // stage the tables (8-byte words)
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(t.base);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(smem_raw);
+        for (size_t i = threadIdx.x; i < t.bytes / 8; i += blockDim.x) dst[i] = src[i];
     }
-    for (int i = threadIdx.x; i < 4 * nshell; i += blockDim.x) s_meta[i] = t.shell_meta[i];
-    __syncthreads();
+    const double* gx = reinterpret_cast<const double*>(smem_raw + t.o_gx);
+    const double* gy = reinterpret_cast<const double*>(smem_raw + t.o_gy);
+    const double* gz = reinterpret_cast<const double*>(smem_raw + t.o_gz);
+    const double* sx = reinterpret_cast<const double*>(smem_raw + t.o_sx);
+    const double* sy = reinterpret_cast<const double*>(smem_raw + t.o_sy);
+    const double* sz = reinterpret_cast<const double*>(smem_raw + t.o_sz);
+    const double* s_exp = reinterpret_cast<const double*>(smem_raw + t.o_exp);
+    const double* s_coef = reinterpret_cast<const double*>(smem_raw + t.o_coef);
+    const int* gprim = reinterpret_cast<const int*>(smem_raw + t.o_gprim);
+    const int* gnprim = reinterpret_cast<const int*>(smem_raw + t.o_gnprim);
+    const int* gmem = reinterpret_cast<const int*>(smem_raw + t.o_gmem);
+    const int* gnmem = reinterpret_cast<const int*>(smem_raw + t.o_gnmem);
+    const int* mshell = reinterpret_cast<const int*>(smem_raw + t.o_mshell);
+    const int* mcoef = reinterpret_cast<const int*>(smem_raw + t.o_mcoef);
+    const int* ao_meta = reinterpret_cast<const int*>(smem_raw + t.o_aoshell);  // shell | (comp + 1) << 24
+    double* s_pts = reinterpret_cast<double*>(smem_raw + t.bytes);               // [G][3]
+    double2* e01 = reinterpret_cast<double2*>(s_pts + 3 * G);                    // [G][epitch]
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* row = s_rows + (size_t)warp * P * nao;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ng = t.ngroup, nao = t.nao;
+    const int pt = tid & (G - 1), slot = tid / G;
+    constexpr int SLOTS = NWARPS * 32 / G;
     const size_t plane = (size_t)ngrid * nao;
-    const long stride = (long)gridDim.x * nwarps;
-    for (long g = (long)blockIdx.x * nwarps + warp; g < ngrid; g += stride) {
-        const double x = __ldg(coords + 3 * g), y = __ldg(coords + 3 * g + 1), z = __ldg(coords + 3 * g + 2);
-        for (int s = lane; s < nshell; s += 32) {
-            const double dx = x - s_xyz[3 * s], dy = y - s_xyz[3 * s + 1], dz = z - s_xyz[3 * s + 2];
-            const double r2 = dx * dx + dy * dy + dz * dz;
-            const int l = s_meta[4 * s], off = s_meta[4 * s + 1], p0 = s_meta[4 * s + 2], np = s_meta[4 * s + 3];
-            double e0 = 0.0, e1 = 0.0;
-            for (int k = p0; k < p0 + np; ++k) {
-                const double a = s_exp[k];
-                const double ar2 = a * r2;
-                if (ar2 > cutoff) continue;
-                const double v = s_coef[k] * exp(-ar2);
-                e0 += v;
-                e1 = fma(-2.0 * a, v, e1);
-            }
-            if (l == 0) {
-                row[off] = e0;
-                if (DERIV) {
-                    row[nao + off] = e1 * dx;
-                    row[2 * nao + off] = e1 * dy;
-                    row[3 * nao + off] = e1 * dz;
-                }
-            } else {
-                const double d[3] = {dx, dy, dz};
+    const int nblk = (ngrid + G - 1) / G;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int p0 = blk * G;
+        const int np = min(G, ngrid - p0);
+        __syncthreads();  // tables staged (first block) / previous block's phase 2 done with e01 and s_pts
+        if (tid < 3 * np) s_pts[tid] = __ldg(coords + 3 * (size_t)p0 + tid);
+        __syncthreads();
+        // ---- phase 1: radial sums; a half-warp = one group x 16 points
+        if (pt < np) {
+            const double x = s_pts[3 * pt], y = s_pts[3 * pt + 1], z = s_pts[3 * pt + 2];
+            double2* erow = e01 + (size_t)pt * epitch;
+            for (int gi = slot; gi < ng; gi += SLOTS) {
+                const double dx = x - gx[gi], dy = y - gy[gi], dz = z - gz[gi];
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const int q0 = gprim[gi], nq = gnprim[gi], m0 = gmem[gi], nm = gnmem[gi];
+                if (nq <= MAXP) {
+                    double v[MAXP], av[MAXP];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    row[off + j] = d[j] * e0;
-                    if (DERIV) {
-                        const double dj1 = d[j] * e1;
-                        row[nao + off + j] = fma(dj1, dx, j == 0 ? e0 : 0.0);
-                        row[2 * nao + off + j] = fma(dj1, dy, j == 1 ? e0 : 0.0);
-                        row[3 * nao + off + j] = fma(dj1, dz, j == 2 ? e0 : 0.0);
+                    for (int k = 0; k < MAXP; ++k) {
+                        v[k] = 0.0; av[k] = 0.0;
+                        if (k < nq) {
+                            const double al = s_exp[q0 + k];
+                            const double ar2 = al * r2;
+                            if (!(ar2 > cutoff)) { v[k] = exp_neg(-ar2); av[k] = al; }
+                        }
+                    }
+                    for (int m = 0; m < nm; ++m) {
+                        const int c0 = mcoef[m0 + m];
+                        double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+                        for (int k = 0; k < MAXP; ++k) {
+                            if (k < nq && av[k] != 0.0) {
+                                const double tv = s_coef[c0 + k] * v[k];
+                                e0 += tv;
+                                e1 = fma(-2.0 * av[k], tv, e1);
+                            }
+                        }
+                        erow[mshell[m0 + m]] = make_double2(e0, e1);
+                    }
+                } else {
+                    for (int m = 0; m < nm; ++m) {
+                        const int c0 = mcoef[m0 + m];
+                        double e0 = 0.0, e1 = 0.0;
+                        for (int k = 0; k < nq; ++k) {
+                            const double al = s_exp[q0 + k];
+                            const double ar2 = al * r2;
+                            if (ar2 > cutoff) continue;
+                            const double tv = s_coef[c0 + k] * exp_neg(-ar2);
+                            e0 += tv;
+                            e1 = fma(-2.0 * al, tv, e1);
+                        }
+                        erow[mshell[m0 + m]] = make_double2(e0, e1);
                     }
                 }
             }
         }
-        __syncwarp();
-        double* dst = ao + (size_t)g * nao;
-        for (int i = lane; i < nao; i += 32) dst[i] = row[i];
-        if (DERIV) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                double* gd = gout + c * plane + (size_t)g * nao;
-                const double* src = row + (c + 1) * nao;
-                for (int i = lane; i < nao; i += 32) gd[i] = src[i];
+        __syncthreads();
+        // ---- phase 2: a warp per point, lanes over AOs, results straight to global memory (coalesced)
+        for (int r = warp; r < np; r += NWARPS) {
+            const double x = s_pts[3 * r], y = s_pts[3 * r + 1], z = s_pts[3 * r + 2];
+            const double2* erow = e01 + (size_t)r * epitch;
+            double* d0 = ao + (size_t)(p0 + r) * nao + lane;
+            double* d1 = DERIV ? gout + (size_t)(p0 + r) * nao + lane : nullptr;
+            double* d2 = DERIV ? d1 + plane : nullptr;
+            double* d3 = DERIV ? d2 + plane : nullptr;
+            for (int i = lane; i < nao; i += 32) {
+                const int meta = ao_meta[i];
+                const int sh = meta & 0xffffff, comp = (meta >> 24) - 1;  // comp: -1 s, 0..2 p_x p_y p_z
+                const double2 e = erow[sh];
+                const double dx = x - sx[sh], dy = y - sy[sh], dz = z - sz[sh];
+                const double dj = comp == 0 ? dx : (comp == 1 ? dy : (comp == 2 ? dz : 1.0));
+                *d0 = dj * e.x;
+                if (DERIV) {
+                    // s: e1 d;  p_j: d_j e1 d + e0 delta_j
+                    const double dj1 = dj * e.y;
+                    *d1 = fma(dj1, dx, comp == 0 ? e.x : 0.0);
+                    *d2 = fma(dj1, dy, comp == 1 ? e.x : 0.0);
+                    *d3 = fma(dj1, dz, comp == 2 ? e.x : 0.0);
+                    d1 += 32; d2 += 32; d3 += 32;
+                }
+                d0 += 32;
             }
         }
-        __syncwarp();
     }
 }
 
@@ -121,68 +213,139 @@ extern "C" int DFT_EvalAO(XCSolver* solver, int ngrid, unsigned long long d_coor
     CublasHandleWrapper* ctx = solver->context();
     ctx->failed = false;
     if (exp_cutoff <= 0.0) exp_cutoff = 60.0;
+    if (exp_cutoff > 700.0) exp_cutoff = 700.0;  // exp(-700) ~ 1e-304: nothing beyond contributes (and exp_neg stays in range)
 
-    // pack the host tables into one staging block: xyz | exp | coef | meta
-    const size_t nd = (size_t)3 * nshell + 2 * (size_t)nprim_total;
-    const size_t bytes = nd * sizeof(double) + (size_t)4 * nshell * sizeof(int);
-    unsigned char* h = (unsigned char*)malloc(bytes);
-    if (!h) return 2;
-    double* hd = reinterpret_cast<double*>(h);
-    memcpy(hd, shell_xyz, sizeof(double) * 3 * nshell);
-    memcpy(hd + 3 * nshell, prim_exp, sizeof(double) * nprim_total);
-    memcpy(hd + 3 * nshell + nprim_total, prim_coef, sizeof(double) * nprim_total);
-    int* hm = reinterpret_cast<int*>(hd + nd);
+    // ---- group the shells: same centre, same exponents -> one group (exponentials evaluated once)
+    struct HGroup { double x, y, z, amin; int prim_off, nprim, mem_off, nmem; };
+    std::vector<HGroup> groups;
+    std::vector<double> exps, coefs;
+    std::vector<int> shell_group(nshell, -1), ao_shell(nao, -1), ao_comp(nao, -1);
     for (int s = 0; s < nshell; ++s) {
-        if (shell_l[s] < 0 || shell_l[s] > 1) { free(h); return 3; }  // s and p shells only
-        hm[4 * s] = shell_l[s];
-        hm[4 * s + 1] = shell_ao_off[s];
-        hm[4 * s + 2] = shell_prim_off[s];
-        hm[4 * s + 3] = shell_nprim[s];
+        if (shell_l[s] < 0 || shell_l[s] > 1) return 3;  // s and p shells only
+        if (shell_nprim[s] <= 0 || shell_prim_off[s] < 0 || shell_prim_off[s] + shell_nprim[s] > nprim_total) return 3;
+        if (shell_ao_off[s] < 0 || shell_ao_off[s] + (shell_l[s] ? 3 : 1) > nao) return 3;
+        for (int j = 0; j < (shell_l[s] ? 3 : 1); ++j) {
+            ao_shell[shell_ao_off[s] + j] = s;
+            ao_comp[shell_ao_off[s] + j] = shell_l[s] ? j : -1;
+        }
+        int found = -1;
+        for (int g = 0; g < (int)groups.size() && found < 0; ++g) {
+            const HGroup& q = groups[g];
+            if (q.x != shell_xyz[3 * s] || q.y != shell_xyz[3 * s + 1] || q.z != shell_xyz[3 * s + 2]) continue;
+            if (q.nprim != shell_nprim[s]) continue;
+            bool same = true;
+            for (int k = 0; k < q.nprim && same; ++k) same = exps[q.prim_off + k] == prim_exp[shell_prim_off[s] + k];
+            if (same) found = g;
+        }
+        if (found < 0) {
+            HGroup q;
+            q.x = shell_xyz[3 * s]; q.y = shell_xyz[3 * s + 1]; q.z = shell_xyz[3 * s + 2];
+            q.prim_off = (int)exps.size(); q.nprim = shell_nprim[s]; q.mem_off = 0; q.nmem = 0;
+            q.amin = prim_exp[shell_prim_off[s]];
+            for (int k = 0; k < q.nprim; ++k) {
+                const double a = prim_exp[shell_prim_off[s] + k];
+                exps.push_back(a);
+                if (a < q.amin) q.amin = a;
+            }
+            found = (int)groups.size();
+            groups.push_back(q);
+        }
+        shell_group[s] = found;
+        groups[found].nmem++;
     }
-    unsigned char* d = (unsigned char*)ctx->scratch.ensure(bytes, &ctx->failed);
-    if (ctx->failed) { free(h); return 4; }
-    DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // h is pageable: copy is done now
-    free(h);
+    for (int i = 0; i < nao; ++i)
+        if (ao_shell[i] < 0) return 3;  // every AO must belong to a shell
+    const int ngroup = (int)groups.size();
+    if (ngroup > 65535) return 5;
+    std::vector<int> mshell(nshell), mcoef(nshell);
+    {
+        int off = 0;
+        for (auto& q : groups) { q.mem_off = off; off += q.nmem; q.nmem = 0; }
+        for (int s = 0; s < nshell; ++s) {
+            HGroup& q = groups[shell_group[s]];
+            mshell[q.mem_off + q.nmem] = s;
+            mcoef[q.mem_off + q.nmem] = (int)coefs.size();
+            q.nmem++;
+            for (int k = 0; k < shell_nprim[s]; ++k) coefs.push_back(prim_coef[shell_prim_off[s] + k]);
+        }
+    }
+    const int nexp = (int)exps.size(), ncoef = (int)coefs.size();
 
+    // ---- one structure-of-arrays staging block
     Tables t;
-    t.shell_xyz = reinterpret_cast<const double*>(d);
-    t.prim_exp = t.shell_xyz + 3 * nshell;
-    t.prim_coef = t.prim_exp + nprim_total;
-    t.shell_meta = reinterpret_cast<const int*>(t.shell_xyz + nd);
+    memset(&t, 0, sizeof(t));
+    t.ngroup = ngroup; t.nshell = nshell; t.nmember = nshell; t.nexp = nexp; t.ncoef = ncoef; t.nao = nao;
+    size_t off = 0;
+    auto take = [&](size_t nbytes) { const size_t o = off; off += (nbytes + 7) & ~(size_t)7; return o; };
+    t.o_gx = take(8 * (size_t)ngroup); t.o_gy = take(8 * (size_t)ngroup); t.o_gz = take(8 * (size_t)ngroup);
+    t.o_gamin = take(8 * (size_t)ngroup);
+    t.o_sx = take(8 * (size_t)nshell); t.o_sy = take(8 * (size_t)nshell); t.o_sz = take(8 * (size_t)nshell);
+    t.o_exp = take(8 * (size_t)nexp); t.o_coef = take(8 * (size_t)ncoef);
+    t.o_gprim = take(4 * (size_t)ngroup); t.o_gnprim = take(4 * (size_t)ngroup);
+    t.o_gmem = take(4 * (size_t)ngroup); t.o_gnmem = take(4 * (size_t)ngroup);
+    t.o_mshell = take(4 * (size_t)nshell); t.o_mcoef = take(4 * (size_t)nshell);
+    t.o_aoshell = take(4 * (size_t)nao); t.o_aocomp = take(4 * (size_t)nao);
+    off = (off + 15) & ~(size_t)15;   // the per-warp double2 scratch follows
+    const size_t bytes = off;
+    std::vector<unsigned char> h(bytes, 0);
+    auto dptr = [&](size_t o) { return reinterpret_cast<double*>(h.data() + o); };
+    auto iptr = [&](size_t o) { return reinterpret_cast<int*>(h.data() + o); };
+    for (int g = 0; g < ngroup; ++g) {
+        dptr(t.o_gx)[g] = groups[g].x; dptr(t.o_gy)[g] = groups[g].y; dptr(t.o_gz)[g] = groups[g].z;
+        dptr(t.o_gamin)[g] = groups[g].amin;
+        iptr(t.o_gprim)[g] = groups[g].prim_off; iptr(t.o_gnprim)[g] = groups[g].nprim;
+        iptr(t.o_gmem)[g] = groups[g].mem_off; iptr(t.o_gnmem)[g] = groups[g].nmem;
+    }
+    for (int s = 0; s < nshell; ++s) {
+        dptr(t.o_sx)[s] = shell_xyz[3 * s]; dptr(t.o_sy)[s] = shell_xyz[3 * s + 1]; dptr(t.o_sz)[s] = shell_xyz[3 * s + 2];
+        iptr(t.o_mshell)[s] = mshell[s]; iptr(t.o_mcoef)[s] = mcoef[s];
+    }
+    memcpy(dptr(t.o_exp), exps.data(), 8 * (size_t)nexp);
+    memcpy(dptr(t.o_coef), coefs.data(), 8 * (size_t)ncoef);
+    if (nshell >= (1 << 24)) return 5;
+    for (int i = 0; i < nao; ++i) iptr(t.o_aoshell)[i] = ao_shell[i] | ((ao_comp[i] + 1) << 24);
+    memcpy(iptr(t.o_aocomp), ao_comp.data(), 4 * (size_t)nao);
+    unsigned char* d = (unsigned char*)ctx->scratch.ensure(bytes, &ctx->failed);
+    if (ctx->failed) return 4;
+    DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(d, h.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // h is pageable: the copy is done now
+    t.base = d;
+    t.bytes = bytes;
 
-    const int P = deriv ? 4 : 1;
-    const size_t table_bytes = nd * sizeof(double) + (size_t)4 * nshell * sizeof(int);
-    const size_t row_bytes = (size_t)P * nao * sizeof(double);
+    // ---- shared memory: tables + the block's points + radial sums [G][epitch] (epitch odd)
+    const int epitch = nshell | 1;
     const size_t smem_max = 227 * 1024;
-    if (table_bytes + row_bytes > smem_max) {
-        fprintf(stderr, "[dft_b200] DFT_EvalAO: basis too large for the shared-memory staging (%zu B)\n",
-                table_bytes + row_bytes);
+    auto smem_for = [&](int G) { return bytes + sizeof(double) * 3 * G + sizeof(double2) * (size_t)G * epitch + 64; };
+    int shape = ctx->ao_shape;
+    if (shape != 16 && shape != 32) shape = 2 * (smem_for(32) + 1024) <= smem_max ? 32 : 16;
+    const int G = shape, NW = shape == 32 ? 16 : 8;
+    const size_t smem = smem_for(G);
+    if (smem > smem_max) {
+        fprintf(stderr, "[dft_b200] DFT_EvalAO: basis too large for the shared-memory staging (%zu B)\n", smem);
         return 5;
     }
-    int nwarps = (int)((smem_max - table_bytes) / row_bytes);
-    if (nwarps > 16) nwarps = 16;
-    const size_t smem = table_bytes + nwarps * row_bytes;
-    int nsm = 148;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-    int per_sm = (int)(smem_max / smem);
+    if (ctx->num_sms <= 0) cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    int per_sm = (int)(smem_max / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm * nwarps > 64) per_sm = 64 / nwarps;
-    long want = ((long)ngrid + nwarps - 1) / nwarps;
-    int grid = (int)(want < (long)nsm * per_sm ? want : (long)nsm * per_sm);
+    if (per_sm > 64 / NW) per_sm = 64 / NW;
+    const long nblk = ((long)ngrid + G - 1) / G;
+    const int grid = (int)(nblk < (long)ctx->num_sms * per_sm ? nblk : (long)ctx->num_sms * per_sm);
     double* ao_out = reinterpret_cast<double*>(d_ao_ptr);
     double* g_out = reinterpret_cast<double*>(d_ao_grad_ptr);
     const double* coords = reinterpret_cast<const double*>(d_coords_ptr);
-    if (deriv) {
-        DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        eval_kernel<true><<<grid, nwarps * 32, smem, ctx->stream>>>(ngrid, coords, t, nshell, nprim_total, nao,
-                                                                  exp_cutoff, ao_out, g_out);
-    } else {
-        DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        eval_kernel<false><<<grid, nwarps * 32, smem, ctx->stream>>>(ngrid, coords, t, nshell, nprim_total, nao,
-                                                                   exp_cutoff, ao_out, g_out);
-    }
+    if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
+#define DFT_AO_LAUNCH(D_, G_, NW_)                                                                                      \
+    do {                                                                                                                \
+        auto k = eval_kernel<D_, G_, NW_>;                                                                              \
+        DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        k<<<grid, NW_ * 32, smem, ctx->stream>>>(ngrid, coords, t, epitch, exp_cutoff, ao_out, g_out);                  \
+    } while (0)
+    if (deriv) { if (G == 32) DFT_AO_LAUNCH(true, 32, 16); else DFT_AO_LAUNCH(true, 16, 8); }
+    else { if (G == 32) DFT_AO_LAUNCH(false, 32, 16); else DFT_AO_LAUNCH(false, 16, 8); }
+#undef DFT_AO_LAUNCH
+    if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->stream);
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
     DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->timing && !ctx->failed) cudaEventElapsedTime(&ctx->stats.ao_ms, ctx->ev[0], ctx->ev[1]);
     return ctx->failed ? 6 : 0;
 }

@@ -110,7 +110,7 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
     if (ngrid == 0) {
         cudaMemsetAsync(p.vxc, 0, sizeof(double) * n2, ctx->stream);
         cudaMemsetAsync(p.d_exc, 0, sizeof(double), ctx->stream);
-        { const int pb = ctx->stats.plans_built; ctx->stats = XcStats(); ctx->stats.plans_built = pb; }
+        { XcStats z; z.plans_built = ctx->stats.plans_built; z.ao_ms = ctx->stats.ao_ms; ctx->stats = z; }
     } else {
         bool use_tma = false;
         if (ctx->path == PATH_TMA) use_tma = xc::tma_compatible(p);
@@ -240,6 +240,7 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "path")) { c->path = (int)value; return 0; }
     if (!strcmp(key, "timing")) { c->timing = value != 0.0; return 0; }
     if (!strcmp(key, "l2_prefetch")) { c->l2_prefetch = value != 0.0; return 0; }
+    if (!strcmp(key, "ao_shape")) { c->ao_shape = (int)value; return 0; }
     if (!strcmp(key, "tma_3d")) { c->tma_3d = value != 0.0; return 0; }
     if (!strcmp(key, "vxc_shape")) { const int v = (int)value; if (v != 0 && v != 64 && v != 128 && v != 160) return 3; c->vxc_shape = v; return 0; }
     if (!strcmp(key, "vxc_vk")) { c->vxc_vk = value == 16.0 ? 16 : 8; return 0; }
@@ -254,6 +255,7 @@ double DFT_GetStat(XCSolver* solver, const char* key) {
     if (!strcmp(key, "vxc_ms")) return c->stats.vxc_ms;
     if (!strcmp(key, "reduce_ms")) return c->stats.reduce_ms;
     if (!strcmp(key, "total_ms")) return c->stats.total_ms;
+    if (!strcmp(key, "ao_ms")) return c->stats.ao_ms;
     if (!strcmp(key, "launches")) return c->stats.launches;
     if (!strcmp(key, "plans_built")) return c->stats.plans_built;
     if (!strcmp(key, "path")) return c->stats.path;

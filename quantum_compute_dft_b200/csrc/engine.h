@@ -33,6 +33,7 @@ enum XcPath { PATH_AUTO = 0, PATH_GENERIC = 1, PATH_TMA = 2 };
 
 struct XcStats {
     float density_ms = 0.f, vxc_ms = 0.f, reduce_ms = 0.f, total_ms = 0.f;
+    float ao_ms = 0.f;    // last DFT_EvalAO kernel
     int launches = 0;
     int path = 0;
     int plans_built = 0;  // TMA path: launch plans (tensor maps, geometry) encoded so far; a steady SCF loop builds one
@@ -50,6 +51,7 @@ struct CublasHandleWrapper {
     bool timing = true;
     bool l2_prefetch = false;      // TMA density kernel: L2-prefetch the epilogue's grad tiles
     bool tma_3d = true;            // TMA V kernel: one 3-D TMA load per plane and stage instead of one per 16-column block
+    int ao_shape = 0;              // DFT_EvalAO block shape: 0 = auto, 16 (points, 8 warps) | 32 (points, 16 warps)
     int vxc_shape = 0;             // TMA V kernel output tile: 0 = auto, 64 | 128 | 160 (= 160 x 80)
     int vxc_vk = 16;               // TMA V kernel, 128 x 128 tile: grid rows per ring stage (8: 5 stages, 16: 2 stages)
 

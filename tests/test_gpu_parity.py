@@ -282,6 +282,13 @@ def test_ao_evaluation_on_gpu(oracle, engine_lib):
         d_ao2 = DeviceArray(ao_o.shape)
         s.eval_ao(d_c, basis, d_ao2, None)
         np.testing.assert_allclose(d_ao2.get(), d_ao.get(), rtol=1e-14, atol=1e-300)  # deriv=0 kernel contracts FMAs differently
+        for shape in (16, 32):     # both block shapes of the kernel write identical values
+            s.set_option("ao_shape", shape)
+            d_ao3 = DeviceArray(ao_o.shape); d_g3 = DeviceArray(g_o.shape)
+            s.eval_ao(d_c, basis, d_ao3, d_g3)
+            np.testing.assert_array_equal(d_ao3.get(), d_ao.get())
+            np.testing.assert_array_equal(d_g3.get(), d_g.get())
+        s.set_option("ao_shape", 0)
 
 
 def test_coulomb_through_c_abi(oracle, engine_lib):
