@@ -53,7 +53,7 @@ int DFT_CommDestroy(XCSolver* solver);
 //       "vxc_vk" 8|16 (tuning: grid rows per ring stage of the 128 x 128 V kernel)
 //       "ao_shape" 0|16|32 (tuning: grid points per block of DFT_EvalAO; 0 = chosen from the basis size)
 //       "tma_3d" 0|1 (tuning: 3-D tensor maps in the V kernel, one TMA load per plane and stage; default 1)
-//       "l2_prefetch" 0|1 (tuning: L2 prefetch of the density kernel's epilogue pieces, default 0)
+//       "l2_prefetch" 0|1 (tuning: short-range L2 prefetch in the density kernel, default 0: measured no gain)
 //       "timing" 0|1 (record the per-kernel CUDA events behind DFT_GetStat, default 1)
 int DFT_SetOption(XCSolver* solver, const char* key, double value);
 // keys: "density_ms", "vxc_ms", "reduce_ms", "total_ms" (CUDA-event times of the last
@@ -79,6 +79,9 @@ unsigned long long DFT_GetStream(XCSolver* solver);
 // throughput in TFLOP/s on the current device; `iters` inner iterations per thread.
 double DFT_MicrobenchDMMA(int iters);
 double DFT_MicrobenchDFMA(int iters);
+// FP64 tensor throughput (TFLOP/s) with exactly `warps_per_sm` (1..8) resident warps per SM: shows how many
+// warps per SM sub-partition the DMMA pipe needs to saturate.
+double DFT_MicrobenchDMMAWarps(int warps_per_sm, int iters);
 
 const char* DFT_B200_Version(void);
 }

@@ -47,7 +47,7 @@ CublasHandleWrapper::CublasHandleWrapper() {
 CublasHandleWrapper::~CublasHandleWrapper() {
     if (stream) cudaStreamSynchronize(stream);
     xc::free_tma_plan(this);
-    dsym.release(); coef.release(); epart.release(); vpart.release(); result.release(); scratch.release();
+    dsym.release(); rho.release(); coef.release(); epart.release(); vpart.release(); result.release(); scratch.release();
     if (h_scalar) cudaFreeHost(h_scalar);
     for (auto& e : ev)
         if (e) cudaEventDestroy(e);
@@ -55,7 +55,7 @@ CublasHandleWrapper::~CublasHandleWrapper() {
 }
 
 size_t CublasHandleWrapper::workspace_bytes() const {
-    return dsym.capacity + coef.capacity + epart.capacity + vpart.capacity + result.capacity + scratch.capacity;
+    return dsym.capacity + rho.capacity + coef.capacity + epart.capacity + vpart.capacity + result.capacity + scratch.capacity;
 }
 
 // ------------------------------------------------------------------------- solver classes
@@ -270,7 +270,7 @@ int DFT_DebugRead(XCSolver* solver, const char* what, void* dst, unsigned long l
     CublasHandleWrapper* c = solver->context();
     DeviceBuffer* b = !strcmp(what, "coef") ? &c->coef : !strcmp(what, "epart") ? &c->epart
                     : !strcmp(what, "dsym") ? &c->dsym : !strcmp(what, "vpart") ? &c->vpart
-                    : !strcmp(what, "scratch") ? &c->scratch : nullptr;
+                    : !strcmp(what, "scratch") ? &c->scratch : !strcmp(what, "rho") ? &c->rho : nullptr;
     if (!b || !b->ptr) return 2;
     if (nbytes > b->capacity) nbytes = b->capacity;
     cudaStreamSynchronize(c->stream);

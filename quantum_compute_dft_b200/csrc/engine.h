@@ -49,7 +49,7 @@ struct CublasHandleWrapper {
     bool exact_functionals = false;
     int path = PATH_AUTO;
     bool timing = true;
-    bool l2_prefetch = false;      // TMA density kernel: L2-prefetch the epilogue's grad tiles
+    bool l2_prefetch = false;      // TMA density kernel: short-range L2 prefetch of A tiles and epilogue pieces (measured: no gain)
     bool tma_3d = true;            // TMA V kernel: one 3-D TMA load per plane and stage instead of one per 16-column block
     int ao_shape = 0;              // DFT_EvalAO block shape: 0 = auto, 16 (points, 8 warps) | 32 (points, 16 warps)
     int vxc_shape = 0;             // TMA V kernel output tile: 0 = auto, 64 | 128 | 160 (= 160 x 80)
@@ -57,6 +57,7 @@ struct CublasHandleWrapper {
 
     // workspaces
     DeviceBuffer dsym;     // symmetrised, zero-padded density matrix
+    DeviceBuffer rho;      // per-point partial (rho, grad rho / 2) row sums of the density kernel's two warp columns
     DeviceBuffer coef;     // per-point (a,bx,by,bz)
     DeviceBuffer epart;    // per-CTA partial E_xc
     DeviceBuffer vpart;    // split-K partial V tiles

@@ -39,6 +39,39 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* out) 
     if (s == 123.456) out[0] = s;
 }
 
+// DMMA throughput with exactly `warps_per_sm` resident warps per SM (one CTA per SM, the rest of the SM kept
+// free by a large dynamic shared-memory request): how many warps per SM sub-partition does the FP64 tensor
+// pipe need?  (It shapes the kernels: a lone warp per sub-partition reaches only about half the peak.)
+double run_dmma_warps(int warps_per_sm, int iters) {
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    double* d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return -1.0;
+    const int threads = warps_per_sm * 32;
+    const int smem = 200 * 1024;  // one CTA per SM
+    cudaFuncSetAttribute(dmma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    dmma_peak_kernel<<<nsm, threads, smem>>>(iters / 4 + 1, d);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        dmma_peak_kernel<<<nsm, threads, smem>>>(iters, d);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    return (double)nsm * warps_per_sm * (double)iters * 8.0 * 512.0 / (best * 1e-3) / 1e12;
+}
+
 template <typename K>
 double run_peak(K kernel, int iters, double flops_per_thread_iter) {
     int dev = 0, nsm = 148;
@@ -75,6 +108,12 @@ extern "C" double DFT_MicrobenchDMMA(int iters) {
     if (iters <= 0) iters = 4096;
     // 8 DMMA.8x8x4 per warp-iteration = 8 * 512 flop per 32 threads
     return run_peak(dmma_peak_kernel, iters, 8.0 * 512.0 / 32.0);
+}
+
+extern "C" double DFT_MicrobenchDMMAWarps(int warps_per_sm, int iters) {
+    if (iters <= 0) iters = 4096;
+    if (warps_per_sm < 1 || warps_per_sm > 8) return -1.0;
+    return run_dmma_warps(warps_per_sm, iters);
 }
 
 extern "C" double DFT_MicrobenchDFMA(int iters) {

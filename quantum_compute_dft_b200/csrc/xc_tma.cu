@@ -59,7 +59,7 @@ constexpr int NCONS = NCW * 32;             // 256 consumer threads = 2 warpgrou
 constexpr int NTHREADS = NCONS + 128;       // + 1 producer warpgroup
 constexpr int REGS_CONSUMER = 232;          // 384 threads x 168 = 256 x 232 + 128 x 40
 constexpr int REGS_PRODUCER = 40;
-constexpr int MB = 128;                     // grid rows per density block
+constexpr int MB = 64;                      // grid rows per density block (one consumer group's)
 
 struct SubProblem {
     int rows;    // rows of this sub-problem
@@ -71,14 +71,12 @@ struct SubProblem {
 };
 
 struct DensityParams {
-    CUtensorMap map_a[2];     // Phi of each sub-problem, box 16 x 128 (k-loop A operand, LDA pieces)
-    CUtensorMap map_e[2][4];  // the four planes, box 16 x 64 (GGA epilogue pieces)
+    CUtensorMap map_a[2];     // Phi of each sub-problem, box 16 x 64 (k-loop A operand)
+    CUtensorMap map_e[2][4];  // the four planes, box 16 x 64 (epilogue pieces)
     CUtensorMap map_d;        // [2][NP][KP] symmetrised density (plain, shifted), box 16 x NT
     SubProblem sub[2];
-    int nsub, xc_mode, nblocks, ntiles, nk, NP, l2_prefetch;
-    const double* w;
-    double* coef;
-    double* exc_part;
+    int nsub, nblocks, ntiles, nk, NP, l2_prefetch, coef_rows;
+    double* rho;       // [2 warp columns][coef_rows][4]: partial (rho, drho/2) row sums, summed by the point kernel
     long long* phase;  // DFT_PHASE_TIMING builds: [CTA][warp][4] cycles in {k-loop, piece wait, piece math, block tail}
 };
 
@@ -134,15 +132,22 @@ __device__ __forceinline__ xcfun::PointCoef eval_mode(int mode, double rho, doub
 // ------------------------------------------------------------------------------------------------
 // density kernel
 // ------------------------------------------------------------------------------------------------
-// Ring contents per (block, column tile): nk k-chunks {A: Phi[128 rows][16 k], D: Dsym[NT cols][16 k]}
-// followed by the tile's epilogue pieces.  A GGA piece is {Phi, dxPhi, dyPhi, dzPhi}[64 rows][16 cols]
-// (4 boxes of 8 KB); an LDA piece is Phi[128 rows][16 cols].  Every warp waits for and releases every
-// stage; only the two (GGA) or four (LDA) warps whose accumulator columns fall into a piece read it.
+// The 8 consumer warps form TWO independent groups of 4 (2 x 2 warps, warp tile 32 x (8 NF2)); each
+// group works through its own blocks of 64 grid points with its own TMA ring (producer warps 8 and
+// 9), and group 1 starts half a column-tile period after group 0.  While one group is in its
+// epilogue (no tensor work) the other one is in its k-loop, so the DMMA pipe stays busy: a
+// "ping-pong" of two CTAs' worth of work inside one CTA.
 //
-// Consumer warps form a 4 (rows) x 2 (columns) grid, warp tile 32 x (8 NF2): a lane then owns 4
-// fragment rows, and its partial row sums rs[4][NPL] stay in registers for the WHOLE block (all
-// column tiles, all pieces).  A piece costs its owners 64 shared loads + 64 FMAs in 16 independent
-// chains; the cross-lane reduction happens once per block.
+// Ring contents per (block, column tile): nk k-chunks {A: Phi[64 rows][16 k], D: Dsym[NT cols][16 k]}
+// followed by the tile's epilogue pieces.  A GGA piece is {Phi, dxPhi, dyPhi, dzPhi}[64 rows][16 cols]
+// (4 boxes of 8 KB); an LDA piece is Phi[64 rows][16 cols].  Every warp of the group waits for and
+// releases every stage; only the two warps whose accumulator columns fall into a piece read it.
+//
+// A lane owns 4 fragment rows, and its partial row sums rs[4][NPL] stay in registers for the WHOLE
+// block (all column tiles, all pieces).  A piece costs its owners 64 shared loads + 64 FMAs in 16
+// independent chains; the cross-lane reduction happens once per block.
+constexpr int GW = 4;                        // warps per consumer group
+
 template <int NF2, int NPL>
 struct DensitySmem {
     static_assert(NF2 % 2 == 0, "a warp's columns are whole 16-column groups");
@@ -150,25 +155,21 @@ struct DensitySmem {
     static constexpr int A_BYTES = MB * 128;
     static constexpr int D_BYTES = NT * 128;
     static constexpr int K_BYTES = A_BYTES + D_BYTES;
-    static constexpr int PLANE_BYTES = 64 * 128;                          // one plane of a GGA piece
-    static constexpr int PIECE_BYTES = NPL == 4 ? 4 * PLANE_BYTES : MB * 128;
+    static constexpr int PLANE_BYTES = MB * 128;                          // one plane of a piece
+    static constexpr int PIECE_BYTES = NPL * PLANE_BYTES;
     static constexpr int STAGE_BYTES = K_BYTES > PIECE_BYTES ? K_BYTES : PIECE_BYTES;
-    static constexpr int FIXED_BYTES = 2 * MB * 4 * 8 + 256 + 1024;       // red[], barriers, E partials, alignment slack
-    static constexpr int STAGES = (232448 - FIXED_BYTES) / STAGE_BYTES < 6 ? (232448 - FIXED_BYTES) / STAGE_BYTES : 6;
+    static constexpr int FIXED_BYTES = 512 + 1024;                        // barriers, alignment slack
+    static constexpr int STAGES = (232448 - FIXED_BYTES) / (2 * STAGE_BYTES) < 4 ? (232448 - FIXED_BYTES) / (2 * STAGE_BYTES) : 4;
+    static_assert(STAGES >= 2, "ring depth");
     static constexpr int NCG = NT / 16;                                   // 16-column groups per tile (= NF2)
-    static constexpr int NPIECES = (NPL == 4 ? 2 : 1) * NCG;
-    static constexpr int RED_OFF = STAGES * STAGE_BYTES;                  // double red[2 wn][128][4]
-    static constexpr int BAR_OFF = RED_OFF + 2 * MB * 4 * 8;              // full[STAGES], empty[STAGES]
-    static constexpr int ESUM_OFF = BAR_OFF + 2 * STAGES * 8;
-    static constexpr int TOTAL = ESUM_OFF + 8 * 8 + 1024;                 // + alignment slack
+    static constexpr int NPIECES = NCG;
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;               // one group's ring
+    static constexpr int BAR_OFF = 2 * RING_BYTES;                        // [2 groups]{full[STAGES], empty[STAGES]}
+    static constexpr int TOTAL = BAR_OFF + 2 * 2 * STAGES * 8 + 1024;     // + alignment slack
     static_assert(TOTAL <= 232448, "shared memory");
 
-    // piece pc -> (row half h, column group cg); consecutive pieces go to different warps
-    __host__ __device__ static constexpr int piece_half(int pc) { return NPL == 4 ? (pc & 1) : 0; }
-    __host__ __device__ static constexpr int piece_cg(int pc) {
-        const int i = NPL == 4 ? (pc >> 1) : pc;
-        return (i & 1) * (NCG / 2) + (i >> 1);
-    }
+    // piece pc -> column group; consecutive pieces go to different warp columns
+    __host__ __device__ static constexpr int piece_cg(int pc) { return (pc & 1) * (NCG / 2) + (pc >> 1); }
 };
 
 template <int NF2, int NPL>
@@ -179,51 +180,70 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (tma::smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - tma::smem_u32(smem_raw));
-    uint64_t* full = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF);
-    uint64_t* empty = full + L::STAGES;
-    double* red = reinterpret_cast<double*>(sm + L::RED_OFF);
-    double* esum = reinterpret_cast<double*>(sm + L::ESUM_OFF);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int s = 0; s < L::STAGES; ++s) {
-            tma::mbar_init(&full[s], 1);
-            tma::mbar_init(&empty[s], NCW);
-        }
+        uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF);
+        for (int g = 0; g < 2; ++g)
+            for (int s = 0; s < L::STAGES; ++s) {
+                tma::mbar_init(&bars[g * 2 * L::STAGES + s], 1);
+                tma::mbar_init(&bars[g * 2 * L::STAGES + L::STAGES + s], GW);
+            }
         tma::fence_barrier_init();
     }
     __syncthreads();
 
     const int nblocks = P.nblocks, ntiles = P.ntiles, nk = P.nk;
+    // consumer group / ring of this warp: warps 0-3 -> 0, 4-7 -> 1, producer warps 8 -> 0, 9 -> 1
+    const int grp = warp < NCW ? warp >> 2 : (warp - NCW) & 1;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF) + grp * 2 * L::STAGES;
+    uint64_t* empty = full + L::STAGES;
+    unsigned char* ring = sm + grp * L::RING_BYTES;
+    const uint32_t ring_u32 = base + grp * L::RING_BYTES;
+    const int b_first = 2 * blockIdx.x + grp, b_step = 2 * gridDim.x;
 
     if (warp >= NCW) {
-        // ===================== producer warpgroup: one elected lane drives TMA =====================
+        // ===================== producer warpgroup: warps 8 and 9, one elected lane each =====================
         reg_dec<REGS_PRODUCER>();
-        if (warp == NCW && lane == 0) {
+        if (warp < NCW + 2 && lane == 0) {
             tma::prefetch_map(&P.map_a[0]);
             if (P.nsub > 1) tma::prefetch_map(&P.map_a[1]);
             tma::prefetch_map(&P.map_d);
-            constexpr int NPF = NPL == 4 ? 3 * L::NPIECES : 0;  // gradient boxes of one tile's pieces
             uint32_t it = 0;
-            for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+            // Short-range L2 prefetch: the ring is only STAGES deep, which covers L2 latency but not DRAM
+            // latency when this group has the tensor pipe to itself.  A tiles are requested PF k-chunks
+            // ahead, the pieces of a tile during its last k-chunks -- a few microseconds ahead, a few MB in
+            // flight over the whole GPU (a prefetch a whole k-loop ahead was evicted before use and
+            // doubled the DRAM traffic).
+            constexpr int PF = 6;
+            const bool pf = P.l2_prefetch != 0;
+            for (int b = b_first; b < nblocks; b += b_step) {
                 const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
                 const int blk = b - P.sub[si].blk0;
                 const int drow0 = P.sub[si].shift * P.NP;
+                const int bn = b + b_step;  // this group's next block
+                const int sin = (P.nsub > 1 && bn >= P.sub[1].blk0) ? 1 : 0;
+                const int blkn = bn - P.sub[sin].blk0;
                 for (int nt = 0; nt < ntiles; ++nt) {
+                    const int pc0 = nk > L::NPIECES ? nk - L::NPIECES : 0;  // chunk at which piece prefetch starts
                     for (int kc = 0; kc < nk; ++kc, ++it) {
-                        if (NPL == 4 && P.l2_prefetch) {
-                            // optional: pull the gradient boxes of this tile's pieces into L2 while the
-                            // k-loop runs, spread evenly over its chunks
-                            const int lo = (kc * NPF) / nk, hi = ((kc + 1) * NPF) / nk;
-                            for (int x = lo; x < hi; ++x) {
-                                const int pc = x / 3, pl = 1 + x % 3;
-                                tma::prefetch_2d(&P.map_e[si][pl], nt * NT + 16 * L::piece_cg(pc),
-                                                 blk * MB + 64 * L::piece_half(pc));
+                        if (pf) {
+                            const int ka = kc + PF;
+                            if (ka < nk) tma::prefetch_2d(&P.map_a[si], ka * 16, blk * MB);
+                            else if (nt + 1 < ntiles) { if (ka - nk < nk) tma::prefetch_2d(&P.map_a[si], (ka - nk) * 16, blk * MB); }
+                            else if (bn < nblocks && ka - nk < nk) tma::prefetch_2d(&P.map_a[sin], (ka - nk) * 16, blkn * MB);
+                            if (kc >= pc0) {
+                                // pieces [lo, hi) of this tile; all of them by the last chunk
+                                const int span = nk - pc0;
+                                const int lo = ((kc - pc0) * L::NPIECES) / span, hi = ((kc - pc0 + 1) * L::NPIECES) / span;
+                                for (int pc = lo; pc < hi; ++pc)
+                                    for (int p = 0; p < NPL; ++p)
+                                        tma::prefetch_2d(&P.map_e[si][p], nt * NT + 16 * L::piece_cg(pc), blk * MB);
                             }
                         }
                         const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
                         tma::mbar_wait(&empty[s], ph ^ 1u);
-                        unsigned char* st = sm + s * L::STAGE_BYTES;
+                        unsigned char* st = ring + s * L::STAGE_BYTES;
                         tma::mbar_arrive_expect_tx(&full[s], L::K_BYTES);
                         tma::load_2d(st, &P.map_a[si], kc * 16, blk * MB, &full[s]);
                         tma::load_2d(st + L::A_BYTES, &P.map_d, kc * 16, drow0 + nt * NT, &full[s]);
@@ -231,16 +251,11 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                     for (int pc = 0; pc < L::NPIECES; ++pc, ++it) {
                         const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
                         tma::mbar_wait(&empty[s], ph ^ 1u);
-                        unsigned char* st = sm + s * L::STAGE_BYTES;
+                        unsigned char* st = ring + s * L::STAGE_BYTES;
                         tma::mbar_arrive_expect_tx(&full[s], L::PIECE_BYTES);
                         const int c0 = nt * NT + 16 * L::piece_cg(pc);
-                        if (NPL == 4) {
-                            const int r0 = blk * MB + 64 * L::piece_half(pc);
-                            for (int p = 0; p < 4; ++p)
-                                tma::load_2d(st + p * L::PLANE_BYTES, &P.map_e[si][p], c0, r0, &full[s]);
-                        } else {
-                            tma::load_2d(st, &P.map_a[si], c0, blk * MB, &full[s]);
-                        }
+                        for (int p = 0; p < NPL; ++p)
+                            tma::load_2d(st + p * L::PLANE_BYTES, &P.map_e[si][p], c0, blk * MB, &full[s]);
                     }
                 }
             }
@@ -248,9 +263,10 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
         return;
     }
 
-    // ===================== consumers: 8 warps (4 x 2), warp tile 32 x (8 NF2) =====================
+    // ===================== consumers: 2 groups x (2 x 2 warps), warp tile 32 x (8 NF2) =====================
     reg_inc<REGS_CONSUMER>();
-    const int wm = warp >> 1, wn = warp & 1;
+    const int gw = warp & 3;
+    const int wm = gw >> 1, wn = gw & 1;
     const int q = lane >> 2, qcol = lane & 3;
     // fragment row -> tile row.  A side: {0,3,4,7 | 1,2,5,6}; B side: {0,2,4,6 | 1,3,5,7}.  Both make
     // the k-loop loads conflict-free under SWIZZLE_128B, and together they make the epilogue loads
@@ -277,20 +293,23 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
         for (int sx = 0; sx < 2; ++sx)
             eoff[e][sx] = (uint32_t)(rho * 128 + ((((4 * sx + (nc >> 1)) ^ rho) & 7) << 4) + ((nc & 1) << 3));
     }
-    // this warp's rows inside a piece: GGA pieces hold one 64-row half, LDA pieces all 128 rows
-    const int prow0 = NPL == 4 ? (wm & 1) * 32 : wm * 32;
-    // red[wn][row][plane]: slot (row of fragment row q of fragment mf, plane qcol) is this lane's alone
-    double* red_mine = red + ((wn * MB + wm * 32 + rho) * 4 + qcol);  // + 32 doubles per fragment mf
+    const int prow0 = wm * 32;  // this warp's rows inside a piece
 
-    double e_acc = 0.0;
+    // group 1 starts half a column-tile period late (only worth it when there are several blocks to do)
+    if (grp == 1 && nblocks > 8 * (int)gridDim.x) {
+        const long long t_start = clock64(), delay = (long long)nk * 2048;
+        while (clock64() - t_start < delay) __nanosleep(2000);
+    }
+
     uint32_t it = 0;
 #ifdef DFT_PHASE_TIMING
     long long t_k = 0, t_w = 0, t_m = 0, t_t = 0, t0 = clock64(), t1;
+    int n_iv = 0;
 #define PHASE_MARK(acc_) do { t1 = clock64(); acc_ += t1 - t0; t0 = t1; } while (0)
 #else
 #define PHASE_MARK(acc_) do { } while (0)
 #endif
-    for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    for (int b = b_first; b < nblocks; b += b_step) {
         const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
         const int blk = b - P.sub[si].blk0;
         double rs[4][NPL];  // per-lane partial row sums of the whole block
@@ -305,12 +324,17 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             for (int mf = 0; mf < 4; ++mf)
 #pragma unroll
                 for (int nf = 0; nf < NF2; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+#ifdef DFT_PHASE_TIMING
+            if (gw == 0 && lane == 0 && P.phase && n_iv > 0 && n_iv <= 64)
+                P.phase[65536 + ((size_t)blockIdx.x * 2 + grp) * 128 + 2 * (n_iv - 1) + 1] = clock64();
+            ++n_iv;
+#endif
 
             for (int kc = 0; kc < nk; ++kc, ++it) {
                 const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
                 tma::mbar_wait(&full[s], ph);
-                const uint32_t a_base = base + s * L::STAGE_BYTES + a_row;
-                const uint32_t b_base = base + s * L::STAGE_BYTES + L::A_BYTES + b_row;
+                const uint32_t a_base = ring_u32 + s * L::STAGE_BYTES + a_row;
+                const uint32_t b_base = ring_u32 + s * L::STAGE_BYTES + L::A_BYTES + b_row;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     double a[4], bf[NF2];
@@ -327,15 +351,18 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                 if (lane == 0) tma::mbar_arrive(&empty[s]);
             }
             PHASE_MARK(t_k);
+#ifdef DFT_PHASE_TIMING
+            if (gw == 0 && lane == 0 && P.phase && n_iv >= 1 && n_iv <= 64) P.phase[65536 + ((size_t)blockIdx.x * 2 + grp) * 128 + 2 * (n_iv - 1)] = t0;
+#endif
             // ---- epilogue: row-dots of C with the plane tiles, straight from the ring
             for (int pc = 0; pc < L::NPIECES; ++pc, ++it) {
                 const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
                 tma::mbar_wait(&full[s], ph);
                 PHASE_MARK(t_w);
                 const int cg = L::piece_cg(pc);
-                if ((NPL == 1 || (wm >> 1) == L::piece_half(pc)) && cg / (NF2 / 2) == wn) {
+                if (cg / (NF2 / 2) == wn) {
                     // plain shared-memory loads (not asm volatile): the compiler batches them freely
-                    const unsigned char* pbase = sm + s * L::STAGE_BYTES + prow0 * 128;
+                    const unsigned char* pbase = ring + s * L::STAGE_BYTES + prow0 * 128;
                     const int nfp = cg % (NF2 / 2);
 #pragma unroll
                     for (int np = 0; np < NF2 / 2; ++np) {
@@ -361,8 +388,11 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                 PHASE_MARK(t_m);
             }
         }
-        // ---- once per block: reduce the partial row sums over the 4 lanes of a fragment row.
-        // GGA: transpose-reduce (3 shuffles per row) after which lane qcol holds plane qcol.
+        // ---- once per block: reduce the partial row sums over the 4 lanes of a fragment row and hand them
+        // to the point kernel.  GGA: transpose-reduce (3 shuffles per row) after which lane qcol holds plane
+        // qcol; the 4 lanes of a row write 32 contiguous bytes.  No barrier: the two warp columns' partial
+        // sums are added by the point kernel.
+        double* rho_mine = P.rho + ((size_t)wn * P.coef_rows + P.sub[si].coef0 + (size_t)blk * MB + wm * 32 + rho) * 4 + qcol;
         if (NPL == 4) {
             const bool b0 = (qcol & 1) != 0, b1 = (qcol & 2) != 0;
 #pragma unroll
@@ -374,7 +404,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                 const double s1 = k1 + __shfl_xor_sync(0xffffffffu, g1v, 1);
                 // round 2 (lane ^ 2): keep plane 2 b1 + b0 = qcol
                 const double k = b1 ? s1 : s0, g = b1 ? s0 : s1;
-                red_mine[mf * 32] = k + __shfl_xor_sync(0xffffffffu, g, 2);
+                rho_mine[mf * 32] = k + __shfl_xor_sync(0xffffffffu, g, 2);
             }
         } else {
 #pragma unroll
@@ -382,35 +412,9 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                 double v = rs[mf][0];
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
-                red_mine[mf * 32] = qcol == 0 ? v : 0.0;
+                rho_mine[mf * 32] = qcol == 0 ? v : 0.0;
             }
         }
-        tma::named_bar_sync(1, NCONS);
-        if (tid < MB) {
-            const int r = tid;
-            const int j = blk * MB + r;
-            double2 c01 = make_double2(0.0, 0.0), c23 = make_double2(0.0, 0.0);
-            if (j < P.sub[si].rows) {
-                const long g = (long)P.sub[si].gmul * j + P.sub[si].gadd;
-                const double* rr = red + r * 4;  // + 4 MB doubles for wn = 1
-                const double rhov = rr[0] + rr[4 * MB];
-                double dx = 0.0, dy = 0.0, dz = 0.0;
-                if (NPL == 4) {
-                    dx = 2.0 * (rr[1] + rr[4 * MB + 1]);
-                    dy = 2.0 * (rr[2] + rr[4 * MB + 2]);
-                    dz = 2.0 * (rr[3] + rr[4 * MB + 3]);
-                }
-                const xcfun::PointCoef pc = eval_mode(P.xc_mode, rhov, dx, dy, dz, __ldg(P.w + g));
-                c01 = make_double2(pc.a, pc.bx);
-                c23 = make_double2(pc.by, pc.bz);
-                e_acc += pc.exc;
-            }
-            // coefficient rows are stored per sub-problem, padded to whole blocks (zeros past the end)
-            double2* cp = reinterpret_cast<double2*>(P.coef) + 2 * ((size_t)P.sub[si].coef0 + j);
-            cp[0] = c01;
-            cp[1] = c23;
-        }
-        tma::named_bar_sync(1, NCONS);
         PHASE_MARK(t_t);
     }
 #ifdef DFT_PHASE_TIMING
@@ -419,14 +423,62 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
         o[0] = t_k; o[1] = t_w; o[2] = t_m; o[3] = t_t;
     }
 #endif
-    // ---- per-CTA E_xc partial (fixed order)
-    if (warp < MB / 32) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) e_acc += __shfl_xor_sync(0xffffffffu, e_acc, o);
-        if (lane == 0) esum[warp] = e_acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// point kernel -- subsystem (c)
+// ------------------------------------------------------------------------------------------------
+// One thread per grid point (coefficient row): adds the two partial row sums the density kernel left,
+// evaluates the functional ONCE (the reference evaluates it twice, dft_solver.cu:309-513) and writes the
+// point's coefficients (a, bx, by, bz) for the V kernel; E_xc = sum w rho eps is reduced with warp shuffles
+// and a fixed-order block sum into one partial per CTA (replaces reduce_sum_kernel's 65 536 same-address
+// atomics, :285-292).  HBM-bound: 64 + 8 bytes in, 32 bytes out per point, at full occupancy -- inside the
+// density kernel only 64 of 384 threads could evaluate while the tensor pipe waited.
+struct PointParams {
+    SubProblem sub[2];
+    int nsub, xc_mode, coef_rows;
+    const double* rho;   // [2][coef_rows][4]
+    const double* w;
+    double* coef;        // [coef_rows][4]
+    double* exc_part;    // [gridDim.x]
+};
+
+constexpr int POINT_THREADS = 256;
+
+__global__ void __launch_bounds__(POINT_THREADS)
+xc_point_kernel(const PointParams P) {
+    const int row = blockIdx.x * POINT_THREADS + threadIdx.x;
+    double e = 0.0;
+    if (row < P.coef_rows) {
+        const int si = (P.nsub > 1 && row >= P.sub[1].coef0) ? 1 : 0;
+        const int j = row - P.sub[si].coef0;
+        double2 c01 = make_double2(0.0, 0.0), c23 = make_double2(0.0, 0.0);
+        if (j < P.sub[si].rows) {  // rows past the end of a sub-problem are padding: zero coefficients
+            const double2* r0 = reinterpret_cast<const double2*>(P.rho) + 2 * (size_t)row;
+            const double2* r1 = r0 + 2 * (size_t)P.coef_rows;
+            const double2 a0 = __ldg(r0), a1 = __ldg(r0 + 1), b0 = __ldg(r1), b1 = __ldg(r1 + 1);
+            const long g = (long)P.sub[si].gmul * j + P.sub[si].gadd;
+            const xcfun::PointCoef pc = eval_mode(P.xc_mode, a0.x + b0.x, 2.0 * (a0.y + b0.y), 2.0 * (a1.x + b1.x),
+                                                  2.0 * (a1.y + b1.y), __ldg(P.w + g));
+            c01 = make_double2(pc.a, pc.bx);
+            c23 = make_double2(pc.by, pc.bz);
+            e = pc.exc;
+        }
+        double2* cp = reinterpret_cast<double2*>(P.coef) + 2 * (size_t)row;
+        cp[0] = c01;
+        cp[1] = c23;
     }
-    tma::named_bar_sync(1, NCONS);
-    if (tid == 0) P.exc_part[blockIdx.x] = (esum[0] + esum[1]) + (esum[2] + esum[3]);
+    __shared__ double wsum[POINT_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < POINT_THREADS / 32; ++k) t += wsum[k];
+        P.exc_part[blockIdx.x] = t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -654,14 +706,20 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
 
 // out[i][j] = sum over slices of T(i+s, j+s) + T(j+s, i+s), s = column shift of the slice's
 // sub-problem; T = M where the tile was computed (lda_half: the mirror tile otherwise).
-// Fixed summation order -> bit-reproducible and exactly symmetric.
-__global__ void finalize_tma_kernel(int nao, int ldv, int mpv, int NT, int nsub, int slices_per_sub, int shift1,
-                                    int lda_half, const double* __restrict__ vpart, double* __restrict__ vxc,
-                                    int nepart, const double* __restrict__ epart, double* __restrict__ d_exc) {
+// One warp per output element: lanes stride over the slices (all partial loads in flight at once --
+// a serial loop over up to 148 slices was latency-bound at ~20 us for the small molecules), then a
+// shuffle tree.  Fixed summation order -> bit-reproducible and exactly symmetric.
+constexpr int FIN_THREADS = 256;
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_tma_kernel(int nao, int ldv, int mpv, int NT, int nsub, int slices_per_sub, int shift1, int lda_half,
+                    const double* __restrict__ vpart, double* __restrict__ vxc, int nepart,
+                    const double* __restrict__ epart, double* __restrict__ d_exc) {
     const size_t n2 = (size_t)nao * nao;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const size_t idx = (size_t)blockIdx.x * (FIN_THREADS / 32) + (threadIdx.x >> 5);
     if (idx < n2) {
         const int i0 = (int)(idx / nao), j0 = (int)(idx % nao);
+        const size_t ss = (size_t)mpv * ldv;
         double s = 0.0;
         for (int su = 0; su < nsub; ++su) {
             const int sh = su ? shift1 : 0;
@@ -671,20 +729,20 @@ __global__ void finalize_tma_kernel(int nao, int ldv, int mpv, int NT, int nsub,
                 if (i / NT > j / NT) o1 = o2;
                 else if (j / NT > i / NT) o2 = o1;
             }
-            for (int sl = 0; sl < slices_per_sub; ++sl) {
-                const double* p = vpart + (size_t)(su * slices_per_sub + sl) * mpv * ldv;
-                s += p[o1] + p[o2];
-            }
+            const double* p = vpart + (size_t)su * slices_per_sub * ss;
+            for (int sl = lane; sl < slices_per_sub; sl += 32) s += __ldg(p + sl * ss + o1) + __ldg(p + sl * ss + o2);
         }
-        vxc[idx] = s;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) vxc[idx] = s;
     }
     if (blockIdx.x == 0) {
-        __shared__ double sh[256];
+        __shared__ double sh[FIN_THREADS];
         double e = 0.0;
-        for (int k = threadIdx.x; k < nepart; k += blockDim.x) e += epart[k];
+        for (int k = threadIdx.x; k < nepart; k += FIN_THREADS) e += epart[k];
         sh[threadIdx.x] = e;
         __syncthreads();
-        for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        for (int o = FIN_THREADS / 2; o > 0; o >>= 1) {
             if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
             __syncthreads();
         }
@@ -815,17 +873,18 @@ static Geometry make_geometry(int ngrid, int nao) {
 struct PlanKey {
     Problem prob;
     int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk;
-    const void *dsym, *coef, *epart, *vpart;  // engine workspaces (grow-only: may move when they grow)
+    const void *dsym, *coef, *epart, *vpart, *rho;  // engine workspaces (grow-only: may move when they grow)
 };
 
 struct Plan {
     bool valid = false;
     PlanKey key;
     DensityParams dp;
+    PointParams pp;
     VxcParams vp;
     const void* dfunc = nullptr;
     const void* vfunc = nullptr;
-    int dgrid = 0, dsmem = 0, vsmem = 0;
+    int dgrid = 0, dsmem = 0, vsmem = 0, pgrid = 0;
     dim3 vgrid;
     // symmetrize_pad / finalize arguments
     int KP = 0, NP = 0, nsub = 0, ldv = 0, mpv = 0, fin_nt = 0, nsl = 0, shift1 = 0, lda_half = 0;
@@ -840,10 +899,12 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
     const int ntiles = (g.ncols + NT - 1) / NT;
     const int NP = ntiles * NT;
     const int KP = ((g.ncols + 15) / 16) * 16;
-    const int grid1 = g.nblocks < nsm ? g.nblocks : nsm;
+    const int grid1 = (g.nblocks + 1) / 2 < nsm ? (g.nblocks + 1) / 2 : nsm;  // two consumer groups per CTA
+    const int pgrid = (g.coef_rows + POINT_THREADS - 1) / POINT_THREADS;
 
     double* dsym = (double*)ctx->dsym.ensure(sizeof(double) * (size_t)g.nsub * NP * KP, &ctx->failed);
-    double* epart = (double*)ctx->epart.ensure(sizeof(double) * grid1, &ctx->failed);
+    double* epart = (double*)ctx->epart.ensure(sizeof(double) * pgrid, &ctx->failed);
+    double* rho = (double*)ctx->rho.ensure(sizeof(double) * 8 * (size_t)g.coef_rows, &ctx->failed);
     if (ctx->failed) return;
 
     DensityParams& dp = pl.dp;
@@ -853,17 +914,25 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
     for (int s = 0; s < g.nsub; ++s) {
         ok = ok && make_sub_map(&dp.map_a[s], p.ao, ngrid, nao, g.split, s, MB);
         for (int i = 0; i < 4; ++i)
-            ok = ok && make_sub_map(&dp.map_e[s][i], planes[i < NPL ? i : 0], ngrid, nao, g.split, s, 64);
+            ok = ok && make_sub_map(&dp.map_e[s][i], planes[i < NPL ? i : 0], ngrid, nao, g.split, s, MB);
     }
     if (!ok) { ctx->failed = true; return; }
     dp.sub[0] = g.sub[0]; dp.sub[1] = g.sub[1];
     dp.nsub = g.nsub;
-    dp.xc_mode = p.xc_type == 2 ? 4 : p.xc_type * 2 + (ctx->exact_functionals ? 1 : 0);
     dp.nblocks = g.nblocks; dp.ntiles = ntiles; dp.nk = KP / 16; dp.NP = NP;
     dp.l2_prefetch = ctx->l2_prefetch ? 1 : 0;
-    dp.w = p.w; dp.coef = coef; dp.exc_part = epart;
+    dp.coef_rows = g.coef_rows; dp.rho = rho;
+
+    PointParams& pp = pl.pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.sub[0] = g.sub[0]; pp.sub[1] = g.sub[1];
+    pp.nsub = g.nsub; pp.coef_rows = g.coef_rows;
+    pp.xc_mode = p.xc_type == 2 ? 4 : p.xc_type * 2 + (ctx->exact_functionals ? 1 : 0);
+    pp.rho = rho; pp.w = p.w; pp.coef = coef; pp.exc_part = epart;
+    pl.pgrid = pgrid;
 #ifdef DFT_PHASE_TIMING
-    dp.phase = (long long*)ctx->scratch.ensure(sizeof(long long) * (8192 + 160 * 9 * 4), &ctx->failed);
+    dp.phase = (long long*)ctx->scratch.ensure(sizeof(long long) * (65536 + 160 * 256), &ctx->failed);
+    if (dp.phase) cudaMemsetAsync(dp.phase, 0, sizeof(long long) * 8192, ctx->stream);
 #endif
 
     auto dk = density_tma_kernel<NF2, NPL>;
@@ -925,7 +994,7 @@ static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry&
     vp.coef = coef; vp.vpart = vpart;
 #ifdef DFT_PHASE_TIMING
     {   // the density kernel's phase record occupies the first 148*8*4 entries of `scratch`
-        long long* ph = (long long*)ctx->scratch.ensure(sizeof(long long) * (8192 + (size_t)tiles * nsl * g.nsub * (NCW + 1) * 4), &ctx->failed);
+        long long* ph = (long long*)ctx->scratch.ensure(sizeof(long long) * (65536 + 160 * 256), &ctx->failed);
         vp.phase = ph ? ph + 8192 : nullptr;
     }
 #endif
@@ -986,6 +1055,7 @@ static PlanKey make_key(const CublasHandleWrapper* ctx, const Problem& p) {
     k.exact = ctx->exact_functionals; k.l2_prefetch = ctx->l2_prefetch; k.tma_3d = ctx->tma_3d;
     k.vxc_shape = ctx->vxc_shape; k.vxc_vk = ctx->vxc_vk;
     k.dsym = ctx->dsym.ptr; k.coef = ctx->coef.ptr; k.epart = ctx->epart.ptr; k.vpart = ctx->vpart.ptr;
+    k.rho = ctx->rho.ptr;
     return k;
 }
 
@@ -996,15 +1066,16 @@ static void run_plan(CublasHandleWrapper* ctx, const Problem& p, Plan& pl) {
                                                                                          pl.dsym);
     void* dargs[1] = {&pl.dp};
     DFT_CUDA_CHECK(ctx, cudaLaunchKernel(pl.dfunc, dim3(pl.dgrid), dim3(NTHREADS), dargs, (size_t)pl.dsmem, st));
+    xc_point_kernel<<<pl.pgrid, POINT_THREADS, 0, st>>>(pl.pp);
     if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
     void* vargs[1] = {&pl.vp};
     DFT_CUDA_CHECK(ctx, cudaLaunchKernel(pl.vfunc, pl.vgrid, dim3(NTHREADS), vargs, (size_t)pl.vsmem, st));
     if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
     const size_t n2 = (size_t)p.nao * p.nao;
-    finalize_tma_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(p.nao, pl.ldv, pl.mpv, pl.fin_nt, pl.nsub, pl.nsl, pl.shift1,
-                                                                      pl.lda_half, pl.vpart, p.vxc, pl.dgrid, pl.epart, p.d_exc);
+    finalize_tma_kernel<<<(unsigned)((n2 + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32)), FIN_THREADS, 0, st>>>(p.nao, pl.ldv, pl.mpv, pl.fin_nt, pl.nsub, pl.nsl, pl.shift1,
+                                                                      pl.lda_half, pl.vpart, p.vxc, pl.pgrid, pl.epart, p.d_exc);
     if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
-    ctx->stats.launches = 4;
+    ctx->stats.launches = 5;
     ctx->stats.path = PATH_TMA;
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
 }

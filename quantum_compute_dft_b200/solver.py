@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "DFT_CreateSolver", "DFT_DestroySolver", "DFT_ComputeXC", "DFT_ComputeCoulomb",
     "DFT_EvalAO", "DFT_CommGetUniqueId", "DFT_CommInit", "DFT_CommDestroy",
     "DFT_SetOption", "DFT_GetStat", "DFT_ComputeXCAsync", "DFT_StreamSynchronize", "DFT_GetStream",
-    "DFT_MicrobenchDMMA", "DFT_MicrobenchDFMA", "DFT_B200_Version",
+    "DFT_MicrobenchDMMA", "DFT_MicrobenchDFMA", "DFT_MicrobenchDMMAWarps", "DFT_B200_Version",
 ]
 
 _c_dp = ctypes.POINTER(ctypes.c_double)
@@ -74,6 +74,8 @@ def load_library(lib_path=DEFAULT_LIB):
     lib.DFT_MicrobenchDMMA.restype = ctypes.c_double
     lib.DFT_MicrobenchDFMA.argtypes = [ctypes.c_int]
     lib.DFT_MicrobenchDFMA.restype = ctypes.c_double
+    lib.DFT_MicrobenchDMMAWarps.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.DFT_MicrobenchDMMAWarps.restype = ctypes.c_double
     lib.DFT_B200_Version.restype = ctypes.c_char_p
     return lib
 

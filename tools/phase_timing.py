@@ -21,11 +21,30 @@ print(wl, "E_xc", e, "density_ms", s.stat("density_ms"), "vxc_ms", s.stat("vxc_m
 s.lib.DFT_DebugRead.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_uint64]
 nblk = min(148, (dp.ngrid + 127) // 128 + 1)
 nv = int(os.environ.get("V_CTAS", "144"))
-raw = np.zeros(8192 + nv * 9 * 4, dtype=np.int64)
+raw = np.zeros(65536 + 160 * 256, dtype=np.int64)
 rc = s.lib.DFT_DebugRead(s.solver, b"scratch", raw.ctypes.data_as(ctypes.c_void_p), raw.nbytes)
 assert rc == 0, rc
 buf = raw[:nblk * 32].reshape(nblk, 8, 4)
-vb = raw[8192:].reshape(nv, 9, 4).astype(float)
+vb = raw[8192:8192 + nv * 36].reshape(nv, 9, 4).astype(float)
+# density kernel: the first 64 non-k-loop intervals (epilogue + block tail) of each consumer group
+iv = raw[65536:65536 + nblk * 256].reshape(nblk, 2, 64, 2)
+ov_tot = ep_tot = 0.0
+for c in range(nblk):
+    a, b = iv[c, 0], iv[c, 1]
+    a = a[(a[:, 0] > 0) & (a[:, 1] > a[:, 0])]; b = b[(b[:, 0] > 0) & (b[:, 1] > b[:, 0])]
+    if len(a) == 0 or len(b) == 0:
+        continue
+    t_lo, t_hi = max(a[0, 0], b[0, 0]), min(a[-1, 1], b[-1, 1])
+    for s0, s1 in a:
+        ep_tot += max(0, min(s1, t_hi) - max(s0, t_lo))
+        for r0, r1 in b:
+            ov_tot += max(0, min(s1, r1, t_hi) - max(s0, r0, t_lo))
+if ep_tot > 0:
+    a0 = iv[0, 0]; b0 = iv[0, 1]
+    print("density kernel ping-pong: %.1f %% of group 0's epilogue time overlaps group 1's epilogues" % (100 * ov_tot / ep_tot))
+    print("  CTA 0 group 0 epilogue starts (cycles, rel):", (a0[:6, 0] - a0[0, 0]).tolist(), "lengths", (a0[:6, 1] - a0[:6, 0]).tolist())
+    print("  CTA 0 group 1 epilogue starts (cycles, rel):", (b0[:6, 0] - a0[0, 0]).tolist(), "lengths", (b0[:6, 1] - b0[:6, 0]).tolist())
+
 tot = buf.sum(axis=2).astype(float)
 print("cycles per warp: mean %.3e  min %.3e  max %.3e  (%.2f ms at 1.965 GHz)" % (tot.mean(), tot.min(), tot.max(), tot.mean() / 1.965e6))
 for i, name in enumerate(("k-loop", "piece wait", "piece math+release", "block tail")):
