@@ -7,6 +7,8 @@
 //   dgemm_colmajor : definition behind XCSolver::safe_cublas_dgemm (dft_solver.h:25-27,
 //                    dft_solver.cu:541-548) so code written against the reference header links.
 //                    Not on the engine's own hot path (V_xc is built by the fused kernels).
+#include <cstdint>
+
 #include "engine.h"
 
 namespace xc {
@@ -15,23 +17,52 @@ namespace {
 constexpr int GEMV_THREADS = 256;
 
 // partial[s][r] = sum_{c in chunk s} A[c*N2 + r] * x[c]
+// VEC = 2: a thread owns two adjacent rows and streams 16-byte loads (N2 even: every column start is
+// 16-byte aligned); 8 columns' loads are issued before the first FMA so that 128 bytes per thread are in
+// flight.  ld.global.nc + no reuse: the ERI passes through L2 once.
+template <int VEC>
 __global__ void __launch_bounds__(GEMV_THREADS)
 gemv_partial_kernel(long N2, int cols_per_chunk, const double* __restrict__ A, const double* __restrict__ x,
                     double* __restrict__ partial) {
-    const long r = (long)blockIdx.x * GEMV_THREADS + threadIdx.x;
+    const long r = ((long)blockIdx.x * GEMV_THREADS + threadIdx.x) * VEC;
     const long c0 = (long)blockIdx.y * cols_per_chunk;
     const long c1 = min(N2, c0 + cols_per_chunk);
     if (r >= N2) return;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    constexpr int U = 8;
+    double acc[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[u][v] = 0.0;
     long c = c0;
-    for (; c + 3 < c1; c += 4) {  // 4 independent loads in flight per thread
-        s0 = fma(__ldg(A + (size_t)c * N2 + r), __ldg(x + c), s0);
-        s1 = fma(__ldg(A + (size_t)(c + 1) * N2 + r), __ldg(x + c + 1), s1);
-        s2 = fma(__ldg(A + (size_t)(c + 2) * N2 + r), __ldg(x + c + 2), s2);
-        s3 = fma(__ldg(A + (size_t)(c + 3) * N2 + r), __ldg(x + c + 3), s3);
+    for (; c + U <= c1; c += U) {
+        double a[U][VEC], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double* p = A + (size_t)(c + u) * N2 + r;
+            if (VEC == 2) {
+                const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+                a[u][0] = t.x; a[u][VEC - 1] = t.y;
+            } else {
+                a[u][0] = __ldg(p);
+            }
+            xv[u] = __ldg(x + c + u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[u][v] = fma(a[u][v], xv[u], acc[u][v]);
     }
-    for (; c < c1; ++c) s0 = fma(__ldg(A + (size_t)c * N2 + r), __ldg(x + c), s0);
-    partial[(size_t)blockIdx.y * N2 + r] = (s0 + s1) + (s2 + s3);
+    for (; c < c1; ++c) {
+        const double xc = __ldg(x + c);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[0][v] = fma(__ldg(A + (size_t)c * N2 + r + v), xc, acc[0][v]);
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const double s = ((acc[0][v] + acc[1][v]) + (acc[2][v] + acc[3][v])) + ((acc[4][v] + acc[5][v]) + (acc[6][v] + acc[7][v]));
+        partial[(size_t)blockIdx.y * N2 + r + v] = s;
+    }
 }
 
 __global__ void gemv_reduce_kernel(long N2, int nchunks, const double* __restrict__ partial,
@@ -67,18 +98,23 @@ __global__ void gemm_simple_kernel(bool ta, bool tb, int m, int n, int k, const 
 void coulomb_gemv(CublasHandleWrapper* ctx, int nao, const double* eri, const double* dm, double* J) {
     if (!ctx || nao <= 0 || !eri || !dm || !J) return;
     const long N2 = (long)nao * nao;
-    const int rblocks = (int)((N2 + GEMV_THREADS - 1) / GEMV_THREADS);
+    const bool vec2 = (N2 % 2 == 0) && ((reinterpret_cast<uintptr_t>(eri) & 15u) == 0);
+    const long rows_per_block = (long)GEMV_THREADS * (vec2 ? 2 : 1);
+    const int rblocks = (int)((N2 + rows_per_block - 1) / rows_per_block);
     // enough CTAs to saturate HBM: aim for >= 8 resident CTAs per SM
-    int nchunks = (148 * 8 + rblocks - 1) / rblocks;
+    if (ctx->num_sms <= 0) cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    int nchunks = (ctx->num_sms * 8 + rblocks - 1) / rblocks;
     if (nchunks > N2 / 8) nchunks = (int)(N2 / 8);
     if (nchunks < 1) nchunks = 1;
     if (nchunks > 65535) nchunks = 65535;
     int cols = (int)((N2 + nchunks - 1) / nchunks);
+    cols = ((cols + 7) / 8) * 8;  // whole unrolled groups
     nchunks = (int)((N2 + cols - 1) / cols);
     double* partial = (double*)ctx->vpart.ensure(sizeof(double) * (size_t)nchunks * N2, &ctx->failed);
     if (ctx->failed) return;
-    gemv_partial_kernel<<<dim3(rblocks, nchunks), GEMV_THREADS, 0, ctx->stream>>>(N2, cols, eri, dm, partial);
-    gemv_reduce_kernel<<<rblocks, GEMV_THREADS, 0, ctx->stream>>>(N2, nchunks, partial, J);
+    if (vec2) gemv_partial_kernel<2><<<dim3(rblocks, nchunks), GEMV_THREADS, 0, ctx->stream>>>(N2, cols, eri, dm, partial);
+    else gemv_partial_kernel<1><<<dim3(rblocks, nchunks), GEMV_THREADS, 0, ctx->stream>>>(N2, cols, eri, dm, partial);
+    gemv_reduce_kernel<<<(int)((N2 + GEMV_THREADS - 1) / GEMV_THREADS), GEMV_THREADS, 0, ctx->stream>>>(N2, nchunks, partial, J);
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
 }
 
