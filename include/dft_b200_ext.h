@@ -63,6 +63,17 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value);
 //       far: a steady SCF loop over the same arrays builds exactly one).
 double DFT_GetStat(XCSolver* solver, const char* key);
 
+// ---- Coulomb and exact exchange in one pass over the ERI ------------
+// d_J (nao,nao) = sum_kl (ij|kl) D[k,l], what DFT_ComputeCoulomb writes (dft_solver.cu:550-555), and
+// d_K (nao,nao) = sum_jl (ij|kl) D[j,l], what the reference's driver computes for B3LYP with
+// cupy.einsum('ijkl,jl->ik', eri, dm) (dft.py:218) in a second pass over the 8 nao^4-byte ERI.
+// Every ERI element is loaded once; J relies on (ij|kl) = (kl|ij), which every ERI tensor has (the
+// reference's column-major gemv reads the transposed matrix).  Enqueued on the engine stream (like DFT_ComputeCoulomb: no host
+// sync); returns 0, or non-zero on bad arguments / CUDA failure.
+int DFT_ComputeCoulombExchange(XCSolver* solver, int nao, unsigned long long d_eri_ptr,
+                               unsigned long long d_dm_ptr, unsigned long long d_J_ptr,
+                               unsigned long long d_K_ptr);
+
 // ---- convenience for callers that keep V_xc/E_xc on the device (no host sync) --------------
 // Same as DFT_ComputeXC but writes E_xc to the device double at d_exc_ptr, does not block the
 // host, and returns 0.  Work is enqueued on the engine stream; DFT_StreamSynchronize waits.

@@ -112,6 +112,13 @@ def sym(v):
     return 0.5 * (v + v.T)
 
 
+def exchange(eri, dm):
+    """K_ik = sum_jl (ij|kl) D_jl: the reference driver's cupy.einsum('ijkl,jl->ik', eri, dm), dft.py:218."""
+    dm = _f64(dm)
+    nao = dm.shape[0]
+    return np.einsum("ijkl,jl->ik", _f64(eri).reshape(nao, nao, nao, nao), dm)
+
+
 def coulomb(eri, dm):
     dm = _f64(dm)
     nao = dm.shape[0]

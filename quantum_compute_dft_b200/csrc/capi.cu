@@ -208,6 +208,16 @@ void DFT_ComputeCoulomb(XCSolver* solver, int nao, unsigned long long d_eri_ptr,
                             reinterpret_cast<const double*>(d_dm_ptr), reinterpret_cast<double*>(d_J_ptr));
 }
 
+int DFT_ComputeCoulombExchange(XCSolver* solver, int nao, unsigned long long d_eri_ptr, unsigned long long d_dm_ptr,
+                               unsigned long long d_J_ptr, unsigned long long d_K_ptr) {
+    if (!solver || nao <= 0 || !d_eri_ptr || !d_dm_ptr || !d_J_ptr || !d_K_ptr) return 1;
+    CublasHandleWrapper* ctx = solver->context();
+    ctx->failed = false;
+    xc::coulomb_exchange(ctx, nao, reinterpret_cast<const double*>(d_eri_ptr), reinterpret_cast<const double*>(d_dm_ptr),
+                         reinterpret_cast<double*>(d_J_ptr), reinterpret_cast<double*>(d_K_ptr));
+    return ctx->failed ? 2 : 0;
+}
+
 int DFT_ComputeXCAsync(XCSolver* solver, int ngrid, int nao, unsigned long long d_dm_ptr,
                        unsigned long long d_ao_ptr, unsigned long long d_ao_grad_ptr,
                        unsigned long long d_weights_ptr, unsigned long long d_vxc_ptr,

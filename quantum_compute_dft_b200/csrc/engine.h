@@ -105,6 +105,8 @@ void free_tma_plan(CublasHandleWrapper* ctx);
 int allreduce_result(CublasHandleWrapper* ctx, double* d_packed, size_t count);
 
 void coulomb_gemv(CublasHandleWrapper* ctx, int nao, const double* eri, const double* dm, double* J);
+// J and the exact-exchange matrix K[i,k] = sum_jl (ij|kl) D[j,l] in ONE pass over the ERI
+void coulomb_exchange(CublasHandleWrapper* ctx, int nao, const double* eri, const double* dm, double* J, double* K);
 
 void dgemm_colmajor(CublasHandleWrapper* ctx, bool transA, bool transB, int m, int n, int k,
                     const double* A, int lda, const double* B, int ldb, double* C, int ldc);

@@ -8,6 +8,7 @@
 //                    dft_solver.cu:541-548) so code written against the reference header links.
 //                    Not on the engine's own hot path (V_xc is built by the fused kernels).
 #include <cstdint>
+#include <cstdio>
 
 #include "engine.h"
 
@@ -93,6 +94,76 @@ __global__ void gemm_simple_kernel(bool ta, bool tb, int m, int n, int k, const 
     if (row < m && col < n) C[(size_t)col * ldc + row] = acc;
 }
 
+// ---- fused Coulomb + exchange: one pass over the ERI -------------------------------------------------
+// J[i,j] = sum_kl (ij|kl) D[k,l]   (the gemv above)          K[i,k] = sum_jl (ij|kl) D[j,l]
+// K is what the reference's driver computes for B3LYP with cupy.einsum('ijkl,jl->ik', eri, dm)
+// (dft.py:218), a second full pass over the 8 nao^4-byte ERI right after the J gemv.  Here every ERI
+// element is loaded once and used twice.  CTA (i, chunk of KC values of k): warp w takes rows j = w, w+8, ..;
+// row (i,j), columns (k0..k0+KC, all l) are KC*nao contiguous doubles.  Per lane: accJ (this row, reduced
+// over the warp once per row) and accK[KC] (summed over this warp's rows, reduced once at the end);
+// every J/K element has one owner and a fixed summation order -> bit-reproducible, no atomics.
+constexpr int JK_KC = 8;
+constexpr int JK_WARPS = 8;
+
+__global__ void __launch_bounds__(JK_WARPS * 32)
+coulomb_exchange_kernel(int n, const double* __restrict__ A, const double* __restrict__ D, double* __restrict__ jpart,
+                        double* __restrict__ K) {
+    extern __shared__ double sm[];
+    double* s_dk = sm;                       // [KC][n]: rows k0.. of D
+    double* s_k = sm + JK_KC * n;            // [JK_WARPS][KC]: per-warp K partials
+    const int i = blockIdx.x, chunk = blockIdx.y, k0 = chunk * JK_KC;
+    const int kc = min(JK_KC, n - k0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t n2 = (size_t)n * n;
+    for (int t = threadIdx.x; t < JK_KC * n; t += blockDim.x) s_dk[t] = (t / n) < kc ? D[(size_t)(k0 + t / n) * n + t % n] : 0.0;
+    __syncthreads();
+    double acck[JK_KC];
+#pragma unroll
+    for (int kk = 0; kk < JK_KC; ++kk) acck[kk] = 0.0;
+    for (int j = warp; j < n; j += JK_WARPS) {
+        const double* row = A + ((size_t)i * n + j) * n2 + (size_t)k0 * n;
+        const double* dj = D + (size_t)j * n;
+        double accj = 0.0;
+        // 4 x KC = 32 loads per lane are issued before the first FMA (the loop is latency-bound otherwise)
+        for (int l0 = lane; l0 < n; l0 += 128) {
+            double a[4][JK_KC], djl[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int l = l0 + 32 * u;
+                const bool ok = l < n;
+                djl[u] = ok ? __ldg(dj + l) : 0.0;
+#pragma unroll
+                for (int kk = 0; kk < JK_KC; ++kk) a[u][kk] = (ok && kk < kc) ? __ldg(row + (size_t)kk * n + l) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int l = min(l0 + 32 * u, n - 1);
+#pragma unroll
+                for (int kk = 0; kk < JK_KC; ++kk) {
+                    accj = fma(a[u][kk], s_dk[kk * n + l], accj);
+                    acck[kk] = fma(a[u][kk], djl[u], acck[kk]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) accj += __shfl_xor_sync(0xffffffffu, accj, o);
+        if (lane == 0) jpart[(size_t)chunk * n2 + (size_t)i * n + j] = accj;
+    }
+#pragma unroll
+    for (int kk = 0; kk < JK_KC; ++kk) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acck[kk] += __shfl_xor_sync(0xffffffffu, acck[kk], o);
+        if (lane == 0) s_k[warp * JK_KC + kk] = acck[kk];
+    }
+    __syncthreads();
+    if (threadIdx.x < kc) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < JK_WARPS; ++w) t += s_k[w * JK_KC + threadIdx.x];
+        K[(size_t)i * n + k0 + threadIdx.x] = t;
+    }
+}
+
 }  // namespace
 
 void coulomb_gemv(CublasHandleWrapper* ctx, int nao, const double* eri, const double* dm, double* J) {
@@ -114,6 +185,20 @@ void coulomb_gemv(CublasHandleWrapper* ctx, int nao, const double* eri, const do
     if (ctx->failed) return;
     if (vec2) gemv_partial_kernel<2><<<dim3(rblocks, nchunks), GEMV_THREADS, 0, ctx->stream>>>(N2, cols, eri, dm, partial);
     else gemv_partial_kernel<1><<<dim3(rblocks, nchunks), GEMV_THREADS, 0, ctx->stream>>>(N2, cols, eri, dm, partial);
+    gemv_reduce_kernel<<<(int)((N2 + GEMV_THREADS - 1) / GEMV_THREADS), GEMV_THREADS, 0, ctx->stream>>>(N2, nchunks, partial, J);
+    DFT_CUDA_CHECK(ctx, cudaGetLastError());
+}
+
+void coulomb_exchange(CublasHandleWrapper* ctx, int nao, const double* eri, const double* dm, double* J, double* K) {
+    if (!ctx || nao <= 0 || !eri || !dm || !J || !K) return;
+    const long N2 = (long)nao * nao;
+    const int nchunks = (nao + JK_KC - 1) / JK_KC;
+    double* partial = (double*)ctx->vpart.ensure(sizeof(double) * (size_t)nchunks * N2, &ctx->failed);
+    if (ctx->failed) return;
+    const size_t smem = sizeof(double) * (size_t)(JK_KC * nao + JK_WARPS * JK_KC);
+    if (smem > 200 * 1024) { fprintf(stderr, "[dft_b200] coulomb_exchange: nao too large\n"); ctx->failed = true; return; }
+    DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(coulomb_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    coulomb_exchange_kernel<<<dim3(nao, nchunks), JK_WARPS * 32, smem, ctx->stream>>>(nao, eri, dm, partial, K);
     gemv_reduce_kernel<<<(int)((N2 + GEMV_THREADS - 1) / GEMV_THREADS), GEMV_THREADS, 0, ctx->stream>>>(N2, nchunks, partial, J);
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
 }

@@ -340,3 +340,32 @@ WORKLOADS = {
     "C4": ("GGA", "DHA"),
     "C5": ("B3LYP", "C33H56N7O17P3S"),
 }
+
+
+# --------------------------------------------------------------------------- grid files
+def load_grid_txt(path):
+    """Read a grid in the reference's on-disk format (grid.py:11-14 `init_grid`): whitespace-separated rows
+    `atom_index x y z w [w]` -- the owning atom, the point in Bohr, the quadrature weight (the reference's
+    files repeat the weight in a sixth column, which `init_grid` ignores).  Returns (coords (n,3) float64,
+    weights (n,) float64, atom_index (n,) int32), C-contiguous: coords feed DFT_EvalAO, weights feed
+    DFT_ComputeXC, exactly as grid.py hands them to PySCF."""
+    data = np.loadtxt(path, dtype=np.float64, ndmin=2)
+    if data.size == 0:
+        return np.zeros((0, 3)), np.zeros((0,)), np.zeros((0,), dtype=np.int32)
+    if data.shape[1] < 5:
+        raise ValueError(f"{path}: expected at least 5 columns (atom x y z w), found {data.shape[1]}")
+    return (np.ascontiguousarray(data[:, 1:4]), np.ascontiguousarray(data[:, 4]),
+            data[:, 0].astype(np.int32))
+
+
+def save_grid_txt(path, coords, weights, atom_index=None):
+    """Write a grid in the same format (weight repeated in the sixth column, 20 significant digits like the
+    reference's files), so that grids generated here can drive the reference's `dft.py <functional> <mol>`."""
+    coords = np.asarray(coords, dtype=np.float64).reshape(-1, 3)
+    weights = np.asarray(weights, dtype=np.float64).reshape(-1)
+    if coords.shape[0] != weights.shape[0]:
+        raise ValueError("coords and weights disagree on the number of points")
+    atom_index = np.zeros(weights.shape[0], dtype=np.int64) if atom_index is None else np.asarray(atom_index)
+    with open(path, "w") as f:
+        for a, (x, y, z), w in zip(atom_index, coords, weights):
+            f.write(f"{int(a)} {x:.20e} {y:.20e} {z:.20e} {w:.20e} {w:.20e}\n")

@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "DFT_EvalAO", "DFT_CommGetUniqueId", "DFT_CommInit", "DFT_CommDestroy",
     "DFT_SetOption", "DFT_GetStat", "DFT_ComputeXCAsync", "DFT_StreamSynchronize", "DFT_GetStream",
     "DFT_MicrobenchDMMA", "DFT_MicrobenchDFMA", "DFT_MicrobenchDMMAWarps", "DFT_B200_Version",
+    "DFT_ComputeCoulombExchange",
 ]
 
 _c_dp = ctypes.POINTER(ctypes.c_double)
@@ -120,6 +121,14 @@ class DFTSolverWrapper:
                                     ctypes.c_uint64(d_dm.data.ptr), ctypes.c_uint64(d_J.data.ptr))
 
     # ---- additive -------------------------------------------------------------------------
+    def compute_coulomb_exchange(self, nao, d_eri, d_dm, d_J, d_K):
+        """J and K = einsum('ijkl,jl->ik', eri, dm) (dft.py:218) in one pass over the ERI."""
+        self.lib.DFT_ComputeCoulombExchange.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_uint64] * 4
+        self.lib.DFT_ComputeCoulombExchange.restype = ctypes.c_int
+        rc = self.lib.DFT_ComputeCoulombExchange(self.solver, nao, d_eri.data.ptr, d_dm.data.ptr, d_J.data.ptr, d_K.data.ptr)
+        if rc != 0:
+            raise RuntimeError(f"DFT_ComputeCoulombExchange failed with code {rc}")
+
     def eval_ao(self, d_coords, basis, d_ao, d_ao_grad=None, exp_cutoff=0.0):
         """GPU replacement of numint.eval_ao (grid.py:30,38).  basis: molgrid.Basis."""
         ngrid = d_coords.shape[0]

@@ -291,6 +291,31 @@ def test_ao_evaluation_on_gpu(oracle, engine_lib):
         s.set_option("ao_shape", 0)
 
 
+@pytest.mark.parametrize("workload_name,scale", [("C4", 0.03), ("C5", 0.008)])
+def test_config_molecules_device_pipeline(oracle, engine_lib, workload_name, scale):
+    """The two multi-GPU configurations' molecules (DHA, nao 152; C33H56N7O17P3S, nao 377 = odd, parity
+    sub-problems) through the whole device pipeline -- DFT_EvalAO on the GPU, then DFT_ComputeXC on the TMA
+    path -- against the CPU oracle working from its own AO evaluation, at a grid size the oracle finishes in
+    seconds.  Tolerances are BASELINE.json's."""
+    from quantum_compute_dft_b200 import workload as W
+    hp = W.host_problem(workload_name, scale=scale)
+    if hp.nao % 2 == 1 and hp.ngrid % 2 == 1:   # odd x odd would take the generic path (DESIGN.md 5.4); C5 itself is even
+        hp = W.HostProblem(hp.name, hp.functional, hp.mol, hp.basis, hp.coords[:-1], hp.weights[:-1], hp.dm)
+    s = W.make_solver(hp.functional, engine_lib)
+    dp = W.device_problem(hp, s)
+    e = s.compute_xc(dp.ngrid, dp.nao, dp.d_dm, dp.d_ao, dp.d_weights, dp.d_vxc, dp.d_ao_grad)
+    v = dp.d_vxc.get()
+    assert s.stat("path") == 2
+    ao_o, g_o = oracle.eval_ao(hp.coords, hp.basis, deriv=1)
+    e_o, v_o = oracle.compute_xc(XC[hp.functional], hp.dm, ao_o, hp.weights, g_o, mode=0)
+    assert abs(e - e_o) <= E_TOL, (e, e_o)
+    np.testing.assert_allclose(0.5 * (v + v.T), oracle.sym(v_o), rtol=0, atol=V_TOL)
+    # the integrated density is the electron count of the synthetic D (tr(DS) = N_e): a physics sanity check
+    rho = np.einsum("gi,ij,gj->g", ao_o, hp.dm, ao_o)
+    assert abs(float(rho @ hp.weights) - 2 * hp.mol.nocc) < 0.10 * 2 * hp.mol.nocc
+    dp.free()
+
+
 def test_coulomb_through_c_abi(oracle, engine_lib):
     from quantum_compute_dft_b200.cuda_rt import DeviceArray
     from quantum_compute_dft_b200.solver import DFTSolverWrapper
@@ -304,3 +329,29 @@ def test_coulomb_through_c_abi(oracle, engine_lib):
         s.compute_coulomb(nao, d_e, d_d, d_j)
         s.synchronize()
         np.testing.assert_allclose(d_j.get(), oracle.coulomb(eri, dm), rtol=1e-12, atol=1e-11)
+
+
+def test_coulomb_exchange_single_pass(oracle, engine_lib):
+    """J and K from one pass over the ERI against the gemv (J) and the driver's einsum (K, dft.py:218).
+    The random ERI has the one symmetry the fused kernel relies on, (ij|kl) = (kl|ij) (the reference's
+    column-major gemv reads the transposed matrix), and no other, and D is non-symmetric, so that an index
+    mix-up cannot hide behind a symmetry."""
+    from quantum_compute_dft_b200.cuda_rt import DeviceArray
+    from quantum_compute_dft_b200.solver import DFTSolverWrapper
+    rng = np.random.default_rng(18)
+    s = DFTSolverWrapper(engine_lib, "B3LYP")
+    for nao in (1, 2, 7, 9, 16, 33, 40):
+        eri = rng.standard_normal((nao * nao, nao * nao))
+        eri = 0.5 * (eri + eri.T)
+        dm = rng.standard_normal((nao, nao))
+        d_e, d_d = DeviceArray.from_host(eri), DeviceArray.from_host(dm)
+        d_j, d_k = DeviceArray((nao, nao), zero=True), DeviceArray((nao, nao), zero=True)
+        s.compute_coulomb_exchange(nao, d_e, d_d, d_j, d_k)
+        s.synchronize()
+        np.testing.assert_allclose(d_j.get(), oracle.coulomb(eri, dm), rtol=1e-12, atol=1e-10)
+        np.testing.assert_allclose(d_k.get(), oracle.exchange(eri, dm), rtol=1e-12, atol=1e-10)
+        # bit-reproducible
+        d_k2 = DeviceArray((nao, nao), zero=True)
+        s.compute_coulomb_exchange(nao, d_e, d_d, d_j, d_k2)
+        s.synchronize()
+        np.testing.assert_array_equal(d_k.get(), d_k2.get())

@@ -30,4 +30,17 @@ for nao in [int(a) for a in sys.argv[1:]] or [7, 36, 152]:
     gbs = 8.0 * n2 * n2 / (ms * 1e-3) / 1e9
     print(json.dumps({"kernel": "coulomb_gemv", "nao": nao, "eri_bytes": 8 * n2 * n2, "ms": ms, "achieved_gbs": gbs,
                       "frac_of_hbm": gbs / peaks["hbm_gbs"]}), flush=True)
+    K = DeviceArray((nao, nao), zero=True)
+    for _ in range(3):
+        s.compute_coulomb_exchange(nao, eri, dm, J, K)
+    s.synchronize()
+    e0.record(s.stream)
+    for _ in range(reps):
+        s.compute_coulomb_exchange(nao, eri, dm, J, K)
+    e1.record(s.stream)
+    e1.synchronize()
+    ms = e0.elapsed_ms(e1) / reps
+    gbs = 8.0 * n2 * n2 / (ms * 1e-3) / 1e9
+    print(json.dumps({"kernel": "coulomb_exchange (J and K, one ERI pass)", "nao": nao, "eri_bytes": 8 * n2 * n2, "ms": ms,
+                      "achieved_gbs": gbs, "frac_of_hbm": gbs / peaks["hbm_gbs"]}), flush=True)
     eri.free()
