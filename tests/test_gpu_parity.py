@@ -355,3 +355,26 @@ def test_coulomb_exchange_single_pass(oracle, engine_lib):
         s.compute_coulomb_exchange(nao, d_e, d_d, d_j, d_k2)
         s.synchronize()
         np.testing.assert_array_equal(d_k.get(), d_k2.get())
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+def test_converged_scf_energy(oracle, engine_lib, functional):
+    """The north_star's third criterion: the CONVERGED SCF total energy within 1e-7 Ha.  The reference's whole
+    per-iteration sequence (dft.py:199-248: upload D, J, E_xc/V_xc, K for B3LYP, Fock build, eigh, energy,
+    convergence test) runs on an asymmetric H4 chain with closed-form s-type integrals, once with every device
+    step through this library's C ABI (DFT_EvalAO, DFT_ComputeCoulombExchange, DFT_ComputeXC) and once with the
+    CPU oracle."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from scf_backends import OracleBackend, h_chain
+    from quantum_compute_dft_b200 import molgrid as M, scf
+    from quantum_compute_dft_b200.solver import DFTSolverWrapper
+    mol, basis = h_chain([0.0, 1.3, 3.1, 4.6])
+    S, H, eri, e_nuc = scf.s_integrals(mol, basis)
+    coords, weights, _ = M.make_grid(mol, scale=0.5)
+    e_o, dm_o, n_o, ok_o = scf.run_scf(S, H, e_nuc, mol.nocc, OracleBackend(oracle, functional, basis, coords, weights, eri), functional)
+    solver = DFTSolverWrapper(engine_lib, functional)
+    e_g, dm_g, n_g, ok_g = scf.run_scf(S, H, e_nuc, mol.nocc, scf.EngineBackend(solver, basis, coords, weights, eri), functional)
+    assert ok_o and ok_g and n_o == n_g
+    assert abs(e_g - e_o) <= 1e-7, (e_g, e_o)
+    np.testing.assert_allclose(dm_g, dm_o, rtol=0, atol=1e-7)
