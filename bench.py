@@ -33,25 +33,50 @@ UNIT = "Mgridpts/s"
 
 # --------------------------------------------------------------------------- helpers
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs.  NVML in-process (a query costs
+    microseconds); spawning nvidia-smi every 100 ms instead was seen to stall kernel launches for
+    milliseconds -- with K = 2 steps that doubled a 2.4 ms step.  nvidia-smi is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples = index, threading.Event(), []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES if the launcher set it
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        act = lambda bit: "Active" if r & bit else "Not Active"
+        return [str(sm), str(mx), act(n.nvmlClocksEventReasonHwSlowdown), act(n.nvmlClocksEventReasonHwThermalSlowdown),
+                act(n.nvmlClocksEventReasonSwThermalSlowdown), act(n.nvmlClocksEventReasonSwPowerCap)]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                p = [x.strip() for x in out.strip().split(",")]
-                if len(p) >= 6:
-                    self.samples.append(p)
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    p = [x.strip() for x in out.strip().split(",")]
+                    if len(p) >= 6:
+                        self.samples.append(p)
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.02 if self.nvml is not None else 0.25)
 
     def summary(self):
         if not self.samples:
@@ -60,7 +85,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peaks():
@@ -347,6 +372,9 @@ def main():
             "gpu_launches": int(solver.stat("launches")) * K,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
             "per_scf_iter_vxc_ms": ms_step, "e_xc": e_xc,
+            "ao_screening": {"density_ksteps_skipped_frac": solver.stat("skip_fraction"),
+                             "note": "share of the density kernel's 32x4 Phi fragments that are exact zeros and "
+                                     "skipped (rank 0); roofline.achieved stays quoted on the DENSE flop count"},
             "ao_eval": None if not ao_ms else {
                 "ms": ao_ms, "bytes_written": 8.0 * n_local * nao * P,
                 "achieved_gbs": 8.0 * n_local * nao * P / (ao_ms * 1e-3) / 1e9,

@@ -52,13 +52,16 @@ int DFT_CommDestroy(XCSolver* solver);
 //       "vxc_shape" 0|64|128|160 (tuning: output tile of the TMA V kernel; 0 = chosen from nao)
 //       "vxc_vk" 8|16 (tuning: grid rows per ring stage of the 128 x 128 V kernel)
 //       "ao_shape" 0|16|32 (tuning: grid points per block of DFT_EvalAO; 0 = chosen from the basis size)
+//       "zero_skip" 0|1 (AO screening inside the contraction kernels: k-steps whose operand fragment is
+//       exactly zero are skipped; results are unchanged; default 1)
 //       "tma_3d" 0|1 (tuning: 3-D tensor maps in the V kernel, one TMA load per plane and stage; default 1)
 //       "l2_prefetch" 0|1 (tuning: short-range L2 prefetch in the density kernel, default 0: measured no gain)
 //       "timing" 0|1 (record the per-kernel CUDA events behind DFT_GetStat, default 1)
 int DFT_SetOption(XCSolver* solver, const char* key, double value);
 // keys: "density_ms", "vxc_ms", "reduce_ms", "total_ms" (CUDA-event times of the last
 //       DFT_ComputeXC on the engine's stream), "launches" (kernels launched by the last call),
-//       "ao_ms" (kernel time of the last DFT_EvalAO),
+//       "ao_ms" (kernel time of the last DFT_EvalAO), "skip_fraction" (share of the density kernel's
+//       k-steps that were exact zeros and skipped in the last call: the AO-screening statistic),
 //       "path" (path actually taken), "workspace_bytes", "plans_built" (TMA launch plans encoded so
 //       far: a steady SCF loop over the same arrays builds exactly one).
 double DFT_GetStat(XCSolver* solver, const char* key);

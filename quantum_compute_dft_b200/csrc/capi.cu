@@ -47,7 +47,7 @@ CublasHandleWrapper::CublasHandleWrapper() {
 CublasHandleWrapper::~CublasHandleWrapper() {
     if (stream) cudaStreamSynchronize(stream);
     xc::free_tma_plan(this);
-    dsym.release(); rho.release(); coef.release(); epart.release(); vpart.release(); result.release(); scratch.release();
+    dsym.release(); counters.release(); rho.release(); coef.release(); epart.release(); vpart.release(); result.release(); scratch.release();
     if (h_scalar) cudaFreeHost(h_scalar);
     for (auto& e : ev)
         if (e) cudaEventDestroy(e);
@@ -110,7 +110,7 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
     if (ngrid == 0) {
         cudaMemsetAsync(p.vxc, 0, sizeof(double) * n2, ctx->stream);
         cudaMemsetAsync(p.d_exc, 0, sizeof(double), ctx->stream);
-        { XcStats z; z.plans_built = ctx->stats.plans_built; z.ao_ms = ctx->stats.ao_ms; ctx->stats = z; }
+        { XcStats z; z.plans_built = ctx->stats.plans_built; z.ao_ms = ctx->stats.ao_ms; z.skip_fraction = ctx->stats.skip_fraction; ctx->stats = z; }
     } else {
         bool use_tma = false;
         if (ctx->path == PATH_TMA) use_tma = xc::tma_compatible(p);
@@ -131,7 +131,19 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
         return ctx->failed ? nan : 0.0;
     }
     DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar, p.d_exc, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    const bool have_counters = ngrid > 0 && ctx->stats.path == PATH_TMA && ctx->counters.ptr;
+    if (have_counters)
+        DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar + 1, ctx->counters.ptr, 2 * sizeof(unsigned long long),
+                                            cudaMemcpyDeviceToHost, ctx->stream));
     DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (have_counters && !ctx->failed) {
+        unsigned long long c[2];
+        memcpy(c, ctx->h_scalar + 1, sizeof(c));
+        ctx->stats.skip_fraction = c[1] ? 1.0 - (double)c[0] / (double)c[1] : 0.0;
+        // adaptive: the zero-skipping V instance pays ~6 % on dense operands; use it only where the density
+        // kernel just skipped a real share of its k-steps (the decision takes effect with the next call)
+        ctx->vxc_skip_on = ctx->stats.skip_fraction >= 0.10;
+    }
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
     if (ctx->timing && ngrid > 0 && !ctx->failed) {
         cudaEventElapsedTime(&ctx->stats.density_ms, ctx->ev[0], ctx->ev[1]);
@@ -251,6 +263,7 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "timing")) { c->timing = value != 0.0; return 0; }
     if (!strcmp(key, "l2_prefetch")) { c->l2_prefetch = value != 0.0; return 0; }
     if (!strcmp(key, "ao_shape")) { c->ao_shape = (int)value; return 0; }
+    if (!strcmp(key, "zero_skip")) { c->zero_skip = value != 0.0; return 0; }
     if (!strcmp(key, "tma_3d")) { c->tma_3d = value != 0.0; return 0; }
     if (!strcmp(key, "vxc_shape")) { const int v = (int)value; if (v != 0 && v != 64 && v != 128 && v != 160) return 3; c->vxc_shape = v; return 0; }
     if (!strcmp(key, "vxc_vk")) { c->vxc_vk = value == 16.0 ? 16 : 8; return 0; }
@@ -268,6 +281,7 @@ double DFT_GetStat(XCSolver* solver, const char* key) {
     if (!strcmp(key, "ao_ms")) return c->stats.ao_ms;
     if (!strcmp(key, "launches")) return c->stats.launches;
     if (!strcmp(key, "plans_built")) return c->stats.plans_built;
+    if (!strcmp(key, "skip_fraction")) return c->stats.skip_fraction;
     if (!strcmp(key, "path")) return c->stats.path;
     if (!strcmp(key, "workspace_bytes")) return (double)c->workspace_bytes();
     if (!strcmp(key, "nranks")) return c->nranks;

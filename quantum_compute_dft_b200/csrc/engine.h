@@ -36,6 +36,7 @@ struct XcStats {
     float ao_ms = 0.f;    // last DFT_EvalAO kernel
     int launches = 0;
     int path = 0;
+    double skip_fraction = 0.0;  // TMA density kernel: fraction of k-steps skipped as exact zeros in the last call
     int plans_built = 0;  // TMA path: launch plans (tensor maps, geometry) encoded so far; a steady SCF loop builds one
 };
 
@@ -50,6 +51,8 @@ struct CublasHandleWrapper {
     int path = PATH_AUTO;
     bool timing = true;
     bool l2_prefetch = false;      // TMA density kernel: short-range L2 prefetch of A tiles and epilogue pieces (measured: no gain)
+    bool vxc_skip_on = true;       // (adaptive) the zero-skipping V instance is used while the density kernel finds zeros
+    bool zero_skip = true;         // TMA kernels: skip k-steps whose operand fragment is all zero (exact: adds nothing)
     bool tma_3d = true;            // TMA V kernel: one 3-D TMA load per plane and stage instead of one per 16-column block
     int ao_shape = 0;              // DFT_EvalAO block shape: 0 = auto, 16 (points, 8 warps) | 32 (points, 16 warps)
     int vxc_shape = 0;             // TMA V kernel output tile: 0 = auto, 64 | 128 | 160 (= 160 x 80)
@@ -57,6 +60,7 @@ struct CublasHandleWrapper {
 
     // workspaces
     DeviceBuffer dsym;     // symmetrised, zero-padded density matrix
+    DeviceBuffer counters; // AO-screening statistics of the density kernel
     DeviceBuffer rho;      // per-point partial (rho, grad rho / 2) row sums of the density kernel's two warp columns
     DeviceBuffer coef;     // per-point (a,bx,by,bz)
     DeviceBuffer epart;    // per-CTA partial E_xc

@@ -75,7 +75,8 @@ struct DensityParams {
     CUtensorMap map_e[2][4];  // the four planes, box 16 x 64 (epilogue pieces)
     CUtensorMap map_d;        // [2][NP][KP] symmetrised density (plain, shifted), box 16 x NT
     SubProblem sub[2];
-    int nsub, nblocks, ntiles, nk, NP, l2_prefetch, coef_rows;
+    int nsub, nblocks, ntiles, nk, NP, l2_prefetch, coef_rows, zero_skip;
+    unsigned long long* counters;  // [2]: k-steps executed, k-steps total (AO screening statistics)
     double* rho;       // [2 warp columns][coef_rows][4]: partial (rho, drho/2) row sums, summed by the point kernel
     long long* phase;  // DFT_PHASE_TIMING builds: [CTA][warp][4] cycles in {k-loop, piece wait, piece math, block tail}
 };
@@ -93,7 +94,7 @@ struct VxcParams {
     SubProblem sub[2];
     int nfull[2];            // whole 16-column blocks of each sub-problem
     int rem[2];              // columns in the partial block (0: none)
-    int use3d;
+    int use3d, zero_skip;
     int nsub, tiles_m, tiles_n, lda_half, rows_per_slice, slices_per_sub, ldv, mpv;
     const double* coef;
     double* vpart;
@@ -294,6 +295,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             eoff[e][sx] = (uint32_t)(rho * 128 + ((((4 * sx + (nc >> 1)) ^ rho) & 7) << 4) + ((nc & 1) << 3));
     }
     const int prow0 = wm * 32;  // this warp's rows inside a piece
+    const bool no_skip = P.zero_skip == 0;
 
     // group 1 starts half a column-tile period late (only worth it when there are several blocks to do)
     if (grp == 1 && nblocks > 8 * (int)gridDim.x) {
@@ -302,6 +304,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
     }
 
     uint32_t it = 0;
+    unsigned int n_ks_done = 0, n_ks_total = 0;
 #ifdef DFT_PHASE_TIMING
     long long t_k = 0, t_w = 0, t_m = 0, t_t = 0, t0 = clock64(), t1;
     int n_iv = 0;
@@ -330,22 +333,40 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             ++n_iv;
 #endif
 
+            n_ks_total += 4 * nk;
             for (int kc = 0; kc < nk; ++kc, ++it) {
                 const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
                 tma::mbar_wait(&full[s], ph);
                 const uint32_t a_base = ring_u32 + s * L::STAGE_BYTES + a_row;
                 const uint32_t b_base = ring_u32 + s * L::STAGE_BYTES + L::A_BYTES + b_row;
+                // AO screening at the tensor-core tile level: far from an atom its AOs are EXACT zeros (the
+                // evaluator drops primitives beyond the cutoff), so a k-step whose 32 x 4 Phi fragment is all
+                // zero adds nothing to C and its 32 DMMAs (and B loads) are branched around -- a warp-uniform
+                // vote, no mask to build or keep valid.  (Predicating the DMMAs off instead does NOT help: a
+                // predicated-off DMMA still pays its statically scheduled issue stall.)  The four warps of a
+                // group see the same AO columns for neighbouring points, so they skip together; the next
+                // k-step's A fragments are in flight meanwhile.
+                double a[2][4];
+#pragma unroll
+                for (int mf = 0; mf < 4; ++mf) a[0][mf] = lds_f64(a_base + mf * 1024 + koff_a[0]);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    double a[4], bf[NF2];
+                    const int cur = ks & 1;
+                    if (ks < 3) {
 #pragma unroll
-                    for (int mf = 0; mf < 4; ++mf) a[mf] = lds_f64(a_base + mf * 1024 + koff_a[ks]);
+                        for (int mf = 0; mf < 4; ++mf) a[cur ^ 1][mf] = lds_f64(a_base + mf * 1024 + koff_a[ks + 1]);
+                    }
+                    const bool nz = ((a[cur][0] != 0.0) | (a[cur][1] != 0.0)) | ((a[cur][2] != 0.0) | (a[cur][3] != 0.0));
+                    if (__any_sync(0xffffffffu, nz | no_skip)) {
+                        double bf[NF2];
 #pragma unroll
-                    for (int nf = 0; nf < NF2; ++nf) bf[nf] = lds_f64(b_base + nf * 1024 + koff_b[ks]);
+                        for (int nf = 0; nf < NF2; ++nf) bf[nf] = lds_f64(b_base + nf * 1024 + koff_b[ks]);
 #pragma unroll
-                    for (int mf = 0; mf < 4; ++mf)
+                        for (int mf = 0; mf < 4; ++mf)
 #pragma unroll
-                        for (int nf = 0; nf < NF2; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
+                            for (int nf = 0; nf < NF2; ++nf) dmma::mma8x8x4(acc[mf][nf], a[cur][mf], bf[nf]);
+                        ++n_ks_done;
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) tma::mbar_arrive(&empty[s]);
@@ -416,6 +437,10 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             }
         }
         PHASE_MARK(t_t);
+    }
+    if (lane == 0 && P.counters) {
+        atomicAdd(&P.counters[0], (unsigned long long)n_ks_done);
+        atomicAdd(&P.counters[1], (unsigned long long)n_ks_total);
     }
 #ifdef DFT_PHASE_TIMING
     if (lane == 0 && P.phase) {
@@ -505,7 +530,7 @@ struct VxcCfg {
     static_assert(TOTAL <= 232448, "shared memory");
 };
 
-template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES>
+template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES, bool SKIP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     using L = VxcCfg<MF, NFN, WM, WN, NPL, VK, STAGES>;
@@ -530,12 +555,12 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         tn = blockIdx.x % P.tiles_n;
     }
     const int m0 = tm * L::MT, n0 = tn * L::NT_;
-    // grid slice of this CTA: rows [jbeg, jend) of sub-problem si
+    // grid slice of this CTA: chunks sl, sl + nsl, sl + 2 nsl, .. (of VK rows) of sub-problem si, dealt
+    // round-robin so that every slice of a tile sees the same mix of dense and (skipped) zero regions
     const int si = blockIdx.y / P.slices_per_sub;
     const int sl = blockIdx.y % P.slices_per_sub;
-    const int jbeg = sl * P.rows_per_slice;
-    const int jend = min(P.sub[si].rows, jbeg + P.rows_per_slice);
-    const int nchunks = jend > jbeg ? (jend - jbeg + VK - 1) / VK : 0;
+    const int total_chunks = (P.sub[si].rows + VK - 1) / VK;
+    const int nchunks = total_chunks > sl ? (total_chunks - sl + P.slices_per_sub - 1) / P.slices_per_sub : 0;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -567,7 +592,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
             long long t_w = 0, t_c = 0, t_start = clock64(), t0 = t_start, t1;
 #endif
             for (int c = 0; c < nchunks; ++c) {
-                const int j0 = jbeg + c * VK;
+                const int j0 = (sl + c * P.slices_per_sub) * VK;
                 const uint32_t s = c % STAGES, ph = (c / STAGES) & 1u;
 #ifdef DFT_PHASE_TIMING
                 t1 = clock64(); t_c += t1 - t0; t0 = t1;
@@ -621,6 +646,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
 #pragma unroll
         for (int nf = 0; nf < NFN; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
 
+    const bool no_skip = P.zero_skip == 0;
     // Fragment addressing.  A DMMA k-step ks contracts 4 grid rows; lane (q, qcol) supplies row
     // krow(ks, qcol) -- rows {0,2,4,6} / {1,3,5,7} of an 8-row group, so that with the 128-byte swizzle
     // the 16 lanes of a load phase hit 16 distinct bank pairs -- and column (8-column group G) * 8 + q.
@@ -670,14 +696,29 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
                 }
                 a[mf] = v;
             }
+            // AO screening at the tile level: if this warp's B fragment of the k-step (its MF x 8 columns x 4 grid
+            // rows) is all zero -- AOs far from the points are exact zeros, zero-weight points have zero
+            // coefficients -- the k-step adds nothing to this warp's rows of M: skip its Phi loads and DMMAs.
+            // (The eight warps share the ring, so a warp that skips mostly waits for the one that cannot: the
+            // gain here is small, unlike in the density kernel where a group's warps skip together.)
+            // SKIP = false is the branch-free instance (ptxas interleaves the next k-step's loads with this one's
+            // DMMAs, ~6 % faster on dense operands); the host picks it when the density kernel of the previous
+            // call found (almost) nothing to skip.
+            bool nz = !SKIP;
+            if (SKIP) {
 #pragma unroll
-            for (int nf = 0; nf < NFN; ++nf)
-                bf[nf] = lds_f64(sb + ((nf & 1) ? b_odd[ks] + (uint32_t)(((nf - 1) / 2) * L::BOXB)
-                                                : b_even[ks] + (uint32_t)((nf / 2) * L::BOXB)));
+                for (int mf = 0; mf < MF; ++mf) nz |= a[mf] != 0.0;
+            }
+            if (!SKIP || __any_sync(0xffffffffu, nz | no_skip)) {
 #pragma unroll
-            for (int mf = 0; mf < MF; ++mf)
+                for (int nf = 0; nf < NFN; ++nf)
+                    bf[nf] = lds_f64(sb + ((nf & 1) ? b_odd[ks] + (uint32_t)(((nf - 1) / 2) * L::BOXB)
+                                                    : b_even[ks] + (uint32_t)((nf / 2) * L::BOXB)));
 #pragma unroll
-                for (int nf = 0; nf < NFN; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
+                for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+                    for (int nf = 0; nf < NFN; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
+            }
         }
         __syncwarp();
         if (lane == 0) tma::mbar_arrive(&empty[s]);
@@ -872,7 +913,7 @@ static Geometry make_geometry(int ngrid, int nao) {
 // addresses, so a plan stays valid when the caller rewrites the CONTENTS of its arrays.
 struct PlanKey {
     Problem prob;
-    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk;
+    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on;
     const void *dsym, *coef, *epart, *vpart, *rho;  // engine workspaces (grow-only: may move when they grow)
 };
 
@@ -921,7 +962,9 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
     dp.nsub = g.nsub;
     dp.nblocks = g.nblocks; dp.ntiles = ntiles; dp.nk = KP / 16; dp.NP = NP;
     dp.l2_prefetch = ctx->l2_prefetch ? 1 : 0;
+    dp.zero_skip = ctx->zero_skip ? 1 : 0;
     dp.coef_rows = g.coef_rows; dp.rho = rho;
+    dp.counters = reinterpret_cast<unsigned long long*>(ctx->counters.ensure(2 * sizeof(unsigned long long), &ctx->failed));
 
     PointParams& pp = pl.pp;
     memset(&pp, 0, sizeof(pp));
@@ -943,7 +986,7 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
 }
 
 // ---- V plan: output tile (WM MF 8) x (WN NFN 8)
-template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES>
+template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES, bool SKIP>
 static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry& g, int nsm, const double* coef, Plan& pl) {
     using VL = VxcCfg<MF, NFN, WM, WN, NPL, VK, STAGES>;
     const int ngrid = p.ngrid, nao = p.nao;
@@ -987,7 +1030,8 @@ static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry&
         }
     }
     if (!ok) { ctx->failed = true; return; }
-    vp.use3d = ok3 ? 1 : 0;  // (a driver that rejects the 3-D form leaves the per-block 2-D loads)
+    vp.use3d = ok3 ? 1 : 0;
+    vp.zero_skip = ctx->zero_skip ? 1 : 0;  // (a driver that rejects the 3-D form leaves the per-block 2-D loads)
     vp.sub[0] = g.sub[0]; vp.sub[1] = g.sub[1];
     vp.nsub = g.nsub; vp.tiles_m = tiles_m; vp.tiles_n = tiles_n; vp.lda_half = lda_half;
     vp.rows_per_slice = rows_per_slice; vp.slices_per_sub = nsl; vp.ldv = ldv; vp.mpv = mpv;
@@ -999,7 +1043,7 @@ static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry&
     }
 #endif
 
-    auto vk = vxc_tma_kernel<MF, NFN, WM, WN, NPL, VK, STAGES>;
+    auto vk = vxc_tma_kernel<MF, NFN, WM, WN, NPL, VK, STAGES, SKIP>;
     DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, VL::TOTAL));
     pl.vfunc = reinterpret_cast<const void*>(vk);
     pl.vgrid = dim3(tiles, nsl * g.nsub); pl.vsmem = VL::TOTAL;
@@ -1036,14 +1080,19 @@ static void build_plan(CublasHandleWrapper* ctx, const Problem& p, int nsm, Plan
     const double cost160 = 1.15 * (double)pad(n, 160) * pad(n, 80);
     int shape = ctx->vxc_shape;
     if (shape == 0) shape = n <= 64 ? 64 : (cost160 < cost128 ? 160 : 128);
+    // zero-skipping V instance only where the density kernel of the previous call actually skipped work
+    const bool vskip = ctx->zero_skip && ctx->vxc_skip_on;
+#define DFT_PLAN_V(...) do { if (vskip) plan_vxc<__VA_ARGS__, true>(ctx, p, g, nsm, coef, pl); \
+                             else plan_vxc<__VA_ARGS__, false>(ctx, p, g, nsm, coef, pl); } while (0)
     if (shape == 64) {
-        plan_vxc<1, 8, 8, 1, NPL, 16, 4>(ctx, p, g, nsm, coef, pl);
+        DFT_PLAN_V(1, 8, 8, 1, NPL, 16, 4);
     } else if (shape == 160) {
-        plan_vxc<5, 5, 4, 2, NPL, 16, 2>(ctx, p, g, nsm, coef, pl);
+        DFT_PLAN_V(5, 5, 4, 2, NPL, 16, 2);
     } else {
-        if (ctx->vxc_vk == 16) plan_vxc<2, 16, 8, 1, NPL, 16, 2>(ctx, p, g, nsm, coef, pl);
-        else plan_vxc<2, 16, 8, 1, NPL, 8, 5>(ctx, p, g, nsm, coef, pl);
+        if (ctx->vxc_vk == 16) DFT_PLAN_V(2, 16, 8, 1, NPL, 16, 2);
+        else DFT_PLAN_V(2, 16, 8, 1, NPL, 8, 5);
     }
+#undef DFT_PLAN_V
 }
 
 static PlanKey make_key(const CublasHandleWrapper* ctx, const Problem& p) {
@@ -1053,7 +1102,7 @@ static PlanKey make_key(const CublasHandleWrapper* ctx, const Problem& p) {
     k.prob.dm = p.dm; k.prob.ao = p.ao; k.prob.gx = p.gx; k.prob.gy = p.gy; k.prob.gz = p.gz; k.prob.w = p.w;
     k.prob.vxc = p.vxc; k.prob.d_exc = p.d_exc;
     k.exact = ctx->exact_functionals; k.l2_prefetch = ctx->l2_prefetch; k.tma_3d = ctx->tma_3d;
-    k.vxc_shape = ctx->vxc_shape; k.vxc_vk = ctx->vxc_vk;
+    k.vxc_shape = ctx->vxc_shape; k.vxc_vk = ctx->vxc_vk; k.zero_skip = ctx->zero_skip; k.vxc_skip_on = ctx->vxc_skip_on;
     k.dsym = ctx->dsym.ptr; k.coef = ctx->coef.ptr; k.epart = ctx->epart.ptr; k.vpart = ctx->vpart.ptr;
     k.rho = ctx->rho.ptr;
     return k;
@@ -1064,6 +1113,7 @@ static void run_plan(CublasHandleWrapper* ctx, const Problem& p, Plan& pl) {
     if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
     symmetrize_pad_tma_kernel<<<dim3((pl.KP + 127) / 128, pl.NP * pl.nsub), 128, 0, st>>>(p.nao, pl.KP, pl.NP, pl.nsub, p.dm,
                                                                                          pl.dsym);
+    if (pl.dp.counters) cudaMemsetAsync(pl.dp.counters, 0, 2 * sizeof(unsigned long long), st);
     void* dargs[1] = {&pl.dp};
     DFT_CUDA_CHECK(ctx, cudaLaunchKernel(pl.dfunc, dim3(pl.dgrid), dim3(NTHREADS), dargs, (size_t)pl.dsmem, st));
     xc_point_kernel<<<pl.pgrid, POINT_THREADS, 0, st>>>(pl.pp);

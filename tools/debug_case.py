@@ -14,7 +14,7 @@ rng = np.random.default_rng(seed)
 dm, ao, w, grad = _random_case(rng, ngrid, nao)
 res = {}
 variants = (("generic", {"path": 1}), ("tma", {}), ("tma-again", {}), ("vk16", {"vxc_vk": 16}), ("v64", {"vxc_shape": 64}),
-            ("v128", {"vxc_shape": 128}), ("v160", {"vxc_shape": 160}), ("pf", {"l2_prefetch": 1}), ("no3d", {"tma_3d": 0}))
+            ("v128", {"vxc_shape": 128}), ("v160", {"vxc_shape": 160}), ("noskip", {"zero_skip": 0}), ("no3d", {"tma_3d": 0}))
 for name, opt in variants:
     e, v, s = _run_engine(DEFAULT_LIB, fn, dm, ao, w, grad, opt)
     res[name] = (e, v)

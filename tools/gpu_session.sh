@@ -21,7 +21,7 @@ print('DMMA TFLOP/s', l.DFT_MicrobenchDMMA(8192)); print('DFMA TFLOP/s', l.DFT_M
     ncu:*)   W=${what#ncu:}; CMD="python bench.py --workload $W --steps 2 --warmup 3 --no-cpu-baseline"
              timeout 600 $CMD > $OUT/ncu_plain_$W.log 2>&1 && \
              timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$W.csv $CMD > $OUT/ncu_list_$W.log 2>&1 && \
-             timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'density_tma|vxc_tma|density_kernel|vxc_kernel|eval_kernel' -s 4 -c 2 -o $OUT/prof_$W $CMD > $OUT/ncu_full_$W.log 2>&1
+             timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'density_tma|vxc_tma|xc_point|eval_kernel' -c 7 -o $OUT/prof_$W $CMD > $OUT/ncu_full_$W.log 2>&1
              echo "ncu $W rc=$?" | tee -a $OUT/summary.txt; tail -3 $OUT/ncu_full_$W.log ;;
     *) echo "unknown step $what" ;;
   esac

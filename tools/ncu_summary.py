@@ -27,7 +27,8 @@ def to_bytes(v, unit):
 fam = {}
 for r in rows[2:]:
     name = r[ix["Kernel Name"]]
-    key = "density" if "density" in name else "vxc" if "vxc" in name else "ao_eval" if "eval_kernel" in name else name[:40]
+    key = ("density" if "density" in name else "vxc" if "vxc_tma" in name else "point" if "xc_point" in name
+           else "ao_eval" if "eval_kernel" in name else name[:40])
     rd = to_bytes(num(r, "dram__bytes_read.sum"), units[ix["dram__bytes_read.sum"]])
     wr = to_bytes(num(r, "dram__bytes_write.sum"), units[ix["dram__bytes_write.sum"]])
     stalls = {}
