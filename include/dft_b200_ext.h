@@ -54,6 +54,8 @@ int DFT_CommDestroy(XCSolver* solver);
 //       "ao_shape" 0|16|32 (tuning: grid points per block of DFT_EvalAO; 0 = chosen from the basis size)
 //       "zero_skip" 0|1 (AO screening inside the contraction kernels: k-steps whose operand fragment is
 //       exactly zero are skipped; results are unchanged; default 1)
+//       "vxc_skip" -1|0|1 (the zero-skipping instance of the V kernel: -1 = adaptive, used while the density
+//       kernel of the previous call skipped >= 10 % of its k-steps; default -1)
 //       "tma_3d" 0|1 (tuning: 3-D tensor maps in the V kernel, one TMA load per plane and stage; default 1)
 //       "l2_prefetch" 0|1 (tuning: short-range L2 prefetch in the density kernel, default 0: measured no gain)
 //       "timing" 0|1 (record the per-kernel CUDA events behind DFT_GetStat, default 1)

@@ -142,7 +142,7 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
         ctx->stats.skip_fraction = c[1] ? 1.0 - (double)c[0] / (double)c[1] : 0.0;
         // adaptive: the zero-skipping V instance pays ~6 % on dense operands; use it only where the density
         // kernel just skipped a real share of its k-steps (the decision takes effect with the next call)
-        ctx->vxc_skip_on = ctx->stats.skip_fraction >= 0.10;
+        if (ctx->vxc_skip < 0) ctx->vxc_skip_on = ctx->stats.skip_fraction >= 0.10;
     }
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
     if (ctx->timing && ngrid > 0 && !ctx->failed) {
@@ -263,6 +263,7 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "timing")) { c->timing = value != 0.0; return 0; }
     if (!strcmp(key, "l2_prefetch")) { c->l2_prefetch = value != 0.0; return 0; }
     if (!strcmp(key, "ao_shape")) { c->ao_shape = (int)value; return 0; }
+    if (!strcmp(key, "vxc_skip")) { c->vxc_skip = (int)value; if (c->vxc_skip >= 0) c->vxc_skip_on = c->vxc_skip != 0; return 0; }
     if (!strcmp(key, "zero_skip")) { c->zero_skip = value != 0.0; return 0; }
     if (!strcmp(key, "tma_3d")) { c->tma_3d = value != 0.0; return 0; }
     if (!strcmp(key, "vxc_shape")) { const int v = (int)value; if (v != 0 && v != 64 && v != 128 && v != 160) return 3; c->vxc_shape = v; return 0; }
