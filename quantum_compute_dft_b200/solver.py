@@ -187,6 +187,21 @@ class DFTSolverWrapper:
         self.lib.DFT_CommDestroy(self.solver)
 
 
+def shard_indices(ngrid, rank, nranks, block=8192):
+    """Grid points of `rank` when the grid is dealt to the ranks in INTERLEAVED blocks of `block` points
+    (block b goes to rank b mod nranks).  Grid points are independent, so any partition is valid (SURVEY.md
+    8e); with AO screening the cost of a point depends on how many atoms are near it, and a contiguous
+    range (one end of the molecule) would not be representative: interleaving keeps the ranks balanced.
+    `block` is even, so every shard keeps an even number of leading points per block (16-byte aligned AO
+    rows for odd nao).  Returns a sorted int64 index array."""
+    if nranks <= 1:
+        return np.arange(ngrid, dtype=np.int64)
+    nblk = (ngrid + block - 1) // block
+    mine = np.arange(rank, nblk, nranks, dtype=np.int64)
+    idx = (mine[:, None] * block + np.arange(block, dtype=np.int64)[None, :]).ravel()
+    return idx[idx < ngrid]
+
+
 def shard_bounds(ngrid, rank, nranks, align=2):
     """Contiguous grid-point range of `rank`: [r*ngrid/N, (r+1)*ngrid/N) rounded to
     `align` points so every shard starts on a 16-byte boundary of the AO rows."""

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import molgrid
 from .cuda_rt import DeviceArray
-from .solver import DFTSolverWrapper, shard_bounds
+from .solver import DFTSolverWrapper, shard_bounds, shard_indices
 
 FUNCTIONAL_TYPE = {"LDA": 0, "GGA": 1, "B3LYP": 2}
 
@@ -73,12 +73,21 @@ class DeviceProblem:
 
 
 def device_problem(hp, solver, rank=0, nranks=1):
-    """Upload this rank's grid slice and evaluate its AO planes on the GPU."""
-    lo, hi = shard_bounds(hp.ngrid, rank, nranks)
-    n = hi - lo
+    """Upload this rank's share of the grid (interleaved blocks, solver.shard_indices) and evaluate its AO
+    planes on the GPU."""
+    idx = shard_indices(hp.ngrid, rank, nranks)
+    n = int(idx.size)
     nao = hp.nao
-    d_coords = DeviceArray.from_host(hp.coords[lo:hi])
-    d_w = DeviceArray.from_host(hp.weights[lo:hi])
+    if nranks > 1 and n % 2 == 1 and nao % 2 == 1:
+        # odd x odd would leave the TMA path (DESIGN.md 5.4): give the last point a zero-weight twin
+        idx = np.concatenate([idx, idx[-1:]])
+        n += 1
+        w_local = hp.weights[idx].copy()
+        w_local[-1] = 0.0
+    else:
+        w_local = hp.weights[idx]
+    d_coords = DeviceArray.from_host(np.ascontiguousarray(hp.coords[idx]))
+    d_w = DeviceArray.from_host(np.ascontiguousarray(w_local))
     d_dm = DeviceArray.from_host(hp.dm)
     d_ao = DeviceArray((n, nao))
     d_grad = DeviceArray((3, n, nao)) if hp.functional != "LDA" else None
