@@ -652,14 +652,23 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     // the 16 lanes of a load phase hit 16 distinct bank pairs -- and column (8-column group G) * 8 + q.
     // Group G lives in box G/2 at columns 8 (G & 1) + q, whose swizzled offset is c0 ^ ((G & 1) << 6).
     const int ga0 = wm * MF, gb0 = wn * NFN;  // first 8-column group of this warp in the M / N tile
-    uint32_t a_even[KS], a_odd[KS], b_even[KS], b_odd[KS], c_off[KS];
+    // M-side 8-column group of fragment mf.  Normally consecutive; in the zero-skipping 8 x 1 instance warp w
+    // takes groups w and 15 - w instead of 2w and 2w + 1: two halves of one 16-column box (one or two atoms)
+    // are zero or non-zero together, while groups from opposite ends of the tile average out, which evens the
+    // work of the eight warps that share the ring.
+    constexpr bool MIRROR = SKIP && WM == 8 && WN == 1 && MF == 2;
+    auto mgroup = [&](int mf) { return MIRROR ? (mf == 0 ? wm : 15 - wm) : ga0 + mf; };
+    uint32_t a_off[KS][MF], b_even[KS], b_odd[KS], c_off[KS];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
         const int row = (VK == 16 ? 8 * (ks >> 1) : 0) + 2 * qcol + (ks & 1);
         const uint32_t c0 = (uint32_t)(row * 128 + ((((q >> 1) ^ row) & 7) << 4) + ((q & 1) << 3));
-        const uint32_t pa = (uint32_t)(ga0 & 1), pb = (uint32_t)(gb0 & 1);
-        a_even[ks] = (uint32_t)((ga0 >> 1) * L::BOXB) + (c0 ^ (pa << 6));
-        a_odd[ks] = (uint32_t)(((ga0 >> 1) + (int)pa) * L::BOXB) + (c0 ^ ((pa ^ 1u) << 6));
+        const uint32_t pb = (uint32_t)(gb0 & 1);
+#pragma unroll
+        for (int mf = 0; mf < MF; ++mf) {
+            const int G = mgroup(mf);
+            a_off[ks][mf] = (uint32_t)((G >> 1) * L::BOXB) + (c0 ^ ((uint32_t)(G & 1) << 6));
+        }
         b_even[ks] = (uint32_t)(L::N_OFF + (gb0 >> 1) * L::BOXB) + (c0 ^ (pb << 6));
         b_odd[ks] = (uint32_t)(L::N_OFF + ((gb0 >> 1) + (int)pb) * L::BOXB) + (c0 ^ ((pb ^ 1u) << 6));
         c_off[ks] = (uint32_t)(L::COEF_OFF + row * 32);
@@ -686,8 +695,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
             double a[MF], bf[NFN];
 #pragma unroll
             for (int mf = 0; mf < MF; ++mf) {
-                const uint32_t ad = sb + ((mf & 1) ? a_odd[ks] + (uint32_t)(((mf - 1) / 2) * L::BOXB)
-                                                    : a_even[ks] + (uint32_t)((mf / 2) * L::BOXB));
+                const uint32_t ad = sb + a_off[ks][mf];
                 double v = ca.x * lds_f64(ad);
                 if (NPL == 4) {
                     v = fma(ca.y, lds_f64(ad + L::PLANE_BYTES), v);
@@ -704,12 +712,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
             // SKIP = false is the branch-free instance (ptxas interleaves the next k-step's loads with this one's
             // DMMAs, ~6 % faster on dense operands); the host picks it when the density kernel of the previous
             // call found (almost) nothing to skip.
-            bool nz = !SKIP;
-            if (SKIP) {
-#pragma unroll
-                for (int mf = 0; mf < MF; ++mf) nz |= a[mf] != 0.0;
-            }
-            if (!SKIP || __any_sync(0xffffffffu, nz | no_skip)) {
+            if (!SKIP) {
 #pragma unroll
                 for (int nf = 0; nf < NFN; ++nf)
                     bf[nf] = lds_f64(sb + ((nf & 1) ? b_odd[ks] + (uint32_t)(((nf - 1) / 2) * L::BOXB)
@@ -718,6 +721,24 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
                 for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
                     for (int nf = 0; nf < NFN; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
+            } else {
+                // one vote per 8-column fragment: its NFN DMMAs are skipped when it is all zero
+                unsigned live = 0;
+#pragma unroll
+                for (int mf = 0; mf < MF; ++mf) live |= (__any_sync(0xffffffffu, (a[mf] != 0.0) | no_skip) ? 1u : 0u) << mf;
+                if (live) {
+#pragma unroll
+                    for (int nf = 0; nf < NFN; ++nf)
+                        bf[nf] = lds_f64(sb + ((nf & 1) ? b_odd[ks] + (uint32_t)(((nf - 1) / 2) * L::BOXB)
+                                                        : b_even[ks] + (uint32_t)((nf / 2) * L::BOXB)));
+#pragma unroll
+                    for (int mf = 0; mf < MF; ++mf) {
+                        if (live & (1u << mf)) {
+#pragma unroll
+                            for (int nf = 0; nf < NFN; ++nf) dmma::mma8x8x4(acc[mf][nf], a[mf], bf[nf]);
+                        }
+                    }
+                }
             }
         }
         __syncwarp();
@@ -732,7 +753,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
         for (int nf = 0; nf < NFN; ++nf) {
-            const int r = m0 + (ga0 + mf) * 8 + q;
+            const int r = m0 + mgroup(mf) * 8 + q;
             const int cc = n0 + (gb0 + nf) * 8 + 2 * qcol;
             *reinterpret_cast<double2*>(out + (size_t)r * P.ldv + cc) = make_double2(acc[mf][nf][0], acc[mf][nf][1]);
         }
