@@ -79,6 +79,17 @@ int DFT_ComputeCoulombExchange(XCSolver* solver, int nao, unsigned long long d_e
                                unsigned long long d_dm_ptr, unsigned long long d_J_ptr,
                                unsigned long long d_K_ptr);
 
+// ---- device-resident Fock assembly (host<->device chatter) ---------------
+// The reference's driver downloads J, V_xc and K every iteration and assembles the Fock matrix on the
+// host (dft.py:210-223, :230-236).  With these two calls only F travels (for the host eigh):
+//   DFT_BuildFock:   d_F = Hcore + J + 1/2 (V_raw + V_raw^T) - 1/2 c_hf K     (d_K_ptr may be 0)
+//   DFT_SCFEnergies: out3 = { sum D o Hcore, 1/2 sum D o J, -1/4 c_hf sum D o K }  (host array, blocking)
+int DFT_BuildFock(XCSolver* solver, int nao, unsigned long long d_hcore_ptr, unsigned long long d_J_ptr,
+                  unsigned long long d_vxc_ptr, unsigned long long d_K_ptr, double c_hf,
+                  unsigned long long d_F_ptr);
+int DFT_SCFEnergies(XCSolver* solver, int nao, unsigned long long d_dm_ptr, unsigned long long d_hcore_ptr,
+                    unsigned long long d_J_ptr, unsigned long long d_K_ptr, double c_hf, double* out3);
+
 // ---- convenience for callers that keep V_xc/E_xc on the device (no host sync) --------------
 // Same as DFT_ComputeXC but writes E_xc to the device double at d_exc_ptr, does not block the
 // host, and returns 0.  Work is enqueued on the engine stream; DFT_StreamSynchronize waits.

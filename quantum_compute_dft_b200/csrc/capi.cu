@@ -230,6 +230,27 @@ int DFT_ComputeCoulombExchange(XCSolver* solver, int nao, unsigned long long d_e
     return ctx->failed ? 2 : 0;
 }
 
+int DFT_BuildFock(XCSolver* solver, int nao, unsigned long long d_hcore_ptr, unsigned long long d_J_ptr,
+                  unsigned long long d_vxc_ptr, unsigned long long d_K_ptr, double c_hf, unsigned long long d_F_ptr) {
+    if (!solver || nao <= 0 || !d_hcore_ptr || !d_J_ptr || !d_vxc_ptr || !d_F_ptr) return 1;
+    CublasHandleWrapper* ctx = solver->context();
+    ctx->failed = false;
+    xc::build_fock(ctx, nao, reinterpret_cast<const double*>(d_hcore_ptr), reinterpret_cast<const double*>(d_J_ptr),
+                   reinterpret_cast<const double*>(d_vxc_ptr), reinterpret_cast<const double*>(d_K_ptr), c_hf,
+                   reinterpret_cast<double*>(d_F_ptr));
+    return ctx->failed ? 2 : 0;
+}
+
+int DFT_SCFEnergies(XCSolver* solver, int nao, unsigned long long d_dm_ptr, unsigned long long d_hcore_ptr,
+                    unsigned long long d_J_ptr, unsigned long long d_K_ptr, double c_hf, double* out3) {
+    if (!solver || nao <= 0 || !d_dm_ptr || !d_hcore_ptr || !d_J_ptr || !out3) return 1;
+    CublasHandleWrapper* ctx = solver->context();
+    ctx->failed = false;
+    xc::scf_energies(ctx, nao, reinterpret_cast<const double*>(d_dm_ptr), reinterpret_cast<const double*>(d_hcore_ptr),
+                     reinterpret_cast<const double*>(d_J_ptr), reinterpret_cast<const double*>(d_K_ptr), c_hf, out3);
+    return ctx->failed ? 2 : 0;
+}
+
 int DFT_ComputeXCAsync(XCSolver* solver, int ngrid, int nao, unsigned long long d_dm_ptr,
                        unsigned long long d_ao_ptr, unsigned long long d_ao_grad_ptr,
                        unsigned long long d_weights_ptr, unsigned long long d_vxc_ptr,

@@ -113,6 +113,12 @@ void coulomb_gemv(CublasHandleWrapper* ctx, int nao, const double* eri, const do
 // J and the exact-exchange matrix K[i,k] = sum_jl (ij|kl) D[j,l] in ONE pass over the ERI
 void coulomb_exchange(CublasHandleWrapper* ctx, int nao, const double* eri, const double* dm, double* J, double* K);
 
+// device-resident Fock assembly and SCF energy terms (no J / V_xc / K downloads per iteration)
+void build_fock(CublasHandleWrapper* ctx, int nao, const double* hcore, const double* J, const double* vxc,
+                const double* K, double c_hf, double* F);
+void scf_energies(CublasHandleWrapper* ctx, int nao, const double* dm, const double* hcore, const double* J,
+                  const double* K, double c_hf, double* out3_host);
+
 void dgemm_colmajor(CublasHandleWrapper* ctx, bool transA, bool transB, int m, int n, int k,
                     const double* A, int lda, const double* B, int ldb, double* C, int ldc);
 

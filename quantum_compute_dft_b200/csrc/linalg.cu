@@ -164,6 +164,46 @@ coulomb_exchange_kernel(int n, const double* __restrict__ A, const double* __res
     }
 }
 
+// ---- device-resident Fock assembly and SCF energy terms ------------------------
+// F = Hcore + J + 1/2 (V + V^T) - 1/2 c_hf K            (dft.py:212, :221-223)
+__global__ void fock_kernel(int n, const double* __restrict__ h, const double* __restrict__ J,
+                            const double* __restrict__ v, const double* __restrict__ K, double c_hf,
+                            double* __restrict__ F) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int i = idx / n, j = idx % n;
+    double f = h[idx] + J[idx] + 0.5 * (v[idx] + v[(size_t)j * n + i]);
+    if (K) f -= 0.5 * c_hf * K[idx];
+    F[idx] = f;
+}
+
+// out[0] = sum D o Hcore, out[1] = 1/2 sum D o J, out[2] = -1/4 c_hf sum D o K   (dft.py:230-236)
+// one CTA, fixed-order tree: bit-reproducible
+__global__ void scf_energy_kernel(int n2, const double* __restrict__ D, const double* __restrict__ h,
+                                  const double* __restrict__ J, const double* __restrict__ K, double c_hf,
+                                  double* __restrict__ out) {
+    __shared__ double sh[3][256];
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < n2; i += 256) {
+        const double d = D[i];
+        a = fma(d, h[i], a);
+        b = fma(d, J[i], b);
+        if (K) c = fma(d, K[i], c);
+    }
+    sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b; sh[2][threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int t = 0; t < 3; ++t) sh[t][threadIdx.x] += sh[t][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = sh[0][0];
+        out[1] = 0.5 * sh[1][0];
+        out[2] = -0.25 * c_hf * sh[2][0];
+    }
+}
+
 }  // namespace
 
 void coulomb_gemv(CublasHandleWrapper* ctx, int nao, const double* eri, const double* dm, double* J) {
@@ -201,6 +241,25 @@ void coulomb_exchange(CublasHandleWrapper* ctx, int nao, const double* eri, cons
     coulomb_exchange_kernel<<<dim3(nao, nchunks), JK_WARPS * 32, smem, ctx->stream>>>(nao, eri, dm, partial, K);
     gemv_reduce_kernel<<<(int)((N2 + GEMV_THREADS - 1) / GEMV_THREADS), GEMV_THREADS, 0, ctx->stream>>>(N2, nchunks, partial, J);
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
+}
+
+void build_fock(CublasHandleWrapper* ctx, int nao, const double* hcore, const double* J, const double* vxc,
+                const double* K, double c_hf, double* F) {
+    if (!ctx || nao <= 0 || !hcore || !J || !vxc || !F) return;
+    const int n2 = nao * nao;
+    fock_kernel<<<(n2 + 255) / 256, 256, 0, ctx->stream>>>(nao, hcore, J, vxc, K, c_hf, F);
+    DFT_CUDA_CHECK(ctx, cudaGetLastError());
+}
+
+void scf_energies(CublasHandleWrapper* ctx, int nao, const double* dm, const double* hcore, const double* J,
+                  const double* K, double c_hf, double* out3_host) {
+    if (!ctx || nao <= 0 || !dm || !hcore || !J || !out3_host) return;
+    double* d_out = (double*)ctx->result.ensure(sizeof(double) * ((size_t)nao * nao + 4), &ctx->failed);
+    if (ctx->failed) return;
+    scf_energy_kernel<<<1, 256, 0, ctx->stream>>>(nao * nao, dm, hcore, J, K, c_hf, d_out);
+    DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar + 4, d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int t = 0; t < 3; ++t) out3_host[t] = ctx->h_scalar[4 + t];
 }
 
 void dgemm_colmajor(CublasHandleWrapper* ctx, bool transA, bool transB, int m, int n, int k, const double* A,

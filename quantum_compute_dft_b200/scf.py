@@ -105,6 +105,24 @@ class EngineBackend:
         e = self.solver.compute_xc(self.ngrid, self.nao, self.d_dm, self.d_ao, self.d_w, self.d_v, self.d_grad)
         return e, self.d_v.get()
 
+    # ---- device-resident variant: J, V_xc and K never leave the GPU
+    def fock(self, dm, hcore, c_hf):
+        """Upload D, run J/K and XC, assemble F on the device; returns (F on the host for eigh, E_xc)."""
+        if not hasattr(self, "d_h"):
+            self.d_h = DeviceArray.from_host(hcore)
+            self.d_F = DeviceArray((self.nao, self.nao), zero=True)
+        self.d_dm.set(dm)
+        self.solver.compute_coulomb_exchange(self.nao, self.d_eri, self.d_dm, self.d_J, self.d_K)
+        e_xc = self.solver.compute_xc(self.ngrid, self.nao, self.d_dm, self.d_ao, self.d_w, self.d_v, self.d_grad)
+        self.solver.build_fock(self.nao, self.d_h, self.d_J, self.d_v, self.d_K if c_hf else None, c_hf, self.d_F)
+        self.solver.synchronize()
+        return self.d_F.get(), e_xc
+
+    def energies(self, dm_new, c_hf):
+        """(E_one, E_coul, E_hf) with the NEW density and the J, K still resident from `fock`."""
+        self.d_dm.set(dm_new)
+        return self.solver.scf_energies(self.nao, self.d_dm, self.d_h, self.d_J, self.d_K if c_hf else None, c_hf)
+
 
 # --------------------------------------------------------------------------- the loop (dft.py:183-266)
 def run_scf(S, hcore, e_nuc, nocc, backend, functional, max_cycle=200, e_tol=1e-8, dm_tol=1e-6, verbose=False):
@@ -129,6 +147,26 @@ def run_scf(S, hcore, e_nuc, nocc, backend, functional, max_cycle=200, e_tol=1e-
         if verbose:
             print(f"{cycle + 1:4d} {e_tot:18.10f} {d_e:15.6e} {d_dm:15.6e}")
         if abs(d_e) < e_tol and d_dm < dm_tol:                                  # dft.py:248
+            return e_tot, dm_new, cycle + 1, True
+        dm, e_old = dm_new, e_tot
+    return e_tot, dm, max_cycle, False
+
+
+def run_scf_device(S, hcore, e_nuc, nocc, backend, functional, max_cycle=200, e_tol=1e-8, dm_tol=1e-6):
+    """The same loop with the Fock assembly and the energy sums on the device (`backend.fock`,
+    `backend.energies`): per iteration D goes up and F comes down; J, V_xc and K stay on the GPU."""
+    c_hf = 0.2 if functional.upper() == "B3LYP" else 0.0
+    _, C = eigh(hcore, S)
+    dm = 2.0 * C[:, :nocc] @ C[:, :nocc].T
+    e_old = 0.0
+    for cycle in range(max_cycle):
+        F, e_xc = backend.fock(dm, hcore, c_hf)
+        _, C = eigh(F, S)
+        dm_new = 2.0 * C[:, :nocc] @ C[:, :nocc].T
+        e_one, e_coul, e_hf = backend.energies(dm_new, c_hf)
+        e_tot = e_one + e_coul + e_xc + e_hf + e_nuc
+        d_e, d_dm = e_tot - e_old, np.linalg.norm(dm_new - dm)
+        if abs(d_e) < e_tol and d_dm < dm_tol:
             return e_tot, dm_new, cycle + 1, True
         dm, e_old = dm_new, e_tot
     return e_tot, dm, max_cycle, False

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "DFT_EvalAO", "DFT_CommGetUniqueId", "DFT_CommInit", "DFT_CommDestroy",
     "DFT_SetOption", "DFT_GetStat", "DFT_ComputeXCAsync", "DFT_StreamSynchronize", "DFT_GetStream",
     "DFT_MicrobenchDMMA", "DFT_MicrobenchDFMA", "DFT_MicrobenchDMMAWarps", "DFT_B200_Version",
-    "DFT_ComputeCoulombExchange",
+    "DFT_ComputeCoulombExchange", "DFT_BuildFock", "DFT_SCFEnergies",
 ]
 
 _c_dp = ctypes.POINTER(ctypes.c_double)
@@ -121,6 +121,26 @@ class DFTSolverWrapper:
                                     ctypes.c_uint64(d_dm.data.ptr), ctypes.c_uint64(d_J.data.ptr))
 
     # ---- additive -------------------------------------------------------------------------
+    def build_fock(self, nao, d_hcore, d_J, d_vxc, d_K, c_hf, d_F):
+        """F = Hcore + J + 1/2 (V + V^T) - 1/2 c_hf K on the device (dft.py:212,221-223)."""
+        self.lib.DFT_BuildFock.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_uint64] * 4 + [ctypes.c_double, ctypes.c_uint64]
+        self.lib.DFT_BuildFock.restype = ctypes.c_int
+        rc = self.lib.DFT_BuildFock(self.solver, nao, d_hcore.data.ptr, d_J.data.ptr, d_vxc.data.ptr,
+                                    d_K.data.ptr if d_K is not None else 0, float(c_hf), d_F.data.ptr)
+        if rc != 0:
+            raise RuntimeError(f"DFT_BuildFock failed with code {rc}")
+
+    def scf_energies(self, nao, d_dm, d_hcore, d_J, d_K, c_hf):
+        """(E_one, E_coul, E_hf) = (sum D o H, 1/2 sum D o J, -1/4 c_hf sum D o K), dft.py:230-236."""
+        self.lib.DFT_SCFEnergies.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_uint64] * 4 + [ctypes.c_double, _c_dp]
+        self.lib.DFT_SCFEnergies.restype = ctypes.c_int
+        out = (ctypes.c_double * 3)()
+        rc = self.lib.DFT_SCFEnergies(self.solver, nao, d_dm.data.ptr, d_hcore.data.ptr, d_J.data.ptr,
+                                      d_K.data.ptr if d_K is not None else 0, float(c_hf), out)
+        if rc != 0:
+            raise RuntimeError(f"DFT_SCFEnergies failed with code {rc}")
+        return out[0], out[1], out[2]
+
     def compute_coulomb_exchange(self, nao, d_eri, d_dm, d_J, d_K):
         """J and K = einsum('ijkl,jl->ik', eri, dm) (dft.py:218) in one pass over the ERI."""
         self.lib.DFT_ComputeCoulombExchange.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_uint64] * 4

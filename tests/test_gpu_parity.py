@@ -378,3 +378,9 @@ def test_converged_scf_energy(oracle, engine_lib, functional):
     assert ok_o and ok_g and n_o == n_g
     assert abs(e_g - e_o) <= 1e-7, (e_g, e_o)
     np.testing.assert_allclose(dm_g, dm_o, rtol=0, atol=1e-7)
+    # device-resident Fock assembly and energy sums (DFT_BuildFock, DFT_SCFEnergies): same iteration, same answer
+    solver2 = DFTSolverWrapper(engine_lib, functional)
+    e_d, dm_d, n_d, ok_d = scf.run_scf_device(S, H, e_nuc, mol.nocc, scf.EngineBackend(solver2, basis, coords, weights, eri), functional)
+    assert ok_d and n_d == n_o
+    assert abs(e_d - e_o) <= 1e-7, (e_d, e_o)
+    np.testing.assert_allclose(dm_d, dm_o, rtol=0, atol=1e-7)
