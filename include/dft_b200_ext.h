@@ -50,7 +50,8 @@ int DFT_CommDestroy(XCSolver* solver);
 //       "path" 0 auto | 1 generic (any alignment) | 2 TMA-fed
 //       "deterministic" 0|1 (default 1: fixed-order reductions, bit-reproducible results)
 //       "vxc_shape" 0|64|128|160 (tuning: output tile of the TMA V kernel; 0 = chosen from nao)
-//       "vxc_vk" 8|16 (tuning: grid rows per ring stage of the 128 x 128 V kernel)
+//       "vxc_vk" 0|8|16 (tuning: grid rows per ring stage of the 128 x 128 V kernel; 0 = 16 on dense
+//       operands, 8 with zero skipping)
 //       "ao_shape" 0|16|32 (tuning: grid points per block of DFT_EvalAO; 0 = chosen from the basis size)
 //       "zero_skip" 0|1 (AO screening inside the contraction kernels: k-steps whose operand fragment is
 //       exactly zero are skipped; results are unchanged; default 1)

@@ -57,7 +57,7 @@ struct CublasHandleWrapper {
     bool tma_3d = true;            // TMA V kernel: one 3-D TMA load per plane and stage instead of one per 16-column block
     int ao_shape = 0;              // DFT_EvalAO block shape: 0 = auto, 16 (points, 8 warps) | 32 (points, 16 warps)
     int vxc_shape = 0;             // TMA V kernel output tile: 0 = auto, 64 | 128 | 160 (= 160 x 80)
-    int vxc_vk = 16;               // TMA V kernel, 128 x 128 tile: grid rows per ring stage (8: 5 stages, 16: 2 stages)
+    int vxc_vk = 0;                // TMA V kernel, 128 x 128 tile: grid rows per ring stage (8: 5 stages, 16: 2 stages, 0: auto)
 
     // workspaces
     DeviceBuffer dsym;     // symmetrised, zero-padded density matrix

@@ -95,6 +95,7 @@ struct VxcParams {
     int nfull[2];            // whole 16-column blocks of each sub-problem
     int rem[2];              // columns in the partial block (0: none)
     int use3d, zero_skip;
+    int chunk_stride[2];     // per sub-problem: multiplier (coprime to the chunk count) that scatters consecutive stages over the grid
     int nsub, tiles_m, tiles_n, lda_half, rows_per_slice, slices_per_sub, ldv, mpv;
     const double* coef;
     double* vpart;
@@ -592,7 +593,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
             long long t_w = 0, t_c = 0, t_start = clock64(), t0 = t_start, t1;
 #endif
             for (int c = 0; c < nchunks; ++c) {
-                const int j0 = (sl + c * P.slices_per_sub) * VK;
+                const int j0 = (int)(((long long)(sl + c * P.slices_per_sub) * P.chunk_stride[si]) % total_chunks) * VK;
                 const uint32_t s = c % STAGES, ph = (c / STAGES) & 1u;
 #ifdef DFT_PHASE_TIMING
                 t1 = clock64(); t_c += t1 - t0; t0 = t1;
@@ -1051,6 +1052,19 @@ static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry&
         }
     }
     if (!ok) { ctx->failed = true; return; }
+    for (int s = 0; s < g.nsub; ++s) {
+        // golden-ratio stride, made coprime to the chunk count: consecutive ring stages of a CTA then come from
+        // different atoms' grids, which decorrelates the per-stage work of the eight warps when zero fragments
+        // are skipped (neighbouring chunks have the same zero pattern)
+        const long long T = (g.sub[s].rows + VK - 1) / VK;
+        long long st = 1;
+        if (ctx->zero_skip && ctx->vxc_skip_on && T > 16) {
+            st = (long long)(0.6180339887 * (double)T) | 1;
+            auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
+            while (gcd(st, T) != 1) st += 2;
+        }
+        vp.chunk_stride[s] = (int)st;
+    }
     vp.use3d = ok3 ? 1 : 0;
     vp.zero_skip = ctx->zero_skip ? 1 : 0;  // (a driver that rejects the 3-D form leaves the per-block 2-D loads)
     vp.sub[0] = g.sub[0]; vp.sub[1] = g.sub[1];
@@ -1110,7 +1124,10 @@ static void build_plan(CublasHandleWrapper* ctx, const Problem& p, int nsm, Plan
     } else if (shape == 160) {
         DFT_PLAN_V(5, 5, 4, 2, NPL, 16, 2);
     } else {
-        if (ctx->vxc_vk == 16) DFT_PLAN_V(2, 16, 8, 1, NPL, 16, 2);
+        // rows per ring stage: 16 (2 stages, fewer barriers) on dense operands; 8 (5 stages) when zero fragments
+        // are skipped -- with the stages scattered over the grid, the deeper ring lets the warps drift apart
+        const int vk = ctx->vxc_vk ? ctx->vxc_vk : (vskip ? 8 : 16);
+        if (vk == 16) DFT_PLAN_V(2, 16, 8, 1, NPL, 16, 2);
         else DFT_PLAN_V(2, 16, 8, 1, NPL, 8, 5);
     }
 #undef DFT_PLAN_V
