@@ -41,7 +41,7 @@ CublasHandleWrapper::CublasHandleWrapper() {
     // driver uses (dft.py:178,201,207), so callers need no extra synchronisation.
     DFT_CUDA_CHECK(this, cudaStreamCreateWithFlags(&stream, cudaStreamDefault));
     for (auto& e : ev) DFT_CUDA_CHECK(this, cudaEventCreate(&e));
-    DFT_CUDA_CHECK(this, cudaMallocHost(reinterpret_cast<void**>(&h_scalar), 64));
+    DFT_CUDA_CHECK(this, cudaMallocHost(reinterpret_cast<void**>(&h_scalar), 128));
 }
 
 CublasHandleWrapper::~CublasHandleWrapper() {
@@ -110,7 +110,7 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
     if (ngrid == 0) {
         cudaMemsetAsync(p.vxc, 0, sizeof(double) * n2, ctx->stream);
         cudaMemsetAsync(p.d_exc, 0, sizeof(double), ctx->stream);
-        { XcStats z; z.plans_built = ctx->stats.plans_built; z.ao_ms = ctx->stats.ao_ms; z.skip_fraction = ctx->stats.skip_fraction; ctx->stats = z; }
+        { XcStats z; z.plans_built = ctx->stats.plans_built; z.ao_ms = ctx->stats.ao_ms; z.skip_fraction = ctx->stats.skip_fraction; z.vxc_skip_fraction = ctx->stats.vxc_skip_fraction; ctx->stats = z; }
     } else {
         bool use_tma = false;
         if (ctx->path == PATH_TMA) use_tma = xc::tma_compatible(p);
@@ -133,13 +133,14 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
     DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar, p.d_exc, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     const bool have_counters = ngrid > 0 && ctx->stats.path == PATH_TMA && ctx->counters.ptr;
     if (have_counters)
-        DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar + 1, ctx->counters.ptr, 2 * sizeof(unsigned long long),
+        DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar + 1, ctx->counters.ptr, 4 * sizeof(unsigned long long),
                                             cudaMemcpyDeviceToHost, ctx->stream));
     DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (have_counters && !ctx->failed) {
-        unsigned long long c[2];
+        unsigned long long c[4];
         memcpy(c, ctx->h_scalar + 1, sizeof(c));
         ctx->stats.skip_fraction = c[1] ? 1.0 - (double)c[0] / (double)c[1] : 0.0;
+        ctx->stats.vxc_skip_fraction = c[3] ? 1.0 - (double)c[2] / (double)c[3] : 0.0;
         // adaptive: the zero-skipping V instance pays ~6 % on dense operands; use it only where the density
         // kernel just skipped a real share of its k-steps (the decision takes effect with the next call)
         if (ctx->vxc_skip < 0) ctx->vxc_skip_on = ctx->stats.skip_fraction >= 0.10;
@@ -285,6 +286,13 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "l2_prefetch")) { c->l2_prefetch = value != 0.0; return 0; }
     if (!strcmp(key, "ao_shape")) { c->ao_shape = (int)value; return 0; }
     if (!strcmp(key, "vxc_skip")) { c->vxc_skip = (int)value; if (c->vxc_skip >= 0) c->vxc_skip_on = c->vxc_skip != 0; return 0; }
+    if (!strcmp(key, "dyn_sched")) { c->dyn_sched = value != 0.0; return 0; }
+    if (!strcmp(key, "wait_ns")) { c->wait_ns = value < 0.0 ? 0 : (int)value; return 0; }
+    if (!strcmp(key, "debug_nodmma")) { c->debug_nodmma = value != 0.0; return 0; }
+    if (!strcmp(key, "vxc_scatter")) { c->vxc_scatter = value != 0.0; return 0; }
+    if (!strcmp(key, "vxc_producers")) { c->vxc_producers = value < 1.0 ? 1 : (value > 4.0 ? 4 : (int)value); return 0; }
+    if (!strcmp(key, "vxc_mside_skip")) { c->vxc_mside_skip = value != 0.0; return 0; }
+    if (!strcmp(key, "vxc_skip_mode")) { c->vxc_skip_mode = (int)value; return 0; }
     if (!strcmp(key, "zero_skip")) { c->zero_skip = value != 0.0; return 0; }
     if (!strcmp(key, "tma_3d")) { c->tma_3d = value != 0.0; return 0; }
     if (!strcmp(key, "vxc_shape")) { const int v = (int)value; if (v != 0 && v != 64 && v != 128 && v != 160) return 3; c->vxc_shape = v; return 0; }
@@ -304,6 +312,7 @@ double DFT_GetStat(XCSolver* solver, const char* key) {
     if (!strcmp(key, "launches")) return c->stats.launches;
     if (!strcmp(key, "plans_built")) return c->stats.plans_built;
     if (!strcmp(key, "skip_fraction")) return c->stats.skip_fraction;
+    if (!strcmp(key, "vxc_skip_fraction")) return c->stats.vxc_skip_fraction;
     if (!strcmp(key, "path")) return c->stats.path;
     if (!strcmp(key, "workspace_bytes")) return (double)c->workspace_bytes();
     if (!strcmp(key, "nranks")) return c->nranks;

@@ -37,6 +37,7 @@ struct XcStats {
     int launches = 0;
     int path = 0;
     double skip_fraction = 0.0;  // TMA density kernel: fraction of k-steps skipped as exact zeros in the last call
+    double vxc_skip_fraction = 0.0;  // TMA V kernel, box-bit instances: fraction of (box, k-step) units skipped
     int plans_built = 0;  // TMA path: launch plans (tensor maps, geometry) encoded so far; a steady SCF loop builds one
 };
 
@@ -53,6 +54,13 @@ struct CublasHandleWrapper {
     bool l2_prefetch = false;      // TMA density kernel: short-range L2 prefetch of A tiles and epilogue pieces (measured: no gain)
     int vxc_skip = -1;             // V kernel zero-skipping instance: -1 adaptive (default), 0 never, 1 always
     bool vxc_skip_on = true;       // (adaptive) the zero-skipping V instance is used while the density kernel finds zeros
+    int vxc_skip_mode = 1;         // zero-skipping V instance (128 x 128 tile): 1 M-side votes, 2 | 3 N-side box bits (xc_tma.cu)
+    int vxc_scatter = 1;           // zero-skipping V instances: scatter consecutive ring stages over the grid (golden-ratio stride)
+    int dyn_sched = 1;             // TMA density kernel: hand the 64-point blocks out dynamically (one global counter)
+    int wait_ns = 0;               // TMA kernels: producer / scanner threads sleep this long between barrier polls
+    int debug_nodmma = 0;          // diagnostic only: TMA kernels skip every DMMA (measures the operand-delivery floor)
+    int vxc_producers = 1;         // TMA V kernel: TMA-issuing threads per CTA (1 | 2)
+    int vxc_mside_skip = 1;        // box-bit V instances: also skip on all-zero M-side fragments (per-warp votes)
     bool zero_skip = true;         // TMA kernels: skip k-steps whose operand fragment is all zero (exact: adds nothing)
     bool tma_3d = true;            // TMA V kernel: one 3-D TMA load per plane and stage instead of one per 16-column block
     int ao_shape = 0;              // DFT_EvalAO block shape: 0 = auto, 16 (points, 8 warps) | 32 (points, 16 warps)

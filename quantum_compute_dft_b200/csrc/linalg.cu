@@ -257,9 +257,9 @@ void scf_energies(CublasHandleWrapper* ctx, int nao, const double* dm, const dou
     double* d_out = (double*)ctx->result.ensure(sizeof(double) * ((size_t)nao * nao + 4), &ctx->failed);
     if (ctx->failed) return;
     scf_energy_kernel<<<1, 256, 0, ctx->stream>>>(nao * nao, dm, hcore, J, K, c_hf, d_out);
-    DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar + 4, d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar + 8, d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int t = 0; t < 3; ++t) out3_host[t] = ctx->h_scalar[4 + t];
+    for (int t = 0; t < 3; ++t) out3_host[t] = ctx->h_scalar[8 + t];
 }
 
 void dgemm_colmajor(CublasHandleWrapper* ctx, bool transA, bool transB, int m, int n, int k, const double* A,

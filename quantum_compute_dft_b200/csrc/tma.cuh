@@ -56,6 +56,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// The same with a sleep between polls, for the producer / scanner threads: they share an SM sub-partition's
+// issue slots with two MMA warps, and a thread that polls back to back takes cycles from them.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (ns) __nanosleep(ns);
+        if (++spins > (1u << 24)) {
+            printf("[dft_b200] mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x,
+                   parity);
+            __trap();
+        }
+    }
+}
+
 // 2-D tiled TMA load global -> shared, completion signalled on `bar` (complete_tx::bytes)
 __device__ __forceinline__ void load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(

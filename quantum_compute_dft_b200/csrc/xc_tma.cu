@@ -76,7 +76,10 @@ struct DensityParams {
     CUtensorMap map_d;        // [2][NP][KP] symmetrised density (plain, shifted), box 16 x NT
     SubProblem sub[2];
     int nsub, nblocks, ntiles, nk, NP, l2_prefetch, coef_rows, zero_skip;
+    int wait_ns;       // producer threads sleep this long between polls of an `empty` barrier (0: poll back to back)
+    int debug_nodmma;  // diagnostic: treat every k-step as zero (measures the operand-delivery floor; results are wrong)
     unsigned long long* counters;  // [2]: k-steps executed, k-steps total (AO screening statistics)
+    unsigned int* sched;           // next density block to hand out (dynamic scheduling; reset to 0 before the launch), or null
     double* rho;       // [2 warp columns][coef_rows][4]: partial (rho, drho/2) row sums, summed by the point kernel
     long long* phase;  // DFT_PHASE_TIMING builds: [CTA][warp][4] cycles in {k-loop, piece wait, piece math, block tail}
 };
@@ -95,10 +98,15 @@ struct VxcParams {
     int nfull[2];            // whole 16-column blocks of each sub-problem
     int rem[2];              // columns in the partial block (0: none)
     int use3d, zero_skip;
+    int producers;           // TMA-issuing threads per CTA (1..4)
+    int wait_ns;             // producer / scanner threads sleep this long between barrier polls
+    int debug_nodmma;        // diagnostic: skip every DMMA (operand-delivery floor; results are wrong)
+    int mside_skip;          // box-bit instances: also skip stages / k-steps whose M-side fragments are all zero
     int chunk_stride[2];     // per sub-problem: multiplier (coprime to the chunk count) that scatters consecutive stages over the grid
     int nsub, tiles_m, tiles_n, lda_half, rows_per_slice, slices_per_sub, ldv, mpv;
     const double* coef;
     double* vpart;
+    unsigned long long* counters;  // [2]: (box, k-step) units executed / total (box-bit instances)
     long long* phase;  // DFT_PHASE_TIMING builds: [CTA][9 warps][4] cycles {wait, work, tail, total}
 };
 
@@ -167,7 +175,8 @@ struct DensitySmem {
     static constexpr int NPIECES = NCG;
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;               // one group's ring
     static constexpr int BAR_OFF = 2 * RING_BYTES;                        // [2 groups]{full[STAGES], empty[STAGES]}
-    static constexpr int TOTAL = BAR_OFF + 2 * 2 * STAGES * 8 + 1024;     // + alignment slack
+    static constexpr int BLK_OFF = BAR_OFF + 2 * 2 * STAGES * 8;          // [2 groups][STAGES] block id carried by a stage
+    static constexpr int TOTAL = BLK_OFF + 2 * STAGES * 4 + 8 + 1024;     // + alignment slack
     static_assert(TOTAL <= 232448, "shared memory");
 
     // piece pc -> column group; consecutive pieces go to different warp columns
@@ -203,6 +212,12 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
     unsigned char* ring = sm + grp * L::RING_BYTES;
     const uint32_t ring_u32 = base + grp * L::RING_BYTES;
     const int b_first = 2 * blockIdx.x + grp, b_step = 2 * gridDim.x;
+    // Blocks are handed out dynamically (one global counter): a block of points near many atoms costs several
+    // times one out in the tail, so a static deal leaves the last groups running alone.  The producer draws
+    // the block ids (the next one while the current block streams) and passes each to its consumers in a
+    // shared-memory slot that travels with the block's first ring stage; a stage carrying -1 ends the group.
+    const bool dyn = P.sched != nullptr;
+    const uint32_t blk_slot = base + L::BLK_OFF + grp * L::STAGES * 4;
 
     if (warp >= NCW) {
         // ===================== producer warpgroup: warps 8 and 9, one elected lane each =====================
@@ -219,11 +234,12 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             // doubled the DRAM traffic).
             constexpr int PF = 6;
             const bool pf = P.l2_prefetch != 0;
-            for (int b = b_first; b < nblocks; b += b_step) {
+            int b = dyn ? (int)atomicAdd(P.sched, 1u) : b_first;
+            while (b < nblocks) {
                 const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
                 const int blk = b - P.sub[si].blk0;
                 const int drow0 = P.sub[si].shift * P.NP;
-                const int bn = b + b_step;  // this group's next block
+                const int bn = dyn ? (int)atomicAdd(P.sched, 1u) : b + b_step;  // this group's next block
                 const int sin = (P.nsub > 1 && bn >= P.sub[1].blk0) ? 1 : 0;
                 const int blkn = bn - P.sub[sin].blk0;
                 for (int nt = 0; nt < ntiles; ++nt) {
@@ -244,15 +260,16 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                             }
                         }
                         const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
-                        tma::mbar_wait(&empty[s], ph ^ 1u);
+                        tma::mbar_wait_relaxed(&empty[s], ph ^ 1u, (uint32_t)P.wait_ns);
                         unsigned char* st = ring + s * L::STAGE_BYTES;
+                        if (nt == 0 && kc == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(blk_slot + 4 * s), "r"(b) : "memory");
                         tma::mbar_arrive_expect_tx(&full[s], L::K_BYTES);
                         tma::load_2d(st, &P.map_a[si], kc * 16, blk * MB, &full[s]);
                         tma::load_2d(st + L::A_BYTES, &P.map_d, kc * 16, drow0 + nt * NT, &full[s]);
                     }
                     for (int pc = 0; pc < L::NPIECES; ++pc, ++it) {
                         const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
-                        tma::mbar_wait(&empty[s], ph ^ 1u);
+                        tma::mbar_wait_relaxed(&empty[s], ph ^ 1u, (uint32_t)P.wait_ns);
                         unsigned char* st = ring + s * L::STAGE_BYTES;
                         tma::mbar_arrive_expect_tx(&full[s], L::PIECE_BYTES);
                         const int c0 = nt * NT + 16 * L::piece_cg(pc);
@@ -260,6 +277,13 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                             tma::load_2d(st + p * L::PLANE_BYTES, &P.map_e[si][p], c0, blk * MB, &full[s]);
                     }
                 }
+                b = bn;
+            }
+            if (dyn) {  // no blocks left: one empty stage carrying -1 tells the consumers to stop
+                const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
+                tma::mbar_wait_relaxed(&empty[s], ph ^ 1u, (uint32_t)P.wait_ns);
+                asm volatile("st.shared.s32 [%0], %1;" ::"r"(blk_slot + 4 * s), "r"(-1) : "memory");
+                tma::mbar_arrive(&full[s]);
             }
         }
         return;
@@ -297,6 +321,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
     }
     const int prow0 = wm * 32;  // this warp's rows inside a piece
     const bool no_skip = P.zero_skip == 0;
+    const bool dbg_off = P.debug_nodmma != 0;
 
     // group 1 starts half a column-tile period late (only worth it when there are several blocks to do)
     if (grp == 1 && nblocks > 8 * (int)gridDim.x) {
@@ -313,7 +338,15 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
 #else
 #define PHASE_MARK(acc_) do { } while (0)
 #endif
-    for (int b = b_first; b < nblocks; b += b_step) {
+    for (int b = b_first;; b += b_step) {
+        if (dyn) {  // the block id travels with the block's first stage
+            const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
+            tma::mbar_wait(&full[s], ph);
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(b) : "r"(blk_slot + 4 * s) : "memory");
+            if (b < 0) break;
+        } else if (b >= nblocks) {
+            break;
+        }
         const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
         const int blk = b - P.sub[si].blk0;
         double rs[4][NPL];  // per-lane partial row sums of the whole block
@@ -358,7 +391,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                         for (int mf = 0; mf < 4; ++mf) a[cur ^ 1][mf] = lds_f64(a_base + mf * 1024 + koff_a[ks + 1]);
                     }
                     const bool nz = ((a[cur][0] != 0.0) | (a[cur][1] != 0.0)) | ((a[cur][2] != 0.0) | (a[cur][3] != 0.0));
-                    if (__any_sync(0xffffffffu, nz | no_skip)) {
+                    if (__any_sync(0xffffffffu, nz | no_skip) && !dbg_off) {
                         double bf[NF2];
 #pragma unroll
                         for (int nf = 0; nf < NF2; ++nf) bf[nf] = lds_f64(b_base + nf * 1024 + koff_b[ks]);
@@ -526,12 +559,21 @@ struct VxcCfg {
     static constexpr int COEF_OFF = N_OFF + (NT_ / 16) * BOXB;
     static constexpr int TX_BYTES = COEF_OFF + VK * 32;
     static constexpr int STAGE_BYTES = ((TX_BYTES + 1023) / 1024) * 1024;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 2 * STAGES * 8 + 1024;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;                 // full, empty, ready [STAGES] (8 B each), jbits[STAGES] (4 B each)
+    static constexpr int TOTAL = BAR_OFF + 3 * STAGES * 8 + STAGES * 4 + 4 + 1024;
     static_assert(TOTAL <= 232448, "shared memory");
 };
 
-template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES, bool SKIP>
+// SKIP selects the AO-screening scheme of the instance:
+//   0  none (branch-free; the fastest on dense operands)
+//   1  per-fragment votes on the M side only: every warp votes on its own built B fragments
+//   2  N-side box bits from the scanner warp + one M-side vote per stage
+//   3  N-side box bits from the scanner warp + one M-side vote per k-step
+// In 2 and 3 a warp of the producer warpgroup (the "scanner") looks at the Phi tile of every stage as soon as
+// TMA has delivered it and publishes one bit per 16-column box: is anything in it non-zero?  All eight
+// MMA warps share the N side, so they skip the SAME boxes of a stage -- unlike the M-side votes, which differ
+// from warp to warp and leave the skipping warps waiting for the ring.  Nothing is cached between calls.
+template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES, int SKIP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     using L = VxcCfg<MF, NFN, WM, WN, NPL, VK, STAGES>;
@@ -541,6 +583,9 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     unsigned char* sm = smem_raw + (base - tma::smem_u32(smem_raw));
     uint64_t* full = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF);
     uint64_t* empty = full + STAGES;
+    uint64_t* ready = empty + STAGES;                                 // SKIP >= 2: the scanner has published jbits[s]
+    const uint32_t jbits_u32 = base + L::BAR_OFF + 3 * STAGES * 8;    // SKIP >= 2: live N-side boxes of stage s
+    static_assert(SKIP < 2 || (WN == 1 && NFN % 2 == 0 && NFN <= 64), "box bits: the warps share the whole N tile");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -567,6 +612,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         for (int s = 0; s < STAGES; ++s) {
             tma::mbar_init(&full[s], 1);
             tma::mbar_init(&empty[s], NCW);
+            tma::mbar_init(&ready[s], 1);
         }
         tma::fence_barrier_init();
     }
@@ -579,7 +625,24 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     if (warp >= NCW) {
         reg_dec<REGS_PRODUCER>();
         // ===================== TMA producer =====================
-        if (warp == NCW && lane == 0) {
+        // Issuing threads: lane 0 of warps 8, 10, 11 (and 9 where it is not the scanner).  One thread streams at most
+        // ~23 bytes/clk into shared memory (measured with the DMMAs switched off), well below what the SM can
+        // take, so the stage's transfers are dealt to up to four threads; thread 0 also arms the barrier.  (A
+        // transfer that completes before the barrier is armed only makes its tx-count transiently negative; the
+        // phase cannot complete before thread 0 has arrived.)
+        const int max_prod = SKIP >= 2 ? 3 : 4;
+        const int nprod = P.producers < 1 ? 1 : (P.producers > max_prod ? max_prod : P.producers);
+        const int pw = warp - NCW;                                     // 0..3
+        const int pid = pw == 0 ? 0 : (SKIP >= 2 ? pw - 1 : (pw == 1 ? 3 : pw - 1));   // warp 9 is the last resort
+        if (lane == 0 && pid >= 0 && pid < nprod && !(SKIP >= 2 && pw == 1)) {
+            // transfers of a stage: bits 0..3 = M-side planes, 4 = Phi tile (N side), 5 = coefficients
+            unsigned ops;
+            if (NPL == 4) {
+                constexpr unsigned T[4][4] = {{0x3f, 0, 0, 0}, {0x23, 0x1c, 0, 0}, {0x03, 0x0c, 0x30, 0}, {0x21, 0x12, 0x04, 0x08}};
+                ops = T[nprod - 1][pid];
+            } else {
+                ops = nprod == 1 ? 0x31u : (pid == 0 ? 0x21u : (pid == 1 ? 0x10u : 0u));
+            }
             const double* coef = P.coef + 4 * (size_t)P.sub[si].coef0;
             // blocks of this CTA's M / N tile: fbm / fbn whole ones (one 3-D load), then possibly the partial one
             const int nfull = P.nfull[si], rem = P.rem[si];
@@ -592,47 +655,90 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
 #ifdef DFT_PHASE_TIMING
             long long t_w = 0, t_c = 0, t_start = clock64(), t0 = t_start, t1;
 #endif
-            for (int c = 0; c < nchunks; ++c) {
-                const int j0 = (int)(((long long)(sl + c * P.slices_per_sub) * P.chunk_stride[si]) % total_chunks) * VK;
-                const uint32_t s = c % STAGES, ph = (c / STAGES) & 1u;
+            // chunk of stage c: (sl + c nsl) stride mod total, kept incrementally (no 64-bit division per stage)
+            int cidx = (int)(((long long)sl * P.chunk_stride[si]) % total_chunks);
+            const int cstep = (int)(((long long)P.slices_per_sub * P.chunk_stride[si]) % total_chunks);
+            uint32_t s = 0, ph = 0;
+            const int nloop = ops ? nchunks : 0;  // (a thread without transfers has nothing to wait for)
+            for (int c = 0; c < nloop; ++c) {
+                const int j0 = cidx * VK;
+                cidx += cstep;
+                if (cidx >= total_chunks) cidx -= total_chunks;
 #ifdef DFT_PHASE_TIMING
                 t1 = clock64(); t_c += t1 - t0; t0 = t1;
 #endif
-                tma::mbar_wait(&empty[s], ph ^ 1u);
+                tma::mbar_wait_relaxed(&empty[s], ph ^ 1u, (uint32_t)P.wait_ns);
 #ifdef DFT_PHASE_TIMING
                 t1 = clock64(); t_w += t1 - t0; t0 = t1;
 #endif
                 unsigned char* st = sm + s * L::STAGE_BYTES;
-                tma::mbar_arrive_expect_tx(&full[s], tx);
+                uint64_t* fb = &full[s];
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+                if (pid == 0) tma::mbar_arrive_expect_tx(fb, tx);
+#pragma unroll
                 for (int p = 0; p < NPL; ++p) {
+                    if (!(ops & (1u << p))) continue;
                     unsigned char* dst = st + p * L::PLANE_BYTES;
                     if (P.use3d) {
-                        if (fbm == NBM) tma::load_3d(dst, &P.m3[si][p], 0, j0, bm0, &full[s]);
-                        else if (fbm > 0) tma::load_3d(dst, &P.m3l[si][p], 0, j0, bm0, &full[s]);
+                        if (fbm == NBM) tma::load_3d(dst, &P.m3[si][p], 0, j0, bm0, fb);
+                        else if (fbm > 0) tma::load_3d(dst, &P.m3l[si][p], 0, j0, bm0, fb);
                     } else {
-                        for (int b = 0; b < fbm; ++b) tma::load_2d(dst + b * L::BOXB, &P.p2[si][p], m0 + 16 * b, j0, &full[s]);
+                        for (int b = 0; b < fbm; ++b) tma::load_2d(dst + b * L::BOXB, &P.p2[si][p], m0 + 16 * b, j0, fb);
                     }
-                    if (pm) tma::load_2d(dst + fbm * L::BOXB, &P.p2[si][p], m0 + 16 * fbm, j0, &full[s]);
+                    if (pm) tma::load_2d(dst + fbm * L::BOXB, &P.p2[si][p], m0 + 16 * fbm, j0, fb);
                 }
-                {
+                if (ops & 0x10u) {
                     unsigned char* dst = st + L::N_OFF;
                     if (P.use3d) {
-                        if (fbn == NBN) tma::load_3d(dst, &P.n3[si], 0, j0, bn0, &full[s]);
-                        else if (fbn > 0) tma::load_3d(dst, &P.n3l[si], 0, j0, bn0, &full[s]);
+                        if (fbn == NBN) tma::load_3d(dst, &P.n3[si], 0, j0, bn0, fb);
+                        else if (fbn > 0) tma::load_3d(dst, &P.n3l[si], 0, j0, bn0, fb);
                     } else {
-                        for (int b = 0; b < fbn; ++b) tma::load_2d(dst + b * L::BOXB, &P.p2[si][0], n0 + 16 * b, j0, &full[s]);
+                        for (int b = 0; b < fbn; ++b) tma::load_2d(dst + b * L::BOXB, &P.p2[si][0], n0 + 16 * b, j0, fb);
                     }
-                    if (pn) tma::load_2d(dst + fbn * L::BOXB, &P.p2[si][0], n0 + 16 * fbn, j0, &full[s]);
+                    if (pn) tma::load_2d(dst + fbn * L::BOXB, &P.p2[si][0], n0 + 16 * fbn, j0, fb);
                 }
-                tma::load_1d(st + L::COEF_OFF, coef + 4 * (size_t)j0, VK * 32, &full[s]);
+                if (ops & 0x20u) tma::load_1d(st + L::COEF_OFF, coef + 4 * (size_t)j0, VK * 32, fb);
             }
 #ifdef DFT_PHASE_TIMING
-            if (P.phase) {
+            if (P.phase && pid == 0) {
                 long long* o = P.phase + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (NCW + 1) + NCW) * 4;
                 t1 = clock64();
                 o[0] = t_w; o[1] = t_c + (t1 - t0); o[2] = 0; o[3] = t1 - t_start;
             }
 #endif
+        } else if (SKIP >= 2 && warp == NCW + 1) {
+            // ===================== scanner: one bit per 16-column box of the stage's Phi tile =====================
+            // A box is VK rows x 128 bytes; the lanes read it 16 bytes at a time (the swizzle does not matter for
+            // an any-non-zero test).  Boxes past the edge of the matrix were cleared once and are never written,
+            // so they read as zero and are skipped as well.
+            constexpr int NBN = L::NT_ / 16;
+            constexpr int PER_LANE = (VK * 8 + 31) / 32;
+            for (int c = 0; c < nchunks; ++c) {
+                const uint32_t s = c % STAGES, ph = (c / STAGES) & 1u;
+                tma::mbar_wait_relaxed(&full[s], ph, (uint32_t)P.wait_ns);
+                const uint32_t nb = base + s * L::STAGE_BYTES + L::N_OFF + lane * 16;
+                uint32_t bits = 0;
+#pragma unroll
+                for (int b = 0; b < NBN; ++b) {
+                    bool nz = false;
+#pragma unroll
+                    for (int i = 0; i < PER_LANE; ++i) {
+                        if (VK * 8 % 32 == 0 || lane + 32 * i < VK * 8) {
+                            // integer test (+-0 -> zero): keeps the scanner off the FP64 pipe
+                            uint32_t x0, x1, x2, x3;
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(nb + b * L::BOXB + i * 512));
+                            nz |= ((x0 | x2) | ((x1 | x3) << 1)) != 0u;
+                        }
+                    }
+                    bits |= (__any_sync(0xffffffffu, nz) ? 1u : 0u) << b;
+                }
+                if (lane == 0) {
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(jbits_u32 + 4 * s), "r"(bits) : "memory");
+                    tma::mbar_arrive(&ready[s]);
+                }
+                __syncwarp();
+            }
         }
         return;
     }
@@ -648,6 +754,8 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         for (int nf = 0; nf < NFN; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
 
     const bool no_skip = P.zero_skip == 0;
+    const bool no_mskip = P.mside_skip == 0;
+    unsigned int n_box_done = 0;  // SKIP >= 2: (box, k-step) units executed by this warp
     // Fragment addressing.  A DMMA k-step ks contracts 4 grid rows; lane (q, qcol) supplies row
     // krow(ks, qcol) -- rows {0,2,4,6} / {1,3,5,7} of an 8-row group, so that with the 128-byte swizzle
     // the 16 lanes of a load phase hit 16 distinct bank pairs -- and column (8-column group G) * 8 + q.
@@ -657,7 +765,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     // takes groups w and 15 - w instead of 2w and 2w + 1: two halves of one 16-column box (one or two atoms)
     // are zero or non-zero together, while groups from opposite ends of the tile average out, which evens the
     // work of the eight warps that share the ring.
-    constexpr bool MIRROR = SKIP && WM == 8 && WN == 1 && MF == 2;
+    constexpr bool MIRROR = (SKIP == 1 || SKIP == 3) && WM == 8 && WN == 1 && MF == 2;
     auto mgroup = [&](int mf) { return MIRROR ? (mf == 0 ? wm : 15 - wm) : ga0 + mf; };
     uint32_t a_off[KS][MF], b_even[KS], b_odd[KS], c_off[KS];
 #pragma unroll
@@ -687,6 +795,60 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         t1 = clock64(); t_w += t1 - t0; t0 = t1;
 #endif
         const uint32_t sb = base + s * L::STAGE_BYTES;
+        if constexpr (SKIP >= 2) {
+            // ---- box-bit instance: build the stage's A fragments, then walk the live N-side boxes
+            tma::mbar_wait(&ready[s], ph);
+#ifdef DFT_PHASE_TIMING
+            t1 = clock64(); t_w += t1 - t0; t0 = t1;
+#endif
+            uint32_t jm;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(jm) : "r"(jbits_u32 + 4 * s));
+            double a[KS][MF];
+            unsigned livek = 0;
+            bool nz_all = false;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const double2 ca = lds_f64x2(sb + c_off[ks]);
+                double2 cb = make_double2(0.0, 0.0);
+                if (NPL == 4) cb = lds_f64x2(sb + c_off[ks] + 16);
+                bool nz = false;
+#pragma unroll
+                for (int mf = 0; mf < MF; ++mf) {
+                    const uint32_t ad = sb + a_off[ks][mf];
+                    double v = ca.x * lds_f64(ad);
+                    if (NPL == 4) {
+                        v = fma(ca.y, lds_f64(ad + L::PLANE_BYTES), v);
+                        v = fma(cb.x, lds_f64(ad + 2 * L::PLANE_BYTES), v);
+                        v = fma(cb.y, lds_f64(ad + 3 * L::PLANE_BYTES), v);
+                    }
+                    a[ks][mf] = v;
+                    nz |= v != 0.0;
+                }
+                if (SKIP == 3) livek |= (__any_sync(0xffffffffu, nz | no_mskip) ? 1u : 0u) << ks;
+                nz_all |= nz;
+            }
+            if (SKIP == 2) livek = __any_sync(0xffffffffu, nz_all | no_mskip) ? (1u << KS) - 1u : 0u;
+            if (livek != 0 && jm != 0 && P.debug_nodmma == 0) {
+                n_box_done += (unsigned)(__popc(jm) * __popc(livek));
+#pragma unroll
+                for (int b = 0; b < NFN / 2; ++b) {
+                    if (jm & (1u << b)) {
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            if (SKIP == 2 || (livek & (1u << ks))) {
+                                const double bf0 = lds_f64(sb + b_even[ks] + (uint32_t)(b * L::BOXB));
+                                const double bf1 = lds_f64(sb + b_odd[ks] + (uint32_t)(b * L::BOXB));
+#pragma unroll
+                                for (int mf = 0; mf < MF; ++mf) {
+                                    dmma::mma8x8x4(acc[mf][2 * b], a[ks][mf], bf0);
+                                    dmma::mma8x8x4(acc[mf][2 * b + 1], a[ks][mf], bf1);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        } else
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
             // A fragments: B[k][m] = a Phi + bx dxPhi + by dyPhi + bz dzPhi, built in registers
@@ -758,6 +920,10 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
             const int cc = n0 + (gb0 + nf) * 8 + 2 * qcol;
             *reinterpret_cast<double2*>(out + (size_t)r * P.ldv + cc) = make_double2(acc[mf][nf][0], acc[mf][nf][1]);
         }
+    if (SKIP >= 2 && lane == 0 && P.counters) {
+        atomicAdd(&P.counters[0], (unsigned long long)n_box_done);
+        atomicAdd(&P.counters[1], (unsigned long long)nchunks * KS * (NFN / 2));
+    }
 #ifdef DFT_PHASE_TIMING
     if (lane == 0 && P.phase) {
         long long* o = P.phase + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (NCW + 1) + warp) * 4;
@@ -935,7 +1101,7 @@ static Geometry make_geometry(int ngrid, int nao) {
 // addresses, so a plan stays valid when the caller rewrites the CONTENTS of its arrays.
 struct PlanKey {
     Problem prob;
-    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on;
+    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, vxc_mside_skip, debug_nodmma, wait_ns, dyn_sched;
     const void *dsym, *coef, *epart, *vpart, *rho;  // engine workspaces (grow-only: may move when they grow)
 };
 
@@ -985,8 +1151,10 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
     dp.nblocks = g.nblocks; dp.ntiles = ntiles; dp.nk = KP / 16; dp.NP = NP;
     dp.l2_prefetch = ctx->l2_prefetch ? 1 : 0;
     dp.zero_skip = ctx->zero_skip ? 1 : 0;
+    dp.debug_nodmma = ctx->debug_nodmma; dp.wait_ns = ctx->wait_ns;
+    dp.sched = (ctx->dyn_sched && dp.counters) ? reinterpret_cast<unsigned int*>(dp.counters + 4) : nullptr;
     dp.coef_rows = g.coef_rows; dp.rho = rho;
-    dp.counters = reinterpret_cast<unsigned long long*>(ctx->counters.ensure(2 * sizeof(unsigned long long), &ctx->failed));
+    dp.counters = reinterpret_cast<unsigned long long*>(ctx->counters.ensure(6 * sizeof(unsigned long long), &ctx->failed));
 
     PointParams& pp = pl.pp;
     memset(&pp, 0, sizeof(pp));
@@ -1008,7 +1176,7 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
 }
 
 // ---- V plan: output tile (WM MF 8) x (WN NFN 8)
-template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES, bool SKIP>
+template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES, int SKIP>
 static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry& g, int nsm, const double* coef, Plan& pl) {
     using VL = VxcCfg<MF, NFN, WM, WN, NPL, VK, STAGES>;
     const int ngrid = p.ngrid, nao = p.nao;
@@ -1058,7 +1226,7 @@ static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry&
         // are skipped (neighbouring chunks have the same zero pattern)
         const long long T = (g.sub[s].rows + VK - 1) / VK;
         long long st = 1;
-        if (ctx->zero_skip && ctx->vxc_skip_on && T > 16) {
+        if (ctx->zero_skip && ctx->vxc_skip_on && ctx->vxc_scatter && T > 16) {
             st = (long long)(0.6180339887 * (double)T) | 1;
             auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
             while (gcd(st, T) != 1) st += 2;
@@ -1066,11 +1234,14 @@ static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry&
         vp.chunk_stride[s] = (int)st;
     }
     vp.use3d = ok3 ? 1 : 0;
+    vp.debug_nodmma = ctx->debug_nodmma; vp.wait_ns = ctx->wait_ns;
+    vp.producers = ctx->vxc_producers; vp.mside_skip = ctx->vxc_mside_skip;
     vp.zero_skip = ctx->zero_skip ? 1 : 0;  // (a driver that rejects the 3-D form leaves the per-block 2-D loads)
     vp.sub[0] = g.sub[0]; vp.sub[1] = g.sub[1];
     vp.nsub = g.nsub; vp.tiles_m = tiles_m; vp.tiles_n = tiles_n; vp.lda_half = lda_half;
     vp.rows_per_slice = rows_per_slice; vp.slices_per_sub = nsl; vp.ldv = ldv; vp.mpv = mpv;
     vp.coef = coef; vp.vpart = vpart;
+    vp.counters = pl.dp.counters ? pl.dp.counters + 2 : nullptr;
 #ifdef DFT_PHASE_TIMING
     {   // the density kernel's phase record occupies the first 148*8*4 entries of `scratch`
         long long* ph = (long long*)ctx->scratch.ensure(sizeof(long long) * (65536 + 160 * 256), &ctx->failed);
@@ -1117,8 +1288,14 @@ static void build_plan(CublasHandleWrapper* ctx, const Problem& p, int nsm, Plan
     if (shape == 0) shape = n <= 64 ? 64 : (cost160 < cost128 ? 160 : 128);
     // zero-skipping V instance only where the density kernel of the previous call actually skipped work
     const bool vskip = ctx->zero_skip && ctx->vxc_skip_on;
-#define DFT_PLAN_V(...) do { if (vskip) plan_vxc<__VA_ARGS__, true>(ctx, p, g, nsm, coef, pl); \
-                             else plan_vxc<__VA_ARGS__, false>(ctx, p, g, nsm, coef, pl); } while (0)
+#define DFT_PLAN_V(...) do { if (vskip) plan_vxc<__VA_ARGS__, 1>(ctx, p, g, nsm, coef, pl); \
+                             else plan_vxc<__VA_ARGS__, 0>(ctx, p, g, nsm, coef, pl); } while (0)
+    // 128 x 128 tile: the box-bit instances (vxc_skip_mode 2 | 3) exist in both ring shapes
+#define DFT_PLAN_V128(VK_, ST_) do { \
+        if (!vskip) plan_vxc<2, 16, 8, 1, NPL, VK_, ST_, 0>(ctx, p, g, nsm, coef, pl); \
+        else if (ctx->vxc_skip_mode == 2) plan_vxc<2, 16, 8, 1, NPL, VK_, ST_, 2>(ctx, p, g, nsm, coef, pl); \
+        else if (ctx->vxc_skip_mode == 3) plan_vxc<2, 16, 8, 1, NPL, VK_, ST_, 3>(ctx, p, g, nsm, coef, pl); \
+        else plan_vxc<2, 16, 8, 1, NPL, VK_, ST_, 1>(ctx, p, g, nsm, coef, pl); } while (0)
     if (shape == 64) {
         DFT_PLAN_V(1, 8, 8, 1, NPL, 16, 4);
     } else if (shape == 160) {
@@ -1127,9 +1304,10 @@ static void build_plan(CublasHandleWrapper* ctx, const Problem& p, int nsm, Plan
         // rows per ring stage: 16 (2 stages, fewer barriers) on dense operands; 8 (5 stages) when zero fragments
         // are skipped -- with the stages scattered over the grid, the deeper ring lets the warps drift apart
         const int vk = ctx->vxc_vk ? ctx->vxc_vk : (vskip ? 8 : 16);
-        if (vk == 16) DFT_PLAN_V(2, 16, 8, 1, NPL, 16, 2);
-        else DFT_PLAN_V(2, 16, 8, 1, NPL, 8, 5);
+        if (vk == 16) DFT_PLAN_V128(16, 2);
+        else DFT_PLAN_V128(8, 5);
     }
+#undef DFT_PLAN_V128
 #undef DFT_PLAN_V
 }
 
@@ -1140,7 +1318,8 @@ static PlanKey make_key(const CublasHandleWrapper* ctx, const Problem& p) {
     k.prob.dm = p.dm; k.prob.ao = p.ao; k.prob.gx = p.gx; k.prob.gy = p.gy; k.prob.gz = p.gz; k.prob.w = p.w;
     k.prob.vxc = p.vxc; k.prob.d_exc = p.d_exc;
     k.exact = ctx->exact_functionals; k.l2_prefetch = ctx->l2_prefetch; k.tma_3d = ctx->tma_3d;
-    k.vxc_shape = ctx->vxc_shape; k.vxc_vk = ctx->vxc_vk; k.zero_skip = ctx->zero_skip; k.vxc_skip_on = ctx->vxc_skip_on;
+    k.vxc_shape = ctx->vxc_shape; k.vxc_vk = ctx->vxc_vk; k.zero_skip = ctx->zero_skip; k.vxc_skip_on = ctx->vxc_skip_on; k.vxc_skip_mode = ctx->vxc_skip_mode; k.vxc_scatter = ctx->vxc_scatter;
+    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.vxc_producers = ctx->vxc_producers; k.vxc_mside_skip = ctx->vxc_mside_skip;
     k.dsym = ctx->dsym.ptr; k.coef = ctx->coef.ptr; k.epart = ctx->epart.ptr; k.vpart = ctx->vpart.ptr;
     k.rho = ctx->rho.ptr;
     return k;
@@ -1151,7 +1330,7 @@ static void run_plan(CublasHandleWrapper* ctx, const Problem& p, Plan& pl) {
     if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
     symmetrize_pad_tma_kernel<<<dim3((pl.KP + 127) / 128, pl.NP * pl.nsub), 128, 0, st>>>(p.nao, pl.KP, pl.NP, pl.nsub, p.dm,
                                                                                          pl.dsym);
-    if (pl.dp.counters) cudaMemsetAsync(pl.dp.counters, 0, 2 * sizeof(unsigned long long), st);
+    if (pl.dp.counters) cudaMemsetAsync(pl.dp.counters, 0, 6 * sizeof(unsigned long long), st);
     void* dargs[1] = {&pl.dp};
     DFT_CUDA_CHECK(ctx, cudaLaunchKernel(pl.dfunc, dim3(pl.dgrid), dim3(NTHREADS), dargs, (size_t)pl.dsmem, st));
     xc_point_kernel<<<pl.pgrid, POINT_THREADS, 0, st>>>(pl.pp);

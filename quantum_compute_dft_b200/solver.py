@@ -207,7 +207,7 @@ class DFTSolverWrapper:
         self.lib.DFT_CommDestroy(self.solver)
 
 
-def shard_indices(ngrid, rank, nranks, block=8192):
+def shard_indices(ngrid, rank, nranks, block=1024):
     """Grid points of `rank` when the grid is dealt to the ranks in INTERLEAVED blocks of `block` points
     (block b goes to rank b mod nranks).  Grid points are independent, so any partition is valid (SURVEY.md
     8e); with AO screening the cost of a point depends on how many atoms are near it, and a contiguous

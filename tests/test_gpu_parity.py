@@ -30,7 +30,7 @@ def _run_engine(lib_path, functional, dm, ao, w, grad, options=None, reference_a
     d_v = DeviceArray((nao, nao), zero=True)
     e = s.compute_xc(ngrid, nao, d_dm, d_ao, d_w, d_v, d_g)
     v = d_v.get()
-    stats = {k: s.stat(k) for k in ("path", "launches")} if not reference_abi else {}
+    stats = {k: s.stat(k) for k in ("path", "launches", "skip_fraction", "vxc_skip_fraction")} if not reference_abi else {}
     return e, v, stats
 
 
@@ -211,6 +211,43 @@ def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
         assert s1["path"] == 2, opt
         assert abs(e0 - e1) <= E_TOL * max(1.0, abs(e0) * 1e-3), opt
         np.testing.assert_allclose(v0, v1, rtol=0, atol=V_TOL * max(1.0, np.abs(v0).max() * 1e-3), err_msg=str(opt))
+
+
+def _screened_case(rng, ngrid, nao, rows=64, cols=10):
+    """Random planes with the zero pattern AO screening leaves: for runs of `rows` grid points, runs of about
+    `cols` neighbouring AOs (an atom's shells) are exact zeros in all four planes; a few single-plane zeros on top."""
+    dm, ao, w, grad = _random_case(rng, ngrid, nao)
+    nrb, ncb = (ngrid + rows - 1) // rows, (nao + cols - 1) // cols
+    live = rng.uniform(size=(nrb, ncb)) < 0.45
+    mask = np.repeat(np.repeat(live, rows, axis=0), cols, axis=1)[:ngrid, :nao]
+    ao = ao * mask
+    grad = grad * mask[None]
+    ao[rng.uniform(size=ao.shape) < 0.05] = 0.0      # value zero, gradient not (a p function on its nodal plane)
+    w[rng.uniform(size=ngrid) < 0.1] = 0.0           # zero-weight padding points
+    return dm, np.ascontiguousarray(ao), w, np.ascontiguousarray(grad)
+
+
+@pytest.mark.parametrize("functional", FUNCS)
+@pytest.mark.parametrize("ngrid,nao", [(9000, 377), (6000, 256), (5001, 200), (4000, 129)])
+def test_vxc_zero_skipping_instances_agree(oracle, engine_lib, functional, ngrid, nao):
+    """The zero-skipping V instances (M-side fragment votes; N-side box bits from the scanner warp with a vote per
+    stage or per k-step; 8 or 16 rows per ring stage) drop only DMMAs whose operand fragment is exactly zero, so
+    on screened AO planes they agree with the branch-free instance and with the oracle."""
+    rng = np.random.default_rng(7 * ngrid + nao)
+    dm, ao, w, grad = _screened_case(rng, ngrid, nao)
+    e_o, v_o = oracle.compute_xc(XC[functional], dm, ao, w, grad, mode=0)
+    e0, v0, s0 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"vxc_shape": 128, "vxc_skip": 0})
+    assert s0["path"] == 2 and abs(e0 - e_o) <= E_TOL
+    np.testing.assert_allclose(0.5 * (v0 + v0.T), oracle.sym(v_o), rtol=0, atol=V_TOL)
+    for mode in (1, 2, 3):
+        for vk in (8, 16):
+            opt = {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": mode, "vxc_vk": vk}
+            e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
+            assert s1["path"] == 2 and e1 == e0, opt
+            np.testing.assert_allclose(v1, v0, rtol=0, atol=1e-11 * max(1.0, np.abs(v0).max()), err_msg=str(opt))
+            np.testing.assert_array_equal(v1, v1.T)
+            if mode >= 2:
+                assert 0.05 < s1["vxc_skip_fraction"] < 0.95, (opt, s1["vxc_skip_fraction"])
 
 
 @pytest.mark.parametrize("functional", FUNCS)
