@@ -17,7 +17,8 @@
 //   * phase 1, lanes over POINTS: a half-warp evaluates one group for the 16 points -- the group's data
 //     is uniform over the half-warp (broadcast loads), neighbouring points agree on which primitives
 //     fall beyond the cutoff (AO screening without divergence or compaction; a primitive is dropped
-//     when exp*r^2 > cutoff exactly as in the CPU statement) -- and stores the radial sums
+//     when exp*r^2 > cutoff exactly as in the CPU statement; a group whose most diffuse primitive is
+//     beyond the cutoff is skipped outright) -- and stores the radial sums
 //     (e0, e1) = sum c (1, -2a) exp(-a r^2) of each member shell in a [point][shell] array whose
 //     point pitch is odd in 16-byte units (conflict-free both ways);
 //   * phase 2, lanes over AOs: a warp takes one point, lane i combines its shell's (e0, e1) with the
@@ -92,6 +93,7 @@ eval_kernel(int ngrid, const double* __restrict__ coords, Tables t, int epitch, 
     const double* gx = reinterpret_cast<const double*>(smem_raw + t.o_gx);
     const double* gy = reinterpret_cast<const double*>(smem_raw + t.o_gy);
     const double* gz = reinterpret_cast<const double*>(smem_raw + t.o_gz);
+    const double* gamin = reinterpret_cast<const double*>(smem_raw + t.o_gamin);
     const double* sx = reinterpret_cast<const double*>(smem_raw + t.o_sx);
     const double* sy = reinterpret_cast<const double*>(smem_raw + t.o_sy);
     const double* sz = reinterpret_cast<const double*>(smem_raw + t.o_sz);
@@ -126,7 +128,16 @@ eval_kernel(int ngrid, const double* __restrict__ coords, Tables t, int epitch, 
             for (int gi = slot; gi < ng; gi += SLOTS) {
                 const double dx = x - gx[gi], dy = y - gy[gi], dz = z - gz[gi];
                 const double r2 = dx * dx + dy * dy + dz * dz;
-                const int q0 = gprim[gi], nq = gnprim[gi], m0 = gmem[gi], nm = gnmem[gi];
+                const int m0 = gmem[gi], nm = gnmem[gi];
+                // AO screening at the group level: beyond the cutoff of the group's most diffuse primitive every
+                // primitive is dropped (a >= amin => a r^2 > cutoff), so its shells are exact zeros here -- most
+                // (point, group) pairs of a large molecule.  Neighbouring points and the shells of one centre
+                // decide alike, so the warp rarely diverges.
+                if (gamin[gi] * r2 > cutoff) {
+                    for (int m = 0; m < nm; ++m) erow[mshell[m0 + m]] = make_double2(0.0, 0.0);
+                    continue;
+                }
+                const int q0 = gprim[gi], nq = gnprim[gi];
                 if (nq <= MAXP) {
                     double v[MAXP], av[MAXP];
 #pragma unroll
@@ -182,7 +193,12 @@ eval_kernel(int ngrid, const double* __restrict__ coords, Tables t, int epitch, 
                 const int sh = meta & 0xffffff, comp = (meta >> 24) - 1;  // comp: -1 s, 0..2 p_x p_y p_z
                 const double2 e = erow[sh];
                 const double dx = x - sx[sh], dy = y - sy[sh], dz = z - sz[sh];
-                const double dj = comp == 0 ? dx : (comp == 1 ? dy : (comp == 2 ? dz : 1.0));
+                // (a chain of selects, not nested conditionals: lanes hold different components, and the
+                // nested form compiles to divergent branches)
+                double dj = dz;
+                dj = comp == 1 ? dy : dj;
+                dj = comp == 0 ? dx : dj;
+                dj = comp < 0 ? 1.0 : dj;
                 *d0 = dj * e.x;
                 if (DERIV) {
                     // s: e1 d;  p_j: d_j e1 d + e0 delta_j

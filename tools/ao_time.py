@@ -1,0 +1,19 @@
+"""Time DFT_EvalAO (subsystem a) on a workload's full grid: python tools/ao_time.py C5 [C4 ...]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from quantum_compute_dft_b200 import workload  # noqa: E402
+
+for wl in sys.argv[1:]:
+    hp = workload.host_problem(wl)
+    solver = workload.make_solver(hp.functional)
+    dp = workload.device_problem(hp, solver)
+    best = 1e9
+    for _ in range(4):
+        solver.eval_ao(dp.d_coords, hp.basis, dp.d_ao, dp.d_ao_grad)
+        best = min(best, solver.stat("ao_ms"))
+    P = 1 if hp.functional == "LDA" else 4
+    nbytes = 8.0 * dp.ngrid * dp.nao * P
+    print(f"{wl} {hp.name}: DFT_EvalAO {best:.3f} ms, {nbytes / 1e9:.2f} GB written, {nbytes / best / 1e9:.2f} TB/s", flush=True)
+    dp.free()
