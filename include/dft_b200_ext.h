@@ -49,7 +49,8 @@ int DFT_CommDestroy(XCSolver* solver);
 //       that are the exact derivatives of the energies, i.e. libxc/PySCF numint)
 //       "path" 0 auto | 1 generic (any alignment) | 2 TMA-fed
 //       "deterministic" 0|1 (default 1: fixed-order reductions, bit-reproducible results)
-//       "vxc_shape" 0|64|128|160 (tuning: output tile of the TMA V kernel; 0 = chosen from nao)
+//       "vxc_shape" 0|64|96|128|160 (tuning: output tile of the TMA V kernel -- 64 x 64, 96 x 192, 128 x 128,
+//       160 x 80; 0 = chosen from nao)
 //       "vxc_vk" 0|8|16 (tuning: grid rows per ring stage of the 128 x 128 V kernel; 0 = 16 on dense
 //       operands, 8 with zero skipping)
 //       "ao_shape" 0|16|32 (tuning: grid points per block of DFT_EvalAO; 0 = chosen from the basis size)
@@ -57,6 +58,15 @@ int DFT_CommDestroy(XCSolver* solver);
 //       exactly zero are skipped; results are unchanged; default 1)
 //       "vxc_skip" -1|0|1 (the zero-skipping instance of the V kernel: -1 = adaptive, used while the density
 //       kernel of the previous call skipped >= 10 % of its k-steps; default -1)
+//       "vxc_skip_mode" 1|2|3 (which zero-skipping V instance: 1 = per-fragment votes on the M side (default),
+//       2 | 3 = N-side box bits published by a scanner warp plus an M-side vote per stage | per k-step)
+//       "vxc_producers" 1..4 (tuning: TMA-issuing threads per CTA of the V kernel, default 1)
+//       "vxc_scatter" 0|1 (zero-skipping V instances: scatter consecutive ring stages over the grid, default 1)
+//       "vxc_mside_skip" 0|1 (box-bit V instances: keep the M-side votes, default 1)
+//       "dyn_sched" 0|1 (density kernel: hand the 64-point blocks out dynamically, default 1)
+//       "wait_ns" n (tuning: producer threads sleep n ns between barrier polls, default 0)
+//       "debug_nodmma" 0|1 (DIAGNOSTIC, results are wrong: the TMA kernels skip every DMMA, which measures
+//       their operand-delivery floor; default 0)
 //       "tma_3d" 0|1 (tuning: 3-D tensor maps in the V kernel, one TMA load per plane and stage; default 1)
 //       "l2_prefetch" 0|1 (tuning: short-range L2 prefetch in the density kernel, default 0: measured no gain)
 //       "timing" 0|1 (record the per-kernel CUDA events behind DFT_GetStat, default 1)
@@ -65,6 +75,7 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value);
 //       DFT_ComputeXC on the engine's stream), "launches" (kernels launched by the last call),
 //       "ao_ms" (kernel time of the last DFT_EvalAO), "skip_fraction" (share of the density kernel's
 //       k-steps that were exact zeros and skipped in the last call: the AO-screening statistic),
+//       "vxc_skip_fraction" (box-bit V instances: share of the (box, k-step) units skipped),
 //       "path" (path actually taken), "workspace_bytes", "plans_built" (TMA launch plans encoded so
 //       far: a steady SCF loop over the same arrays builds exactly one).
 double DFT_GetStat(XCSolver* solver, const char* key);

@@ -295,7 +295,7 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "vxc_skip_mode")) { c->vxc_skip_mode = (int)value; return 0; }
     if (!strcmp(key, "zero_skip")) { c->zero_skip = value != 0.0; return 0; }
     if (!strcmp(key, "tma_3d")) { c->tma_3d = value != 0.0; return 0; }
-    if (!strcmp(key, "vxc_shape")) { const int v = (int)value; if (v != 0 && v != 64 && v != 128 && v != 160) return 3; c->vxc_shape = v; return 0; }
+    if (!strcmp(key, "vxc_shape")) { const int v = (int)value; if (v != 0 && v != 64 && v != 96 && v != 128 && v != 160) return 3; c->vxc_shape = v; return 0; }
     if (!strcmp(key, "vxc_vk")) { c->vxc_vk = value == 16.0 ? 16 : (value == 8.0 ? 8 : 0); return 0; }
     if (!strcmp(key, "deterministic")) { return value != 0.0 ? 0 : 3; }  // reductions are always fixed-order
     return 2;

@@ -199,14 +199,16 @@ def test_tma_path_matches_generic_path_at_scale(engine_lib, functional, ngrid, n
 @pytest.mark.parametrize("functional", FUNCS)
 @pytest.mark.parametrize("ngrid,nao", [(20000, 152), (12001, 64), (9000, 377), (6000, 255), (3000, 36), (2500, 7)])
 def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
-    """Every tuning variant of the TMA path (V output tile 64/128/160x80, 8 or 16 rows per ring stage, 3-D or
-    per-block 2-D tensor maps, L2 prefetch) computes the same result as the generic path."""
+    """Every tuning variant of the TMA path (V output tile 64/128/160x80/96x192, 8 or 16 rows per ring stage,
+    one or several TMA-issuing threads, static or dynamic block scheduling, 3-D or per-block 2-D tensor maps, L2
+    prefetch) computes the same result as the generic path."""
     rng = np.random.default_rng(3 * ngrid + nao)
     dm, ao, w, grad = _random_case(rng, ngrid, nao)
     e0, v0, s0 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 1})
     assert s0["path"] == 1
     for opt in ({"vxc_shape": 64}, {"vxc_shape": 128, "vxc_vk": 8}, {"vxc_shape": 128, "vxc_vk": 16}, {"vxc_shape": 160},
-                {"tma_3d": 0}, {"l2_prefetch": 1}):
+                {"vxc_shape": 96, "vxc_vk": 8}, {"vxc_shape": 96, "vxc_vk": 16, "vxc_skip": 0},
+                {"vxc_shape": 128, "vxc_producers": 3}, {"dyn_sched": 0}, {"tma_3d": 0}, {"l2_prefetch": 1}):
         e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
         assert s1["path"] == 2, opt
         assert abs(e0 - e1) <= E_TOL * max(1.0, abs(e0) * 1e-3), opt
