@@ -106,8 +106,8 @@ eval_kernel(int ngrid, const double* __restrict__ coords, Tables t, int epitch, 
     const int* mshell = reinterpret_cast<const int*>(smem_raw + t.o_mshell);
     const int* mcoef = reinterpret_cast<const int*>(smem_raw + t.o_mcoef);
     const int* ao_meta = reinterpret_cast<const int*>(smem_raw + t.o_aoshell);  // shell | (comp + 1) << 24
-    double* s_pts = reinterpret_cast<double*>(smem_raw + t.bytes);               // [G][3]
-    double2* e01 = reinterpret_cast<double2*>(s_pts + 3 * G);                    // [G][epitch]
+    double* s_pts2 = reinterpret_cast<double*>(smem_raw + t.bytes);              // [2][G][3]: this block's points, the next block's
+    double2* e01 = reinterpret_cast<double2*>(s_pts2 + 6 * G);                   // [G][epitch]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ng = t.ngroup, nao = t.nao;
@@ -115,12 +115,25 @@ eval_kernel(int ngrid, const double* __restrict__ coords, Tables t, int epitch, 
     constexpr int SLOTS = NWARPS * 32 / G;
     const size_t plane = (size_t)ngrid * nao;
     const int nblk = (ngrid + G - 1) / G;
-    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    // The coordinates of a block are fetched while the previous block is in phase 1 (double-buffered), so a
+    // block costs two CTA barriers and no exposed global-memory latency.
+    if ((int)blockIdx.x < nblk) {
+        const int p0 = blockIdx.x * G, np = min(G, ngrid - p0);
+        if (tid < 3 * np) s_pts2[tid] = __ldg(coords + 3 * (size_t)p0 + tid);
+    }
+    int buf = 0;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x, buf ^= 1) {
         const int p0 = blk * G;
         const int np = min(G, ngrid - p0);
-        __syncthreads();  // tables staged (first block) / previous block's phase 2 done with e01 and s_pts
-        if (tid < 3 * np) s_pts[tid] = __ldg(coords + 3 * (size_t)p0 + tid);
-        __syncthreads();
+        const double* s_pts = s_pts2 + buf * 3 * G;
+        __syncthreads();  // tables and this block's points staged / previous block's phase 2 done with e01
+        {   // next block's points into the other buffer (last read by the previous block's phase 2)
+            const int nb = blk + gridDim.x;
+            if (nb < nblk) {
+                const int q0 = nb * G, nq = min(G, ngrid - q0);
+                if (tid < 3 * nq) s_pts2[(buf ^ 1) * 3 * G + tid] = __ldg(coords + 3 * (size_t)q0 + tid);
+            }
+        }
         // ---- phase 1: radial sums; a half-warp = one group x 16 points
         if (pt < np) {
             const double x = s_pts[3 * pt], y = s_pts[3 * pt + 1], z = s_pts[3 * pt + 2];
@@ -331,9 +344,9 @@ extern "C" int DFT_EvalAO(XCSolver* solver, int ngrid, unsigned long long d_coor
     // ---- shared memory: tables + the block's points + radial sums [G][epitch] (epitch odd)
     const int epitch = nshell | 1;
     const size_t smem_max = 227 * 1024;
-    auto smem_for = [&](int G) { return bytes + sizeof(double) * 3 * G + sizeof(double2) * (size_t)G * epitch + 64; };
+    auto smem_for = [&](int G) { return bytes + sizeof(double) * 6 * G + sizeof(double2) * (size_t)G * epitch + 64; };
     int shape = ctx->ao_shape;
-    if (shape != 16 && shape != 32) shape = 2 * (smem_for(32) + 1024) <= smem_max ? 32 : 16;
+    if (shape != 8 && shape != 16 && shape != 32) shape = 2 * (smem_for(32) + 1024) <= smem_max ? 32 : 16;
     const int G = shape, NW = shape == 32 ? 16 : 8;
     const size_t smem = smem_for(G);
     if (smem > smem_max) {
@@ -356,8 +369,8 @@ extern "C" int DFT_EvalAO(XCSolver* solver, int ngrid, unsigned long long d_coor
         DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         k<<<grid, NW_ * 32, smem, ctx->stream>>>(ngrid, coords, t, epitch, exp_cutoff, ao_out, g_out);                  \
     } while (0)
-    if (deriv) { if (G == 32) DFT_AO_LAUNCH(true, 32, 16); else DFT_AO_LAUNCH(true, 16, 8); }
-    else { if (G == 32) DFT_AO_LAUNCH(false, 32, 16); else DFT_AO_LAUNCH(false, 16, 8); }
+    if (deriv) { if (G == 32) DFT_AO_LAUNCH(true, 32, 16); else if (G == 16) DFT_AO_LAUNCH(true, 16, 8); else DFT_AO_LAUNCH(true, 8, 8); }
+    else { if (G == 32) DFT_AO_LAUNCH(false, 32, 16); else if (G == 16) DFT_AO_LAUNCH(false, 16, 8); else DFT_AO_LAUNCH(false, 8, 8); }
 #undef DFT_AO_LAUNCH
     if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->stream);
     DFT_CUDA_CHECK(ctx, cudaGetLastError());

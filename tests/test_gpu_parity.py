@@ -321,7 +321,7 @@ def test_ao_evaluation_on_gpu(oracle, engine_lib):
         d_ao2 = DeviceArray(ao_o.shape)
         s.eval_ao(d_c, basis, d_ao2, None)
         np.testing.assert_allclose(d_ao2.get(), d_ao.get(), rtol=1e-14, atol=1e-300)  # deriv=0 kernel contracts FMAs differently
-        for shape in (16, 32):     # both block shapes of the kernel write identical values
+        for shape in (8, 16, 32):  # every block shape of the kernel writes identical values
             s.set_option("ao_shape", shape)
             d_ao3 = DeviceArray(ao_o.shape); d_g3 = DeviceArray(g_o.shape)
             s.eval_ao(d_c, basis, d_ao3, d_g3)
