@@ -117,6 +117,17 @@ def test_ragged_shapes(oracle, engine_lib, functional, ngrid, nao):
 
 
 @pytest.mark.parametrize("functional", FUNCS)
+@pytest.mark.parametrize("ngrid,nao", [(1200, 520), (902, 777), (700, 1000), (640, 1283), (300, 2048), (200, 2049)])
+def test_wide_basis_shapes(oracle, engine_lib, functional, ngrid, nao):
+    """Larger basis sets than the config molecules': many column tiles in both contraction kernels, odd and even
+    nao, up to (and one past) the TMA path's nao limit of 2048, where the generic path takes over."""
+    rng = np.random.default_rng(ngrid * 7 + nao)
+    dm, ao, w, grad = _random_case(rng, ngrid, nao)
+    e, v = _check(oracle, engine_lib, functional, dm, ao, w, grad, vs_reference=False)
+    assert np.isfinite(e)
+
+
+@pytest.mark.parametrize("functional", FUNCS)
 def test_exact_functional_mode(oracle, engine_lib, functional):
     rng = np.random.default_rng(11)
     dm, ao, w, grad = _random_case(rng, 3000, 24)
