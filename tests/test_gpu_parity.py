@@ -226,7 +226,7 @@ def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
         np.testing.assert_allclose(v0, v1, rtol=0, atol=V_TOL * max(1.0, np.abs(v0).max() * 1e-3), err_msg=str(opt))
 
 
-def _screened_case(rng, ngrid, nao, rows=64, cols=10):
+def _screened_case(rng, ngrid, nao, rows=192, cols=10):
     """Random planes with the zero pattern AO screening leaves: for runs of `rows` grid points, runs of about
     `cols` neighbouring AOs (an atom's shells) are exact zeros in all four planes; a few single-plane zeros on top."""
     dm, ao, w, grad = _random_case(rng, ngrid, nao)
