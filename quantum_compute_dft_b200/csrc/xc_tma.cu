@@ -1,21 +1,24 @@
 // xc_tma.cu -- the fast XC path: TMA-fed, mbarrier-pipelined FP64 tensor-core (DMMA) kernels.
 //
-// Two persistent-style, warp-specialised kernels per XC build.  One CTA per SM, 384 threads: two
-// consumer warpgroups (8 warps) and one producer warpgroup whose first lane drives TMA;
-// `setmaxnreg` moves registers from the producer to the consumers (40 / 232 per thread) so that
-// 64 x 40 FP64 accumulator tiles fit without spills.  Neither kernel has a CTA-wide barrier in its
-// main loop: everything a consumer warp touches arrives through one TMA ring (full/empty
-// mbarriers), so the DMMA pipe never drains between tiles.
+// Two persistent-style, warp-specialised contraction kernels per XC build (plus the pointwise kernel between
+// them).  One CTA per SM, 384 threads: two consumer warpgroups (8 warps) and one producer warpgroup whose
+// elected lanes drive TMA; `setmaxnreg` moves registers from the producer to the consumers (40 / 232 per
+// thread) so that 64 x 40 FP64 accumulator tiles fit without spills.  Neither kernel has a CTA-wide barrier
+// in its main loop: everything a consumer warp touches arrives through a TMA ring (full/empty mbarriers),
+// so the DMMA pipe never drains between tiles.
 //
-//   density_tma_kernel   subsystem (b)+(c): for each block of 128 grid points and column tile nt
+//   density_tma_kernel   subsystem (b): for each block of 64 grid points and column tile nt
 //        C = Phi_blk . Dsym[:, nt]                DMMA, operands streamed by TMA (SWIZZLE_128B)
 //        rho += rowsum(C o Phi), grad rho += 2 rowsum(C o dPhi)
 //                                                 the Phi / dPhi tiles of the row-dots come through
 //                                                 the SAME ring as 32 KB "pieces" right behind the
-//                                                 k-chunks (no global gathers, no exposed latency)
-//        pointwise functional once per point -> (a, b) coefficients + E_xc partial
-//     replaces get_rho_kernel / get_rho_sigma_kernel_planar (dft_solver.cu:294-307, :346-380), both
-//     passes of the *_fused_kernel's (:309-513) and reduce_sum_kernel (:285-292).
+//                                                 k-chunks (no global gathers)
+//     two ping-pong consumer groups with a ring each; blocks handed out dynamically; k-steps whose Phi
+//     fragment is exactly zero are skipped (AO screening).
+//     replaces get_rho_kernel / get_rho_sigma_kernel_planar (dft_solver.cu:294-307, :346-380).
+//
+//   xc_point_kernel      subsystem (c): the functional once per point -> (a, b) coefficients + E_xc partials
+//     replaces both passes of the *_fused_kernel's (:309-513) and reduce_sum_kernel (:285-292).
 //
 //   vxc_tma_kernel       subsystem (d): for each (output tile, grid slice)
 //        M += B^T Phi,  B = a o Phi + b . grad Phi
