@@ -20,7 +20,9 @@ def main():
     steps = int(os.environ.get("SWEEP_STEPS", "6"))
     hp = workload.host_problem(wl)
     solver = workload.make_solver(hp.functional)
-    dp = workload.device_problem(hp, solver)
+    # SWEEP_RANKS=N: time rank 0's shard of an N-rank run (the per-GPU problem of a multi-GPU step) on one GPU
+    nranks = int(os.environ.get("SWEEP_RANKS", "1"))
+    dp = workload.device_problem(hp, solver, 0, nranks)
     v_first = None
     for spec in sets:
         opts = dict(DEFAULTS)
@@ -38,7 +40,7 @@ def main():
         v = dp.d_vxc.get()
         if v_first is None:
             v_first = v
-        print(f"{wl} [{spec or 'defaults'}] step {rec[:, 0].mean():.3f} (min {rec[:, 0].min():.3f}) ms  "
+        print(f"{wl} shard 1/{nranks} ({dp.ngrid} pts) [{spec or 'defaults'}] step {rec[:, 0].mean():.3f} (min {rec[:, 0].min():.3f}) ms  "
               f"density {rec[:, 1].mean():.3f}  V {rec[:, 2].mean():.3f} (min {rec[:, 2].min():.3f})  "
               f"E {e!r}  v_skipped {solver.stat('vxc_skip_fraction'):.3f}  d_skipped {solver.stat('skip_fraction'):.3f}  "
               f"max|dV| {np.abs(v - v_first).max():.2e}", flush=True)
