@@ -63,7 +63,11 @@ int DFT_CommDestroy(XCSolver* solver);
 //       "vxc_producers" 1..4 (tuning: TMA-issuing threads per CTA of the V kernel, default 1)
 //       "vxc_scatter" 0|1 (zero-skipping V instances: scatter consecutive ring stages over the grid, default 1)
 //       "vxc_mside_skip" 0|1 (box-bit V instances: keep the M-side votes, default 1)
-//       "dyn_sched" 0|1 (density kernel: hand the 64-point blocks out dynamically, default 1)
+//       "dyn_sched" 0|1 (density kernel: hand the units of work out dynamically, default 1)
+//       "density_unit" 0|1|2 (density kernel, unit of work: 1 = a 64-point block, 0 | 2 = one column tile of a
+//       block, the default)
+//       "stagger_min" n (density kernel: consumer group 1 starts half a tile period late when a CTA has more
+//       than n blocks to do, default 8)
 //       "wait_ns" n (tuning: producer threads sleep n ns between barrier polls, default 0)
 //       "debug_nodmma" 0|1 (DIAGNOSTIC, results are wrong: the TMA kernels skip every DMMA, which measures
 //       their operand-delivery floor; default 0)

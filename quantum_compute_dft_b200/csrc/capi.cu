@@ -286,6 +286,8 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "l2_prefetch")) { c->l2_prefetch = value != 0.0; return 0; }
     if (!strcmp(key, "ao_shape")) { c->ao_shape = (int)value; return 0; }
     if (!strcmp(key, "vxc_skip")) { c->vxc_skip = (int)value; if (c->vxc_skip >= 0) c->vxc_skip_on = c->vxc_skip != 0; return 0; }
+    if (!strcmp(key, "density_unit")) { const int v = (int)value; if (v < 0 || v > 2) return 3; c->density_unit = v; return 0; }
+    if (!strcmp(key, "stagger_min")) { c->stagger_min = value < 0.0 ? 0 : (int)value; return 0; }
     if (!strcmp(key, "dyn_sched")) { c->dyn_sched = value != 0.0; return 0; }
     if (!strcmp(key, "wait_ns")) { c->wait_ns = value < 0.0 ? 0 : (int)value; return 0; }
     if (!strcmp(key, "debug_nodmma")) { c->debug_nodmma = value != 0.0; return 0; }

@@ -56,6 +56,8 @@ struct CublasHandleWrapper {
     bool vxc_skip_on = true;       // (adaptive) the zero-skipping V instance is used while the density kernel finds zeros
     int vxc_skip_mode = 1;         // zero-skipping V instance (128 x 128 tile): 1 M-side votes, 2 | 3 N-side box bits (xc_tma.cu)
     int vxc_scatter = 1;           // zero-skipping V instances: scatter consecutive ring stages over the grid (golden-ratio stride)
+    int density_unit = 0;          // TMA density kernel, unit of work: 0 | 2 = one column tile of a 64-point block (default), 1 = a whole block
+    int stagger_min = 8;           // TMA density kernel: consumer group 1 starts half a tile period late when a CTA has more blocks than this
     int dyn_sched = 1;             // TMA density kernel: hand the 64-point blocks out dynamically (one global counter)
     int wait_ns = 0;               // TMA kernels: producer / scanner threads sleep this long between barrier polls
     int debug_nodmma = 0;          // diagnostic only: TMA kernels skip every DMMA (measures the operand-delivery floor)

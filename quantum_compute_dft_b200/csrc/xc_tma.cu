@@ -79,6 +79,8 @@ struct DensityParams {
     CUtensorMap map_d;        // [2][NP][KP] symmetrised density (plain, shifted), box 16 x NT
     SubProblem sub[2];
     int nsub, nblocks, ntiles, nk, NP, l2_prefetch, coef_rows, zero_skip;
+    int per_tile;      // unit of work: 0 = a 64-point block (all column tiles), 1 = one column tile of a block
+    int stagger_min;   // group 1 starts half a tile period late when the CTA has more than this many blocks to do
     int wait_ns;       // producer threads sleep this long between polls of an `empty` barrier (0: poll back to back)
     int debug_nodmma;  // diagnostic: treat every k-step as zero (measures the operand-delivery floor; results are wrong)
     unsigned long long* counters;  // [2]: k-steps executed, k-steps total (AO screening statistics)
@@ -219,8 +221,14 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
     // times one out in the tail, so a static deal leaves the last groups running alone.  The producer draws
     // the block ids (the next one while the current block streams) and passes each to its consumers in a
     // shared-memory slot that travels with the block's first ring stage; a stage carrying -1 ends the group.
+    // The unit of work is one column tile of a block (a third of a block at C5: a shorter tail, which is what a
+    // multi-GPU shard with ~10 blocks per group notices); the point kernel adds one partial per tile and warp
+    // column.  With `density_unit` 1 it is a whole block, whose partial row sums then stay in registers over
+    // all column tiles.
     const bool dyn = P.sched != nullptr;
     const uint32_t blk_slot = base + L::BLK_OFF + grp * L::STAGES * 4;
+    const bool per_tile = P.per_tile != 0;
+    const int nunits = per_tile ? nblocks * ntiles : nblocks;
 
     if (warp >= NCW) {
         // ===================== producer warpgroup: warps 8 and 9, one elected lane each =====================
@@ -237,21 +245,24 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             // doubled the DRAM traffic).
             constexpr int PF = 6;
             const bool pf = P.l2_prefetch != 0;
-            int b = dyn ? (int)atomicAdd(P.sched, 1u) : b_first;
-            while (b < nblocks) {
+            int u = dyn ? (int)atomicAdd(P.sched, 1u) : b_first;
+            while (u < nunits) {
+                const int b = per_tile ? u / ntiles : u;
+                const int nt0 = per_tile ? u - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
                 const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
                 const int blk = b - P.sub[si].blk0;
                 const int drow0 = P.sub[si].shift * P.NP;
-                const int bn = dyn ? (int)atomicAdd(P.sched, 1u) : b + b_step;  // this group's next block
+                const int un = dyn ? (int)atomicAdd(P.sched, 1u) : u + b_step;  // this group's next unit
+                const int bn = per_tile ? un / ntiles : un;                      // (its block: L2 prefetch only)
                 const int sin = (P.nsub > 1 && bn >= P.sub[1].blk0) ? 1 : 0;
                 const int blkn = bn - P.sub[sin].blk0;
-                for (int nt = 0; nt < ntiles; ++nt) {
+                for (int nt = nt0; nt < nt1; ++nt) {
                     const int pc0 = nk > L::NPIECES ? nk - L::NPIECES : 0;  // chunk at which piece prefetch starts
                     for (int kc = 0; kc < nk; ++kc, ++it) {
                         if (pf) {
                             const int ka = kc + PF;
                             if (ka < nk) tma::prefetch_2d(&P.map_a[si], ka * 16, blk * MB);
-                            else if (nt + 1 < ntiles) { if (ka - nk < nk) tma::prefetch_2d(&P.map_a[si], (ka - nk) * 16, blk * MB); }
+                            else if (nt + 1 < nt1) { if (ka - nk < nk) tma::prefetch_2d(&P.map_a[si], (ka - nk) * 16, blk * MB); }
                             else if (bn < nblocks && ka - nk < nk) tma::prefetch_2d(&P.map_a[sin], (ka - nk) * 16, blkn * MB);
                             if (kc >= pc0) {
                                 // pieces [lo, hi) of this tile; all of them by the last chunk
@@ -265,7 +276,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                         const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
                         tma::mbar_wait_relaxed(&empty[s], ph ^ 1u, (uint32_t)P.wait_ns);
                         unsigned char* st = ring + s * L::STAGE_BYTES;
-                        if (nt == 0 && kc == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(blk_slot + 4 * s), "r"(b) : "memory");
+                        if (nt == nt0 && kc == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(blk_slot + 4 * s), "r"(u) : "memory");
                         tma::mbar_arrive_expect_tx(&full[s], L::K_BYTES);
                         tma::load_2d(st, &P.map_a[si], kc * 16, blk * MB, &full[s]);
                         tma::load_2d(st + L::A_BYTES, &P.map_d, kc * 16, drow0 + nt * NT, &full[s]);
@@ -280,9 +291,9 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                             tma::load_2d(st + p * L::PLANE_BYTES, &P.map_e[si][p], c0, blk * MB, &full[s]);
                     }
                 }
-                b = bn;
+                u = un;
             }
-            if (dyn) {  // no blocks left: one empty stage carrying -1 tells the consumers to stop
+            if (dyn) {  // no units left: one empty stage carrying -1 tells the consumers to stop
                 const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
                 tma::mbar_wait_relaxed(&empty[s], ph ^ 1u, (uint32_t)P.wait_ns);
                 asm volatile("st.shared.s32 [%0], %1;" ::"r"(blk_slot + 4 * s), "r"(-1) : "memory");
@@ -327,7 +338,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
     const bool dbg_off = P.debug_nodmma != 0;
 
     // group 1 starts half a column-tile period late (only worth it when there are several blocks to do)
-    if (grp == 1 && nblocks > 8 * (int)gridDim.x) {
+    if (grp == 1 && nblocks > P.stagger_min * (int)gridDim.x) {
         const long long t_start = clock64(), delay = (long long)nk * 2048;
         while (clock64() - t_start < delay) __nanosleep(2000);
     }
@@ -341,15 +352,17 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
 #else
 #define PHASE_MARK(acc_) do { } while (0)
 #endif
-    for (int b = b_first;; b += b_step) {
-        if (dyn) {  // the block id travels with the block's first stage
+    for (int u = b_first;; u += b_step) {
+        if (dyn) {  // the unit id travels with the unit's first stage
             const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
             tma::mbar_wait(&full[s], ph);
-            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(b) : "r"(blk_slot + 4 * s) : "memory");
-            if (b < 0) break;
-        } else if (b >= nblocks) {
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(u) : "r"(blk_slot + 4 * s) : "memory");
+            if (u < 0) break;
+        } else if (u >= nunits) {
             break;
         }
+        const int b = per_tile ? u / ntiles : u;
+        const int nt0 = per_tile ? u - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
         const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
         const int blk = b - P.sub[si].blk0;
         double rs[4][NPL];  // per-lane partial row sums of the whole block
@@ -358,7 +371,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
 #pragma unroll
             for (int p = 0; p < NPL; ++p) rs[mf][p] = 0.0;
 
-        for (int nt = 0; nt < ntiles; ++nt) {
+        for (int nt = nt0; nt < nt1; ++nt) {
             double acc[4][NF2][2];
 #pragma unroll
             for (int mf = 0; mf < 4; ++mf)
@@ -450,7 +463,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
         // to the point kernel.  GGA: transpose-reduce (3 shuffles per row) after which lane qcol holds plane
         // qcol; the 4 lanes of a row write 32 contiguous bytes.  No barrier: the two warp columns' partial
         // sums are added by the point kernel.
-        double* rho_mine = P.rho + ((size_t)wn * P.coef_rows + P.sub[si].coef0 + (size_t)blk * MB + wm * 32 + rho) * 4 + qcol;
+        double* rho_mine = P.rho + ((size_t)(2 * nt0 + wn) * P.coef_rows + P.sub[si].coef0 + (size_t)blk * MB + wm * 32 + rho) * 4 + qcol;
         if (NPL == 4) {
             const bool b0 = (qcol & 1) != 0, b1 = (qcol & 2) != 0;
 #pragma unroll
@@ -499,7 +512,8 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
 struct PointParams {
     SubProblem sub[2];
     int nsub, xc_mode, coef_rows;
-    const double* rho;   // [2][coef_rows][4]
+    int nparts;          // partial row sums per point: 2 (warp columns), times the column tiles in per-tile mode
+    const double* rho;   // [nparts][coef_rows][4]
     const double* w;
     double* coef;        // [coef_rows][4]
     double* exc_part;    // [gridDim.x]
@@ -517,11 +531,14 @@ xc_point_kernel(const PointParams P) {
         double2 c01 = make_double2(0.0, 0.0), c23 = make_double2(0.0, 0.0);
         if (j < P.sub[si].rows) {  // rows past the end of a sub-problem are padding: zero coefficients
             const double2* r0 = reinterpret_cast<const double2*>(P.rho) + 2 * (size_t)row;
-            const double2* r1 = r0 + 2 * (size_t)P.coef_rows;
-            const double2 a0 = __ldg(r0), a1 = __ldg(r0 + 1), b0 = __ldg(r1), b1 = __ldg(r1 + 1);
+            double2 s0 = __ldg(r0), s1 = __ldg(r0 + 1);
+            for (int part = 1; part < P.nparts; ++part) {   // fixed order: bit-reproducible
+                const double2* rp = r0 + 2 * (size_t)P.coef_rows * part;
+                const double2 t0 = __ldg(rp), t1 = __ldg(rp + 1);
+                s0.x += t0.x; s0.y += t0.y; s1.x += t1.x; s1.y += t1.y;
+            }
             const long g = (long)P.sub[si].gmul * j + P.sub[si].gadd;
-            const xcfun::PointCoef pc = eval_mode(P.xc_mode, a0.x + b0.x, 2.0 * (a0.y + b0.y), 2.0 * (a1.x + b1.x),
-                                                  2.0 * (a1.y + b1.y), __ldg(P.w + g));
+            const xcfun::PointCoef pc = eval_mode(P.xc_mode, s0.x, 2.0 * s0.y, 2.0 * s1.x, 2.0 * s1.y, __ldg(P.w + g));
             c01 = make_double2(pc.a, pc.bx);
             c23 = make_double2(pc.by, pc.bz);
             e = pc.exc;
@@ -1104,7 +1121,7 @@ static Geometry make_geometry(int ngrid, int nao) {
 // addresses, so a plan stays valid when the caller rewrites the CONTENTS of its arrays.
 struct PlanKey {
     Problem prob;
-    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, vxc_mside_skip, debug_nodmma, wait_ns, dyn_sched;
+    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, vxc_mside_skip, debug_nodmma, wait_ns, dyn_sched, stagger_min, density_unit;
     const void *dsym, *coef, *epart, *vpart, *rho;  // engine workspaces (grow-only: may move when they grow)
 };
 
@@ -1136,7 +1153,11 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
 
     double* dsym = (double*)ctx->dsym.ensure(sizeof(double) * (size_t)g.nsub * NP * KP, &ctx->failed);
     double* epart = (double*)ctx->epart.ensure(sizeof(double) * pgrid, &ctx->failed);
-    double* rho = (double*)ctx->rho.ensure(sizeof(double) * 8 * (size_t)g.coef_rows, &ctx->failed);
+    // unit of work (see the kernel): a column tile of a block whenever there are several tiles -- measured faster
+    // at every size (C5: 9.35 -> 9.31 ms on the whole grid, 1.305 -> 1.265 ms on an eighth of it)
+    const bool per_tile = ntiles > 1 && ctx->density_unit != 1;
+    const int nparts = per_tile ? 2 * ntiles : 2;
+    double* rho = (double*)ctx->rho.ensure(sizeof(double) * 4 * (size_t)nparts * g.coef_rows, &ctx->failed);
     if (ctx->failed) return;
 
     DensityParams& dp = pl.dp;
@@ -1154,7 +1175,8 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
     dp.nblocks = g.nblocks; dp.ntiles = ntiles; dp.nk = KP / 16; dp.NP = NP;
     dp.l2_prefetch = ctx->l2_prefetch ? 1 : 0;
     dp.zero_skip = ctx->zero_skip ? 1 : 0;
-    dp.debug_nodmma = ctx->debug_nodmma; dp.wait_ns = ctx->wait_ns;
+    dp.debug_nodmma = ctx->debug_nodmma; dp.wait_ns = ctx->wait_ns; dp.stagger_min = ctx->stagger_min;
+    dp.per_tile = per_tile ? 1 : 0;
     dp.sched = (ctx->dyn_sched && dp.counters) ? reinterpret_cast<unsigned int*>(dp.counters + 4) : nullptr;
     dp.coef_rows = g.coef_rows; dp.rho = rho;
     dp.counters = reinterpret_cast<unsigned long long*>(ctx->counters.ensure(6 * sizeof(unsigned long long), &ctx->failed));
@@ -1162,7 +1184,7 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
     PointParams& pp = pl.pp;
     memset(&pp, 0, sizeof(pp));
     pp.sub[0] = g.sub[0]; pp.sub[1] = g.sub[1];
-    pp.nsub = g.nsub; pp.coef_rows = g.coef_rows;
+    pp.nsub = g.nsub; pp.coef_rows = g.coef_rows; pp.nparts = nparts;
     pp.xc_mode = p.xc_type == 2 ? 4 : p.xc_type * 2 + (ctx->exact_functionals ? 1 : 0);
     pp.rho = rho; pp.w = p.w; pp.coef = coef; pp.exc_part = epart;
     pl.pgrid = pgrid;
@@ -1329,7 +1351,7 @@ static PlanKey make_key(const CublasHandleWrapper* ctx, const Problem& p) {
     k.prob.vxc = p.vxc; k.prob.d_exc = p.d_exc;
     k.exact = ctx->exact_functionals; k.l2_prefetch = ctx->l2_prefetch; k.tma_3d = ctx->tma_3d;
     k.vxc_shape = ctx->vxc_shape; k.vxc_vk = ctx->vxc_vk; k.zero_skip = ctx->zero_skip; k.vxc_skip_on = ctx->vxc_skip_on; k.vxc_skip_mode = ctx->vxc_skip_mode; k.vxc_scatter = ctx->vxc_scatter;
-    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.vxc_producers = ctx->vxc_producers; k.vxc_mside_skip = ctx->vxc_mside_skip;
+    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.stagger_min = ctx->stagger_min; k.density_unit = ctx->density_unit; k.vxc_producers = ctx->vxc_producers; k.vxc_mside_skip = ctx->vxc_mside_skip;
     k.dsym = ctx->dsym.ptr; k.coef = ctx->coef.ptr; k.epart = ctx->epart.ptr; k.vpart = ctx->vpart.ptr;
     k.rho = ctx->rho.ptr;
     return k;

@@ -219,7 +219,8 @@ def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
     assert s0["path"] == 1
     for opt in ({"vxc_shape": 64}, {"vxc_shape": 128, "vxc_vk": 8}, {"vxc_shape": 128, "vxc_vk": 16}, {"vxc_shape": 160},
                 {"vxc_shape": 96, "vxc_vk": 8}, {"vxc_shape": 96, "vxc_vk": 16, "vxc_skip": 0},
-                {"vxc_shape": 128, "vxc_producers": 3}, {"dyn_sched": 0}, {"tma_3d": 0}, {"l2_prefetch": 1}):
+                {"vxc_shape": 128, "vxc_producers": 3}, {"dyn_sched": 0}, {"density_unit": 1}, {"density_unit": 2},
+                {"density_unit": 2, "dyn_sched": 0}, {"tma_3d": 0}, {"l2_prefetch": 1}):
         e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
         assert s1["path"] == 2, opt
         assert abs(e0 - e1) <= E_TOL * max(1.0, abs(e0) * 1e-3), opt
