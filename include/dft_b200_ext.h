@@ -80,8 +80,9 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value);
 //       "ao_ms" (kernel time of the last DFT_EvalAO), "skip_fraction" (share of the density kernel's
 //       k-steps that were exact zeros and skipped in the last call: the AO-screening statistic),
 //       "vxc_skip_fraction" (box-bit V instances: share of the (box, k-step) units skipped),
-//       "path" (path actually taken), "workspace_bytes", "plans_built" (TMA launch plans encoded so
-//       far: a steady SCF loop over the same arrays builds exactly one).
+//       "path" (path actually taken), "workspace_bytes", "nranks" (ranks of the communicator, 1 without
+//       DFT_CommInit), "plans_built" (TMA launch plans encoded so far: a steady SCF loop over the same arrays
+//       builds exactly one).
 double DFT_GetStat(XCSolver* solver, const char* key);
 
 // ---- Coulomb and exact exchange in one pass over the ERI ------------

@@ -72,3 +72,16 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 for needle in ("import oracle", "from oracle", "libxc_oracle", "xc_oracle.c", "oracle/_"):
                     assert needle not in txt, (f, needle)
+
+
+def test_documented_option_keys_match_the_library():
+    """Every DFT_SetOption / DFT_GetStat key the library handles is documented in include/dft_b200_ext.h, and
+    every documented key is handled (doc / code drift check; no GPU needed)."""
+    capi = open(os.path.join(ROOT, "quantum_compute_dft_b200", "csrc", "capi.cu")).read()
+    handled = set(re.findall(r'strcmp\(key, "([a-z_0-9]+)"\)', capi))
+    hdr = open(os.path.join(ROOT, "include", "dft_b200_ext.h")).read()
+    start = hdr.index("// ---- options / statistics")
+    end = hdr.index("double DFT_GetStat")
+    documented = set(re.findall(r'"([a-z_0-9]+)"', hdr[start:end]))
+    assert handled - documented == set(), sorted(handled - documented)
+    assert documented - handled == set(), sorted(documented - handled)
