@@ -69,8 +69,11 @@ int DFT_CommDestroy(XCSolver* solver);
 //       "stagger_min" n (density kernel: consumer group 1 starts half a tile period late when a CTA has more
 //       than n blocks to do, default 8)
 //       "wait_ns" n (tuning: producer threads sleep n ns between barrier polls, default 0)
-//       "debug_nodmma" 0|1 (DIAGNOSTIC, results are wrong: the TMA kernels skip every DMMA, which measures
-//       their operand-delivery floor; default 0)
+//       "raw_convention" 0|1 (default 0: d_vxc is always the symmetric matrix S with 1/2 (S + S^T) = V_xc, which
+//       is all the reference's driver uses (dft.py:212); 1: GGA leaves the reference's own raw, UNSYMMETRISED
+//       B^T Phi with the 4 v_sigma factor (dft_solver.cu:616) for a caller that reads d_vxc directly.  LDA and
+//       B3LYP raw outputs are already symmetric in the reference and identical in both settings)
+//       ("debug_nodmma" exists only in -DDFT_DIAGNOSTICS builds, see the end of this header)
 //       "tma_3d" 0|1 (tuning: 3-D tensor maps in the V kernel, one TMA load per plane and stage; default 1)
 //       "l2_prefetch" 0|1 (tuning: short-range L2 prefetch in the density kernel, default 0: measured no gain)
 //       "timing" 0|1 (record the per-kernel CUDA events behind DFT_GetStat, default 1)
@@ -82,7 +85,9 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value);
 //       "vxc_skip_fraction" (box-bit V instances: share of the (box, k-step) units skipped),
 //       "path" (path actually taken), "workspace_bytes", "nranks" (ranks of the communicator, 1 without
 //       DFT_CommInit), "plans_built" (TMA launch plans encoded so far: a steady SCF loop over the same arrays
-//       builds exactly one).
+//       builds exactly one), "dyn_units" (draws from the density kernel's dynamic work counter in the last call =
+//       units of work + consumer groups when "dyn_sched" is on, 0 with the static deal), "density_units" /
+//       "density_groups" (units of work and consumer groups of the density kernel's last launch).
 double DFT_GetStat(XCSolver* solver, const char* key);
 
 // ---- Coulomb and exact exchange in one pass over the ERI ------------
@@ -128,4 +133,13 @@ double DFT_MicrobenchDFMA(int iters);
 double DFT_MicrobenchDMMAWarps(int warps_per_sm, int iters);
 
 const char* DFT_B200_Version(void);
+
+#ifdef DFT_DIAGNOSTICS
+// ---- diagnostic builds only (python -m quantum_compute_dft_b200.build --diag -> weights/dft_diag.so) ----------
+// Not part of the product library: weights/dft.so neither exports DFT_DebugRead nor accepts the option
+// "debug_nodmma" (TMA kernels run their whole pipeline but skip every DMMA -- RESULTS ARE WRONG; it measures the
+// operand-delivery floor).  DFT_DebugRead copies an engine workspace ("coef", "epart", "dsym", "vpart", "rho",
+// "scratch") to the host.
+int DFT_DebugRead(XCSolver* solver, const char* what, void* dst, unsigned long long nbytes);
+#endif
 }

@@ -66,7 +66,9 @@ public:
 
 protected:
     // Kept so that code written against the reference header still links
-    // (dft_solver.h:25-27).  Implemented with the engine's own FP64 tensor-core GEMM.
+    // (dft_solver.h:25-27).  Implemented by a plain 16 x 16-tile SIMT FP64 GEMM (csrc/linalg.cu,
+    // gemm_simple_kernel): correct for any shape and transposition, NOT tuned and NOT on the XC hot
+    // path -- the engine's contractions are the fused DMMA kernels in csrc/xc_tma.cu.
     void safe_cublas_dgemm(bool transA, bool transB, int m, int n, int k,
                            const double* A, int lda, const double* B, int ldb,
                            double* C, int ldc);

@@ -240,6 +240,7 @@ extern "C" int DFT_EvalAO(XCSolver* solver, int ngrid, unsigned long long d_coor
     if (deriv && !d_ao_grad_ptr) return 1;
     if (ngrid <= 0) return 0;
     CublasHandleWrapper* ctx = solver->context();
+    DeviceGuard guard(ctx->device);
     ctx->failed = false;
     if (exp_cutoff <= 0.0) exp_cutoff = 60.0;
     if (exp_cutoff > 700.0) exp_cutoff = 700.0;  // exp(-700) ~ 1e-304: nothing beyond contributes (and exp_neg stays in range)

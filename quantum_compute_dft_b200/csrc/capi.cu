@@ -42,10 +42,13 @@ CublasHandleWrapper::CublasHandleWrapper() {
     DFT_CUDA_CHECK(this, cudaStreamCreateWithFlags(&stream, cudaStreamDefault));
     for (auto& e : ev) DFT_CUDA_CHECK(this, cudaEventCreate(&e));
     DFT_CUDA_CHECK(this, cudaMallocHost(reinterpret_cast<void**>(&h_scalar), 128));
+    if (h_scalar) { h_scalar[8] = 0.0; h_scalar[9] = 1.0; }  // constant sources of the "this rank failed" element
 }
 
 CublasHandleWrapper::~CublasHandleWrapper() {
+    DeviceGuard guard(device);
     if (stream) cudaStreamSynchronize(stream);
+    xc::comm_destroy(this);
     xc::free_tma_plan(this);
     dsym.release(); counters.release(); rho.release(); coef.release(); epart.release(); vpart.release(); result.release(); scratch.release();
     if (h_scalar) cudaFreeHost(h_scalar);
@@ -63,35 +66,47 @@ XCSolver::XCSolver() : handle_wrapper(new CublasHandleWrapper()) {}
 XCSolver::~XCSolver() = default;
 
 void XCSolver::compute_coulomb(int nao, const double* d_eri, const double* d_dm, double* d_J) {
+    DeviceGuard guard(handle_wrapper->device);
     xc::coulomb_gemv(handle_wrapper.get(), nao, d_eri, d_dm, d_J);
 }
 
 void XCSolver::safe_cublas_dgemm(bool transA, bool transB, int m, int n, int k, const double* A, int lda,
                                  const double* B, int ldb, double* C, int ldc) {
+    DeviceGuard guard(handle_wrapper->device);
     xc::dgemm_colmajor(handle_wrapper.get(), transA, transB, m, n, k, A, lda, B, ldb, C, ldc);
 }
 
 namespace {
 
+// result = failed ranks > 0 ? NaN : E  (multi-GPU, asynchronous variant: the host never sees the reduced failure count)
+__global__ void publish_exc_kernel(const double* __restrict__ e_and_failed, double* __restrict__ out) {
+    out[0] = e_and_failed[1] != 0.0 ? __longlong_as_double(0x7ff8000000000000ll) : e_and_failed[0];
+}
+
 // One XC build on the engine stream.  When `d_exc_out` is null the call blocks and returns E_xc
 // (reference semantics); otherwise E_xc is left on the device and the call returns immediately.
+//
+// Multi-GPU: the packed buffer is [V_xc (nao^2) | E_xc | failed] and EVERY rank that has a usable `nao` reaches the
+// collective, whatever happened locally -- a rank with bad arguments or a failed launch contributes zeros and
+// failed = 1, and every rank returns NaN when the reduced count is non-zero (a rank that left early would leave
+// the others blocked in ncclAllReduce; a rank that contributed an unwritten buffer would corrupt their sums).
 double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const double* d_dm, const double* d_ao,
               const double* d_ao_grad, const double* d_w, double* d_vxc, double* d_exc_out) {
     const double nan = std::numeric_limits<double>::quiet_NaN();
-    if (!ctx || ngrid < 0 || nao <= 0 || !d_dm || !d_ao || !d_w || !d_vxc) return nan;
-    if (xc_type != 0 && !d_ao_grad) {
-        fprintf(stderr, "[dft_b200] GGA/B3LYP need d_ao_grad (3,ngrid,nao)\n");
-        return nan;
-    }
-    int cur = 0;
-    cudaGetDevice(&cur);
-    if (cur != ctx->device) cudaSetDevice(ctx->device);
+    if (!ctx) return nan;
+    DeviceGuard guard(ctx->device);   // (restores the caller's current device on return)
     ctx->failed = false;
+    const bool multi = ctx->nranks > 1 && ctx->nccl_comm;
+    bool bad = ngrid < 0 || nao <= 0 || !d_dm || !d_ao || !d_w || !d_vxc;
+    if (!bad && xc_type != 0 && !d_ao_grad) {
+        fprintf(stderr, "[dft_b200] GGA/B3LYP need d_ao_grad (3,ngrid,nao)\n");
+        bad = true;
+    }
+    if (bad && !(multi && nao > 0 && d_vxc)) return nan;
 
     const size_t n2 = (size_t)nao * nao;
-    const bool multi = ctx->nranks > 1 && ctx->nccl_comm;
-    double* packed = (double*)ctx->result.ensure(sizeof(double) * (n2 + 1), &ctx->failed);
-    if (ctx->failed) return nan;
+    double* packed = (double*)ctx->result.ensure(sizeof(double) * (n2 + 2), &ctx->failed);
+    if (!packed) return nan;
 
     xc::Problem p;
     p.xc_type = xc_type;
@@ -99,7 +114,7 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
     p.nao = nao;
     p.dm = d_dm;
     p.ao = d_ao;
-    const size_t plane = (size_t)ngrid * nao;
+    const size_t plane = (size_t)(ngrid > 0 ? ngrid : 0) * nao;
     p.gx = xc_type ? d_ao_grad : nullptr;
     p.gy = xc_type ? d_ao_grad + plane : nullptr;
     p.gz = xc_type ? d_ao_grad + 2 * plane : nullptr;
@@ -107,46 +122,54 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
     p.vxc = multi ? packed : d_vxc;
     p.d_exc = multi ? packed + n2 : (d_exc_out ? d_exc_out : packed + n2);
 
-    if (ngrid == 0) {
+    if (bad) {
+        ctx->failed = true;
+    } else if (ngrid == 0) {
         cudaMemsetAsync(p.vxc, 0, sizeof(double) * n2, ctx->stream);
         cudaMemsetAsync(p.d_exc, 0, sizeof(double), ctx->stream);
         { XcStats z; z.plans_built = ctx->stats.plans_built; z.ao_ms = ctx->stats.ao_ms; z.skip_fraction = ctx->stats.skip_fraction; z.vxc_skip_fraction = ctx->stats.vxc_skip_fraction; ctx->stats = z; }
     } else {
-        bool use_tma = false;
-        if (ctx->path == PATH_TMA) use_tma = xc::tma_compatible(p);
-        else if (ctx->path == PATH_AUTO) use_tma = xc::tma_compatible(p);
+        const bool use_tma = ctx->path != PATH_GENERIC && xc::tma_compatible(p);
         if (use_tma) xc::run_tma(ctx, p);
         else xc::run_generic(ctx, p);
     }
     if (multi) {
-        if (xc::allreduce_result(ctx, packed, n2 + 1) != 0) ctx->failed = true;
-        DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(d_vxc, packed, sizeof(double) * n2, cudaMemcpyDeviceToDevice, ctx->stream));
-        if (d_exc_out)
-            DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(d_exc_out, packed + n2, sizeof(double), cudaMemcpyDeviceToDevice,
-                                                ctx->stream));
+        const bool local_failed = ctx->failed;
+        if (local_failed) cudaMemsetAsync(packed, 0, sizeof(double) * (n2 + 1), ctx->stream);
+        cudaMemcpyAsync(packed + n2 + 1, ctx->h_scalar + (local_failed ? 9 : 8), sizeof(double), cudaMemcpyHostToDevice,
+                        ctx->stream);
+        // reduced V_xc lands in the caller's array directly (out of place); [E | failed] in place
+        if (xc::allreduce_result(ctx, packed, d_vxc, n2) != 0) ctx->failed = true;
+        if (d_exc_out) publish_exc_kernel<<<1, 1, 0, ctx->stream>>>(packed + n2, d_exc_out);
     }
     if (ctx->timing) cudaEventRecord(ctx->ev[4], ctx->stream);
     if (d_exc_out) {
         DFT_CUDA_CHECK(ctx, cudaGetLastError());
         return ctx->failed ? nan : 0.0;
     }
-    DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar, p.d_exc, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    const bool have_counters = ngrid > 0 && ctx->stats.path == PATH_TMA && ctx->counters.ptr;
+    DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar, multi ? packed + n2 : p.d_exc, (multi ? 2 : 1) * sizeof(double),
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+    const bool have_counters = !bad && ngrid > 0 && ctx->stats.path == PATH_TMA && ctx->counters.ptr;
     if (have_counters)
-        DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar + 1, ctx->counters.ptr, 4 * sizeof(unsigned long long),
+        DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar + 2, ctx->counters.ptr, 5 * sizeof(unsigned long long),
                                             cudaMemcpyDeviceToHost, ctx->stream));
     DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (multi && ctx->h_scalar[1] != 0.0) {
+        if (!ctx->failed) fprintf(stderr, "[dft_b200] rank %d: %d rank(s) failed in this XC build\n", ctx->rank, (int)ctx->h_scalar[1]);
+        ctx->failed = true;
+    }
     if (have_counters && !ctx->failed) {
-        unsigned long long c[4];
-        memcpy(c, ctx->h_scalar + 1, sizeof(c));
+        unsigned long long c[5];
+        memcpy(c, ctx->h_scalar + 2, sizeof(c));
         ctx->stats.skip_fraction = c[1] ? 1.0 - (double)c[0] / (double)c[1] : 0.0;
         ctx->stats.vxc_skip_fraction = c[3] ? 1.0 - (double)c[2] / (double)c[3] : 0.0;
+        ctx->stats.dyn_units = (double)(c[4] & 0xffffffffull);
         // adaptive: the zero-skipping V instance pays ~6 % on dense operands; use it only where the density
         // kernel just skipped a real share of its k-steps (the decision takes effect with the next call)
         if (ctx->vxc_skip < 0) ctx->vxc_skip_on = ctx->stats.skip_fraction >= 0.10;
     }
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
-    if (ctx->timing && ngrid > 0 && !ctx->failed) {
+    if (ctx->timing && !bad && ngrid > 0 && !ctx->failed) {
         cudaEventElapsedTime(&ctx->stats.density_ms, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&ctx->stats.vxc_ms, ctx->ev[1], ctx->ev[2]);
         cudaEventElapsedTime(&ctx->stats.reduce_ms, ctx->ev[2], ctx->ev[4]);
@@ -201,7 +224,7 @@ XCSolver* DFT_CreateSolver(int type) {
 }
 
 void DFT_DestroySolver(XCSolver* solver) {
-    if (solver) delete solver;
+    if (solver) delete solver;   // (~CublasHandleWrapper makes the solver's device current while it frees)
 }
 
 double DFT_ComputeXC(XCSolver* solver, int ngrid, int nao, unsigned long long d_dm_ptr,
@@ -225,6 +248,7 @@ int DFT_ComputeCoulombExchange(XCSolver* solver, int nao, unsigned long long d_e
                                unsigned long long d_J_ptr, unsigned long long d_K_ptr) {
     if (!solver || nao <= 0 || !d_eri_ptr || !d_dm_ptr || !d_J_ptr || !d_K_ptr) return 1;
     CublasHandleWrapper* ctx = solver->context();
+    DeviceGuard guard(ctx->device);
     ctx->failed = false;
     xc::coulomb_exchange(ctx, nao, reinterpret_cast<const double*>(d_eri_ptr), reinterpret_cast<const double*>(d_dm_ptr),
                          reinterpret_cast<double*>(d_J_ptr), reinterpret_cast<double*>(d_K_ptr));
@@ -235,6 +259,7 @@ int DFT_BuildFock(XCSolver* solver, int nao, unsigned long long d_hcore_ptr, uns
                   unsigned long long d_vxc_ptr, unsigned long long d_K_ptr, double c_hf, unsigned long long d_F_ptr) {
     if (!solver || nao <= 0 || !d_hcore_ptr || !d_J_ptr || !d_vxc_ptr || !d_F_ptr) return 1;
     CublasHandleWrapper* ctx = solver->context();
+    DeviceGuard guard(ctx->device);
     ctx->failed = false;
     xc::build_fock(ctx, nao, reinterpret_cast<const double*>(d_hcore_ptr), reinterpret_cast<const double*>(d_J_ptr),
                    reinterpret_cast<const double*>(d_vxc_ptr), reinterpret_cast<const double*>(d_K_ptr), c_hf,
@@ -246,6 +271,7 @@ int DFT_SCFEnergies(XCSolver* solver, int nao, unsigned long long d_dm_ptr, unsi
                     unsigned long long d_J_ptr, unsigned long long d_K_ptr, double c_hf, double* out3) {
     if (!solver || nao <= 0 || !d_dm_ptr || !d_hcore_ptr || !d_J_ptr || !out3) return 1;
     CublasHandleWrapper* ctx = solver->context();
+    DeviceGuard guard(ctx->device);
     ctx->failed = false;
     xc::scf_energies(ctx, nao, reinterpret_cast<const double*>(d_dm_ptr), reinterpret_cast<const double*>(d_hcore_ptr),
                      reinterpret_cast<const double*>(d_J_ptr), reinterpret_cast<const double*>(d_K_ptr), c_hf, out3);
@@ -269,6 +295,7 @@ int DFT_ComputeXCAsync(XCSolver* solver, int ngrid, int nao, unsigned long long 
 
 int DFT_StreamSynchronize(XCSolver* solver) {
     if (!solver) return 1;
+    DeviceGuard guard(solver->context()->device);
     return cudaStreamSynchronize(solver->context()->stream) == cudaSuccess ? 0 : 2;
 }
 
@@ -290,11 +317,14 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "stagger_min")) { c->stagger_min = value < 0.0 ? 0 : (int)value; return 0; }
     if (!strcmp(key, "dyn_sched")) { c->dyn_sched = value != 0.0; return 0; }
     if (!strcmp(key, "wait_ns")) { c->wait_ns = value < 0.0 ? 0 : (int)value; return 0; }
-    if (!strcmp(key, "debug_nodmma")) { c->debug_nodmma = value != 0.0; return 0; }
+#ifdef DFT_DIAGNOSTICS
+    if (!strcmp(key, "debug_nodmma")) { c->debug_nodmma = value != 0.0; return 0; }   // results are WRONG: delivery floor
+#endif
     if (!strcmp(key, "vxc_scatter")) { c->vxc_scatter = value != 0.0; return 0; }
     if (!strcmp(key, "vxc_producers")) { c->vxc_producers = value < 1.0 ? 1 : (value > 4.0 ? 4 : (int)value); return 0; }
     if (!strcmp(key, "vxc_mside_skip")) { c->vxc_mside_skip = value != 0.0; return 0; }
     if (!strcmp(key, "vxc_skip_mode")) { c->vxc_skip_mode = (int)value; return 0; }
+    if (!strcmp(key, "raw_convention")) { c->raw_convention = value != 0.0; return 0; }
     if (!strcmp(key, "zero_skip")) { c->zero_skip = value != 0.0; return 0; }
     if (!strcmp(key, "tma_3d")) { c->tma_3d = value != 0.0; return 0; }
     if (!strcmp(key, "vxc_shape")) { const int v = (int)value; if (v != 0 && v != 64 && v != 96 && v != 128 && v != 160) return 3; c->vxc_shape = v; return 0; }
@@ -313,6 +343,9 @@ double DFT_GetStat(XCSolver* solver, const char* key) {
     if (!strcmp(key, "ao_ms")) return c->stats.ao_ms;
     if (!strcmp(key, "launches")) return c->stats.launches;
     if (!strcmp(key, "plans_built")) return c->stats.plans_built;
+    if (!strcmp(key, "dyn_units")) return c->stats.dyn_units;
+    if (!strcmp(key, "density_units")) return c->stats.density_units;
+    if (!strcmp(key, "density_groups")) return c->stats.density_groups;
     if (!strcmp(key, "skip_fraction")) return c->stats.skip_fraction;
     if (!strcmp(key, "vxc_skip_fraction")) return c->stats.vxc_skip_fraction;
     if (!strcmp(key, "path")) return c->stats.path;
@@ -321,7 +354,9 @@ double DFT_GetStat(XCSolver* solver, const char* key) {
     return -1.0;
 }
 
-// Debug aid (not part of the documented surface): copy an engine workspace to the host.
+#ifdef DFT_DIAGNOSTICS
+// Diagnostic builds only (build.py --diag -> weights/dft_diag.so; declared in include/dft_b200_ext.h under the
+// same macro): copy an engine workspace to the host.
 int DFT_DebugRead(XCSolver* solver, const char* what, void* dst, unsigned long long nbytes) {
     if (!solver || !what || !dst) return 1;
     CublasHandleWrapper* c = solver->context();
@@ -330,9 +365,11 @@ int DFT_DebugRead(XCSolver* solver, const char* what, void* dst, unsigned long l
                     : !strcmp(what, "scratch") ? &c->scratch : !strcmp(what, "rho") ? &c->rho : nullptr;
     if (!b || !b->ptr) return 2;
     if (nbytes > b->capacity) nbytes = b->capacity;
+    DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
     return cudaMemcpy(dst, b->ptr, nbytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 3;
 }
+#endif
 
 const char* DFT_B200_Version(void) { return "quantum_compute_dft_b200 0.1 (sm_100a)"; }
 

@@ -20,6 +20,7 @@ typedef int (*fn_init_rank)(void**, int, NcclId, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*fn_destroy)(void*);
 typedef const char* (*fn_errstr)(int);
+typedef int (*fn_group)(void);
 
 struct NcclApi {
     void* handle = nullptr;
@@ -28,6 +29,7 @@ struct NcclApi {
     fn_allreduce allreduce = nullptr;
     fn_destroy destroy = nullptr;
     fn_errstr errstr = nullptr;
+    fn_group group_start = nullptr, group_end = nullptr;
     bool ok = false;
 };
 
@@ -48,7 +50,9 @@ NcclApi& nccl() {
     api.allreduce = (fn_allreduce)dlsym(api.handle, "ncclAllReduce");
     api.destroy = (fn_destroy)dlsym(api.handle, "ncclCommDestroy");
     api.errstr = (fn_errstr)dlsym(api.handle, "ncclGetErrorString");
-    api.ok = api.get_id && api.init_rank && api.allreduce && api.destroy;
+    api.group_start = (fn_group)dlsym(api.handle, "ncclGroupStart");
+    api.group_end = (fn_group)dlsym(api.handle, "ncclGroupEnd");
+    api.ok = api.get_id && api.init_rank && api.allreduce && api.destroy && api.group_start && api.group_end;
     return api;
 }
 
@@ -58,16 +62,33 @@ constexpr int kNcclSum = 0;
 }  // namespace
 
 namespace xc {
-int allreduce_result(CublasHandleWrapper* ctx, double* d_packed, size_t count) {
+// One grouped NCCL operation (a single launch): V_xc = sum over ranks of d_packed[0 .. n2), written OUT OF PLACE
+// straight into the caller's array (no copy-back), and [E_xc | failed ranks] = d_packed[n2 .. n2 + 2) in place.
+int allreduce_result(CublasHandleWrapper* ctx, double* d_packed, double* d_vxc, size_t n2) {
     if (!ctx || ctx->nranks <= 1 || !ctx->nccl_comm) return 0;
     NcclApi& api = nccl();
     if (!api.ok) return 1;
-    int rc = api.allreduce(d_packed, d_packed, count, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
+    int rc = api.group_start();
+    if (rc == 0) rc = api.allreduce(d_packed, d_vxc, n2, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
+    if (rc == 0) rc = api.allreduce(d_packed + n2, d_packed + n2, 2, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
+    const int rc_end = api.group_end();
+    if (rc == 0) rc = rc_end;
     if (rc != 0) {
         fprintf(stderr, "[dft_b200] ncclAllReduce failed: %s\n", api.errstr ? api.errstr(rc) : "?");
         return 2;
     }
     return 0;
+}
+
+void comm_destroy(CublasHandleWrapper* ctx) {
+    if (!ctx) return;
+    if (ctx->nccl_comm) {
+        NcclApi& api = nccl();
+        if (api.ok) api.destroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    ctx->rank = 0;
+    ctx->nranks = 1;
 }
 }  // namespace xc
 
@@ -86,12 +107,14 @@ int DFT_CommGetUniqueId(void* out_id_128_bytes) {
 int DFT_CommInit(XCSolver* solver, int rank, int nranks, const void* id_128_bytes) {
     if (!solver || !id_128_bytes || nranks < 1 || rank < 0 || rank >= nranks) return 1;
     CublasHandleWrapper* ctx = solver->context();
-    if (nranks == 1) { ctx->rank = 0; ctx->nranks = 1; return 0; }
+    DeviceGuard guard(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    xc::comm_destroy(ctx);   // (a second DFT_CommInit replaces the communicator instead of leaking it)
+    if (nranks == 1) return 0;
     NcclApi& api = nccl();
     if (!api.ok) return 2;
     NcclId id;
     memcpy(&id, id_128_bytes, sizeof(id));
-    cudaSetDevice(ctx->device);
     void* comm = nullptr;
     int rc = api.init_rank(&comm, nranks, id, rank);
     if (rc != 0) {
@@ -107,13 +130,9 @@ int DFT_CommInit(XCSolver* solver, int rank, int nranks, const void* id_128_byte
 int DFT_CommDestroy(XCSolver* solver) {
     if (!solver) return 1;
     CublasHandleWrapper* ctx = solver->context();
-    if (ctx->nccl_comm) {
-        NcclApi& api = nccl();
-        if (api.ok) api.destroy(ctx->nccl_comm);
-        ctx->nccl_comm = nullptr;
-    }
-    ctx->rank = 0;
-    ctx->nranks = 1;
+    DeviceGuard guard(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    xc::comm_destroy(ctx);
     return 0;
 }
 }

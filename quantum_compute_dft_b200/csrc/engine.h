@@ -21,6 +21,22 @@
         }                                                                                      \
     } while (0)
 
+// Makes `device` current for the scope and restores the caller's device afterwards: every extern "C" entry
+// point and the context destructor run under one, so a process that drives several GPUs never launches on
+// the engine stream, allocates or frees while another device is current.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 struct DeviceBuffer {
     void* ptr = nullptr;
     size_t capacity = 0;
@@ -39,6 +55,8 @@ struct XcStats {
     double skip_fraction = 0.0;  // TMA density kernel: fraction of k-steps skipped as exact zeros in the last call
     double vxc_skip_fraction = 0.0;  // TMA V kernel, box-bit instances: fraction of (box, k-step) units skipped
     int plans_built = 0;  // TMA path: launch plans (tensor maps, geometry) encoded so far; a steady SCF loop builds one
+    int density_units = 0, density_groups = 0;  // TMA density kernel: units of work and consumer groups (2 per CTA) of the last launch
+    double dyn_units = 0.0;  // TMA density kernel: draws from the dynamic work counter in the last call (units + consumer groups; 0 = static deal)
 };
 
 struct CublasHandleWrapper {
@@ -60,9 +78,10 @@ struct CublasHandleWrapper {
     int stagger_min = 8;           // TMA density kernel: consumer group 1 starts half a tile period late when a CTA has more blocks than this
     int dyn_sched = 1;             // TMA density kernel: hand the 64-point blocks out dynamically (one global counter)
     int wait_ns = 0;               // TMA kernels: producer / scanner threads sleep this long between barrier polls
-    int debug_nodmma = 0;          // diagnostic only: TMA kernels skip every DMMA (measures the operand-delivery floor)
+    int debug_nodmma = 0;          // -DDFT_DIAGNOSTICS builds only: TMA kernels skip every DMMA (measures the operand-delivery floor)
     int vxc_producers = 1;         // TMA V kernel: TMA-issuing threads per CTA (1 | 2)
     int vxc_mside_skip = 1;        // box-bit V instances: also skip on all-zero M-side fragments (per-warp votes)
+    bool raw_convention = false;   // GGA only: leave the reference's raw unsymmetrised B^T Phi in d_vxc (dft_solver.cu:616) instead of the symmetric matrix
     bool zero_skip = true;         // TMA kernels: skip k-steps whose operand fragment is all zero (exact: adds nothing)
     bool tma_3d = true;            // TMA V kernel: one 3-D TMA load per plane and stage instead of one per 16-column block
     int ao_shape = 0;              // DFT_EvalAO block shape: 0 = auto, 16 (points, 8 warps) | 32 (points, 16 warps)
@@ -116,8 +135,9 @@ bool tma_compatible(const Problem& p);
 void run_tma(CublasHandleWrapper* ctx, const Problem& p);
 void free_tma_plan(CublasHandleWrapper* ctx);
 
-// all-reduce of [V | E] over the communicator (comm.cu); no-op when nranks == 1
-int allreduce_result(CublasHandleWrapper* ctx, double* d_packed, size_t count);
+// all-reduce of [V | E | failed ranks] over the communicator (comm.cu); no-op when nranks == 1
+int allreduce_result(CublasHandleWrapper* ctx, double* d_packed, double* d_vxc, size_t n2);
+void comm_destroy(CublasHandleWrapper* ctx);
 
 void coulomb_gemv(CublasHandleWrapper* ctx, int nao, const double* eri, const double* dm, double* J);
 // J and the exact-exchange matrix K[i,k] = sum_jl (ij|kl) D[j,l] in ONE pass over the ERI

@@ -44,14 +44,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Waits are bounded by WALL TIME, not by a poll count: under time-slicing with another process, ncu kernel
+// replay or a preempted context a legitimate wait can take arbitrarily many polls, and a trap poisons the whole
+// CUDA context (the caller's arrays included).  Release builds therefore only give up after MBAR_TIMEOUT_NS
+// (20 s -- far beyond any preemption gap, far below a driver watchdog-free hang going unnoticed) and then
+// trap so that a protocol bug still surfaces as a failed launch rather than a hung GPU; the clock is read
+// once per 4096 polls, so the common path is a bare try_wait loop.
+#ifndef DFT_MBAR_TIMEOUT_NS
+#define DFT_MBAR_TIMEOUT_NS 20000000000ull
+#endif
+__device__ __noinline__ void mbar_timeout_trap(uint32_t parity) {
+    printf("[dft_b200] mbarrier wait exceeded %llu ns (block %d,%d thread %d parity %u)\n",
+           (unsigned long long)DFT_MBAR_TIMEOUT_NS, blockIdx.x, blockIdx.y, threadIdx.x, parity);
+    __trap();
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) {
-            printf("[dft_b200] mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x,
-                   parity);
-            __trap();
+        if ((++spins & 4095u) == 0) {
+            const uint64_t t = globaltimer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > DFT_MBAR_TIMEOUT_NS) mbar_timeout_trap(parity);
         }
     }
 }
@@ -60,12 +81,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // issue slots with two MMA warps, and a thread that polls back to back takes cycles from them.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (ns) __nanosleep(ns);
-        if (++spins > (1u << 24)) {
-            printf("[dft_b200] mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x,
-                   parity);
-            __trap();
+        if ((++spins & 4095u) == 0) {
+            const uint64_t t = globaltimer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > DFT_MBAR_TIMEOUT_NS) mbar_timeout_trap(parity);
         }
     }
 }

@@ -248,7 +248,7 @@ vxc_kernel(int ngrid, int nao, int tiles_n, int rows_per_slice, int NP,
 
 // out[i][j] = sum_s (M_s[i][j] + M_s[j][i])  (fixed order -> bit-reproducible and exactly
 // symmetric); block 0 additionally reduces the per-CTA E_xc partials in a fixed order.
-__global__ void finalize_kernel(int nao, int NP, int nslices, const double* __restrict__ vpart,
+__global__ void finalize_kernel(int nao, int NP, int nslices, int raw, const double* __restrict__ vpart,
                                 double* __restrict__ vxc, int nepart,
                                 const double* __restrict__ epart, double* __restrict__ d_exc) {
     const size_t n2 = (size_t)nao * nao;
@@ -258,7 +258,7 @@ __global__ void finalize_kernel(int nao, int NP, int nslices, const double* __re
         double s = 0.0;
         for (int sl = 0; sl < nslices; ++sl) {
             const double* p = vpart + (size_t)sl * NP * NP;
-            s += p[(size_t)i * NP + j] + p[(size_t)j * NP + i];
+            s += raw ? 2.0 * p[(size_t)i * NP + j] : p[(size_t)i * NP + j] + p[(size_t)j * NP + i];
         }
         vxc[idx] = s;
     }
@@ -325,7 +325,7 @@ void run_generic(CublasHandleWrapper* ctx, const Problem& p) {
                                                                         p.gx, p.gy, p.gz, coef, vpart);
     if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
     const size_t n2 = (size_t)nao * nao;
-    finalize_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(nao, NP, nslices, vpart, p.vxc, nblk, epart,
+    finalize_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(nao, NP, nslices, (ctx->raw_convention && p.xc_type == 1) ? 1 : 0, vpart, p.vxc, nblk, epart,
                                                                   p.d_exc);
     if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
     ctx->stats.launches = 4;

@@ -335,7 +335,11 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
     }
     const int prow0 = wm * 32;  // this warp's rows inside a piece
     const bool no_skip = P.zero_skip == 0;
+#ifdef DFT_DIAGNOSTICS
     const bool dbg_off = P.debug_nodmma != 0;
+#else
+    constexpr bool dbg_off = false;
+#endif
 
     // group 1 starts half a column-tile period late (only worth it when there are several blocks to do)
     if (grp == 1 && nblocks > P.stagger_min * (int)gridDim.x) {
@@ -848,7 +852,10 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
                 nz_all |= nz;
             }
             if (SKIP == 2) livek = __any_sync(0xffffffffu, nz_all | no_mskip) ? (1u << KS) - 1u : 0u;
-            if (livek != 0 && jm != 0 && P.debug_nodmma == 0) {
+#ifdef DFT_DIAGNOSTICS
+            if (P.debug_nodmma != 0) livek = 0;
+#endif
+            if (livek != 0 && jm != 0) {
                 n_box_done += (unsigned)(__popc(jm) * __popc(livek));
 #pragma unroll
                 for (int b = 0; b < NFN / 2; ++b) {
@@ -955,35 +962,69 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
 
 // out[i][j] = sum over slices of T(i+s, j+s) + T(j+s, i+s), s = column shift of the slice's
 // sub-problem; T = M where the tile was computed (lda_half: the mirror tile otherwise).
-// One warp per output element: lanes stride over the slices (all partial loads in flight at once --
-// a serial loop over up to 148 slices was latency-bound at ~20 us for the small molecules), then a
-// shuffle tree.  Fixed summation order -> bit-reproducible and exactly symmetric.
+// One CTA per 32 x 32 output tile: thread (row, tx) sums, over the slices in a fixed order, the partial it
+// reads DIRECTLY, T(i0 + row, j0 + tx), and the one whose TRANSPOSE the tile needs, T(j0 + row, i0 + tx) --
+// both are coalesced along tx -- and the transposed sums change hands through shared memory.  (Round 1 read
+// T(j, i) with a warp per output element: 32 x 8 bytes from 32 different rows per request, 48 us at nao 377.)
+// Fixed summation order -> bit-reproducible and exactly symmetric.  `raw` (GGA, option "raw_convention"):
+// out = 2 sum T(i, j), the reference's own unsymmetrised B^T Phi (dft_solver.cu:616).
 constexpr int FIN_THREADS = 256;
+constexpr int FIN_TILE = 32;
 __global__ void __launch_bounds__(FIN_THREADS)
-finalize_tma_kernel(int nao, int ldv, int mpv, int NT, int nsub, int slices_per_sub, int shift1, int lda_half,
+finalize_tma_kernel(int nao, int ldv, int mpv, int NT, int nsub, int slices_per_sub, int shift1, int lda_half, int raw,
                     const double* __restrict__ vpart, double* __restrict__ vxc, int nepart,
                     const double* __restrict__ epart, double* __restrict__ d_exc) {
-    const size_t n2 = (size_t)nao * nao;
-    const int lane = threadIdx.x & 31;
-    const size_t idx = (size_t)blockIdx.x * (FIN_THREADS / 32) + (threadIdx.x >> 5);
-    if (idx < n2) {
-        const int i0 = (int)(idx / nao), j0 = (int)(idx % nao);
-        const size_t ss = (size_t)mpv * ldv;
-        double s = 0.0;
-        for (int su = 0; su < nsub; ++su) {
-            const int sh = su ? shift1 : 0;
-            const int i = i0 + sh, j = j0 + sh;
-            size_t o1 = (size_t)i * ldv + j, o2 = (size_t)j * ldv + i;
-            if (lda_half) {
-                if (i / NT > j / NT) o1 = o2;
-                else if (j / NT > i / NT) o2 = o1;
-            }
-            const double* p = vpart + (size_t)su * slices_per_sub * ss;
-            for (int sl = lane; sl < slices_per_sub; sl += 32) s += __ldg(p + sl * ss + o1) + __ldg(p + sl * ss + o2);
-        }
+    __shared__ double tr[FIN_TILE][FIN_TILE + 1];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int ntile = (nao + FIN_TILE - 1) / FIN_TILE;
+    const int i0 = (blockIdx.x / ntile) * FIN_TILE, j0 = (blockIdx.x % ntile) * FIN_TILE;
+    const size_t ss = (size_t)mpv * ldv;
+    // sum over the slices of sub-problem `p` at element q, two chains, fixed order
+    auto slice_sum = [&](const double* q) {
+        double s0 = 0.0, s1 = 0.0;
+        int sl = 0;
+        for (; sl + 1 < slices_per_sub; sl += 2) { s0 += __ldg(q + sl * ss); s1 += __ldg(q + (sl + 1) * ss); }
+        if (sl < slices_per_sub) s0 += __ldg(q + sl * ss);
+        return s0 + s1;
+    };
+    // T(a, b) of a shifted index pair exists unless only the upper block triangle was computed and (a, b) is below it
+    auto computed = [&](int a, int b) { return !(lda_half && a / NT > b / NT); };
+    double out[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int su = 0; su < nsub; ++su) {
+        const int sh = su ? shift1 : 0;
+        const double* p = vpart + (size_t)su * slices_per_sub * ss;
+        double d[4];
+        if (su) __syncthreads();   // (tr is reused)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) vxc[idx] = s;
+        for (int r = 0; r < 4; ++r) {
+            const int row = ty + 8 * r;
+            d[r] = 0.0;
+            {   // direct: T(I + sh, J + sh), (I, J) = (i0 + row, j0 + tx)
+                const int I = i0 + row + sh, J = j0 + tx + sh;
+                if (i0 + row < nao && j0 + tx < nao && computed(I, J)) d[r] = slice_sum(p + (size_t)I * ldv + J);
+            }
+            double t = 0.0;
+            if (!raw) {   // for the transpose: T(I' + sh, J' + sh), (I', J') = (j0 + row, i0 + tx)
+                const int I = j0 + row + sh, J = i0 + tx + sh;
+                if (j0 + row < nao && i0 + tx < nao && computed(I, J)) t = slice_sum(p + (size_t)I * ldv + J);
+            }
+            tr[row][tx] = t;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = ty + 8 * r;
+            const int I = i0 + row + sh, J = j0 + tx + sh;
+            const double tt = tr[tx][row];   // sum T(J, I) of this thread's output element (I, J)
+            if (raw) out[r] += 2.0 * d[r];
+            else if (computed(I, J) && computed(J, I)) out[r] += d[r] + tt;
+            else out[r] += 2.0 * (d[r] + tt);   // (exactly one of the two exists; the other term is 0)
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int row = ty + 8 * r;
+        if (i0 + row < nao && j0 + tx < nao) vxc[(size_t)(i0 + row) * nao + j0 + tx] = out[r];
     }
     if (blockIdx.x == 0) {
         __shared__ double sh[FIN_THREADS];
@@ -1177,9 +1218,12 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
     dp.zero_skip = ctx->zero_skip ? 1 : 0;
     dp.debug_nodmma = ctx->debug_nodmma; dp.wait_ns = ctx->wait_ns; dp.stagger_min = ctx->stagger_min;
     dp.per_tile = per_tile ? 1 : 0;
-    dp.sched = (ctx->dyn_sched && dp.counters) ? reinterpret_cast<unsigned int*>(dp.counters + 4) : nullptr;
     dp.coef_rows = g.coef_rows; dp.rho = rho;
+    // (the counters must exist before `sched` is derived from them: round 1 had these two statements the other
+    // way round, so `sched` was always null and the dynamic deal never ran)
     dp.counters = reinterpret_cast<unsigned long long*>(ctx->counters.ensure(6 * sizeof(unsigned long long), &ctx->failed));
+    if (ctx->failed) return;
+    dp.sched = ctx->dyn_sched ? reinterpret_cast<unsigned int*>(dp.counters + 4) : nullptr;
 
     PointParams& pp = pl.pp;
     memset(&pp, 0, sizeof(pp));
@@ -1370,12 +1414,16 @@ static void run_plan(CublasHandleWrapper* ctx, const Problem& p, Plan& pl) {
     void* vargs[1] = {&pl.vp};
     DFT_CUDA_CHECK(ctx, cudaLaunchKernel(pl.vfunc, pl.vgrid, dim3(NTHREADS), vargs, (size_t)pl.vsmem, st));
     if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
-    const size_t n2 = (size_t)p.nao * p.nao;
-    finalize_tma_kernel<<<(unsigned)((n2 + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32)), FIN_THREADS, 0, st>>>(p.nao, pl.ldv, pl.mpv, pl.fin_nt, pl.nsub, pl.nsl, pl.shift1,
-                                                                      pl.lda_half, pl.vpart, p.vxc, pl.pgrid, pl.epart, p.d_exc);
+    const int fin_tiles = (p.nao + FIN_TILE - 1) / FIN_TILE;
+    const int raw = (ctx->raw_convention && p.xc_type == 1) ? 1 : 0;
+    finalize_tma_kernel<<<fin_tiles * fin_tiles, FIN_THREADS, 0, st>>>(p.nao, pl.ldv, pl.mpv, pl.fin_nt, pl.nsub, pl.nsl, pl.shift1, pl.lda_half, raw,
+                                                                      pl.vpart, p.vxc, pl.pgrid, pl.epart, p.d_exc);
     if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
     ctx->stats.launches = 5;
     ctx->stats.path = PATH_TMA;
+    ctx->stats.density_units = pl.dp.per_tile ? pl.dp.nblocks * pl.dp.ntiles : pl.dp.nblocks;
+    ctx->stats.density_groups = 2 * pl.dgrid;
+    ctx->stats.dyn_units = 0.0;
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
 }
 

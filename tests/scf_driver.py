@@ -1,4 +1,4 @@
-"""Host-side SCF driver: the reference's main loop (dft.py:183-266) over this engine's C ABI.
+"""TEST INFRASTRUCTURE (not product code). Host-side SCF driver: the reference's main loop (dft.py:183-266) over this engine's C ABI.
 
 The reference takes its one- and two-electron integrals from PySCF (grid.py:61-66), which is not
 installable here; for s-type basis functions (hydrogen chains in STO-3G) the integrals are closed-form,
@@ -17,8 +17,8 @@ import numpy as np
 from scipy.linalg import eigh
 from scipy.special import erf
 
-from .cuda_rt import DeviceArray
-from .molgrid import ATOMIC_NUMBER
+from quantum_compute_dft_b200.cuda_rt import DeviceArray
+from quantum_compute_dft_b200.molgrid import ATOMIC_NUMBER
 
 
 # --------------------------------------------------------------------------- s-type integrals

@@ -11,6 +11,7 @@ def _declared_symbols():
     for h in ("dft_solver.h", "dft_b200_ext.h"):
         txt = open(os.path.join(ROOT, "include", h)).read()
         txt = re.sub(r"//[^\n]*", "", txt)
+        txt = re.sub(r"#ifdef DFT_DIAGNOSTICS.*?#endif", "", txt, flags=re.S)   # diagnostic builds only
         names |= set(re.findall(r"\b(DFT_[A-Za-z0-9_]+)\s*\(", txt))
     return names
 
@@ -24,6 +25,8 @@ def test_every_declared_symbol_is_exported(engine_lib):
     for s in declared:
         assert getattr(lib, s) is not None
     assert b"sm_100a" in lib.DFT_B200_Version()
+    # diagnostics (wrong-result options, workspace dumps) are not part of the product library
+    assert not hasattr(lib, "DFT_DebugRead")
 
 
 def test_reference_binding_signature(engine_lib):

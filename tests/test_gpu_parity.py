@@ -30,7 +30,8 @@ def _run_engine(lib_path, functional, dm, ao, w, grad, options=None, reference_a
     d_v = DeviceArray((nao, nao), zero=True)
     e = s.compute_xc(ngrid, nao, d_dm, d_ao, d_w, d_v, d_g)
     v = d_v.get()
-    stats = {k: s.stat(k) for k in ("path", "launches", "skip_fraction", "vxc_skip_fraction")} if not reference_abi else {}
+    stats = {k: s.stat(k) for k in ("path", "launches", "skip_fraction", "vxc_skip_fraction", "dyn_units", "density_units",
+                                    "density_groups")} if not reference_abi else {}
     return e, v, stats
 
 
@@ -227,6 +228,50 @@ def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
         np.testing.assert_allclose(v0, v1, rtol=0, atol=V_TOL * max(1.0, np.abs(v0).max() * 1e-3), err_msg=str(opt))
 
 
+@pytest.mark.parametrize("functional", FUNCS)
+@pytest.mark.parametrize("ngrid,nao", [(30000, 152), (20000, 377), (5000, 36), (200, 7)])
+def test_dynamic_scheduling_actually_runs(engine_lib, functional, ngrid, nao):
+    """The density kernel's dynamic deal (units drawn from a global counter, ids passed to the consumers with the unit's
+    first ring stage, -1 sentinel) must really execute when `dyn_sched` is on: every consumer group draws once per
+    unit it takes plus once to learn that none is left, so the counter ends at units + groups.  (In round 1 a
+    mis-ordered assignment left the counter pointer null and both settings ran the static deal.)"""
+    rng = np.random.default_rng(5 * ngrid + nao)
+    dm, ao, w, grad = _random_case(rng, ngrid, nao)
+    e0, v0, s0 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"dyn_sched": 0})
+    assert s0["path"] == 2 and s0["dyn_units"] == 0
+    for opt in ({"dyn_sched": 1}, {"dyn_sched": 1, "density_unit": 1}, {}):
+        e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
+        assert s1["path"] == 2
+        assert s1["density_units"] > 0 and s1["dyn_units"] == s1["density_units"] + s1["density_groups"], (opt, s1)
+        assert abs(e1 - e0) <= 1e-12 * max(1.0, abs(e0)), opt
+        np.testing.assert_allclose(v1, v0, rtol=0, atol=1e-12 * max(1.0, np.abs(v0).max()), err_msg=str(opt))
+
+
+def test_raw_gga_convention(oracle, engine_lib):
+    """Option "raw_convention": GGA leaves the reference's own unsymmetrised B^T Phi (dft_solver.cu:616) in d_vxc;
+    by default the engine writes the symmetric matrix with the same 1/2 (V + V^T).  Checked against the oracle's raw
+    output and, where it travelled, the reference's CUDA."""
+    rng = np.random.default_rng(23)
+    for ngrid, nao in ((3000, 19), (2500, 36), (1800, 130)):
+        dm, ao, w, grad = _random_case(rng, ngrid, nao)
+        e_o, v_o = oracle.compute_xc(1, dm, ao, w, grad, mode=0)          # raw reference convention
+        assert np.max(np.abs(v_o - v_o.T)) > 1e-6                            # really unsymmetric
+        for path in (1, 2):
+            e, v, st = _run_engine(engine_lib, "GGA", dm, ao, w, grad, {"raw_convention": 1, "path": path})
+            if path == 2:
+                assert st["path"] == 2
+            assert abs(e - e_o) <= E_TOL
+            np.testing.assert_allclose(v, v_o, rtol=0, atol=V_TOL)
+        ref = _run_reference_so("GGA", dm, ao, w, grad)
+        if ref is not None:
+            np.testing.assert_allclose(v, ref[1], rtol=0, atol=V_TOL)
+        # LDA / B3LYP: the option changes nothing
+        for fn in ("LDA", "B3LYP"):
+            _, va, _ = _run_engine(engine_lib, fn, dm, ao, w, grad, {"raw_convention": 1})
+            _, vb, _ = _run_engine(engine_lib, fn, dm, ao, w, grad)
+            np.testing.assert_array_equal(va, vb)
+
+
 def _screened_case(rng, ngrid, nao, rows=192, cols=10):
     """Random planes with the zero pattern AO screening leaves: for runs of `rows` grid points, runs of about
     `cols` neighbouring AOs (an atom's shells) are exact zeros in all four planes; a few single-plane zeros on top."""
@@ -418,7 +463,8 @@ def test_converged_scf_energy(oracle, engine_lib, functional):
     import sys
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from scf_backends import OracleBackend, h_chain
-    from quantum_compute_dft_b200 import molgrid as M, scf
+    from quantum_compute_dft_b200 import molgrid as M
+    import scf_driver as scf
     from quantum_compute_dft_b200.solver import DFTSolverWrapper
     mol, basis = h_chain([0.0, 1.3, 3.1, 4.6])
     S, H, eri, e_nuc = scf.s_integrals(mol, basis)

@@ -1,9 +1,10 @@
-"""Host SCF driver (quantum_compute_dft_b200/scf.py, the mirror of dft.py:183-266): closed-form s-type
+"""Host SCF driver (tests/scf_driver.py, the mirror of dft.py:183-266): closed-form s-type
 integrals pinned against literature values, and the loop itself with the CPU oracle as backend."""
 import numpy as np
 import pytest
 
-from quantum_compute_dft_b200 import molgrid as M, scf
+from quantum_compute_dft_b200 import molgrid as M
+import scf_driver as scf
 from scf_backends import OracleBackend, h_chain
 
 
