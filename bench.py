@@ -135,54 +135,132 @@ def cpu_port_baseline(hp, sample_points):
             "seconds": best}
 
 
+# --------------------------------------------------------------------------- shared by both arms
+def needs_l2_flush(hp, n_local):
+    """Inputs per rank vs L2 (126 MB): flush explicitly when they could stay cache-resident."""
+    P = 1 if hp.functional == "LDA" else 4
+    return 8.0 * n_local * P * hp.nao < 4 * 126e6
+
+
+def bench_config(args, hp, need_flush):
+    """The `config` object -- built by ONE function so that both arms print the identical object (the driver compares
+    them: `same_config`).  Everything arm-specific (engine path, rank count) lives outside it."""
+    return {"workload": f"{args.workload}: {hp.name}", "functional": hp.functional, "ngrid": hp.ngrid, "nao": hp.nao,
+            "basis": "sto-3g", "grid": "synthetic, PySCF level-3 point counts" if args.scale == 1.0 else
+            f"synthetic, PySCF level-3 point counts x {args.scale}",
+            "density": "seeded idempotent D = 2CC^T",
+            "parallelism": "grid points sharded over n_gpus ranks (the reference's own code is single-GPU)",
+            "l2": "explicit 384 MB flush between timed steps" if need_flush else "AO planes far larger than L2"}
+
+
+def load_reference_lib():
+    """ctypes handle of the reference's own CUDA (dft_solver.cu compiled UNMODIFIED for sm_100a by oracle/Makefile
+    into oracle/_ref/dft_ref.so), bound exactly as dft.py:27-50 binds it; None if the prebuilt .so did not travel."""
+    import ctypes
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "dft_ref.so")
+    if not os.path.exists(ref_so):
+        return None
+    lib = ctypes.CDLL(ref_so)
+    lib.DFT_CreateSolver.argtypes = [ctypes.c_int]; lib.DFT_CreateSolver.restype = ctypes.c_void_p
+    lib.DFT_DestroySolver.argtypes = [ctypes.c_void_p]; lib.DFT_DestroySolver.restype = None
+    lib.DFT_ComputeXC.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_uint64] * 5
+    lib.DFT_ComputeXC.restype = ctypes.c_double
+    return lib
+
+
+def reference_xc(lib, functional, ngrid, nao, d_dm, d_ao, d_grad, d_w, d_vxc):
+    """One call of the reference's DFT_ComputeXC on device arrays; returns (E_xc, raw V_xc on the host)."""
+    from quantum_compute_dft_b200 import cuda_rt, workload
+    s = lib.DFT_CreateSolver(workload.FUNCTIONAL_TYPE[functional])
+    e = lib.DFT_ComputeXC(s, ngrid, nao, d_dm.data.ptr, d_ao.data.ptr, d_grad.data.ptr if d_grad is not None else 0,
+                          d_w.data.ptr, d_vxc.data.ptr)
+    cuda_rt.synchronize()
+    v = d_vxc.get()
+    lib.DFT_DestroySolver(s)
+    return e, v
+
+
+def parity_record(e, v, e_ref, v_ref, against):
+    """E_xc / sym(V_xc) differences in BASELINE.json's terms (|dE| <= 1e-8 Ha, max |d 1/2 (V + V^T)| <= 1e-9)."""
+    de = abs(float(e) - float(e_ref))
+    dv = float(np.max(np.abs(0.5 * (v + v.T) - 0.5 * (v_ref + v_ref.T))))
+    return {"e_xc_abs_err": de, "vxc_max_abs_err": dv, "e_xc": float(e), "e_xc_ref": float(e_ref),
+            "tolerance": {"e_xc": 1e-8, "vxc": 1e-9}, "ok": bool(de <= 1e-8 and dv <= 1e-9), "against": against}
+
+
 # --------------------------------------------------------------------------- reference arm
 def run_reference_arm(args, rank, world):
     """The reference's own implementation of the path.  Its implementation IS CUDA
     (/root/reference/src/dft_solver.cu), compiled unmodified for sm_100a into oracle/_ref/dft_ref.so by
-    oracle/Makefile; it runs on the same B200 through its own C ABI on a bounded sample of the workload
-    (it materialises a full (ngrid,nao) B matrix and takes O(nao^2) uncoalesced work per point).  If the
-    prebuilt .so did not travel, the oracle's CPU port is timed on the host cores instead."""
+    oracle/Makefile; it runs on the same B200 through its own C ABI on the WHOLE grid of the workload (the same
+    `config` as our arm).  Nothing of the engine is in this process: the AO planes come from the CPU oracle
+    (oracle.eval_ao, chunk by chunk, uploaded with cudaMemcpy) and the device arrays from the ctypes CUDA-runtime
+    shim, so the only native code on the timed path is dft_ref.so (+ cuBLAS).  If the prebuilt .so did not travel,
+    the oracle's CPU port is timed on the host cores instead."""
     if rank != 0:
         return
-    import ctypes
+    from oracle import oracle as O
     from quantum_compute_dft_b200 import cuda_rt, workload
     from quantum_compute_dft_b200.cuda_rt import DeviceArray
     hp = workload.host_problem(args.workload, scale=args.scale)
-    cfg = {"workload": f"{args.workload}: {hp.name}", "ngrid": hp.ngrid, "nao": hp.nao, "basis": "sto-3g",
-           "grid": "synthetic level-3-sized", "parallelism": "1 GPU (reference is single-GPU)"}
-    ref_so = os.path.join(ROOT, "oracle", "_ref", "dft_ref.so")
+    n = hp.ngrid if args.ref_sample <= 0 else min(hp.ngrid, args.ref_sample)
+    need_flush = needs_l2_flush(hp, n)
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": cfg}
-    if os.path.exists(ref_so) and cuda_rt.device_count() > 0:
+            "dtype": "f64", "data": "synthetic", "config": bench_config(args, hp, need_flush)}
+    lib = load_reference_lib() if cuda_rt.device_count() > 0 else None
+    if lib is not None:
         cuda_rt.set_device(0)
-        n = min(hp.ngrid, args.ref_sample)
-        solver = workload.make_solver(hp.functional)     # only used for DFT_EvalAO (input generation)
-        hp_s = workload.HostProblem(hp.name, hp.functional, hp.mol, hp.basis, hp.coords[:n], hp.weights[:n], hp.dm)
-        dp = workload.device_problem(hp_s, solver)
-        lib = ctypes.CDLL(ref_so)
-        lib.DFT_CreateSolver.argtypes = [ctypes.c_int]; lib.DFT_CreateSolver.restype = ctypes.c_void_p
-        lib.DFT_ComputeXC.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_uint64] * 5
-        lib.DFT_ComputeXC.restype = ctypes.c_double
+        nao, lda = hp.nao, hp.functional == "LDA"
+        d_ao = DeviceArray((n, nao))
+        d_grad = None if lda else DeviceArray((3, n, nao))
+        CH = 32768
+        for o in range(0, n, CH):   # AO planes from the CPU oracle, uploaded chunk by chunk
+            m = min(CH, n - o)
+            if lda:
+                ao = O.eval_ao(hp.coords[o:o + m], hp.basis, deriv=0)
+            else:
+                ao, g = O.eval_ao(hp.coords[o:o + m], hp.basis, deriv=1)
+                for c in range(3):
+                    cuda_rt.check(cuda_rt.rt().cudaMemcpy(d_grad.data.ptr + 8 * ((c * n + o) * nao), g[c].ctypes.data,
+                                                          8 * m * nao, cuda_rt.H2D), "H2D grad")
+            cuda_rt.check(cuda_rt.rt().cudaMemcpy(d_ao.data.ptr + 8 * o * nao, ao.ctypes.data, 8 * m * nao, cuda_rt.H2D), "H2D ao")
+        d_dm, d_w = DeviceArray.from_host(hp.dm), DeviceArray.from_host(hp.weights[:n])
+        d_vxc = DeviceArray((nao, nao), zero=True)
         s = lib.DFT_CreateSolver(workload.FUNCTIONAL_TYPE[hp.functional])
-        call = lambda: lib.DFT_ComputeXC(s, n, hp.nao, dp.d_dm.data.ptr, dp.d_ao.data.ptr,
-                                         dp.d_ao_grad.data.ptr if dp.d_ao_grad else 0, dp.d_weights.data.ptr,
-                                         dp.d_vxc.data.ptr)
+        call = lambda: lib.DFT_ComputeXC(s, n, nao, d_dm.data.ptr, d_ao.data.ptr, d_grad.data.ptr if d_grad else 0,
+                                         d_w.data.ptr, d_vxc.data.ptr)
+        flush_buf = DeviceArray((48 * 1024 * 1024,), np.float64) if need_flush else None
+        e_xc = None
         for _ in range(max(1, args.warmup)):
-            call()
+            e_xc = call()
         cuda_rt.synchronize()
         e0, e1 = cuda_rt.Event(), cuda_rt.Event()
-        e0.record(0)
-        for _ in range(args.steps):
-            call()
-        e1.record(0)
-        e1.synchronize()
-        ms = e0.elapsed_ms(e1) / args.steps
+        total_ms = 0.0
+        if not need_flush:
+            e0.record(0)
+            for _ in range(args.steps):
+                call()
+            e1.record(0)
+            e1.synchronize()
+            total_ms = e0.elapsed_ms(e1)
+        else:
+            for _ in range(args.steps):
+                flush_buf.fill_zero()
+                cuda_rt.synchronize()
+                e0.record(0)
+                call()
+                e1.record(0)
+                e1.synchronize()
+                total_ms += e0.elapsed_ms(e1)
+        ms = total_ms / args.steps
         val = n / (ms * 1e-3) / 1e6
-        line.update({"value": val, "ms_per_step": ms,
+        sample = (f"the whole grid ({n} points) per step" if n == hp.ngrid else
+                  f"first {n} of {hp.ngrid} grid points per step")
+        line.update({"value": val, "ms_per_step": ms, "e_xc": e_xc,
                      "cpu_baseline": {"value": val, "unit": UNIT, "cores": 0, "kind": "reference",
-                                      "sample": f"reference CUDA (dft_solver.cu, unmodified, sm_100a) on the same B200, "
-                                                f"first {n} of {hp.ngrid} grid points per step"},
+                                      "sample": "reference CUDA (dft_solver.cu, unmodified, sm_100a) on the same B200, "
+                                                + sample + "; inputs from the CPU oracle's AO evaluation"},
                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     else:
         cb = cpu_port_baseline(hp, args.cpu_sample)
@@ -203,7 +281,8 @@ def main():
                     "C33H56N7O17P3S, the configuration the metric's target is quoted on")
     ap.add_argument("--scale", type=float, default=1.0, help="grid size factor (1.0 = PySCF level-3 point counts)")
     ap.add_argument("--cpu-sample", type=int, default=60000)
-    ap.add_argument("--ref-sample", type=int, default=65536)
+    ap.add_argument("--ref-sample", type=int, default=0, help="reference arm: grid points per step (0 = the whole grid)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity check of the timed inputs (sweeps, ncu runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 generic, 2 TMA")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
@@ -258,10 +337,8 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    # inputs per rank vs L2 (126 MB): flush explicitly when they could stay cache-resident
     P = 1 if hp.functional == "LDA" else 4
-    input_bytes = 8.0 * n_local * P * nao
-    need_flush = input_bytes < 4 * 126e6
+    need_flush = needs_l2_flush(hp, n_local)
     flush_buf = cuda_rt.DeviceArray((48 * 1024 * 1024,), np.float64) if need_flush else None  # 384 MB
 
     for _ in range(args.warmup):
@@ -321,6 +398,46 @@ def main():
         times = t.numpy()
     total_ms, e2e_ms, dens_ms, vxc_ms = (float(x) for x in times)
 
+    # ---- parity of exactly what was timed (outside every timed region): the result of the last step against the
+    # reference's own CUDA on the same inputs and, at N > 1, against a 1-GPU recomputation by this engine on rank 0
+    parity = None
+    if not args.no_parity:
+        v_timed = dp.d_vxc.get()           # after the all-reduce: every rank holds the global matrix
+        ranks_diff = 0.0
+        if dist is not None:               # ... and they must all hold the SAME one
+            import torch
+            t0_ = torch.from_numpy(v_timed.copy())
+            dist.broadcast(t0_, src=0)
+            td = torch.tensor([float(np.max(np.abs(v_timed - t0_.numpy())))], dtype=torch.float64)
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            ranks_diff = float(td[0])
+        if rank == 0:
+            if world > 1:
+                solver1 = workload.make_solver(hp.functional)
+                solver1.set_option("path", args.path)
+                dp_full = workload.device_problem(hp, solver1)
+                e1 = solver1.compute_xc(dp_full.ngrid, nao, dp_full.d_dm, dp_full.d_ao, dp_full.d_weights, dp_full.d_vxc,
+                                        dp_full.d_ao_grad)
+                v1 = dp_full.d_vxc.get()
+                single = parity_record(e_host, v_timed, e1, v1, "this engine on 1 GPU (rank 0), whole grid")
+            else:
+                dp_full, single = dp, None
+            ref = load_reference_lib()
+            if ref is not None:
+                d_vref = cuda_rt.DeviceArray((nao, nao), zero=True)
+                e_r, v_r = reference_xc(ref, hp.functional, dp_full.ngrid, nao, dp_full.d_dm, dp_full.d_ao, dp_full.d_ao_grad,
+                                        dp_full.d_weights, d_vref)
+                parity = parity_record(e_host, v_timed, e_r, v_r,
+                                       "reference CUDA (dft_solver.cu unmodified, oracle/_ref/dft_ref.so) on the same "
+                                       "device arrays, whole grid, one GPU")
+            else:
+                parity = {"against": None, "ok": None, "note": "oracle/_ref/dft_ref.so did not travel"}
+            if single is not None:
+                parity["vs_single_gpu"] = single
+                parity["ranks_max_abs_diff"] = ranks_diff
+                parity["ok"] = bool(parity.get("ok") in (True, None) and single["ok"] and ranks_diff <= 1e-12)
+        barrier()
+
     if rank == 0:
         K = args.steps
         ms_step = total_ms / K
@@ -359,19 +476,16 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {hp.name}", "functional": hp.functional, "ngrid": hp.ngrid,
-                       "nao": nao, "basis": "sto-3g", "grid": "synthetic, PySCF level-3 point counts",
-                       "density": "seeded idempotent D = 2CC^T", "parallelism": f"grid-sharded x{world}",
-                       "l2": "explicit 384 MB flush between timed steps" if need_flush else
-                             "inputs per rank (%.1f GB) far larger than L2" % (input_bytes / 1e9),
-                       "path": int(solver.stat("path"))},
+            "config": bench_config(args, hp, need_flush),
+            "engine": {"path": int(solver.stat("path")), "ranks": world, "points_per_rank": n_local,
+                       "input_gb_per_rank": 8.0 * n_local * P * nao / 1e9, "options": args.opt},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 8,
                     "note": "per SCF iteration the driver uploads D (dft.py:200) and downloads V_xc (dft.py:211) + E_xc; "
                             "AO planes stay resident across iterations as in dft.py:155-176"},
             "gpu_launches": int(solver.stat("launches")) * K,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
-            "per_scf_iter_vxc_ms": ms_step, "e_xc": e_xc,
+            "per_scf_iter_vxc_ms": ms_step, "e_xc": e_host, "parity": parity,
             "ao_screening": {"density_ksteps_skipped_frac": solver.stat("skip_fraction"),
                              "note": "share of the density kernel's 32x4 Phi fragments that are exact zeros and "
                                      "skipped (rank 0); roofline.achieved stays quoted on the DENSE flop count"},

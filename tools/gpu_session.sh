@@ -8,7 +8,7 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.csv 2>&1
 for what in "$@"; do
   case $what in
-    tests)   timeout 900 python -m pytest tests -m gpu -x -q > $OUT/tests.log 2>&1; echo "tests rc=$?" | tee -a $OUT/summary.txt; tail -15 $OUT/tests.log ;;
+    tests)   timeout 2400 python -m pytest tests -m gpu -x -q --durations=8 > $OUT/tests.log 2>&1; echo "tests rc=$?" | tee -a $OUT/summary.txt; tail -15 $OUT/tests.log ;;
     golden)  timeout 300 python tools/make_reference_golden.py $OUT/golden > $OUT/golden.log 2>&1; echo "golden rc=$?" | tee -a $OUT/summary.txt; tail -20 $OUT/golden.log ;;
     smoke)   timeout 300 python __graft_entry__.py --smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/summary.txt; tail -5 $OUT/smoke.log ;;
     micro)   timeout 120 python -c "
@@ -17,12 +17,14 @@ l=load_library()
 print('DMMA TFLOP/s', l.DFT_MicrobenchDMMA(8192)); print('DFMA TFLOP/s', l.DFT_MicrobenchDFMA(8192))" > $OUT/micro.log 2>&1; echo "micro rc=$?" | tee -a $OUT/summary.txt; cat $OUT/micro.log ;;
     bench:*) W=${what#bench:}; timeout 600 python bench.py --workload $W --steps 5 --warmup 3 > $OUT/bench_$W.json 2> $OUT/bench_$W.err; echo "bench $W rc=$?" | tee -a $OUT/summary.txt; cat $OUT/bench_$W.json; tail -3 $OUT/bench_$W.err ;;
     benchx:*) A=${what#benchx:}; W=${A%%:*}; X=${A#*:}; timeout 600 python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline $X > $OUT/benchx_${W}_$(echo $X | tr -d ' -').json 2> $OUT/benchx_$W.err; echo "benchx $W [$X] rc=$?" | tee -a $OUT/summary.txt; tail -1 $OUT/benchx_${W}_$(echo $X | tr -d ' -').json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['config']['workload'], 'ms', d['ms_per_step'], 'dens', d['roofline']['density_ms'], 'vxc', d['roofline']['vxc_ms'])" ;;
-    ref:*)   W=${what#ref:}; timeout 600 python bench.py --impl reference --workload $W --steps 2 --warmup 1 > $OUT/ref_$W.json 2> $OUT/ref_$W.err; echo "ref $W rc=$?" | tee -a $OUT/summary.txt; cat $OUT/ref_$W.json; tail -3 $OUT/ref_$W.err ;;
+    ref:*)   W=${what#ref:}; timeout 900 python bench.py --impl reference --workload $W --steps 3 --warmup 1 > $OUT/ref_$W.json 2> $OUT/ref_$W.err; echo "ref $W rc=$?" | tee -a $OUT/summary.txt; cat $OUT/ref_$W.json; tail -3 $OUT/ref_$W.err ;;
     ncu:*)   W=${what#ncu:}; CMD="python bench.py --workload $W --steps 2 --warmup 3 --no-cpu-baseline"
              timeout 600 $CMD > $OUT/ncu_plain_$W.log 2>&1 && \
              timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$W.csv $CMD > $OUT/ncu_list_$W.log 2>&1 && \
              timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'density_tma|vxc_tma|xc_point|eval_kernel' -c 7 -o $OUT/prof_$W $CMD > $OUT/ncu_full_$W.log 2>&1
              echo "ncu $W rc=$?" | tee -a $OUT/summary.txt; tail -3 $OUT/ncu_full_$W.log ;;
+    sweep8)  SWEEP_RANKS=8 timeout 600 python tools/vxc_sweep.py C5 "dyn_sched=1" "dyn_sched=0" "dyn_sched=1,density_unit=1" "dyn_sched=0,density_unit=1" "dyn_sched=1" "dyn_sched=0" > $OUT/sweep8.txt 2>&1; echo "sweep8 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweep8.txt ;;
+    sweep1)  timeout 600 python tools/vxc_sweep.py C5 "dyn_sched=1" "dyn_sched=0" > $OUT/sweep1.txt 2>&1; echo "sweep1 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweep1.txt ;;
     *) echo "unknown step $what" ;;
   esac
 done

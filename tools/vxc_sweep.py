@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quantum_compute_dft_b200 import workload  # noqa: E402
 
 DEFAULTS = {"vxc_skip": -1, "vxc_skip_mode": 1, "vxc_vk": 0, "vxc_shape": 0, "zero_skip": 1, "tma_3d": 1,
-            "vxc_scatter": 1, "vxc_producers": 1, "vxc_mside_skip": 1, "debug_nodmma": 0, "wait_ns": 0, "dyn_sched": 1, "l2_prefetch": 0, "stagger_min": 8, "density_unit": 0}
+            "vxc_scatter": 1, "vxc_producers": 1, "vxc_mside_skip": 1, "wait_ns": 0, "dyn_sched": 1, "l2_prefetch": 0, "stagger_min": 8, "density_unit": 0}
 
 
 def main():
@@ -19,7 +19,14 @@ def main():
     sets = sys.argv[2:] or [""]
     steps = int(os.environ.get("SWEEP_STEPS", "6"))
     hp = workload.host_problem(wl)
-    solver = workload.make_solver(hp.functional)
+    # SWEEP_LIB=diag: the -DDFT_DIAGNOSTICS build (python -m quantum_compute_dft_b200.build --diag), which alone
+    # accepts debug_nodmma=1 (operand-delivery floor; results are wrong)
+    lib_tag = os.environ.get("SWEEP_LIB", "")
+    lib_path = None
+    if lib_tag:
+        from quantum_compute_dft_b200.solver import DEFAULT_LIB
+        lib_path = DEFAULT_LIB.replace(".so", f"_{lib_tag}.so")
+    solver = workload.make_solver(hp.functional, lib_path)
     # SWEEP_RANKS=N: time rank 0's shard of an N-rank run (the per-GPU problem of a multi-GPU step) on one GPU
     nranks = int(os.environ.get("SWEEP_RANKS", "1"))
     dp = workload.device_problem(hp, solver, 0, nranks)
