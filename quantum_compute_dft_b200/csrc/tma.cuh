@@ -59,7 +59,7 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 #ifndef DFT_MBAR_TIMEOUT_NS
 #define DFT_MBAR_TIMEOUT_NS 20000000000ull
 #endif
-__device__ __noinline__ void mbar_timeout_trap(uint32_t parity) {
+__device__ __forceinline__ void mbar_timeout_trap(uint32_t parity) {
     printf("[dft_b200] mbarrier wait exceeded %llu ns (block %d,%d thread %d parity %u)\n",
            (unsigned long long)DFT_MBAR_TIMEOUT_NS, blockIdx.x, blockIdx.y, threadIdx.x, parity);
     __trap();

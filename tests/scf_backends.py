@@ -5,15 +5,15 @@ XC = {"LDA": 0, "GGA": 1, "B3LYP": 2}
 
 
 class OracleBackend:
-    def __init__(self, oracle, functional, basis, coords, weights, eri):
-        self.o, self.xc_type, self.eri, self.w = oracle, XC[functional.upper()], eri, weights
+    def __init__(self, oracle, functional, basis, coords, weights, eri, mode=0):
+        self.o, self.xc_type, self.eri, self.w, self.mode = oracle, XC[functional.upper()], eri, weights, mode
         self.ao, self.grad = oracle.eval_ao(coords, basis, deriv=1)
 
     def coulomb_exchange(self, dm):
         return np.einsum("ijkl,kl->ij", self.eri, dm), np.einsum("ijkl,jl->ik", self.eri, dm)
 
     def xc(self, dm):
-        return self.o.compute_xc(self.xc_type, dm, self.ao, self.w, self.grad, mode=0)
+        return self.o.compute_xc(self.xc_type, dm, self.ao, self.w, self.grad, mode=self.mode)
 
 
 def h_chain(positions_bohr):

@@ -29,7 +29,12 @@ def _boys0(t):
     return np.where(small, 1.0 - t / 3.0, 0.5 * np.sqrt(np.pi / ts) * erf(np.sqrt(ts)))
 
 
-def s_integrals(mol, basis):
+def s_kinetic(mol, basis):
+    """Kinetic-energy matrix alone (the shim's int1e_kin, grid.py:62)."""
+    return s_integrals(mol, basis, kinetic_only=True)
+
+
+def s_integrals(mol, basis, kinetic_only=False):
     """Overlap S, core Hamiltonian T + V_nuc, ERI (nao,nao,nao,nao) and E_nuc for a basis of contracted s
     functions (`basis.prim_coef` already contains the primitive normalisation)."""
     if np.any(basis.shell_l != 0):
@@ -57,6 +62,8 @@ def s_integrals(mol, basis):
     # contract primitives -> AOs
     C = np.zeros((npn, n))
     C[np.arange(npn), ow] = 1.0
+    if kinetic_only:
+        return C.T @ t_pp @ C
     S = C.T @ s_pp @ C
     H = C.T @ (t_pp + v_pp) @ C
     # (ab|cd) over primitive pairs
@@ -125,18 +132,52 @@ class EngineBackend:
 
 
 # --------------------------------------------------------------------------- the loop (dft.py:183-266)
-def run_scf(S, hcore, e_nuc, nocc, backend, functional, max_cycle=200, e_tol=1e-8, dm_tol=1e-6, verbose=False):
-    """Plain fixed-point SCF exactly as the reference drives it (its DIIS object is PySCF's and is left out:
-    both backends then follow the identical iteration).  Returns (E_tot, dm, cycles, converged)."""
+class CDIIS:
+    """Pulay DIIS on the commutator error S D F - F D S (what PySCF's scf.diis.CDIIS, dft.py:184,225, does)."""
+
+    def __init__(self, space=8):
+        self.space, self._f, self._e = space, [], []
+
+    def update(self, s, d, f):
+        sdf = s @ d @ f
+        self._f.append(np.array(f, dtype=np.float64))
+        self._e.append((sdf - sdf.T).ravel())
+        if len(self._f) > self.space:
+            self._f.pop(0)
+            self._e.pop(0)
+        n = len(self._f)
+        if n < 2:
+            return f
+        B = np.zeros((n + 1, n + 1))
+        for i in range(n):
+            for j in range(n):
+                B[i, j] = self._e[i] @ self._e[j]
+        B[n, :n] = B[:n, n] = 1.0
+        rhs = np.zeros(n + 1)
+        rhs[n] = 1.0
+        try:
+            c = np.linalg.solve(B, rhs)[:n]
+        except np.linalg.LinAlgError:
+            c = np.linalg.lstsq(B, rhs, rcond=None)[0][:n]
+        return sum(ci * fi for ci, fi in zip(c, self._f))
+
+
+def run_scf(S, hcore, e_nuc, nocc, backend, functional, max_cycle=200, e_tol=1e-8, dm_tol=1e-6, verbose=False, diis=False):
+    """The reference's SCF loop (dft.py:199-248).  `diis=False`: plain fixed-point iteration (both backends then
+    follow the identical iteration); `diis=True`: with the commutator DIIS of dft.py:225.
+    Returns (E_tot, dm, cycles, converged)."""
     c_hf = 0.2 if functional.upper() == "B3LYP" else 0.0                        # dft.py:197
     _, C = eigh(hcore, S)
     dm = 2.0 * C[:, :nocc] @ C[:, :nocc].T
     e_old = 0.0
+    adiis = CDIIS() if diis else None
     for cycle in range(max_cycle):
         J, K = backend.coulomb_exchange(dm)                                     # dft.py:203, :218
         e_xc, v_raw = backend.xc(dm)                                            # dft.py:205-208
         vxc = 0.5 * (v_raw + v_raw.T)                                           # dft.py:212
         F = hcore + J + vxc - c_hf * 0.5 * K                                    # dft.py:221-223
+        if adiis is not None:
+            F = adiis.update(S, dm, F)                                          # dft.py:225
         _, C = eigh(F, S)
         dm_new = 2.0 * C[:, :nocc] @ C[:, :nocc].T
         e_one = np.sum(dm_new * hcore)                                          # dft.py:230-236

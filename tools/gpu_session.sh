@@ -9,6 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --fo
 for what in "$@"; do
   case $what in
     tests)   timeout 2400 python -m pytest tests -m gpu -x -q --durations=8 > $OUT/tests.log 2>&1; echo "tests rc=$?" | tee -a $OUT/summary.txt; tail -15 $OUT/tests.log ;;
+    pyt:*)   K=${what#pyt:}; timeout 1800 python -m pytest tests -m gpu -x -q -s -k "$K" > $OUT/pyt.log 2>&1; echo "pytest -k $K rc=$?" | tee -a $OUT/summary.txt; tail -25 $OUT/pyt.log ;;
     golden)  timeout 300 python tools/make_reference_golden.py $OUT/golden > $OUT/golden.log 2>&1; echo "golden rc=$?" | tee -a $OUT/summary.txt; tail -20 $OUT/golden.log ;;
     smoke)   timeout 300 python __graft_entry__.py --smoke > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/summary.txt; tail -5 $OUT/smoke.log ;;
     micro)   timeout 120 python -c "
