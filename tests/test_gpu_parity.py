@@ -412,6 +412,36 @@ def test_config_molecules_device_pipeline(oracle, engine_lib, workload_name, sca
     dp.free()
 
 
+@pytest.mark.parametrize("functional", FUNCS)
+def test_grid_file_drives_device_pipeline(engine_lib, h2_fixture, tmp_path, functional):
+    """a grid in the reference's on-disk format (grid.py:11-14, `atom x y z w w`) drives the whole
+    device pipeline -- load_grid_txt -> DFT_EvalAO -> DFT_ComputeXC -- with no PySCF in between.  The file is the
+    reference's own grid_txt/h2_grid.txt where `make -C oracle ref` staged it, otherwise the same grid written back
+    in that format from tests/golden/h2_grid.npz; the result is pinned by the H2 known-answer values (SURVEY KAT-2)."""
+    from quantum_compute_dft_b200 import molgrid as M
+    from quantum_compute_dft_b200.cuda_rt import DeviceArray
+    from quantum_compute_dft_b200.solver import DFTSolverWrapper
+    mol, basis, coords0, w0, dm = h2_fixture
+    staged = os.path.join(ROOT, "oracle", "_ref", "driver", "grid_txt", "h2_grid.txt")
+    path = staged if os.path.exists(staged) else str(tmp_path / "h2_grid.txt")
+    if path != staged:
+        M.save_grid_txt(path, coords0, w0, np.repeat([0, 1], len(w0) // 2))
+    coords, w, atom = M.load_grid_txt(path)
+    assert coords.shape == (19616, 3) and set(np.unique(atom)) == {0, 1}
+    np.testing.assert_array_equal(coords, coords0); np.testing.assert_array_equal(w, w0)
+    s = DFTSolverWrapper(engine_lib, functional)
+    d_c, d_w, d_dm = DeviceArray.from_host(coords), DeviceArray.from_host(w), DeviceArray.from_host(dm)
+    d_ao, d_g = DeviceArray((len(w), 2)), DeviceArray((3, len(w), 2))
+    s.eval_ao(d_c, basis, d_ao, d_g)
+    d_v = DeviceArray((2, 2), zero=True)
+    e = s.compute_xc(len(w), 2, d_dm, d_ao, d_w, d_v, d_g if functional != "LDA" else None)
+    v = d_v.get()
+    kat = {"LDA": (-0.683240084985, -0.448744125728, -0.302576546237),
+           "GGA": (-0.714211888015, -0.463813769518, -0.311372142021),
+           "B3LYP": (-0.591838579199, -0.379855055638, -0.254425920412)}[functional]
+    assert abs(e - kat[0]) < 1e-10 and abs(v[0, 0] - kat[1]) < 1e-10 and abs(v[0, 1] - kat[2]) < 1e-10
+
+
 _FULL = [("C1", ["LDA"]), ("C3", ["B3LYP"]), ("C2", ["GGA", "LDA", "B3LYP"]), ("C4", ["GGA"]), ("C5", ["B3LYP", "LDA"])]
 
 
