@@ -49,8 +49,8 @@ int DFT_CommDestroy(XCSolver* solver);
 //       that are the exact derivatives of the energies, i.e. libxc/PySCF numint)
 //       "path" 0 auto | 1 generic (any alignment) | 2 TMA-fed
 //       "deterministic" 0|1 (default 1: fixed-order reductions, bit-reproducible results)
-//       "vxc_shape" 0|64|96|128|160 (tuning: output tile of the TMA V kernel -- 64 x 64, 96 x 192, 128 x 128,
-//       160 x 80; 0 = chosen from nao)
+//       "vxc_shape" 0|64|128|160 (tuning: output tile of the TMA V kernel -- 64 x 64, 128 x 128, 160 x 80;
+//       0 = chosen from nao)
 //       "vxc_vk" 0|8|16 (tuning: grid rows per ring stage of the 128 x 128 V kernel; 0 = 16 on dense
 //       operands, 8 with zero skipping)
 //       "ao_shape" 0|16|32 (tuning: grid points per block of DFT_EvalAO; 0 = chosen from the basis size)
@@ -58,11 +58,11 @@ int DFT_CommDestroy(XCSolver* solver);
 //       exactly zero are skipped; results are unchanged; default 1)
 //       "vxc_skip" -1|0|1 (the zero-skipping instance of the V kernel: -1 = adaptive, used while the density
 //       kernel of the previous call skipped >= 10 % of its k-steps; default -1)
-//       "vxc_skip_mode" 1|2|3 (which zero-skipping V instance: 1 = per-fragment votes on the M side (default),
-//       2 | 3 = N-side box bits published by a scanner warp plus an M-side vote per stage | per k-step)
+//       "vxc_skip_mode" 4|1 (which zero-skipping V instance on the 128 x 128 tile: 4 = staged B, builder warps
+//       combine the planes once per CTA and all MMA warps skip the same all-zero fragments (default); 1 = round 1's
+//       per-warp votes on the M side, kept for comparison)
 //       "vxc_producers" 1..4 (tuning: TMA-issuing threads per CTA of the V kernel, default 1)
 //       "vxc_scatter" 0|1 (zero-skipping V instances: scatter consecutive ring stages over the grid, default 1)
-//       "vxc_mside_skip" 0|1 (box-bit V instances: keep the M-side votes, default 1)
 //       "dyn_sched" 0|1 (density kernel: hand the units of work out dynamically, default 1)
 //       "density_unit" 0|1|2 (density kernel, unit of work: 1 = a 64-point block, 0 | 2 = one column tile of a
 //       block, the default)
@@ -82,7 +82,8 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value);
 //       DFT_ComputeXC on the engine's stream), "launches" (kernels launched by the last call),
 //       "ao_ms" (kernel time of the last DFT_EvalAO), "skip_fraction" (share of the density kernel's
 //       k-steps that were exact zeros and skipped in the last call: the AO-screening statistic),
-//       "vxc_skip_fraction" (box-bit V instances: share of the (box, k-step) units skipped),
+//       "vxc_skip_fraction" (staged-B V kernel: share of its (8-column fragment, k-step) units -- 2 DMMAs each --
+//       that were skipped as exact zeros in the last call),
 //       "path" (path actually taken), "workspace_bytes", "nranks" (ranks of the communicator, 1 without
 //       DFT_CommInit), "plans_built" (TMA launch plans encoded so far: a steady SCF loop over the same arrays
 //       builds exactly one), "dyn_units" (draws from the density kernel's dynamic work counter in the last call =

@@ -322,12 +322,11 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
 #endif
     if (!strcmp(key, "vxc_scatter")) { c->vxc_scatter = value != 0.0; return 0; }
     if (!strcmp(key, "vxc_producers")) { c->vxc_producers = value < 1.0 ? 1 : (value > 4.0 ? 4 : (int)value); return 0; }
-    if (!strcmp(key, "vxc_mside_skip")) { c->vxc_mside_skip = value != 0.0; return 0; }
-    if (!strcmp(key, "vxc_skip_mode")) { c->vxc_skip_mode = (int)value; return 0; }
+    if (!strcmp(key, "vxc_skip_mode")) { const int v = (int)value; if (v != 1 && v != 4) return 3; c->vxc_skip_mode = v; return 0; }
     if (!strcmp(key, "raw_convention")) { c->raw_convention = value != 0.0; return 0; }
     if (!strcmp(key, "zero_skip")) { c->zero_skip = value != 0.0; return 0; }
     if (!strcmp(key, "tma_3d")) { c->tma_3d = value != 0.0; return 0; }
-    if (!strcmp(key, "vxc_shape")) { const int v = (int)value; if (v != 0 && v != 64 && v != 96 && v != 128 && v != 160) return 3; c->vxc_shape = v; return 0; }
+    if (!strcmp(key, "vxc_shape")) { const int v = (int)value; if (v != 0 && v != 64 && v != 128 && v != 160) return 3; c->vxc_shape = v; return 0; }
     if (!strcmp(key, "vxc_vk")) { c->vxc_vk = value == 16.0 ? 16 : (value == 8.0 ? 8 : 0); return 0; }
     if (!strcmp(key, "deterministic")) { return value != 0.0 ? 0 : 3; }  // reductions are always fixed-order
     return 2;

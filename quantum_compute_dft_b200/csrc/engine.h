@@ -72,7 +72,7 @@ struct CublasHandleWrapper {
     bool l2_prefetch = false;      // TMA density kernel: short-range L2 prefetch of A tiles and epilogue pieces (measured: no gain)
     int vxc_skip = -1;             // V kernel zero-skipping instance: -1 adaptive (default), 0 never, 1 always
     bool vxc_skip_on = true;       // (adaptive) the zero-skipping V instance is used while the density kernel finds zeros
-    int vxc_skip_mode = 1;         // zero-skipping V instance (128 x 128 tile): 1 M-side votes, 2 | 3 N-side box bits (xc_tma.cu)
+    int vxc_skip_mode = 4;         // zero-skipping V instance (128 x 128 tile): 4 staged B with uniform fragment skipping (default), 1 per-warp M-side votes
     int vxc_scatter = 1;           // zero-skipping V instances: scatter consecutive ring stages over the grid (golden-ratio stride)
     int density_unit = 0;          // TMA density kernel, unit of work: 0 | 2 = one column tile of a 64-point block (default), 1 = a whole block
     int stagger_min = 8;           // TMA density kernel: consumer group 1 starts half a tile period late when a CTA has more blocks than this
@@ -80,7 +80,6 @@ struct CublasHandleWrapper {
     int wait_ns = 0;               // TMA kernels: producer / scanner threads sleep this long between barrier polls
     int debug_nodmma = 0;          // -DDFT_DIAGNOSTICS builds only: TMA kernels skip every DMMA (measures the operand-delivery floor)
     int vxc_producers = 1;         // TMA V kernel: TMA-issuing threads per CTA (1 | 2)
-    int vxc_mside_skip = 1;        // box-bit V instances: also skip on all-zero M-side fragments (per-warp votes)
     bool raw_convention = false;   // GGA only: leave the reference's raw unsymmetrised B^T Phi in d_vxc (dft_solver.cu:616) instead of the symmetric matrix
     bool zero_skip = true;         // TMA kernels: skip k-steps whose operand fragment is all zero (exact: adds nothing)
     bool tma_3d = true;            // TMA V kernel: one 3-D TMA load per plane and stage instead of one per 16-column block

@@ -106,7 +106,6 @@ struct VxcParams {
     int producers;           // TMA-issuing threads per CTA (1..4)
     int wait_ns;             // producer / scanner threads sleep this long between barrier polls
     int debug_nodmma;        // diagnostic: skip every DMMA (operand-delivery floor; results are wrong)
-    int mside_skip;          // box-bit instances: also skip stages / k-steps whose M-side fragments are all zero
     int chunk_stride[2];     // per sub-problem: multiplier (coprime to the chunk count) that scatters consecutive stages over the grid
     int nsub, tiles_m, tiles_n, lda_half, rows_per_slice, slices_per_sub, ldv, mpv;
     const double* coef;
@@ -583,20 +582,18 @@ struct VxcCfg {
     static constexpr int COEF_OFF = N_OFF + (NT_ / 16) * BOXB;
     static constexpr int TX_BYTES = COEF_OFF + VK * 32;
     static constexpr int STAGE_BYTES = ((TX_BYTES + 1023) / 1024) * 1024;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;                 // full, empty, ready [STAGES] (8 B each), jbits[STAGES] (4 B each)
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;                 // full, empty [STAGES] (8 B each)
     static constexpr int TOTAL = BAR_OFF + 3 * STAGES * 8 + STAGES * 4 + 4 + 1024;
     static_assert(TOTAL <= 232448, "shared memory");
 };
 
 // SKIP selects the AO-screening scheme of the instance:
 //   0  none (branch-free; the fastest on dense operands)
-//   1  per-fragment votes on the M side only: every warp votes on its own built B fragments
-//   2  N-side box bits from the scanner warp + one M-side vote per stage
-//   3  N-side box bits from the scanner warp + one M-side vote per k-step
-// In 2 and 3 a warp of the producer warpgroup (the "scanner") looks at the Phi tile of every stage as soon as
-// TMA has delivered it and publishes one bit per 16-column box: is anything in it non-zero?  All eight
-// MMA warps share the N side, so they skip the SAME boxes of a stage -- unlike the M-side votes, which differ
-// from warp to warp and leave the skipping warps waiting for the ring.  Nothing is cached between calls.
+//   1  per-fragment votes on the M side: every warp votes on its own built B fragments (round 1's scheme, kept
+//      for comparison: the warps skip different fragments and then wait for each other on the shared ring)
+// (Round 1 also carried N-side "box bit" instances fed by a scanner warp and a 96 x 192 tile; both measured no
+// better than SKIP 1 -- profiles/r1_s53_vxc_instances_C5.txt, r1_s57_vxc_tile_96x192_C5.txt -- and were removed
+// when the staged-B kernel below replaced them.)
 template <int MF, int NFN, int WM, int WN, int NPL, int VK, int STAGES, int SKIP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vxc_tma_kernel(const __grid_constant__ VxcParams P) {
@@ -607,9 +604,6 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     unsigned char* sm = smem_raw + (base - tma::smem_u32(smem_raw));
     uint64_t* full = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF);
     uint64_t* empty = full + STAGES;
-    uint64_t* ready = empty + STAGES;                                 // SKIP >= 2: the scanner has published jbits[s]
-    const uint32_t jbits_u32 = base + L::BAR_OFF + 3 * STAGES * 8;    // SKIP >= 2: live N-side boxes of stage s
-    static_assert(SKIP < 2 || (WN == 1 && NFN % 2 == 0 && NFN <= 64), "box bits: the warps share the whole N tile");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -636,7 +630,6 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         for (int s = 0; s < STAGES; ++s) {
             tma::mbar_init(&full[s], 1);
             tma::mbar_init(&empty[s], NCW);
-            tma::mbar_init(&ready[s], 1);
         }
         tma::fence_barrier_init();
     }
@@ -654,11 +647,9 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         // take, so the stage's transfers are dealt to up to four threads; thread 0 also arms the barrier.  (A
         // transfer that completes before the barrier is armed only makes its tx-count transiently negative; the
         // phase cannot complete before thread 0 has arrived.)
-        const int max_prod = SKIP >= 2 ? 3 : 4;
-        const int nprod = P.producers < 1 ? 1 : (P.producers > max_prod ? max_prod : P.producers);
-        const int pw = warp - NCW;                                     // 0..3
-        const int pid = pw == 0 ? 0 : (SKIP >= 2 ? pw - 1 : (pw == 1 ? 3 : pw - 1));   // warp 9 is the last resort
-        if (lane == 0 && pid >= 0 && pid < nprod && !(SKIP >= 2 && pw == 1)) {
+        const int nprod = P.producers < 1 ? 1 : (P.producers > 4 ? 4 : P.producers);
+        const int pid = warp - NCW;                                    // 0..3
+        if (lane == 0 && pid < nprod) {
             // transfers of a stage: bits 0..3 = M-side planes, 4 = Phi tile (N side), 5 = coefficients
             unsigned ops;
             if (NPL == 4) {
@@ -730,39 +721,6 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
                 o[0] = t_w; o[1] = t_c + (t1 - t0); o[2] = 0; o[3] = t1 - t_start;
             }
 #endif
-        } else if (SKIP >= 2 && warp == NCW + 1) {
-            // ===================== scanner: one bit per 16-column box of the stage's Phi tile =====================
-            // A box is VK rows x 128 bytes; the lanes read it 16 bytes at a time (the swizzle does not matter for
-            // an any-non-zero test).  Boxes past the edge of the matrix were cleared once and are never written,
-            // so they read as zero and are skipped as well.
-            constexpr int NBN = L::NT_ / 16;
-            constexpr int PER_LANE = (VK * 8 + 31) / 32;
-            for (int c = 0; c < nchunks; ++c) {
-                const uint32_t s = c % STAGES, ph = (c / STAGES) & 1u;
-                tma::mbar_wait_relaxed(&full[s], ph, (uint32_t)P.wait_ns);
-                const uint32_t nb = base + s * L::STAGE_BYTES + L::N_OFF + lane * 16;
-                uint32_t bits = 0;
-#pragma unroll
-                for (int b = 0; b < NBN; ++b) {
-                    bool nz = false;
-#pragma unroll
-                    for (int i = 0; i < PER_LANE; ++i) {
-                        if (VK * 8 % 32 == 0 || lane + 32 * i < VK * 8) {
-                            // integer test (+-0 -> zero): keeps the scanner off the FP64 pipe
-                            uint32_t x0, x1, x2, x3;
-                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(nb + b * L::BOXB + i * 512));
-                            nz |= ((x0 | x2) | ((x1 | x3) << 1)) != 0u;
-                        }
-                    }
-                    bits |= (__any_sync(0xffffffffu, nz) ? 1u : 0u) << b;
-                }
-                if (lane == 0) {
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(jbits_u32 + 4 * s), "r"(bits) : "memory");
-                    tma::mbar_arrive(&ready[s]);
-                }
-                __syncwarp();
-            }
         }
         return;
     }
@@ -778,8 +736,6 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         for (int nf = 0; nf < NFN; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
 
     const bool no_skip = P.zero_skip == 0;
-    const bool no_mskip = P.mside_skip == 0;
-    unsigned int n_box_done = 0;  // SKIP >= 2: (box, k-step) units executed by this warp
     // Fragment addressing.  A DMMA k-step ks contracts 4 grid rows; lane (q, qcol) supplies row
     // krow(ks, qcol) -- rows {0,2,4,6} / {1,3,5,7} of an 8-row group, so that with the 128-byte swizzle
     // the 16 lanes of a load phase hit 16 distinct bank pairs -- and column (8-column group G) * 8 + q.
@@ -789,7 +745,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     // takes groups w and 15 - w instead of 2w and 2w + 1: two halves of one 16-column box (one or two atoms)
     // are zero or non-zero together, while groups from opposite ends of the tile average out, which evens the
     // work of the eight warps that share the ring.
-    constexpr bool MIRROR = (SKIP == 1 || SKIP == 3) && WM == 8 && WN == 1 && MF == 2;
+    constexpr bool MIRROR = SKIP == 1 && WM == 8 && WN == 1 && MF == 2;
     auto mgroup = [&](int mf) { return MIRROR ? (mf == 0 ? wm : 15 - wm) : ga0 + mf; };
     uint32_t a_off[KS][MF], b_even[KS], b_odd[KS], c_off[KS];
 #pragma unroll
@@ -819,63 +775,6 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         t1 = clock64(); t_w += t1 - t0; t0 = t1;
 #endif
         const uint32_t sb = base + s * L::STAGE_BYTES;
-        if constexpr (SKIP >= 2) {
-            // ---- box-bit instance: build the stage's A fragments, then walk the live N-side boxes
-            tma::mbar_wait(&ready[s], ph);
-#ifdef DFT_PHASE_TIMING
-            t1 = clock64(); t_w += t1 - t0; t0 = t1;
-#endif
-            uint32_t jm;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(jm) : "r"(jbits_u32 + 4 * s));
-            double a[KS][MF];
-            unsigned livek = 0;
-            bool nz_all = false;
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                const double2 ca = lds_f64x2(sb + c_off[ks]);
-                double2 cb = make_double2(0.0, 0.0);
-                if (NPL == 4) cb = lds_f64x2(sb + c_off[ks] + 16);
-                bool nz = false;
-#pragma unroll
-                for (int mf = 0; mf < MF; ++mf) {
-                    const uint32_t ad = sb + a_off[ks][mf];
-                    double v = ca.x * lds_f64(ad);
-                    if (NPL == 4) {
-                        v = fma(ca.y, lds_f64(ad + L::PLANE_BYTES), v);
-                        v = fma(cb.x, lds_f64(ad + 2 * L::PLANE_BYTES), v);
-                        v = fma(cb.y, lds_f64(ad + 3 * L::PLANE_BYTES), v);
-                    }
-                    a[ks][mf] = v;
-                    nz |= v != 0.0;
-                }
-                if (SKIP == 3) livek |= (__any_sync(0xffffffffu, nz | no_mskip) ? 1u : 0u) << ks;
-                nz_all |= nz;
-            }
-            if (SKIP == 2) livek = __any_sync(0xffffffffu, nz_all | no_mskip) ? (1u << KS) - 1u : 0u;
-#ifdef DFT_DIAGNOSTICS
-            if (P.debug_nodmma != 0) livek = 0;
-#endif
-            if (livek != 0 && jm != 0) {
-                n_box_done += (unsigned)(__popc(jm) * __popc(livek));
-#pragma unroll
-                for (int b = 0; b < NFN / 2; ++b) {
-                    if (jm & (1u << b)) {
-#pragma unroll
-                        for (int ks = 0; ks < KS; ++ks) {
-                            if (SKIP == 2 || (livek & (1u << ks))) {
-                                const double bf0 = lds_f64(sb + b_even[ks] + (uint32_t)(b * L::BOXB));
-                                const double bf1 = lds_f64(sb + b_odd[ks] + (uint32_t)(b * L::BOXB));
-#pragma unroll
-                                for (int mf = 0; mf < MF; ++mf) {
-                                    dmma::mma8x8x4(acc[mf][2 * b], a[ks][mf], bf0);
-                                    dmma::mma8x8x4(acc[mf][2 * b + 1], a[ks][mf], bf1);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        } else
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
             // A fragments: B[k][m] = a Phi + bx dxPhi + by dyPhi + bz dzPhi, built in registers
@@ -947,10 +846,6 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
             const int cc = n0 + (gb0 + nf) * 8 + 2 * qcol;
             *reinterpret_cast<double2*>(out + (size_t)r * P.ldv + cc) = make_double2(acc[mf][nf][0], acc[mf][nf][1]);
         }
-    if (SKIP >= 2 && lane == 0 && P.counters) {
-        atomicAdd(&P.counters[0], (unsigned long long)n_box_done);
-        atomicAdd(&P.counters[1], (unsigned long long)nchunks * KS * (NFN / 2));
-    }
 #ifdef DFT_PHASE_TIMING
     if (lane == 0 && P.phase) {
         long long* o = P.phase + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (NCW + 1) + warp) * 4;
@@ -958,6 +853,271 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         o[0] = t_w; o[1] = t_c; o[2] = t1 - t0; o[3] = t1 - t_start;
     }
 #endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// V kernel, staged-B instance (the default where AO screening finds zeros to skip)
+// ------------------------------------------------------------------------------------------------
+// Same mathematics and the same 128 x 128 output tile per CTA as vxc_tma_kernel, organised so that the zero
+// skipping is UNIFORM over the eight MMA warps:
+//
+//   TMA  -> raw ring (RS stages): the NPL plane tiles of the M columns [8 boxes][8 rows][16] + the 8 coefficient rows
+//   BUILDERS (the four warps of the producer warpgroup, 80 registers each) combine the planes with the
+//        points' coefficients ONCE per CTA, B = a Phi + b . grad Phi, 16 bytes per thread and step, into the MMA
+//        ring in the same swizzled box layout, and publish one bit per (k-step, 8-column fragment): is anything
+//        in that 8 x 4 piece of B non-zero?  (zero AOs, zero-weight and density-gated points all end up there)
+//   TMA  -> MMA ring (MS stages): the Phi tile of the N columns goes straight in beside the built B
+//   MMA warps, 1 x 8: warp w owns ALL 128 M columns and the 16 N columns of box w (64 accumulator doubles per
+//        lane).  Every warp reads the same A fragments -- one shared load each instead of 4 loads + 4 FP64 ops
+//        (18 shared loads per 32 DMMAs instead of 26) -- so every warp skips exactly the same fragments: no warp
+//        waits on the ring for another one that could not skip (round 1's per-warp votes made the stage time the
+//        maximum over the warps, i.e. almost nothing was gained: 11.8 ms with 45 % of the DMMAs skipped).  A warp
+//        whose own N box is all zero in a stage leaves the whole stage out, which only frees the tensor pipe for
+//        the warp it shares an SM sub-partition with.
+// One fragment bit = 2 DMMAs behind a uniform branch (the mask is made a uniform register with a warp
+// reduction), loads batched per k-step.  Nothing is cached between calls; a skipped DMMA would have added
+// exact zeros, so results are bit-identical to the branch-free instance.
+template <int NPL>
+struct StagedCfg {
+    static constexpr int VK = 8, MT = 128, NT_ = 128;
+    static constexpr int BOXB = VK * 128;                    // one 16-column box: 1 KB
+    static constexpr int PLANE_BYTES = (MT / 16) * BOXB;     // 8 KB
+    static constexpr int RS = NPL == 4 ? 3 : 6;              // raw ring depth
+    static constexpr int MS = NPL == 4 ? 7 : 8;              // MMA ring depth
+    static constexpr int COEF_OFF = NPL * PLANE_BYTES;
+    static constexpr int RAW_BYTES = ((COEF_OFF + VK * 32 + 1023) / 1024) * 1024;
+    static constexpr int NB_OFF = PLANE_BYTES;               // MMA stage: [B 8 KB][Phi tile 8 KB][4 mask words]
+    static constexpr int MASK_OFF = 2 * PLANE_BYTES;
+    static constexpr int MMA_BYTES = 2 * PLANE_BYTES + 1024;
+    static constexpr int MMA_OFF = RS * RAW_BYTES;
+    static constexpr int BAR_OFF = MMA_OFF + MS * MMA_BYTES;  // raw_full[RS], raw_empty[RS], mma_full[MS], mma_empty[MS]
+    static constexpr int TOTAL = BAR_OFF + (2 * RS + 2 * MS) * 8 + 1024;
+    static_assert(TOTAL <= 232448, "shared memory");
+    static constexpr int REGS_MMA = 216, REGS_BUILD = 80;    // 256 x 216 + 128 x 80 = 65536
+};
+
+__device__ __forceinline__ double2 lds_f64x2_plain(const unsigned char* p) { return *reinterpret_cast<const double2*>(p); }
+
+template <int NPL>
+__global__ void __launch_bounds__(NTHREADS, 1)
+vxc_staged_kernel(const __grid_constant__ VxcParams P) {
+    using L = StagedCfg<NPL>;
+    constexpr int VK = L::VK, RS = L::RS, MS = L::MS;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (tma::smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - tma::smem_u32(smem_raw));
+    uint64_t* raw_full = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF);
+    uint64_t* raw_empty = raw_full + RS;
+    uint64_t* mma_full = raw_empty + RS;
+    uint64_t* mma_empty = mma_full + MS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int tm, tn;
+    if (P.lda_half) {
+        int t = blockIdx.x;
+        tm = 0;
+        while (t >= P.tiles_n - tm) { t -= P.tiles_n - tm; ++tm; }
+        tn = tm + t;
+    } else {
+        tm = blockIdx.x / P.tiles_n;
+        tn = blockIdx.x % P.tiles_n;
+    }
+    const int m0 = tm * L::MT, n0 = tn * L::NT_;
+    const int si = blockIdx.y / P.slices_per_sub;
+    const int sl = blockIdx.y % P.slices_per_sub;
+    const int total_chunks = (P.sub[si].rows + VK - 1) / VK;
+    const int nchunks = total_chunks > sl ? (total_chunks - sl + P.slices_per_sub - 1) / P.slices_per_sub : 0;
+
+    constexpr int NISSUE = NPL;   // TMA-issuing threads of the raw ring: lane 0 of builder warp p brings plane p
+    if (tid == 0) {
+        for (int s = 0; s < RS; ++s) { tma::mbar_init(&raw_full[s], NISSUE); tma::mbar_init(&raw_empty[s], 4); }
+        for (int s = 0; s < MS; ++s) { tma::mbar_init(&mma_full[s], 5); tma::mbar_init(&mma_empty[s], NCW); }
+        tma::fence_barrier_init();
+    }
+    // boxes past the edge of the matrix are never written by TMA: clear both rings once
+    for (int o = tid * 16; o < L::BAR_OFF; o += NTHREADS * 16) *reinterpret_cast<double2*>(sm + o) = make_double2(0.0, 0.0);
+    tma::fence_proxy_async();
+    __syncthreads();
+
+    if (warp >= NCW) {
+        // ===================== builders (and, lane 0 of each, the TMA issue) =====================
+        reg_dec<L::REGS_BUILD>();
+        const int p = warp - NCW;                 // 0..3: builder warp, and the plane whose loads it issues
+        const int bt = tid - NCONS;               // 0..127
+        const int nfull = P.nfull[si], rem = P.rem[si];
+        constexpr int NB = L::MT / 16;
+        const int bm0 = m0 / 16, bn0 = n0 / 16;
+        const int fbm = min(max(nfull - bm0, 0), NB), fbn = min(max(nfull - bn0, 0), NB);
+        const bool pm = rem > 0 && nfull >= bm0 && nfull - bm0 < NB;
+        const bool pn = rem > 0 && nfull >= bn0 && nfull - bn0 < NB;
+        const uint32_t tx_plane = (uint32_t)((fbm + (pm ? 1 : 0)) * L::BOXB);
+        const uint32_t tx_n = (uint32_t)((fbn + (pn ? 1 : 0)) * L::BOXB);
+        const double* coef = P.coef + 4 * (size_t)P.sub[si].coef0;
+        // chunk of step c: (sl + c nsl) stride mod total, kept incrementally; `cidx_issue` runs RS - 1 steps ahead
+        const int cstep = (int)(((long long)P.slices_per_sub * P.chunk_stride[si]) % total_chunks);
+        int cidx_issue = (int)(((long long)sl * P.chunk_stride[si]) % total_chunks);
+        int cidx_n = cidx_issue;
+        auto next_chunk = [&](int& ci) { const int j0 = ci * VK; ci += cstep; if (ci >= total_chunks) ci -= total_chunks; return j0; };
+        auto issue_raw = [&](int c) {   // this thread's share of raw stage c: plane p (+ the coefficient rows with plane 0)
+            const int s = c % RS;
+            tma::mbar_wait_relaxed(&raw_empty[s], ((c / RS) & 1) ^ 1u, (uint32_t)P.wait_ns);
+            const int j0 = next_chunk(cidx_issue);
+            unsigned char* st = sm + s * L::RAW_BYTES;
+            uint64_t* fb = &raw_full[s];
+            tma::mbar_arrive_expect_tx(fb, tx_plane + (p == 0 ? VK * 32 : 0));
+            unsigned char* dst = st + p * L::PLANE_BYTES;
+            if (P.use3d) {
+                if (fbm == NB) tma::load_3d(dst, &P.m3[si][p], 0, j0, bm0, fb);
+                else if (fbm > 0) tma::load_3d(dst, &P.m3l[si][p], 0, j0, bm0, fb);
+            } else {
+                for (int b = 0; b < fbm; ++b) tma::load_2d(dst + b * L::BOXB, &P.p2[si][p], m0 + 16 * b, j0, fb);
+            }
+            if (pm) tma::load_2d(dst + fbm * L::BOXB, &P.p2[si][p], m0 + 16 * fbm, j0, fb);
+            if (p == 0) tma::load_1d(st + L::COEF_OFF, coef + 4 * (size_t)j0, VK * 32, fb);
+        };
+        const bool issuer = lane == 0 && p < NISSUE;
+        if (issuer)
+            for (int c = 0; c < RS - 1 && c < nchunks; ++c) issue_raw(c);
+        // the 16-byte granule of this thread in step i: offset (i * 128 + bt) * 16 of a plane tile, i.e. box
+        // 2 i + (bt >> 6), box row (bt >> 3) & 7 -- the same row for all four, so the coefficients are loaded once
+        const int row = (bt >> 3) & 7;
+        const int ks_row = row & 1;                       // k-step 0 takes rows {0,2,4,6}, k-step 1 rows {1,3,5,7}
+        const int half = (((bt & 7) ^ row) >> 2) & 1;     // un-swizzled 16-byte chunk >> 2: lower / upper 8 columns
+        const uint32_t bit0 = 1u << (ks_row * 16 + 2 * (bt >> 6) + half);
+        for (int c = 0; c < nchunks; ++c) {
+            if (issuer && c + RS - 1 < nchunks) issue_raw(c + RS - 1);
+            const int rs = c % RS, ms = c % MS;
+            tma::mbar_wait(&mma_empty[ms], ((c / MS) & 1) ^ 1u);
+            unsigned char* mst = sm + L::MMA_OFF + ms * L::MMA_BYTES;
+            if (p == (NPL == 4 ? 1 : 0) && lane == 0) {   // the Phi tile of the N columns goes straight into the MMA stage
+                const int j0 = next_chunk(cidx_n);
+                uint64_t* fb = &mma_full[ms];
+                tma::mbar_arrive_expect_tx(fb, tx_n);
+                unsigned char* dst = mst + L::NB_OFF;
+                if (P.use3d) {
+                    if (fbn == NB) tma::load_3d(dst, &P.n3[si], 0, j0, bn0, fb);
+                    else if (fbn > 0) tma::load_3d(dst, &P.n3l[si], 0, j0, bn0, fb);
+                } else {
+                    for (int b = 0; b < fbn; ++b) tma::load_2d(dst + b * L::BOXB, &P.p2[si][0], n0 + 16 * b, j0, fb);
+                }
+                if (pn) tma::load_2d(dst + fbn * L::BOXB, &P.p2[si][0], n0 + 16 * fbn, j0, fb);
+            }
+            tma::mbar_wait(&raw_full[rs], (c / RS) & 1);
+            const unsigned char* rst = sm + rs * L::RAW_BYTES;
+            const double2 ca = lds_f64x2_plain(rst + L::COEF_OFF + row * 32);
+            double2 cb = make_double2(0.0, 0.0);
+            if (NPL == 4) cb = lds_f64x2_plain(rst + L::COEF_OFF + row * 32 + 16);
+            uint32_t bits = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int o = (i * 128 + bt) * 16;
+                const double2 f0 = lds_f64x2_plain(rst + o);
+                double2 v = make_double2(ca.x * f0.x, ca.x * f0.y);
+                if (NPL == 4) {
+                    const double2 f1 = lds_f64x2_plain(rst + L::PLANE_BYTES + o);
+                    const double2 f2 = lds_f64x2_plain(rst + 2 * L::PLANE_BYTES + o);
+                    const double2 f3 = lds_f64x2_plain(rst + 3 * L::PLANE_BYTES + o);
+                    v.x = fma(ca.y, f1.x, v.x); v.y = fma(ca.y, f1.y, v.y);
+                    v.x = fma(cb.x, f2.x, v.x); v.y = fma(cb.x, f2.y, v.y);
+                    v.x = fma(cb.y, f3.x, v.x); v.y = fma(cb.y, f3.y, v.y);
+                }
+                *reinterpret_cast<double2*>(mst + o) = v;
+                if ((v.x != 0.0) | (v.y != 0.0)) bits |= bit0 << (4 * i);
+            }
+            bits = __reduce_or_sync(0xffffffffu, bits);
+            if (lane == 0) *reinterpret_cast<uint32_t*>(mst + L::MASK_OFF + 4 * p) = bits;
+            __syncwarp();
+            if (lane == 0) {
+                tma::mbar_arrive(&mma_full[ms]);
+                tma::mbar_arrive(&raw_empty[rs]);
+            }
+        }
+        return;
+    }
+
+    // ===================== MMA warps, 1 x 8 =====================
+    reg_inc<L::REGS_MMA>();
+    const int q = lane >> 2, qcol = lane & 3;
+    double acc[16][2][2];
+#pragma unroll
+    for (int g = 0; g < 16; ++g)
+#pragma unroll
+        for (int nf = 0; nf < 2; ++nf) acc[g][nf][0] = acc[g][nf][1] = 0.0;
+    // fragment addressing (same maps as vxc_tma_kernel): k-step ks contracts box rows 2 qcol + ks; lane (q, qcol)
+    // supplies column 8 (G & 1) + q of box G >> 1, whose swizzled offset is c0 ^ ((G & 1) << 6)
+    // (the four offsets are laundered through an opaque move: left to itself the compiler re-derives them from
+    // threadIdx in front of every load -- three logic instructions per fragment)
+    uint32_t c0[2][2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        const int row = 2 * qcol + ks;
+        const uint32_t v = (uint32_t)(row * 128 + ((((q >> 1) ^ row) & 7) << 4) + ((q & 1) << 3));
+        asm volatile("mov.u32 %0, %1;" : "=r"(c0[ks][0]) : "r"(v));
+        asm volatile("mov.u32 %0, %1;" : "=r"(c0[ks][1]) : "r"(v ^ 64u));
+    }
+    const uint32_t nb_off = (uint32_t)(L::NB_OFF + warp * L::BOXB);
+    const bool no_skip = P.zero_skip == 0;
+    unsigned int n_done = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int ms = c % MS;
+        tma::mbar_wait(&mma_full[ms], (c / MS) & 1);
+        const uint32_t sb = base + L::MMA_OFF + ms * L::MMA_BYTES;
+        uint32_t m0w, m1w, m2w, m3w;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m0w), "=r"(m1w), "=r"(m2w), "=r"(m3w) : "r"(sb + L::MASK_OFF));
+        uint32_t m = (m0w | m1w) | (m2w | m3w);
+        // this warp's Phi fragments of both k-steps (B operand of the DMMAs)
+        double bf[2][2];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            bf[ks][0] = lds_f64(sb + nb_off + c0[ks][0]);
+            bf[ks][1] = lds_f64(sb + nb_off + c0[ks][1]);
+        }
+        const bool nz = ((bf[0][0] != 0.0) | (bf[0][1] != 0.0)) | ((bf[1][0] != 0.0) | (bf[1][1] != 0.0));
+        if (no_skip) m = 0xffffffffu;
+        m = __reduce_or_sync(0xffffffffu, m);   // (all lanes hold the same word: this makes it a UNIFORM register)
+        if (__any_sync(0xffffffffu, nz | no_skip) && m != 0u) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const uint32_t mk = (m >> (16 * ks)) & 0xffffu;
+                if (mk == 0u) continue;
+                double a[16];
+#pragma unroll
+                for (int g = 0; g < 16; ++g)
+                    if (mk & (1u << g)) a[g] = lds_f64(sb + (uint32_t)((g >> 1) * L::BOXB) + c0[ks][g & 1]);
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    // A REAL branch around the fragment's two DMMAs: ptxas if-converts a plain `if` of this size into
+                    // predicated DMMAs, and a predicated-off DMMA still pays its statically scheduled issue stall
+                    // (measured in round 1: 15.3 against 12.4 ms).  A loop with a run-time trip count of 0 or 1
+                    // cannot be if-converted.
+                    int rep;   // (opaque to the compiler, or it proves rep <= 1 and turns the loop back into an `if`)
+                    asm volatile("bfe.u32 %0, %1, %2, 1;" : "=r"(rep) : "r"(mk), "r"(g));
+#pragma unroll 1
+                    for (int r = 0; r < rep; ++r) {
+                        dmma::mma8x8x4(acc[g][0], a[g], bf[ks][0]);
+                        dmma::mma8x8x4(acc[g][1], a[g], bf[ks][1]);
+                    }
+                }
+                n_done += __popc(mk);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(&mma_empty[ms]);
+    }
+    // ---- partial tile out
+    double* out = P.vpart + (size_t)blockIdx.y * P.mpv * P.ldv;
+#pragma unroll
+    for (int g = 0; g < 16; ++g)
+#pragma unroll
+        for (int nf = 0; nf < 2; ++nf) {
+            const int r = m0 + g * 8 + q;
+            const int cc = n0 + warp * 16 + nf * 8 + 2 * qcol;
+            *reinterpret_cast<double2*>(out + (size_t)r * P.ldv + cc) = make_double2(acc[g][nf][0], acc[g][nf][1]);
+        }
+    if (lane == 0 && P.counters) {   // (fragment, k-step) units executed / total: the V kernel's screening statistic
+        atomicAdd(&P.counters[0], (unsigned long long)n_done);
+        atomicAdd(&P.counters[1], (unsigned long long)nchunks * 32ull);
+    }
 }
 
 // out[i][j] = sum over slices of T(i+s, j+s) + T(j+s, i+s), s = column shift of the slice's
@@ -1162,7 +1322,7 @@ static Geometry make_geometry(int ngrid, int nao) {
 // addresses, so a plan stays valid when the caller rewrites the CONTENTS of its arrays.
 struct PlanKey {
     Problem prob;
-    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, vxc_mside_skip, debug_nodmma, wait_ns, dyn_sched, stagger_min, density_unit;
+    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, debug_nodmma, wait_ns, dyn_sched, stagger_min, density_unit;
     const void *dsym, *coef, *epart, *vpart, *rho;  // engine workspaces (grow-only: may move when they grow)
 };
 
@@ -1304,7 +1464,7 @@ static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry&
     }
     vp.use3d = ok3 ? 1 : 0;
     vp.debug_nodmma = ctx->debug_nodmma; vp.wait_ns = ctx->wait_ns;
-    vp.producers = ctx->vxc_producers; vp.mside_skip = ctx->vxc_mside_skip;
+    vp.producers = ctx->vxc_producers;
     vp.zero_skip = ctx->zero_skip ? 1 : 0;  // (a driver that rejects the 3-D form leaves the per-block 2-D loads)
     vp.sub[0] = g.sub[0]; vp.sub[1] = g.sub[1];
     vp.nsub = g.nsub; vp.tiles_m = tiles_m; vp.tiles_n = tiles_n; vp.lda_half = lda_half;
@@ -1318,10 +1478,19 @@ static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry&
     }
 #endif
 
-    auto vk = vxc_tma_kernel<MF, NFN, WM, WN, NPL, VK, STAGES, SKIP>;
-    DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, VL::TOTAL));
-    pl.vfunc = reinterpret_cast<const void*>(vk);
-    pl.vgrid = dim3(tiles, nsl * g.nsub); pl.vsmem = VL::TOTAL;
+    if constexpr (SKIP == 4) {   // staged-B instance (128 x 128 tile, 8 rows per stage): same maps, its own kernel
+        static_assert(VL::MT == 128 && VL::NT_ == 128 && VK == 8, "staged V kernel shape");
+        auto vk = vxc_staged_kernel<NPL>;
+        DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, StagedCfg<NPL>::TOTAL));
+        pl.vfunc = reinterpret_cast<const void*>(vk);
+        pl.vsmem = StagedCfg<NPL>::TOTAL;
+    } else {
+        auto vk = vxc_tma_kernel<MF, NFN, WM, WN, NPL, VK, STAGES, SKIP>;
+        DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, VL::TOTAL));
+        pl.vfunc = reinterpret_cast<const void*>(vk);
+        pl.vsmem = VL::TOTAL;
+    }
+    pl.vgrid = dim3(tiles, nsl * g.nsub);
     pl.ldv = ldv; pl.mpv = mpv; pl.fin_nt = VL::NT_; pl.nsl = nsl; pl.shift1 = g.split ? 1 : 0; pl.lda_half = lda_half;
     pl.vpart = vpart;
 }
@@ -1359,23 +1528,17 @@ static void build_plan(CublasHandleWrapper* ctx, const Problem& p, int nsm, Plan
     const bool vskip = ctx->zero_skip && ctx->vxc_skip_on;
 #define DFT_PLAN_V(...) do { if (vskip) plan_vxc<__VA_ARGS__, 1>(ctx, p, g, nsm, coef, pl); \
                              else plan_vxc<__VA_ARGS__, 0>(ctx, p, g, nsm, coef, pl); } while (0)
-    // 128 x 128 tile: the box-bit instances (vxc_skip_mode 2 | 3) exist in both ring shapes
+    // 128 x 128 tile with zero skipping: the staged-B instance (uniform skipping; vxc_skip_mode 4, the default) or
+    // round 1's per-warp M-side votes (vxc_skip_mode 1, kept for comparison)
 #define DFT_PLAN_V128(VK_, ST_) do { \
         if (!vskip) plan_vxc<2, 16, 8, 1, NPL, VK_, ST_, 0>(ctx, p, g, nsm, coef, pl); \
-        else if (ctx->vxc_skip_mode == 2) plan_vxc<2, 16, 8, 1, NPL, VK_, ST_, 2>(ctx, p, g, nsm, coef, pl); \
-        else if (ctx->vxc_skip_mode == 3) plan_vxc<2, 16, 8, 1, NPL, VK_, ST_, 3>(ctx, p, g, nsm, coef, pl); \
         else plan_vxc<2, 16, 8, 1, NPL, VK_, ST_, 1>(ctx, p, g, nsm, coef, pl); } while (0)
     if (shape == 64) {
         DFT_PLAN_V(1, 8, 8, 1, NPL, 16, 4);
     } else if (shape == 160) {
         DFT_PLAN_V(5, 5, 4, 2, NPL, 16, 2);
-    } else if (shape == 96) {
-        // 96 x 192 (4 x 2 warps, warp tile 24 x 96): 4.5 KB of operands per grid row for 36.9 kflop -- 20 % fewer
-        // bytes per flop than 128 x 128, which is what matters where zero skipping leaves the kernel bound by
-        // operand delivery rather than by the tensor pipe
-        const int vk = ctx->vxc_vk ? ctx->vxc_vk : 8;
-        if (vk == 16) DFT_PLAN_V(3, 12, 4, 2, NPL, 16, 3);
-        else DFT_PLAN_V(3, 12, 4, 2, NPL, 8, 5);
+    } else if (vskip && ctx->vxc_skip_mode != 1) {
+        plan_vxc<2, 16, 8, 1, NPL, 8, 5, 4>(ctx, p, g, nsm, coef, pl);
     } else {
         // rows per ring stage: 16 (2 stages, fewer barriers) on dense operands; 8 (5 stages) when zero fragments
         // are skipped -- with the stages scattered over the grid, the deeper ring lets the warps drift apart
@@ -1395,7 +1558,7 @@ static PlanKey make_key(const CublasHandleWrapper* ctx, const Problem& p) {
     k.prob.vxc = p.vxc; k.prob.d_exc = p.d_exc;
     k.exact = ctx->exact_functionals; k.l2_prefetch = ctx->l2_prefetch; k.tma_3d = ctx->tma_3d;
     k.vxc_shape = ctx->vxc_shape; k.vxc_vk = ctx->vxc_vk; k.zero_skip = ctx->zero_skip; k.vxc_skip_on = ctx->vxc_skip_on; k.vxc_skip_mode = ctx->vxc_skip_mode; k.vxc_scatter = ctx->vxc_scatter;
-    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.stagger_min = ctx->stagger_min; k.density_unit = ctx->density_unit; k.vxc_producers = ctx->vxc_producers; k.vxc_mside_skip = ctx->vxc_mside_skip;
+    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.stagger_min = ctx->stagger_min; k.density_unit = ctx->density_unit; k.vxc_producers = ctx->vxc_producers;
     k.dsym = ctx->dsym.ptr; k.coef = ctx->coef.ptr; k.epart = ctx->epart.ptr; k.vpart = ctx->vpart.ptr;
     k.rho = ctx->rho.ptr;
     return k;

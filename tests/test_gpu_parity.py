@@ -211,7 +211,7 @@ def test_tma_path_matches_generic_path_at_scale(engine_lib, functional, ngrid, n
 @pytest.mark.parametrize("functional", FUNCS)
 @pytest.mark.parametrize("ngrid,nao", [(20000, 152), (12001, 64), (9000, 377), (6000, 255), (3000, 36), (2500, 7)])
 def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
-    """Every tuning variant of the TMA path (V output tile 64/128/160x80/96x192, 8 or 16 rows per ring stage,
+    """Every tuning variant of the TMA path (V output tile 64/128/160x80, staged-B or per-warp skipping, 8 or 16 rows per ring stage,
     one or several TMA-issuing threads, static or dynamic block scheduling, 3-D or per-block 2-D tensor maps, L2
     prefetch) computes the same result as the generic path."""
     rng = np.random.default_rng(3 * ngrid + nao)
@@ -219,8 +219,9 @@ def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
     e0, v0, s0 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 1})
     assert s0["path"] == 1
     for opt in ({"vxc_shape": 64}, {"vxc_shape": 128, "vxc_vk": 8}, {"vxc_shape": 128, "vxc_vk": 16}, {"vxc_shape": 160},
-                {"vxc_shape": 96, "vxc_vk": 8}, {"vxc_shape": 96, "vxc_vk": 16, "vxc_skip": 0},
-                {"vxc_shape": 128, "vxc_producers": 3}, {"dyn_sched": 0}, {"density_unit": 1}, {"density_unit": 2},
+                {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 4}, {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 1},
+                {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 4, "tma_3d": 0},
+                {"vxc_shape": 128, "vxc_skip": 0, "vxc_producers": 3}, {"dyn_sched": 0}, {"density_unit": 1}, {"density_unit": 2},
                 {"density_unit": 2, "dyn_sched": 0}, {"tma_3d": 0}, {"l2_prefetch": 1}):
         e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
         assert s1["path"] == 2, opt
@@ -289,24 +290,25 @@ def _screened_case(rng, ngrid, nao, rows=192, cols=10):
 @pytest.mark.parametrize("functional", FUNCS)
 @pytest.mark.parametrize("ngrid,nao", [(9000, 377), (6000, 256), (5001, 200), (4000, 129)])
 def test_vxc_zero_skipping_instances_agree(oracle, engine_lib, functional, ngrid, nao):
-    """The zero-skipping V instances (M-side fragment votes; N-side box bits from the scanner warp with a vote per
-    stage or per k-step; 8 or 16 rows per ring stage) drop only DMMAs whose operand fragment is exactly zero, so
-    on screened AO planes they agree with the branch-free instance and with the oracle."""
+    """The zero-skipping V instances -- the staged-B kernel (builder warps combine the planes once per CTA, all MMA
+    warps skip the same all-zero fragments: mode 4, the default) and round 1's per-warp M-side votes (mode 1, 8 or 16
+    rows per ring stage) -- drop only DMMAs whose operand fragment is exactly zero, so on screened AO planes they
+    agree with the branch-free instance and with the oracle."""
     rng = np.random.default_rng(7 * ngrid + nao)
     dm, ao, w, grad = _screened_case(rng, ngrid, nao)
     e_o, v_o = oracle.compute_xc(XC[functional], dm, ao, w, grad, mode=0)
     e0, v0, s0 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"vxc_shape": 128, "vxc_skip": 0})
     assert s0["path"] == 2 and abs(e0 - e_o) <= E_TOL
     np.testing.assert_allclose(0.5 * (v0 + v0.T), oracle.sym(v_o), rtol=0, atol=V_TOL)
-    for mode in (1, 2, 3):
-        for vk in (8, 16):
-            opt = {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": mode, "vxc_vk": vk}
-            e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
-            assert s1["path"] == 2 and e1 == e0, opt
-            np.testing.assert_allclose(v1, v0, rtol=0, atol=1e-11 * max(1.0, np.abs(v0).max()), err_msg=str(opt))
-            np.testing.assert_array_equal(v1, v1.T)
-            if mode >= 2:
-                assert 0.05 < s1["vxc_skip_fraction"] < 0.95, (opt, s1["vxc_skip_fraction"])
+    for opt in ({"vxc_skip_mode": 4}, {"vxc_skip_mode": 4, "vxc_scatter": 0}, {"vxc_skip_mode": 1, "vxc_vk": 8},
+                {"vxc_skip_mode": 1, "vxc_vk": 16}):
+        opt = dict(opt, vxc_shape=128, vxc_skip=1)
+        e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
+        assert s1["path"] == 2 and e1 == e0, opt
+        np.testing.assert_allclose(v1, v0, rtol=0, atol=1e-11 * max(1.0, np.abs(v0).max()), err_msg=str(opt))
+        np.testing.assert_array_equal(v1, v1.T)
+        if opt["vxc_skip_mode"] == 4:
+            assert 0.05 < s1["vxc_skip_fraction"] < 0.95, (opt, s1["vxc_skip_fraction"])
 
 
 @pytest.mark.parametrize("functional", FUNCS)
