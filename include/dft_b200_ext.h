@@ -47,7 +47,8 @@ int DFT_CommDestroy(XCSolver* solver);
 // ---- options / statistics ------------------------------------------------------------------
 // keys: "exact_functionals" 0|1 (0 = reference bug-compatible potentials, default; 1 = potentials
 //       that are the exact derivatives of the energies, i.e. libxc/PySCF numint)
-//       "path" 0 auto | 1 generic (any alignment) | 2 TMA-fed
+//       "path" 0 auto | 1 generic (any alignment) | 2 TMA-fed DMMA kernels | 3 single-pass small-basis kernel (nao <= 48;
+//       what auto picks there)
 //       "deterministic" 0|1 (default 1: fixed-order reductions, bit-reproducible results)
 //       "vxc_shape" 0|64|128|160 (tuning: output tile of the TMA V kernel -- 64 x 64, 128 x 128, 160 x 80;
 //       0 = chosen from nao)

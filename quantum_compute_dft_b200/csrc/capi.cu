@@ -129,8 +129,13 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
         cudaMemsetAsync(p.d_exc, 0, sizeof(double), ctx->stream);
         { XcStats z; z.plans_built = ctx->stats.plans_built; z.ao_ms = ctx->stats.ao_ms; z.skip_fraction = ctx->stats.skip_fraction; z.vxc_skip_fraction = ctx->stats.vxc_skip_fraction; ctx->stats = z; }
     } else {
-        const bool use_tma = ctx->path != PATH_GENERIC && xc::tma_compatible(p);
-        if (use_tma) xc::run_tma(ctx, p);
+        // auto: the single-pass small-basis kernel up to nao 48, the TMA / DMMA kernels where the inputs are
+        // TMA-addressable, the generic kernels otherwise; "path" forces one (a forced path that cannot take the
+        // inputs falls through to the next)
+        const bool use_small = (ctx->path == PATH_AUTO || ctx->path == PATH_SMALL) && xc::small_compatible(p);
+        const bool use_tma = !use_small && ctx->path != PATH_GENERIC && xc::tma_compatible(p);
+        if (use_small) xc::run_small(ctx, p);
+        else if (use_tma) xc::run_tma(ctx, p);
         else xc::run_generic(ctx, p);
     }
     if (multi) {

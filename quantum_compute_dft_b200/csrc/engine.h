@@ -45,7 +45,7 @@ struct DeviceBuffer {
     void release();
 };
 
-enum XcPath { PATH_AUTO = 0, PATH_GENERIC = 1, PATH_TMA = 2 };
+enum XcPath { PATH_AUTO = 0, PATH_GENERIC = 1, PATH_TMA = 2, PATH_SMALL = 3 };
 
 struct XcStats {
     float density_ms = 0.f, vxc_ms = 0.f, reduce_ms = 0.f, total_ms = 0.f;
@@ -133,6 +133,9 @@ void run_generic(CublasHandleWrapper* ctx, const Problem& p);
 bool tma_compatible(const Problem& p);
 void run_tma(CublasHandleWrapper* ctx, const Problem& p);
 void free_tma_plan(CublasHandleWrapper* ctx);
+// small-basis single-pass path (nao <= 48): xc_small.cu
+bool small_compatible(const Problem& p);
+void run_small(CublasHandleWrapper* ctx, const Problem& p);
 
 // all-reduce of [V | E | failed ranks] over the communicator (comm.cu); no-op when nranks == 1
 int allreduce_result(CublasHandleWrapper* ctx, double* d_packed, double* d_vxc, size_t n2);

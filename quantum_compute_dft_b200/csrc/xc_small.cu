@@ -1,0 +1,344 @@
+// xc_small.cu -- the small-basis XC path (nao <= 48: H2O 7, benzene 36): ONE pass over the AO planes.
+//
+// At these sizes the whole call is HBM / latency bound (4 nao^2 flop against 8 (P nao + 1) bytes per
+// point puts the ridge near nao ~ 100), and the tensor-tile machinery of xc_tma.cu -- two full passes over the planes,
+// five launches, 64- and 128-wide DMMA tiles that are mostly padding at nao 7 -- is the wrong tool.  Here a
+// block of 32 grid points goes through EVERYTHING while it sits in shared memory, so every plane byte is read from
+// HBM exactly once per XC build (the algorithmic figure of SURVEY.md 8d):
+//
+//   cp.async (double-buffered)  the block's NPL plane tiles [32 rows][nao] + its 32 weights
+//   step 1  C = Phi_blk . Dsym                        DMMA m8n8k4, warp w owns rows 8w .. 8w+7
+//   step 2  rho, grad rho / 2 = rowsum(C o plane)     from the accumulator fragments, quad shuffles
+//   step 3  the functional, ONCE per point            one warp, lane = point (all 32 lanes do distinct points);
+//                                                     the evaluating warp rotates from block to block
+//   step 4  B = a Phi + b . grad Phi                  built in registers as DMMA A fragments
+//   step 5  M += B^T Phi                              DMMA, K = the warp's 8 rows; each warp keeps a private
+//                                                     (NP x NP) accumulator over all the blocks it sees
+//   end     warp accumulators -> CTA partial (fixed order) -> global;  xc_small_finalize sums the CTA
+//           partials in a fixed order, writes M + M^T and E_xc.  Bit-reproducible, two launches per build.
+//
+// CTAs are 4 warps; several are resident per SM (2 at benzene/GGA, where a double-buffered block is 74 KB) so that
+// one CTA's functional evaluation runs under another's tensor work.  Any alignment and any ngrid work: the copies
+// fall back from 16- to 8-byte cp.async when a plane base or the row pitch is not 16-byte aligned, and rows past
+// the end of the grid are zero-filled (zero weight -> zero coefficients).
+//
+// Replaces, for small nao, the same reference code as xc_tma.cu: get_rho[_sigma]_kernel (dft_solver.cu:294-380),
+// *_fused_kernel (:309-513), reduce_sum_kernel (:285-292), cublasDgemm (:580,:616,:663), symmetrize (:515-527).
+#include <cstdio>
+
+#include "dmma.cuh"
+#include "engine.h"
+#include "xc_functionals.cuh"
+
+namespace xc {
+namespace smallpath {
+
+constexpr int TR = 32;            // grid points per block
+constexpr int NWARP = 4;
+constexpr int THREADS = NWARP * 32;
+
+__device__ __forceinline__ xcfun::PointCoef eval_mode(int mode, double rho, double gx, double gy, double gz, double w) {
+    switch (mode) {
+        case 0: return xcfun::evaluate_point<0, false>(rho, gx, gy, gz, w);
+        case 1: return xcfun::evaluate_point<0, true>(rho, gx, gy, gz, w);
+        case 2: return xcfun::evaluate_point<1, false>(rho, gx, gy, gz, w);
+        case 3: return xcfun::evaluate_point<1, true>(rho, gx, gy, gz, w);
+        default: return xcfun::evaluate_point<2, false>(rho, gx, gy, gz, w);
+    }
+}
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// leading dimension of Dsym in shared memory: = 4 mod 16 doubles, so that the B-operand loads of step 1
+// (4 consecutive k rows x 4 consecutive columns per half-warp) hit 16 distinct bank pairs
+__host__ __device__ constexpr int ldd_for(int NP) { return ((NP + 11) / 16) * 16 + 4; }
+
+struct SmallParams {
+    int ngrid, nao, xc_mode, nblocks, vec16;
+    const double* dm;
+    const double* plane[4];
+    const double* w;
+    double* vpart;   // [gridDim.x][NP * NP]
+    double* epart;   // [gridDim.x]
+};
+
+// shared-memory layout (doubles): Dsym[NP][LDD] | 2 x { planes[NPL][TR * nao] (padded to even), w[TR] } | rho[TR][4] | coef[TR][4]
+template <int NF, int NPL>
+__global__ void __launch_bounds__(THREADS)
+xc_small_kernel(const SmallParams P) {
+    constexpr int NP = 8 * NF, LDD = ldd_for(NP);
+    extern __shared__ double smd[];
+    const int nao = P.nao;
+    const int tile_d = (TR * nao + 1) & ~1;             // doubles per plane tile (even: keeps 16-byte alignment)
+    const int buf_d = NPL * tile_d + TR;                // + the weights
+    double* dsym = smd;
+    double* buf0 = dsym + NP * LDD;
+    double* rho_s = buf0 + 2 * buf_d;                    // [TR][4]
+    double* coef_s = rho_s + TR * 4;                     // [TR][4]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = lane >> 2, qc = lane & 3;
+
+    // ---- Dsym = 1/2 (D + D^T), zero-padded (replaces symmetrize_pad; nao^2 doubles from L2 per CTA)
+    for (int i = tid; i < NP * LDD; i += THREADS) {
+        const int r = i / LDD, c = i - r * LDD;
+        double v = 0.0;
+        if (r < nao && c < nao) v = 0.5 * (__ldg(P.dm + (size_t)r * nao + c) + __ldg(P.dm + (size_t)c * nao + r));
+        dsym[i] = v;
+    }
+
+    // ---- asynchronous block loads: contiguous TR * nao doubles per plane; rows past the grid are zero-filled
+    auto issue_block = [&](int blk, double* buf) {
+        const long g0 = (long)blk * TR;
+        const long valid = (long)min((long)TR, (long)P.ngrid - g0) * nao;   // doubles of this block that exist
+        const uint32_t sb = (uint32_t)__cvta_generic_to_shared(buf);
+        if (P.vec16) {
+            const int n16 = tile_d / 2;
+            for (int p = 0; p < NPL; ++p) {
+                const double* src = P.plane[p] + g0 * nao;
+                for (int i = tid; i < n16; i += THREADS) {
+                    const long rem = valid - 2l * i;
+                    cp_async_16(sb + (uint32_t)(p * tile_d + 2 * i) * 8u, src + 2 * i, rem >= 2 ? 16 : (rem == 1 ? 8 : 0));
+                }
+            }
+        } else {
+            for (int p = 0; p < NPL; ++p) {
+                const double* src = P.plane[p] + g0 * nao;
+                for (int i = tid; i < TR * nao; i += THREADS)
+                    cp_async_8(sb + (uint32_t)(p * tile_d + i) * 8u, src + i, i < valid ? 8 : 0);
+            }
+        }
+        if (tid < TR) cp_async_8(sb + (uint32_t)(NPL * tile_d + tid) * 8u, P.w + g0 + tid, g0 + tid < P.ngrid ? 8 : 0);
+        cp_async_commit();
+    };
+
+    double acc[NF][NF][2];
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double e_acc = 0.0;
+    const int nk = (nao + 3) / 4;    // k-steps of step 1 that contain real columns
+
+    int it = 0;
+    if ((int)blockIdx.x < P.nblocks) issue_block(blockIdx.x, buf0);
+    for (int blk = blockIdx.x; blk < P.nblocks; blk += gridDim.x, ++it) {
+        double* buf = buf0 + (it & 1) * buf_d;
+        cp_async_wait_all();
+        __syncthreads();               // this block has landed for everyone; everyone is done with the other buffer
+        if (blk + (int)gridDim.x < P.nblocks) issue_block(blk + gridDim.x, buf0 + ((it + 1) & 1) * buf_d);
+
+        // ---- step 1: C[8 rows of this warp][NP] = Phi . Dsym
+        const double* phi = buf;
+        const double* my_row = phi + (size_t)(8 * warp + q) * nao;   // fragment row of this lane
+        double c[NF][2];
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) c[nf][0] = c[nf][1] = 0.0;
+        for (int ks = 0; ks < nk; ++ks) {
+            const int k = 4 * ks + qc;
+            const double a = k < nao ? my_row[k] : 0.0;
+            const double* drow = dsym + k * LDD + q;                  // Dsym[k][8 nf + q]
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(c[nf], a, drow[8 * nf]);
+        }
+        // ---- step 2: row sums of C o plane; lane holds columns 8 nf + 2 qc + {0, 1} of row 8 warp + q
+        double s[NPL];
+#pragma unroll
+        for (int p = 0; p < NPL; ++p) s[p] = 0.0;
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) {
+            const int col = 8 * nf + 2 * qc;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (col + e < nao) {
+#pragma unroll
+                    for (int p = 0; p < NPL; ++p) s[p] = fma(c[nf][e], my_row[p * tile_d + col + e], s[p]);
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NPL; ++p) {
+            s[p] += __shfl_xor_sync(0xffffffffu, s[p], 1);
+            s[p] += __shfl_xor_sync(0xffffffffu, s[p], 2);
+        }
+        if (qc == 0) {
+#pragma unroll
+            for (int p = 0; p < NPL; ++p) rho_s[(8 * warp + q) * 4 + p] = s[p];
+        }
+        __syncthreads();
+        // ---- step 3: the functional, lane = point; the evaluating warp rotates
+        if (warp == (it & (NWARP - 1))) {
+            const double* r = rho_s + lane * 4;
+            const double wgt = buf[NPL * tile_d + lane];
+            const xcfun::PointCoef pc = NPL == 4 ? eval_mode(P.xc_mode, r[0], 2.0 * r[1], 2.0 * r[2], 2.0 * r[3], wgt)
+                                                 : eval_mode(P.xc_mode, r[0], 0.0, 0.0, 0.0, wgt);
+            e_acc += pc.exc;
+            double* o = coef_s + lane * 4;
+            o[0] = pc.a; o[1] = pc.bx; o[2] = pc.by; o[3] = pc.bz;
+        }
+        __syncthreads();
+        // ---- steps 4 + 5: M += B^T Phi over this warp's 8 rows (two k-steps of 4 points)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const int pt = 8 * warp + 4 * ks + qc;                   // the point this lane supplies
+            const double* cf = coef_s + pt * 4;
+            const double ca = cf[0];
+            double cbx = 0.0, cby = 0.0, cbz = 0.0;
+            if (NPL == 4) { cbx = cf[1]; cby = cf[2]; cbz = cf[3]; }
+            const double* prow = phi + (size_t)pt * nao;
+            double ph[NF], bb[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const int col = 8 * f + q;
+                const bool in = col < nao;
+                ph[f] = in ? prow[col] : 0.0;
+                double v = ca * ph[f];
+                if (NPL == 4) {
+                    v = fma(cbx, in ? prow[tile_d + col] : 0.0, v);
+                    v = fma(cby, in ? prow[2 * tile_d + col] : 0.0, v);
+                    v = fma(cbz, in ? prow[3 * tile_d + col] : 0.0, v);
+                }
+                bb[f] = v;
+            }
+#pragma unroll
+            for (int mf = 0; mf < NF; ++mf)
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], bb[mf], ph[nf]);
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- warp accumulators -> CTA partial, fixed order (warp 0 + warp 1 + ...), through the free buffers
+    double* red = buf0;                                   // NP * NP doubles <= 2304 fit in any buffer pair
+    for (int w = 0; w < NWARP; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int mf = 0; mf < NF; ++mf)
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double* d = red + (8 * mf + q) * NP + 8 * nf + 2 * qc + e;
+                        *d = (w == 0 ? 0.0 : *d) + acc[mf][nf][e];
+                    }
+        }
+        __syncthreads();
+    }
+    double* out = P.vpart + (size_t)blockIdx.x * NP * NP;
+    for (int i = tid; i < NP * NP; i += THREADS) out[i] = red[i];
+    // E_xc: lanes -> warps -> CTA in a fixed order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e_acc += __shfl_xor_sync(0xffffffffu, e_acc, o);
+    if (lane == 0) rho_s[warp] = e_acc;
+    __syncthreads();
+    if (tid == 0) {
+        double e = 0.0;
+        for (int w = 0; w < NWARP; ++w) e += rho_s[w];
+        P.epart[blockIdx.x] = e;
+    }
+}
+
+// out[i][j] = sum over CTAs of M[i][j] + M[j][i] (raw: 2 M[i][j]); E_xc = sum of the CTA partials.  One thread per
+// output element, partials read with two independent chains, fixed order.
+__global__ void __launch_bounds__(256)
+xc_small_finalize(int nao, int NP, int ncta, int raw, const double* __restrict__ vpart, const double* __restrict__ epart,
+                  double* __restrict__ vxc, double* __restrict__ d_exc) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx < nao * nao) {
+        const int i = idx / nao, j = idx - i * nao;
+        const double* a = vpart + (size_t)i * NP + j;
+        const double* b = raw ? a : vpart + (size_t)j * NP + i;
+        const size_t ss = (size_t)NP * NP;
+        double s0 = 0.0, s1 = 0.0;
+        int c = 0;
+        for (; c + 1 < ncta; c += 2) {
+            s0 += __ldg(a + c * ss) + __ldg(b + c * ss);
+            s1 += __ldg(a + (c + 1) * ss) + __ldg(b + (c + 1) * ss);
+        }
+        if (c < ncta) s0 += __ldg(a + c * ss) + __ldg(b + c * ss);
+        vxc[idx] = s0 + s1;
+    }
+    if (blockIdx.x == 0) {
+        __shared__ double sh[256];
+        double e = 0.0;
+        for (int k = threadIdx.x; k < ncta; k += 256) e += epart[k];
+        sh[threadIdx.x] = e;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) *d_exc = sh[0];
+    }
+}
+
+template <int NF, int NPL>
+static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
+    constexpr int NP = 8 * NF, LDD = ldd_for(NP);
+    const int nao = p.nao;
+    const int tile_d = (TR * nao + 1) & ~1;
+    const size_t smem = sizeof(double) * ((size_t)NP * LDD + 2 * ((size_t)NPL * tile_d + TR) + 2 * TR * 4);
+    auto k = xc_small_kernel<NF, NPL>;
+    DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    DFT_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, THREADS, smem));
+    if (per_sm < 1) { ctx->failed = true; return; }
+    if (per_sm > 4) per_sm = 4;     // (more resident CTAs only add partials to the final sum)
+    const int nblocks = (p.ngrid + TR - 1) / TR;
+    int grid = nsm * per_sm;
+    if (grid > nblocks) grid = nblocks;
+    double* vpart = (double*)ctx->vpart.ensure(sizeof(double) * (size_t)grid * NP * NP, &ctx->failed);
+    double* epart = (double*)ctx->epart.ensure(sizeof(double) * grid, &ctx->failed);
+    if (ctx->failed) return;
+
+    SmallParams sp;
+    sp.ngrid = p.ngrid; sp.nao = nao; sp.nblocks = nblocks;
+    sp.xc_mode = p.xc_type == 2 ? 4 : p.xc_type * 2 + (ctx->exact_functionals ? 1 : 0);
+    sp.dm = p.dm; sp.w = p.w;
+    sp.plane[0] = p.ao; sp.plane[1] = p.gx; sp.plane[2] = p.gy; sp.plane[3] = p.gz;
+    // 16-byte copies need 16-byte aligned plane bases and a block pitch (TR * nao * 8 bytes, always a multiple of
+    // 16) -- i.e. only the bases matter
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    sp.vec16 = al16(p.ao) && (NPL == 1 || (al16(p.gx) && al16(p.gy) && al16(p.gz))) ? 1 : 0;
+    sp.vpart = vpart; sp.epart = epart;
+
+    cudaStream_t st = ctx->stream;
+    if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
+    k<<<grid, THREADS, smem, st>>>(sp);
+    if (ctx->timing) { cudaEventRecord(ctx->ev[1], st); cudaEventRecord(ctx->ev[2], st); }
+    const int raw = (ctx->raw_convention && p.xc_type == 1) ? 1 : 0;
+    xc_small_finalize<<<(nao * nao + 255) / 256, 256, 0, st>>>(nao, NP, grid, raw, vpart, epart, p.vxc, p.d_exc);
+    if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
+    ctx->stats.launches = 2;
+    ctx->stats.path = PATH_SMALL;
+    DFT_CUDA_CHECK(ctx, cudaGetLastError());
+}
+
+}  // namespace smallpath
+
+bool small_compatible(const Problem& p) { return p.nao >= 1 && p.nao <= 48 && p.ngrid >= 1; }
+
+void run_small(CublasHandleWrapper* ctx, const Problem& p) {
+    using namespace smallpath;
+    if (ctx->num_sms <= 0) cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int nf = (p.nao + 7) / 8;
+#define DFT_SMALL(NF_) do { if (p.xc_type == 0) launch<NF_, 1>(ctx, p, ctx->num_sms); else launch<NF_, 4>(ctx, p, ctx->num_sms); } while (0)
+    switch (nf) {
+        case 1: DFT_SMALL(1); break;
+        case 2: DFT_SMALL(2); break;
+        case 3: DFT_SMALL(3); break;
+        case 4: DFT_SMALL(4); break;
+        case 5: DFT_SMALL(5); break;
+        default: DFT_SMALL(6); break;
+    }
+#undef DFT_SMALL
+}
+
+}  // namespace xc

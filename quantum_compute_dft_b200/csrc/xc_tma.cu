@@ -62,6 +62,7 @@ constexpr int NCONS = NCW * 32;             // 256 consumer threads = 2 warpgrou
 constexpr int NTHREADS = NCONS + 128;       // + 1 producer warpgroup
 constexpr int REGS_CONSUMER = 232;          // 384 threads x 168 = 256 x 232 + 128 x 40
 constexpr int REGS_PRODUCER = 40;
+static_assert(256 * REGS_CONSUMER + 128 * REGS_PRODUCER <= 384 * 168, "setmaxnreg budget");
 constexpr int MB = 64;                      // grid rows per density block (one consumer group's)
 
 struct SubProblem {
@@ -893,7 +894,11 @@ struct StagedCfg {
     static constexpr int BAR_OFF = MMA_OFF + MS * MMA_BYTES;  // raw_full[RS], raw_empty[RS], mma_full[MS], mma_empty[MS]
     static constexpr int TOTAL = BAR_OFF + (2 * RS + 2 * MS) * 8 + 1024;
     static_assert(TOTAL <= 232448, "shared memory");
-    static constexpr int REGS_MMA = 216, REGS_BUILD = 80;    // 256 x 216 + 128 x 80 = 65536
+    // setmaxnreg only redistributes what the CTA was LAUNCHED with: 384 threads x 168 registers = 64512.  A pair that
+    // asks for more never gets it and setmaxnreg.inc waits forever (no timeout can catch that).
+    static constexpr int REGS_MMA = 216, REGS_BUILD = 72;
+    static_assert(NCONS * REGS_MMA + 128 * REGS_BUILD <= NTHREADS * 168, "setmaxnreg budget");
+    static_assert(REGS_MMA % 8 == 0 && REGS_BUILD % 8 == 0, "setmaxnreg granularity");
 };
 
 __device__ __forceinline__ double2 lds_f64x2_plain(const unsigned char* p) { return *reinterpret_cast<const double2*>(p); }
@@ -1074,6 +1079,9 @@ vxc_staged_kernel(const __grid_constant__ VxcParams P) {
         }
         const bool nz = ((bf[0][0] != 0.0) | (bf[0][1] != 0.0)) | ((bf[1][0] != 0.0) | (bf[1][1] != 0.0));
         if (no_skip) m = 0xffffffffu;
+#ifdef DFT_DIAGNOSTICS
+        if (P.debug_nodmma) m = 0u;              // delivery + build floor (results are wrong)
+#endif
         m = __reduce_or_sync(0xffffffffu, m);   // (all lanes hold the same word: this makes it a UNIFORM register)
         if (__any_sync(0xffffffffu, nz | no_skip) && m != 0u) {
 #pragma unroll

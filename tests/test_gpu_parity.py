@@ -118,6 +118,46 @@ def test_ragged_shapes(oracle, engine_lib, functional, ngrid, nao):
 
 
 @pytest.mark.parametrize("functional", FUNCS)
+@pytest.mark.parametrize("ngrid,nao", [(1, 1), (2, 7), (31, 3), (32, 8), (33, 9), (100, 16), (257, 17), (1000, 24), (999, 25),
+                                       (4097, 32), (3001, 33), (2500, 36), (5000, 40), (1300, 41), (6000, 47), (2222, 48),
+                                       (34310, 7), (50001, 36)])
+def test_small_basis_shapes_on_every_path(oracle, engine_lib, functional, ngrid, nao):
+    """nao <= 48 has three implementations: the single-pass small-basis kernel (what auto picks; one to six 8-column
+    fragments, ragged last block, odd and even pitch), the TMA / DMMA kernels and the generic kernels.  All against
+    the oracle (and the reference CUDA), plus the small-basis kernel with plane pointers that are only 8-byte
+    aligned (its 8-byte cp.async fallback)."""
+    from quantum_compute_dft_b200.cuda_rt import DeviceArray
+    from quantum_compute_dft_b200.solver import DFTSolverWrapper
+    rng = np.random.default_rng(31 * ngrid + nao)
+    dm, ao, w, grad = _random_case(rng, ngrid, nao)
+    e_o, v_o = oracle.compute_xc(XC[functional], dm, ao, w, grad, mode=0)
+    for path in (0, 1, 2, 3):
+        e, v, st = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": path})
+        if path in (0, 3):
+            assert st["path"] == 3 and st["launches"] == 2
+        assert abs(e - e_o) <= E_TOL, (path, e, e_o)
+        np.testing.assert_allclose(0.5 * (v + v.T), oracle.sym(v_o), rtol=0, atol=V_TOL, err_msg=f"path {path}")
+        np.testing.assert_array_equal(v, v.T)
+    ref = _run_reference_so(functional, dm, ao, w, grad)
+    if ref is not None:
+        assert abs(e - ref[0]) <= E_TOL
+        np.testing.assert_allclose(0.5 * (v + v.T), 0.5 * (ref[1] + ref[1].T), rtol=0, atol=V_TOL)
+    # planes at an address that is 8 mod 16: one spare double in front of each array
+    s = DFTSolverWrapper(engine_lib, functional)
+    pad = lambda a: DeviceArray.from_host(np.concatenate([[0.0], np.ascontiguousarray(a).ravel()]))
+    d_ao, d_g, d_dm, d_w = pad(ao), pad(grad), DeviceArray.from_host(dm), DeviceArray.from_host(w)
+    d_v = DeviceArray((nao, nao), zero=True)
+
+    class _Off:
+        def __init__(self, d):
+            self.data = type("D", (), {"ptr": d.data.ptr + 8})()
+    e2 = s.compute_xc(ngrid, nao, d_dm, _Off(d_ao), d_w, d_v, _Off(d_g) if functional != "LDA" else None)
+    assert s.stat("path") == 3
+    assert abs(e2 - e_o) <= E_TOL
+    np.testing.assert_allclose(0.5 * (d_v.get() + d_v.get().T), oracle.sym(v_o), rtol=0, atol=V_TOL)
+
+
+@pytest.mark.parametrize("functional", FUNCS)
 @pytest.mark.parametrize("ngrid,nao", [(1200, 520), (902, 777), (700, 1000), (640, 1283), (300, 2048), (200, 2049)])
 def test_wide_basis_shapes(oracle, engine_lib, functional, ngrid, nao):
     """Larger basis sets than the config molecules': many column tiles in both contraction kernels, odd and even
@@ -174,10 +214,12 @@ def test_idempotent_and_deterministic(engine_lib, functional):
     """Same inputs -> bit-identical outputs, call after call and solver after solver."""
     rng = np.random.default_rng(14)
     dm, ao, w, grad = _random_case(rng, 20000, 36)
-    r = [_run_engine(engine_lib, functional, dm, ao, w, grad) for _ in range(3)]
-    for e, v, _ in r[1:]:
-        assert e == r[0][0]
-        np.testing.assert_array_equal(v, r[0][1])
+    for path in (1, 2, 3):
+        r = [_run_engine(engine_lib, functional, dm, ao, w, grad, {"path": path}) for _ in range(3)]
+        assert r[0][2]["path"] == path
+        for e, v, _ in r[1:]:
+            assert e == r[0][0]
+            np.testing.assert_array_equal(v, r[0][1])
 
 
 @pytest.mark.parametrize("functional", FUNCS)
@@ -202,7 +244,7 @@ def test_tma_path_matches_generic_path_at_scale(engine_lib, functional, ngrid, n
     rng = np.random.default_rng(ngrid + nao)
     dm, ao, w, grad = _random_case(rng, ngrid, nao)
     e0, v0, s0 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 1})
-    e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 0})
+    e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 2})
     assert s0["path"] == 1 and s1["path"] == 2
     assert abs(e0 - e1) <= E_TOL * max(1.0, abs(e0) * 1e-3)
     np.testing.assert_allclose(v0, v1, rtol=0, atol=V_TOL * max(1.0, np.abs(v0).max() * 1e-3))
@@ -223,7 +265,7 @@ def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
                 {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 4, "tma_3d": 0},
                 {"vxc_shape": 128, "vxc_skip": 0, "vxc_producers": 3}, {"dyn_sched": 0}, {"density_unit": 1}, {"density_unit": 2},
                 {"density_unit": 2, "dyn_sched": 0}, {"tma_3d": 0}, {"l2_prefetch": 1}):
-        e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
+        e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, dict(opt, path=2))
         assert s1["path"] == 2, opt
         assert abs(e0 - e1) <= E_TOL * max(1.0, abs(e0) * 1e-3), opt
         np.testing.assert_allclose(v0, v1, rtol=0, atol=V_TOL * max(1.0, np.abs(v0).max() * 1e-3), err_msg=str(opt))
@@ -238,10 +280,10 @@ def test_dynamic_scheduling_actually_runs(engine_lib, functional, ngrid, nao):
     mis-ordered assignment left the counter pointer null and both settings ran the static deal.)"""
     rng = np.random.default_rng(5 * ngrid + nao)
     dm, ao, w, grad = _random_case(rng, ngrid, nao)
-    e0, v0, s0 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"dyn_sched": 0})
+    e0, v0, s0 = _run_engine(engine_lib, functional, dm, ao, w, grad, {"dyn_sched": 0, "path": 2})
     assert s0["path"] == 2 and s0["dyn_units"] == 0
     for opt in ({"dyn_sched": 1}, {"dyn_sched": 1, "density_unit": 1}, {}):
-        e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
+        e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, dict(opt, path=2))
         assert s1["path"] == 2
         assert s1["density_units"] > 0 and s1["dyn_units"] == s1["density_units"] + s1["density_groups"], (opt, s1)
         assert abs(e1 - e0) <= 1e-12 * max(1.0, abs(e0)), opt
@@ -257,10 +299,10 @@ def test_raw_gga_convention(oracle, engine_lib):
         dm, ao, w, grad = _random_case(rng, ngrid, nao)
         e_o, v_o = oracle.compute_xc(1, dm, ao, w, grad, mode=0)          # raw reference convention
         assert np.max(np.abs(v_o - v_o.T)) > 1e-6                            # really unsymmetric
-        for path in (1, 2):
+        for path in (1, 2, 3):
             e, v, st = _run_engine(engine_lib, "GGA", dm, ao, w, grad, {"raw_convention": 1, "path": path})
-            if path == 2:
-                assert st["path"] == 2
+            if path == 2 or (path == 3 and nao <= 48):
+                assert st["path"] == path
             assert abs(e - e_o) <= E_TOL
             np.testing.assert_allclose(v, v_o, rtol=0, atol=V_TOL)
         ref = _run_reference_so("GGA", dm, ao, w, grad)
@@ -323,6 +365,7 @@ def test_launch_plan_reuse(oracle, engine_lib, functional):
     dm, ao, w, grad = _random_case(rng, ngrid, nao)
     dm2 = 0.5 * dm + 0.1 * np.eye(nao)
     s = DFTSolverWrapper(engine_lib, functional)
+    s.set_option("path", 2)     # (auto would take the plan-free small-basis kernel at nao 36)
     d_dm, d_ao, d_w = DeviceArray.from_host(dm), DeviceArray.from_host(ao), DeviceArray.from_host(w)
     d_g = DeviceArray.from_host(grad) if functional != "LDA" else None
     d_v = DeviceArray((nao, nao), zero=True)
@@ -481,8 +524,8 @@ def test_full_size_configs_against_reference_cuda(engine_lib, workload_name, fun
         e = s.compute_xc(n, nao, dp.d_dm, dp.d_ao, dp.d_weights, dp.d_vxc, grad)
         v = dp.d_vxc.get()
         assert s.stat("launches") > 0
-        if nao % 2 == 0 or n % 2 == 0:
-            assert s.stat("path") == 2            # the TMA path is what the bench times
+        # the paths the bench times: the single-pass kernel for the small molecules, the TMA / DMMA kernels otherwise
+        assert s.stat("path") == (3 if nao <= 48 else 2)
         r = lib.DFT_CreateSolver(XC[fn])
         e_r = lib.DFT_ComputeXC(r, n, nao, dp.d_dm.data.ptr, dp.d_ao.data.ptr, grad.data.ptr if grad is not None else 0,
                                 dp.d_weights.data.ptr, d_vref.data.ptr)

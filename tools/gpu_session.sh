@@ -6,6 +6,13 @@ TAG=${1:-s}; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.csv 2>&1
+# every session starts with a bounded canary: a new kernel that deadlocks (e.g. a setmaxnreg.inc that can never be
+# satisfied has no timeout) must cost one minute, not the whole call -- and must not be followed by more launches
+timeout 120 python tools/canary.py > $OUT/canary.log 2>&1
+rc=$?
+echo "canary rc=$rc" | tee -a $OUT/summary.txt
+tail -5 $OUT/canary.log
+if [ $rc -ne 0 ]; then echo "canary failed: session aborted" | tee -a $OUT/summary.txt; exit 1; fi
 for what in "$@"; do
   case $what in
     tests)   timeout 2400 python -m pytest tests -m gpu -x -q --durations=8 > $OUT/tests.log 2>&1; echo "tests rc=$?" | tee -a $OUT/summary.txt; tail -15 $OUT/tests.log ;;
