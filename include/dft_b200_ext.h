@@ -59,9 +59,10 @@ int DFT_CommDestroy(XCSolver* solver);
 //       exactly zero are skipped; results are unchanged; default 1)
 //       "vxc_skip" -1|0|1 (the zero-skipping instance of the V kernel: -1 = adaptive, used while the density
 //       kernel of the previous call skipped >= 10 % of its k-steps; default -1)
-//       "vxc_skip_mode" 4|1 (which zero-skipping V instance on the 128 x 128 tile: 4 = staged B, builder warps
-//       combine the planes once per CTA and all MMA warps skip the same all-zero fragments (default); 1 = round 1's
-//       per-warp votes on the M side, kept for comparison)
+//       "vxc_skip_mode" 1|4 (which zero-skipping V instance on the 128 x 128 tile: 1 = per-warp votes on the M-side
+//       fragments (default); 4 = staged B: builder warps combine the planes once per CTA and all MMA warps skip the same
+//       all-zero fragments -- executes 46 % of the DMMAs at C5 but is operand-delivery bound at 12.5 ms against 11.8 ms
+//       for mode 1; kept selectable as the base for sparse operand delivery)
 //       "vxc_producers" 1..4 (tuning: TMA-issuing threads per CTA of the V kernel, default 1)
 //       "vxc_scatter" 0|1 (zero-skipping V instances: scatter consecutive ring stages over the grid, default 1)
 //       "dyn_sched" 0|1 (density kernel: hand the units of work out dynamically, default 1)

@@ -61,6 +61,20 @@ size_t CublasHandleWrapper::workspace_bytes() const {
     return dsym.capacity + rho.capacity + coef.capacity + epart.capacity + vpart.capacity + result.capacity + scratch.capacity;
 }
 
+namespace xc {
+void resolve_times(CublasHandleWrapper* c) {
+    if (!c || !c->times_pending) return;
+    DeviceGuard guard(c->device);
+    c->times_pending = false;
+    if (cudaEventSynchronize(c->ev[4]) == cudaSuccess) {
+        cudaEventElapsedTime(&c->stats.density_ms, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&c->stats.vxc_ms, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&c->stats.reduce_ms, c->ev[2], c->ev[4]);
+        cudaEventElapsedTime(&c->stats.total_ms, c->ev[0], c->ev[4]);
+    }
+}
+}  // namespace xc
+
 // ------------------------------------------------------------------------- solver classes
 XCSolver::XCSolver() : handle_wrapper(new CublasHandleWrapper()) {}
 XCSolver::~XCSolver() = default;
@@ -96,6 +110,7 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
     if (!ctx) return nan;
     DeviceGuard guard(ctx->device);   // (restores the caller's current device on return)
     ctx->failed = false;
+    ctx->times_pending = false;       // (the events are about to be recorded again; unread intervals are dropped)
     const bool multi = ctx->nranks > 1 && ctx->nccl_comm;
     bool bad = ngrid < 0 || nao <= 0 || !d_dm || !d_ao || !d_w || !d_vxc;
     if (!bad && xc_type != 0 && !d_ao_grad) {
@@ -174,12 +189,9 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
         if (ctx->vxc_skip < 0) ctx->vxc_skip_on = ctx->stats.skip_fraction >= 0.10;
     }
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
-    if (ctx->timing && !bad && ngrid > 0 && !ctx->failed) {
-        cudaEventElapsedTime(&ctx->stats.density_ms, ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&ctx->stats.vxc_ms, ctx->ev[1], ctx->ev[2]);
-        cudaEventElapsedTime(&ctx->stats.reduce_ms, ctx->ev[2], ctx->ev[4]);
-        cudaEventElapsedTime(&ctx->stats.total_ms, ctx->ev[0], ctx->ev[4]);
-    }
+    // (the four event intervals are read when DFT_GetStat asks for one: four driver calls per XC build are real money
+    // at H2O size, where the whole call is ~20 us)
+    ctx->times_pending = ctx->timing && !bad && ngrid > 0 && !ctx->failed;
     return ctx->failed ? nan : ctx->h_scalar[0];
 }
 
@@ -340,6 +352,7 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
 double DFT_GetStat(XCSolver* solver, const char* key) {
     if (!solver || !key) return -1.0;
     CublasHandleWrapper* c = solver->context();
+    if (strstr(key, "_ms") && strcmp(key, "ao_ms")) xc::resolve_times(c);
     if (!strcmp(key, "density_ms")) return c->stats.density_ms;
     if (!strcmp(key, "vxc_ms")) return c->stats.vxc_ms;
     if (!strcmp(key, "reduce_ms")) return c->stats.reduce_ms;

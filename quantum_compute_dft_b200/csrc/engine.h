@@ -64,6 +64,7 @@ struct CublasHandleWrapper {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool failed = false;
+    bool times_pending = false;   // the last XC build's event intervals have not been read into `stats` yet
 
     // options (DFT_SetOption)
     bool exact_functionals = false;
@@ -72,7 +73,7 @@ struct CublasHandleWrapper {
     bool l2_prefetch = false;      // TMA density kernel: short-range L2 prefetch of A tiles and epilogue pieces (measured: no gain)
     int vxc_skip = -1;             // V kernel zero-skipping instance: -1 adaptive (default), 0 never, 1 always
     bool vxc_skip_on = true;       // (adaptive) the zero-skipping V instance is used while the density kernel finds zeros
-    int vxc_skip_mode = 4;         // zero-skipping V instance (128 x 128 tile): 4 staged B with uniform fragment skipping (default), 1 per-warp M-side votes
+    int vxc_skip_mode = 1;         // zero-skipping V instance (128 x 128 tile): 1 per-warp M-side votes (default), 4 staged B with uniform fragment skipping (experimental: measured 12.5 ms against 11.8 ms at C5)
     int vxc_scatter = 1;           // zero-skipping V instances: scatter consecutive ring stages over the grid (golden-ratio stride)
     int density_unit = 0;          // TMA density kernel, unit of work: 0 | 2 = one column tile of a 64-point block (default), 1 = a whole block
     int stagger_min = 8;           // TMA density kernel: consumer group 1 starts half a tile period late when a CTA has more blocks than this
@@ -140,6 +141,8 @@ void run_small(CublasHandleWrapper* ctx, const Problem& p);
 // all-reduce of [V | E | failed ranks] over the communicator (comm.cu); no-op when nranks == 1
 int allreduce_result(CublasHandleWrapper* ctx, double* d_packed, double* d_vxc, size_t n2);
 void comm_destroy(CublasHandleWrapper* ctx);
+// reads the last XC build's CUDA-event intervals into ctx->stats if that has not happened yet (capi.cu)
+void resolve_times(CublasHandleWrapper* ctx);
 
 void coulomb_gemv(CublasHandleWrapper* ctx, int nao, const double* eri, const double* dm, double* J);
 // J and the exact-exchange matrix K[i,k] = sum_jl (ij|kl) D[j,l] in ONE pass over the ERI

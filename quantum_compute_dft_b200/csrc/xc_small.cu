@@ -33,9 +33,8 @@
 namespace xc {
 namespace smallpath {
 
-constexpr int TR = 32;            // grid points per block
-constexpr int NWARP = 4;
-constexpr int THREADS = NWARP * 32;
+constexpr int TR = 8;             // grid points per warp step (one DMMA row fragment)
+constexpr int MAXW = 8;           // warps per CTA (fewer where shared memory does not hold 8 double-buffered tiles)
 
 __device__ __forceinline__ xcfun::PointCoef eval_mode(int mode, double rho, double gx, double gy, double gz, double w) {
     switch (mode) {
@@ -69,40 +68,43 @@ struct SmallParams {
     double* epart;   // [gridDim.x]
 };
 
-// shared-memory layout (doubles): Dsym[NP][LDD] | 2 x { planes[NPL][TR * nao] (padded to even), w[TR] } | rho[TR][4] | coef[TR][4]
+// Every warp is autonomous: it streams its own 8-point tiles (cp.async, double-buffered, private shared memory),
+// takes each through steps 1-5 without a single CTA barrier, and keeps a private (NP x NP) accumulator in
+// registers.  The four lanes of a fragment row evaluate that row's functional redundantly -- 4 x the FP64 work of
+// the point kernel, still a small share of the step -- which keeps rho, the coefficients and E_xc in registers
+// (the coefficients of the points a lane supplies to the M += B^T Phi fragments come by shuffle).
+// shared-memory layout (doubles): Dsym[NP][LDD] | per warp: 2 x { planes[NPL][8 * nao], w[8] }
 template <int NF, int NPL>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(MAXW * 32)
 xc_small_kernel(const SmallParams P) {
     constexpr int NP = 8 * NF, LDD = ldd_for(NP);
     extern __shared__ double smd[];
     const int nao = P.nao;
-    const int tile_d = (TR * nao + 1) & ~1;             // doubles per plane tile (even: keeps 16-byte alignment)
-    const int buf_d = NPL * tile_d + TR;                // + the weights
-    double* dsym = smd;
-    double* buf0 = dsym + NP * LDD;
-    double* rho_s = buf0 + 2 * buf_d;                    // [TR][4]
-    double* coef_s = rho_s + TR * 4;                     // [TR][4]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_d = TR * nao;                         // doubles per plane tile (even)
+    const int buf_d = NPL * tile_d + TR;                 // + the weights
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int q = lane >> 2, qc = lane & 3;
+    double* dsym = smd;
+    double* buf0 = dsym + NP * LDD + (size_t)warp * 2 * buf_d;
 
     // ---- Dsym = 1/2 (D + D^T), zero-padded (replaces symmetrize_pad; nao^2 doubles from L2 per CTA)
-    for (int i = tid; i < NP * LDD; i += THREADS) {
+    for (int i = tid; i < NP * LDD; i += blockDim.x) {
         const int r = i / LDD, c = i - r * LDD;
         double v = 0.0;
         if (r < nao && c < nao) v = 0.5 * (__ldg(P.dm + (size_t)r * nao + c) + __ldg(P.dm + (size_t)c * nao + r));
         dsym[i] = v;
     }
 
-    // ---- asynchronous block loads: contiguous TR * nao doubles per plane; rows past the grid are zero-filled
-    auto issue_block = [&](int blk, double* buf) {
+    // ---- asynchronous tile loads: 8 * nao contiguous doubles per plane; rows past the grid are zero-filled
+    auto issue_tile = [&](int blk, double* buf) {
         const long g0 = (long)blk * TR;
-        const long valid = (long)min((long)TR, (long)P.ngrid - g0) * nao;   // doubles of this block that exist
+        const long valid = (long)min((long)TR, (long)P.ngrid - g0) * nao;   // doubles of this tile that exist
         const uint32_t sb = (uint32_t)__cvta_generic_to_shared(buf);
         if (P.vec16) {
             const int n16 = tile_d / 2;
             for (int p = 0; p < NPL; ++p) {
                 const double* src = P.plane[p] + g0 * nao;
-                for (int i = tid; i < n16; i += THREADS) {
+                for (int i = lane; i < n16; i += 32) {
                     const long rem = valid - 2l * i;
                     cp_async_16(sb + (uint32_t)(p * tile_d + 2 * i) * 8u, src + 2 * i, rem >= 2 ? 16 : (rem == 1 ? 8 : 0));
                 }
@@ -110,11 +112,10 @@ xc_small_kernel(const SmallParams P) {
         } else {
             for (int p = 0; p < NPL; ++p) {
                 const double* src = P.plane[p] + g0 * nao;
-                for (int i = tid; i < TR * nao; i += THREADS)
-                    cp_async_8(sb + (uint32_t)(p * tile_d + i) * 8u, src + i, i < valid ? 8 : 0);
+                for (int i = lane; i < tile_d; i += 32) cp_async_8(sb + (uint32_t)(p * tile_d + i) * 8u, src + i, i < valid ? 8 : 0);
             }
         }
-        if (tid < TR) cp_async_8(sb + (uint32_t)(NPL * tile_d + tid) * 8u, P.w + g0 + tid, g0 + tid < P.ngrid ? 8 : 0);
+        if (lane < TR) cp_async_8(sb + (uint32_t)(NPL * tile_d + lane) * 8u, P.w + g0 + lane, g0 + lane < P.ngrid ? 8 : 0);
         cp_async_commit();
     };
 
@@ -125,18 +126,19 @@ xc_small_kernel(const SmallParams P) {
         for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     double e_acc = 0.0;
     const int nk = (nao + 3) / 4;    // k-steps of step 1 that contain real columns
+    const int first = blockIdx.x * nwarp + warp, stride = gridDim.x * nwarp;
 
+    if (first < P.nblocks) issue_tile(first, buf0);
+    __syncthreads();                 // Dsym is complete (the only CTA barrier before the final reduction)
     int it = 0;
-    if ((int)blockIdx.x < P.nblocks) issue_block(blockIdx.x, buf0);
-    for (int blk = blockIdx.x; blk < P.nblocks; blk += gridDim.x, ++it) {
-        double* buf = buf0 + (it & 1) * buf_d;
+    for (int blk = first; blk < P.nblocks; blk += stride, ++it) {
+        const double* phi = buf0 + (it & 1) * buf_d;
         cp_async_wait_all();
-        __syncthreads();               // this block has landed for everyone; everyone is done with the other buffer
-        if (blk + (int)gridDim.x < P.nblocks) issue_block(blk + gridDim.x, buf0 + ((it + 1) & 1) * buf_d);
+        __syncwarp();                // the tile has landed for every lane; every lane is done with the other buffer
+        if (blk + stride < P.nblocks) issue_tile(blk + stride, buf0 + ((it + 1) & 1) * buf_d);
 
-        // ---- step 1: C[8 rows of this warp][NP] = Phi . Dsym
-        const double* phi = buf;
-        const double* my_row = phi + (size_t)(8 * warp + q) * nao;   // fragment row of this lane
+        // ---- step 1: C[8 rows][NP] = Phi . Dsym
+        const double* my_row = phi + (size_t)q * nao;                 // fragment row of this lane
         double c[NF][2];
 #pragma unroll
         for (int nf = 0; nf < NF; ++nf) c[nf][0] = c[nf][1] = 0.0;
@@ -147,7 +149,7 @@ xc_small_kernel(const SmallParams P) {
 #pragma unroll
             for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(c[nf], a, drow[8 * nf]);
         }
-        // ---- step 2: row sums of C o plane; lane holds columns 8 nf + 2 qc + {0, 1} of row 8 warp + q
+        // ---- step 2: row sums of C o plane; lane holds columns 8 nf + 2 qc + {0, 1} of row q
         double s[NPL];
 #pragma unroll
         for (int p = 0; p < NPL; ++p) s[p] = 0.0;
@@ -167,30 +169,22 @@ xc_small_kernel(const SmallParams P) {
             s[p] += __shfl_xor_sync(0xffffffffu, s[p], 1);
             s[p] += __shfl_xor_sync(0xffffffffu, s[p], 2);
         }
-        if (qc == 0) {
-#pragma unroll
-            for (int p = 0; p < NPL; ++p) rho_s[(8 * warp + q) * 4 + p] = s[p];
-        }
-        __syncthreads();
-        // ---- step 3: the functional, lane = point; the evaluating warp rotates
-        if (warp == (it & (NWARP - 1))) {
-            const double* r = rho_s + lane * 4;
-            const double wgt = buf[NPL * tile_d + lane];
-            const xcfun::PointCoef pc = NPL == 4 ? eval_mode(P.xc_mode, r[0], 2.0 * r[1], 2.0 * r[2], 2.0 * r[3], wgt)
-                                                 : eval_mode(P.xc_mode, r[0], 0.0, 0.0, 0.0, wgt);
-            e_acc += pc.exc;
-            double* o = coef_s + lane * 4;
-            o[0] = pc.a; o[1] = pc.bx; o[2] = pc.by; o[3] = pc.bz;
-        }
-        __syncthreads();
-        // ---- steps 4 + 5: M += B^T Phi over this warp's 8 rows (two k-steps of 4 points)
+        // ---- step 3: the functional of row q (the same in the four lanes of the row)
+        const double wgt = phi[NPL * tile_d + q];
+        const xcfun::PointCoef pc = NPL == 4 ? eval_mode(P.xc_mode, s[0], 2.0 * s[1], 2.0 * s[2], 2.0 * s[3], wgt)
+                                             : eval_mode(P.xc_mode, s[0], 0.0, 0.0, 0.0, wgt);
+        if (qc == 0) e_acc += pc.exc;
+        // ---- steps 4 + 5: M += B^T Phi over the 8 rows (two k-steps of 4 points)
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            const int pt = 8 * warp + 4 * ks + qc;                   // the point this lane supplies
-            const double* cf = coef_s + pt * 4;
-            const double ca = cf[0];
+            const int pt = 4 * ks + qc;                               // the point this lane supplies
+            const double ca = __shfl_sync(0xffffffffu, pc.a, 4 * pt);
             double cbx = 0.0, cby = 0.0, cbz = 0.0;
-            if (NPL == 4) { cbx = cf[1]; cby = cf[2]; cbz = cf[3]; }
+            if (NPL == 4) {
+                cbx = __shfl_sync(0xffffffffu, pc.bx, 4 * pt);
+                cby = __shfl_sync(0xffffffffu, pc.by, 4 * pt);
+                cbz = __shfl_sync(0xffffffffu, pc.bz, 4 * pt);
+            }
             const double* prow = phi + (size_t)pt * nao;
             double ph[NF], bb[NF];
 #pragma unroll
@@ -215,9 +209,9 @@ xc_small_kernel(const SmallParams P) {
     cp_async_wait_all();
     __syncthreads();
 
-    // ---- warp accumulators -> CTA partial, fixed order (warp 0 + warp 1 + ...), through the free buffers
-    double* red = buf0;                                   // NP * NP doubles <= 2304 fit in any buffer pair
-    for (int w = 0; w < NWARP; ++w) {
+    // ---- warp accumulators -> CTA partial, fixed order (warp 0 + warp 1 + ...), through Dsym's and the tiles' space
+    double* red = smd;
+    for (int w = 0; w < nwarp; ++w) {
         if (warp == w) {
 #pragma unroll
             for (int mf = 0; mf < NF; ++mf)
@@ -232,38 +226,38 @@ xc_small_kernel(const SmallParams P) {
         __syncthreads();
     }
     double* out = P.vpart + (size_t)blockIdx.x * NP * NP;
-    for (int i = tid; i < NP * NP; i += THREADS) out[i] = red[i];
+    for (int i = tid; i < NP * NP; i += blockDim.x) out[i] = red[i];
     // E_xc: lanes -> warps -> CTA in a fixed order
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e_acc += __shfl_xor_sync(0xffffffffu, e_acc, o);
-    if (lane == 0) rho_s[warp] = e_acc;
+    __syncthreads();
+    if (lane == 0) red[NP * NP + warp] = e_acc;
     __syncthreads();
     if (tid == 0) {
         double e = 0.0;
-        for (int w = 0; w < NWARP; ++w) e += rho_s[w];
+        for (int w = 0; w < nwarp; ++w) e += red[NP * NP + w];
         P.epart[blockIdx.x] = e;
     }
 }
 
-// out[i][j] = sum over CTAs of M[i][j] + M[j][i] (raw: 2 M[i][j]); E_xc = sum of the CTA partials.  One thread per
-// output element, partials read with two independent chains, fixed order.
+// out[i][j] = sum over CTAs of M[i][j] + M[j][i] (raw: 2 M[i][j]); E_xc = sum of the CTA partials.  One WARP per
+// output element: the lanes stride over the CTA partials (all loads in flight at once -- a serial loop over 296
+// partials took 90 us at benzene size), then a shuffle tree.  Fixed order -> bit-reproducible, exactly symmetric.
 __global__ void __launch_bounds__(256)
 xc_small_finalize(int nao, int NP, int ncta, int raw, const double* __restrict__ vpart, const double* __restrict__ epart,
                   double* __restrict__ vxc, double* __restrict__ d_exc) {
-    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (idx < nao * nao) {
         const int i = idx / nao, j = idx - i * nao;
         const double* a = vpart + (size_t)i * NP + j;
         const double* b = raw ? a : vpart + (size_t)j * NP + i;
         const size_t ss = (size_t)NP * NP;
-        double s0 = 0.0, s1 = 0.0;
-        int c = 0;
-        for (; c + 1 < ncta; c += 2) {
-            s0 += __ldg(a + c * ss) + __ldg(b + c * ss);
-            s1 += __ldg(a + (c + 1) * ss) + __ldg(b + (c + 1) * ss);
-        }
-        if (c < ncta) s0 += __ldg(a + c * ss) + __ldg(b + c * ss);
-        vxc[idx] = s0 + s1;
+        double s = 0.0;
+        for (int c = lane; c < ncta; c += 32) s += __ldg(a + c * ss) + __ldg(b + c * ss);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) vxc[idx] = s;
     }
     if (blockIdx.x == 0) {
         __shared__ double sh[256];
@@ -283,17 +277,34 @@ template <int NF, int NPL>
 static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     constexpr int NP = 8 * NF, LDD = ldd_for(NP);
     const int nao = p.nao;
-    const int tile_d = (TR * nao + 1) & ~1;
-    const size_t smem = sizeof(double) * ((size_t)NP * LDD + 2 * ((size_t)NPL * tile_d + TR) + 2 * TR * 4);
+    const size_t warp_d = 2 * ((size_t)NPL * TR * nao + TR);          // doubles of one warp's two buffers
     auto k = xc_small_kernel<NF, NPL>;
-    DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    DFT_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, THREADS, smem));
-    if (per_sm < 1) { ctx->failed = true; return; }
-    if (per_sm > 4) per_sm = 4;     // (more resident CTAs only add partials to the final sum)
+    // launch shape of this (instance, nao), worked out ONCE: warps per CTA so that the CTA's shared memory (Dsym + the
+    // warps' buffers, at least the NP^2 + 8 doubles of the final reduction) fits, resident CTAs per SM from the
+    // occupancy calculator -- at H2O size the whole call is ~20 us and two driver queries per call were a third of it
+    // (function attributes are per device: one slot per device ordinal)
+    struct Shape { int nao, nwarp, per_sm; size_t smem; };
+    static Shape cache[16] = {};
+    Shape& sh = cache[ctx->device & 15];
+    if (sh.nao != nao || sh.per_sm <= 0) {
+        int nwarp = MAXW;
+        auto smem_for = [&](int nw) {
+            size_t d = (size_t)NP * LDD + (size_t)nw * warp_d;
+            if (d < (size_t)NP * NP + 8) d = (size_t)NP * NP + 8;
+            return d * sizeof(double);
+        };
+        while (nwarp > 1 && smem_for(nwarp) > 110 * 1024) nwarp >>= 1;   // aim at two resident CTAs per SM
+        const size_t smem = smem_for(nwarp);
+        int per_sm = 0;
+        DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DFT_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, nwarp * 32, smem));
+        if (per_sm < 1) { ctx->failed = true; return; }
+        if (per_sm * nwarp > 16) per_sm = 16 / nwarp > 0 ? 16 / nwarp : 1;   // (more resident warps only add partials)
+        sh.nao = nao; sh.nwarp = nwarp; sh.per_sm = per_sm; sh.smem = smem;
+    }
     const int nblocks = (p.ngrid + TR - 1) / TR;
-    int grid = nsm * per_sm;
-    if (grid > nblocks) grid = nblocks;
+    int grid = nsm * sh.per_sm;
+    if (grid > (nblocks + sh.nwarp - 1) / sh.nwarp) grid = (nblocks + sh.nwarp - 1) / sh.nwarp;
     double* vpart = (double*)ctx->vpart.ensure(sizeof(double) * (size_t)grid * NP * NP, &ctx->failed);
     double* epart = (double*)ctx->epart.ensure(sizeof(double) * grid, &ctx->failed);
     if (ctx->failed) return;
@@ -303,18 +314,17 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     sp.xc_mode = p.xc_type == 2 ? 4 : p.xc_type * 2 + (ctx->exact_functionals ? 1 : 0);
     sp.dm = p.dm; sp.w = p.w;
     sp.plane[0] = p.ao; sp.plane[1] = p.gx; sp.plane[2] = p.gy; sp.plane[3] = p.gz;
-    // 16-byte copies need 16-byte aligned plane bases and a block pitch (TR * nao * 8 bytes, always a multiple of
-    // 16) -- i.e. only the bases matter
+    // 16-byte copies need 16-byte aligned plane bases (a tile starts 64 nao bytes into a plane per 8 points)
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     sp.vec16 = al16(p.ao) && (NPL == 1 || (al16(p.gx) && al16(p.gy) && al16(p.gz))) ? 1 : 0;
     sp.vpart = vpart; sp.epart = epart;
 
     cudaStream_t st = ctx->stream;
     if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
-    k<<<grid, THREADS, smem, st>>>(sp);
+    k<<<grid, sh.nwarp * 32, sh.smem, st>>>(sp);
     if (ctx->timing) { cudaEventRecord(ctx->ev[1], st); cudaEventRecord(ctx->ev[2], st); }
     const int raw = (ctx->raw_convention && p.xc_type == 1) ? 1 : 0;
-    xc_small_finalize<<<(nao * nao + 255) / 256, 256, 0, st>>>(nao, NP, grid, raw, vpart, epart, p.vxc, p.d_exc);
+    xc_small_finalize<<<(nao * nao + 7) / 8, 256, 0, st>>>(nao, NP, grid, raw, vpart, epart, p.vxc, p.d_exc);
     if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
     ctx->stats.launches = 2;
     ctx->stats.path = PATH_SMALL;

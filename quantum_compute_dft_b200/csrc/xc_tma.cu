@@ -883,8 +883,10 @@ struct StagedCfg {
     static constexpr int VK = 8, MT = 128, NT_ = 128;
     static constexpr int BOXB = VK * 128;                    // one 16-column box: 1 KB
     static constexpr int PLANE_BYTES = (MT / 16) * BOXB;     // 8 KB
-    static constexpr int RS = NPL == 4 ? 3 : 6;              // raw ring depth
-    static constexpr int MS = NPL == 4 ? 7 : 8;              // MMA ring depth
+    // ring depths: the raw ring carries the memory latency (RS - 1 stages of 33 KB in flight; with 3 stages the
+    // kernel ran at 22.8 ms at C5, waiting for HBM), the MMA ring only decouples builders and MMA warps
+    static constexpr int RS = NPL == 4 ? 5 : 8;              // raw ring depth
+    static constexpr int MS = NPL == 4 ? 3 : 6;              // MMA ring depth
     static constexpr int COEF_OFF = NPL * PLANE_BYTES;
     static constexpr int RAW_BYTES = ((COEF_OFF + VK * 32 + 1023) / 1024) * 1024;
     static constexpr int NB_OFF = PLANE_BYTES;               // MMA stage: [B 8 KB][Phi tile 8 KB][4 mask words]
@@ -894,17 +896,19 @@ struct StagedCfg {
     static constexpr int BAR_OFF = MMA_OFF + MS * MMA_BYTES;  // raw_full[RS], raw_empty[RS], mma_full[MS], mma_empty[MS]
     static constexpr int TOTAL = BAR_OFF + (2 * RS + 2 * MS) * 8 + 1024;
     static_assert(TOTAL <= 232448, "shared memory");
-    // setmaxnreg only redistributes what the CTA was LAUNCHED with: 384 threads x 168 registers = 64512.  A pair that
-    // asks for more never gets it and setmaxnreg.inc waits forever (no timeout can catch that).
-    static constexpr int REGS_MMA = 216, REGS_BUILD = 72;
-    static_assert(NCONS * REGS_MMA + 128 * REGS_BUILD <= NTHREADS * 168, "setmaxnreg budget");
-    static_assert(REGS_MMA % 8 == 0 && REGS_BUILD % 8 == 0, "setmaxnreg granularity");
+    // 16 warps: 0-7 MMA, 8-11 builders, 12-15 TMA issue (lane 0 of each; an issuing thread must not share its warp
+    // with lanes that sit in barrier waits).  setmaxnreg only redistributes what the CTA was LAUNCHED with:
+    // 512 threads x 128 registers = 65536; a set that asks for more never gets it and setmaxnreg.inc waits forever.
+    static constexpr int THREADS = 512;
+    static constexpr int REGS_MMA = 216, REGS_BUILD = 56, REGS_ISSUE = 24;
+    static_assert(NCONS * REGS_MMA + 128 * REGS_BUILD + 128 * REGS_ISSUE <= THREADS * 128, "setmaxnreg budget");
+    static_assert(REGS_MMA % 8 == 0 && REGS_BUILD % 8 == 0 && REGS_ISSUE % 8 == 0, "setmaxnreg granularity");
 };
 
 __device__ __forceinline__ double2 lds_f64x2_plain(const unsigned char* p) { return *reinterpret_cast<const double2*>(p); }
 
 template <int NPL>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(StagedCfg<NPL>::THREADS, 1)
 vxc_staged_kernel(const __grid_constant__ VxcParams P) {
     using L = StagedCfg<NPL>;
     constexpr int VK = L::VK, RS = L::RS, MS = L::MS;
@@ -933,43 +937,47 @@ vxc_staged_kernel(const __grid_constant__ VxcParams P) {
     const int total_chunks = (P.sub[si].rows + VK - 1) / VK;
     const int nchunks = total_chunks > sl ? (total_chunks - sl + P.slices_per_sub - 1) / P.slices_per_sub : 0;
 
-    constexpr int NISSUE = NPL;   // TMA-issuing threads of the raw ring: lane 0 of builder warp p brings plane p
+    constexpr int NBUILD = 4;     // builder warps 8-11
+    constexpr int NISSUE = NPL;   // issuing threads of the raw ring: lane 0 of warp 12 + p brings plane p
     if (tid == 0) {
-        for (int s = 0; s < RS; ++s) { tma::mbar_init(&raw_full[s], NISSUE); tma::mbar_init(&raw_empty[s], 4); }
-        for (int s = 0; s < MS; ++s) { tma::mbar_init(&mma_full[s], 5); tma::mbar_init(&mma_empty[s], NCW); }
+        for (int s = 0; s < RS; ++s) { tma::mbar_init(&raw_full[s], NISSUE); tma::mbar_init(&raw_empty[s], NBUILD); }
+        for (int s = 0; s < MS; ++s) { tma::mbar_init(&mma_full[s], NBUILD + 1); tma::mbar_init(&mma_empty[s], NCW); }
         tma::fence_barrier_init();
     }
     // boxes past the edge of the matrix are never written by TMA: clear both rings once
-    for (int o = tid * 16; o < L::BAR_OFF; o += NTHREADS * 16) *reinterpret_cast<double2*>(sm + o) = make_double2(0.0, 0.0);
+    for (int o = tid * 16; o < L::BAR_OFF; o += L::THREADS * 16) *reinterpret_cast<double2*>(sm + o) = make_double2(0.0, 0.0);
     tma::fence_proxy_async();
     __syncthreads();
 
-    if (warp >= NCW) {
-        // ===================== builders (and, lane 0 of each, the TMA issue) =====================
-        reg_dec<L::REGS_BUILD>();
-        const int p = warp - NCW;                 // 0..3: builder warp, and the plane whose loads it issues
-        const int bt = tid - NCONS;               // 0..127
+    if (warp >= NCW + 4) {
+        // ===================== TMA issue: lane 0 of warps 12-15, one plane each =====================
+        // (Round 2's first version let lane 0 of each builder warp issue the loads: the issuing lane then shares a warp
+        // with 31 lanes that sit in mbarrier.try_wait, and it ran at 1.6 us per stage -- the try_wait time limit --
+        // with the DMMAs switched off.  One issuing thread for everything ran at 9.8 ms: ~63 cycles per TMA
+        // instruction + a cycle per ~38 bytes.)
+        reg_dec<L::REGS_ISSUE>();
+        const int p = warp - NCW - 4;             // plane of this thread
+        if (lane != 0 || p >= NISSUE) return;
         const int nfull = P.nfull[si], rem = P.rem[si];
         constexpr int NB = L::MT / 16;
         const int bm0 = m0 / 16, bn0 = n0 / 16;
         const int fbm = min(max(nfull - bm0, 0), NB), fbn = min(max(nfull - bn0, 0), NB);
         const bool pm = rem > 0 && nfull >= bm0 && nfull - bm0 < NB;
         const bool pn = rem > 0 && nfull >= bn0 && nfull - bn0 < NB;
-        const uint32_t tx_plane = (uint32_t)((fbm + (pm ? 1 : 0)) * L::BOXB);
+        const bool with_coef = p == 0, with_n = p == NISSUE - 1;   // the Phi tile of the N columns rides with the last plane
+        const uint32_t tx_raw = (uint32_t)((fbm + (pm ? 1 : 0)) * L::BOXB + (with_coef ? VK * 32 : 0));
         const uint32_t tx_n = (uint32_t)((fbn + (pn ? 1 : 0)) * L::BOXB);
         const double* coef = P.coef + 4 * (size_t)P.sub[si].coef0;
-        // chunk of step c: (sl + c nsl) stride mod total, kept incrementally; `cidx_issue` runs RS - 1 steps ahead
+        // chunk of step c: (sl + c nsl) stride mod total, kept incrementally
         const int cstep = (int)(((long long)P.slices_per_sub * P.chunk_stride[si]) % total_chunks);
-        int cidx_issue = (int)(((long long)sl * P.chunk_stride[si]) % total_chunks);
-        int cidx_n = cidx_issue;
+        int cidx_raw = (int)(((long long)sl * P.chunk_stride[si]) % total_chunks);
+        int cidx_n = cidx_raw;
         auto next_chunk = [&](int& ci) { const int j0 = ci * VK; ci += cstep; if (ci >= total_chunks) ci -= total_chunks; return j0; };
-        auto issue_raw = [&](int c) {   // this thread's share of raw stage c: plane p (+ the coefficient rows with plane 0)
-            const int s = c % RS;
-            tma::mbar_wait_relaxed(&raw_empty[s], ((c / RS) & 1) ^ 1u, (uint32_t)P.wait_ns);
-            const int j0 = next_chunk(cidx_issue);
-            unsigned char* st = sm + s * L::RAW_BYTES;
-            uint64_t* fb = &raw_full[s];
-            tma::mbar_arrive_expect_tx(fb, tx_plane + (p == 0 ? VK * 32 : 0));
+        auto issue_raw = [&](int c) {   // plane p of raw stage c (+ the 8 coefficient rows with plane 0)
+            const int j0 = next_chunk(cidx_raw);
+            unsigned char* st = sm + (c % RS) * L::RAW_BYTES;
+            uint64_t* fb = &raw_full[c % RS];
+            tma::mbar_arrive_expect_tx(fb, tx_raw);
             unsigned char* dst = st + p * L::PLANE_BYTES;
             if (P.use3d) {
                 if (fbm == NB) tma::load_3d(dst, &P.m3[si][p], 0, j0, bm0, fb);
@@ -978,37 +986,57 @@ vxc_staged_kernel(const __grid_constant__ VxcParams P) {
                 for (int b = 0; b < fbm; ++b) tma::load_2d(dst + b * L::BOXB, &P.p2[si][p], m0 + 16 * b, j0, fb);
             }
             if (pm) tma::load_2d(dst + fbm * L::BOXB, &P.p2[si][p], m0 + 16 * fbm, j0, fb);
-            if (p == 0) tma::load_1d(st + L::COEF_OFF, coef + 4 * (size_t)j0, VK * 32, fb);
+            if (with_coef) tma::load_1d(st + L::COEF_OFF, coef + 4 * (size_t)j0, VK * 32, fb);
         };
-        const bool issuer = lane == 0 && p < NISSUE;
-        if (issuer)
-            for (int c = 0; c < RS - 1 && c < nchunks; ++c) issue_raw(c);
+        auto issue_n = [&](int c) {     // the Phi tile of the N columns goes straight into MMA stage c
+            const int j0 = next_chunk(cidx_n);
+            uint64_t* fb = &mma_full[c % MS];
+            tma::mbar_arrive_expect_tx(fb, tx_n);
+            unsigned char* dst = sm + L::MMA_OFF + (c % MS) * L::MMA_BYTES + L::NB_OFF;
+            if (P.use3d) {
+                if (fbn == NB) tma::load_3d(dst, &P.n3[si], 0, j0, bn0, fb);
+                else if (fbn > 0) tma::load_3d(dst, &P.n3l[si], 0, j0, bn0, fb);
+            } else {
+                for (int b = 0; b < fbn; ++b) tma::load_2d(dst + b * L::BOXB, &P.p2[si][0], n0 + 16 * b, j0, fb);
+            }
+            if (pn) tma::load_2d(dst + fbn * L::BOXB, &P.p2[si][0], n0 + 16 * fbn, j0, fb);
+        };
+        // Both rings are kept as full as their consumers allow: whichever slot is free gets its load (non-blocking
+        // tests -- a blocking wait on one ring would hold up the other)
+        int c_raw = 0, c_n = with_n ? 0 : nchunks;
+        uint32_t idle = 0;
+        uint64_t t0 = 0;
+        while (c_raw < nchunks || c_n < nchunks) {
+            bool did = false;
+            if (c_n < nchunks && tma::mbar_test_wait(&mma_empty[c_n % MS], ((c_n / MS) & 1) ^ 1u)) { issue_n(c_n++); did = true; }
+            if (c_raw < nchunks && tma::mbar_test_wait(&raw_empty[c_raw % RS], ((c_raw / RS) & 1) ^ 1u)) { issue_raw(c_raw++); did = true; }
+            if (did) { idle = 0; continue; }
+            if (P.wait_ns) __nanosleep(P.wait_ns);
+            if ((++idle & 4095u) == 0) {   // wall-time bound, as in tma::mbar_wait
+                const uint64_t t = tma::globaltimer_ns();
+                if (idle == 4096u) t0 = t;
+                else if (t - t0 > DFT_MBAR_TIMEOUT_NS) tma::mbar_timeout_trap(0);
+            }
+        }
+        return;
+    }
+    if (warp >= NCW) {
+        // ===================== builders: warps 8-11 =====================
+        reg_dec<L::REGS_BUILD>();
+        const int bt = tid - NCONS;               // 0..127
+        const int bw = warp - NCW;                // 0..3
         // the 16-byte granule of this thread in step i: offset (i * 128 + bt) * 16 of a plane tile, i.e. box
         // 2 i + (bt >> 6), box row (bt >> 3) & 7 -- the same row for all four, so the coefficients are loaded once
         const int row = (bt >> 3) & 7;
-        const int ks_row = row & 1;                       // k-step 0 takes rows {0,2,4,6}, k-step 1 rows {1,3,5,7}
         const int half = (((bt & 7) ^ row) >> 2) & 1;     // un-swizzled 16-byte chunk >> 2: lower / upper 8 columns
-        const uint32_t bit0 = 1u << (ks_row * 16 + 2 * (bt >> 6) + half);
+        // k-step 0 takes box rows {0,2,4,6}, k-step 1 rows {1,3,5,7}
+        const uint32_t bit0 = 1u << ((row & 1) * 16 + 2 * (bt >> 6) + half);
         for (int c = 0; c < nchunks; ++c) {
-            if (issuer && c + RS - 1 < nchunks) issue_raw(c + RS - 1);
             const int rs = c % RS, ms = c % MS;
             tma::mbar_wait(&mma_empty[ms], ((c / MS) & 1) ^ 1u);
-            unsigned char* mst = sm + L::MMA_OFF + ms * L::MMA_BYTES;
-            if (p == (NPL == 4 ? 1 : 0) && lane == 0) {   // the Phi tile of the N columns goes straight into the MMA stage
-                const int j0 = next_chunk(cidx_n);
-                uint64_t* fb = &mma_full[ms];
-                tma::mbar_arrive_expect_tx(fb, tx_n);
-                unsigned char* dst = mst + L::NB_OFF;
-                if (P.use3d) {
-                    if (fbn == NB) tma::load_3d(dst, &P.n3[si], 0, j0, bn0, fb);
-                    else if (fbn > 0) tma::load_3d(dst, &P.n3l[si], 0, j0, bn0, fb);
-                } else {
-                    for (int b = 0; b < fbn; ++b) tma::load_2d(dst + b * L::BOXB, &P.p2[si][0], n0 + 16 * b, j0, fb);
-                }
-                if (pn) tma::load_2d(dst + fbn * L::BOXB, &P.p2[si][0], n0 + 16 * fbn, j0, fb);
-            }
             tma::mbar_wait(&raw_full[rs], (c / RS) & 1);
             const unsigned char* rst = sm + rs * L::RAW_BYTES;
+            unsigned char* mst = sm + L::MMA_OFF + ms * L::MMA_BYTES;
             const double2 ca = lds_f64x2_plain(rst + L::COEF_OFF + row * 32);
             double2 cb = make_double2(0.0, 0.0);
             if (NPL == 4) cb = lds_f64x2_plain(rst + L::COEF_OFF + row * 32 + 16);
@@ -1030,7 +1058,7 @@ vxc_staged_kernel(const __grid_constant__ VxcParams P) {
                 if ((v.x != 0.0) | (v.y != 0.0)) bits |= bit0 << (4 * i);
             }
             bits = __reduce_or_sync(0xffffffffu, bits);
-            if (lane == 0) *reinterpret_cast<uint32_t*>(mst + L::MASK_OFF + 4 * p) = bits;
+            if (lane == 0) *reinterpret_cast<uint32_t*>(mst + L::MASK_OFF + 4 * bw) = bits;
             __syncwarp();
             if (lane == 0) {
                 tma::mbar_arrive(&mma_full[ms]);
@@ -1342,7 +1370,7 @@ struct Plan {
     VxcParams vp;
     const void* dfunc = nullptr;
     const void* vfunc = nullptr;
-    int dgrid = 0, dsmem = 0, vsmem = 0, pgrid = 0;
+    int dgrid = 0, dsmem = 0, vsmem = 0, pgrid = 0, vthreads = NTHREADS;
     dim3 vgrid;
     // symmetrize_pad / finalize arguments
     int KP = 0, NP = 0, nsub = 0, ldv = 0, mpv = 0, fin_nt = 0, nsl = 0, shift1 = 0, lda_half = 0;
@@ -1492,11 +1520,13 @@ static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry&
         DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, StagedCfg<NPL>::TOTAL));
         pl.vfunc = reinterpret_cast<const void*>(vk);
         pl.vsmem = StagedCfg<NPL>::TOTAL;
+        pl.vthreads = StagedCfg<NPL>::THREADS;
     } else {
         auto vk = vxc_tma_kernel<MF, NFN, WM, WN, NPL, VK, STAGES, SKIP>;
         DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(vk, cudaFuncAttributeMaxDynamicSharedMemorySize, VL::TOTAL));
         pl.vfunc = reinterpret_cast<const void*>(vk);
         pl.vsmem = VL::TOTAL;
+        pl.vthreads = NTHREADS;
     }
     pl.vgrid = dim3(tiles, nsl * g.nsub);
     pl.ldv = ldv; pl.mpv = mpv; pl.fin_nt = VL::NT_; pl.nsl = nsl; pl.shift1 = g.split ? 1 : 0; pl.lda_half = lda_half;
@@ -1545,7 +1575,7 @@ static void build_plan(CublasHandleWrapper* ctx, const Problem& p, int nsm, Plan
         DFT_PLAN_V(1, 8, 8, 1, NPL, 16, 4);
     } else if (shape == 160) {
         DFT_PLAN_V(5, 5, 4, 2, NPL, 16, 2);
-    } else if (vskip && ctx->vxc_skip_mode != 1) {
+    } else if (vskip && ctx->vxc_skip_mode == 4) {
         plan_vxc<2, 16, 8, 1, NPL, 8, 5, 4>(ctx, p, g, nsm, coef, pl);
     } else {
         // rows per ring stage: 16 (2 stages, fewer barriers) on dense operands; 8 (5 stages) when zero fragments
@@ -1583,7 +1613,7 @@ static void run_plan(CublasHandleWrapper* ctx, const Problem& p, Plan& pl) {
     xc_point_kernel<<<pl.pgrid, POINT_THREADS, 0, st>>>(pl.pp);
     if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
     void* vargs[1] = {&pl.vp};
-    DFT_CUDA_CHECK(ctx, cudaLaunchKernel(pl.vfunc, pl.vgrid, dim3(NTHREADS), vargs, (size_t)pl.vsmem, st));
+    DFT_CUDA_CHECK(ctx, cudaLaunchKernel(pl.vfunc, pl.vgrid, dim3(pl.vthreads), vargs, (size_t)pl.vsmem, st));
     if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
     const int fin_tiles = (p.nao + FIN_TILE - 1) / FIN_TILE;
     const int raw = (ctx->raw_convention && p.xc_type == 1) ? 1 : 0;

@@ -29,10 +29,11 @@ print('DMMA TFLOP/s', l.DFT_MicrobenchDMMA(8192)); print('DFMA TFLOP/s', l.DFT_M
     ncu:*)   W=${what#ncu:}; CMD="python bench.py --workload $W --steps 2 --warmup 3 --no-cpu-baseline"
              timeout 600 $CMD > $OUT/ncu_plain_$W.log 2>&1 && \
              timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$W.csv $CMD > $OUT/ncu_list_$W.log 2>&1 && \
-             timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'density_tma|vxc_tma|xc_point|eval_kernel' -c 7 -o $OUT/prof_$W $CMD > $OUT/ncu_full_$W.log 2>&1
+             timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'density_tma|vxc_tma|vxc_staged|xc_point|eval_kernel|xc_small' -c 7 -o $OUT/prof_$W $CMD > $OUT/ncu_full_$W.log 2>&1
              echo "ncu $W rc=$?" | tee -a $OUT/summary.txt; tail -3 $OUT/ncu_full_$W.log ;;
     sweep8)  SWEEP_RANKS=8 timeout 600 python tools/vxc_sweep.py C5 "dyn_sched=1" "dyn_sched=0" "dyn_sched=1,density_unit=1" "dyn_sched=0,density_unit=1" "dyn_sched=1" "dyn_sched=0" > $OUT/sweep8.txt 2>&1; echo "sweep8 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweep8.txt ;;
     sweepv)  timeout 600 python tools/vxc_sweep.py C5 "vxc_skip_mode=4" "vxc_skip_mode=1" "vxc_skip=0" "vxc_skip_mode=4,vxc_scatter=0" > $OUT/sweepv.txt 2>&1; echo "sweepv rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweepv.txt ;;
+    sweepd)  SWEEP_LIB=diag timeout 600 python tools/vxc_sweep.py C5 "vxc_skip_mode=4" "vxc_skip_mode=4,debug_nodmma=1" "vxc_skip_mode=4,debug_nodmma=1,vxc_scatter=0" > $OUT/sweepd.txt 2>&1; echo "sweepd rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweepd.txt ;;
     sweep1)  timeout 600 python tools/vxc_sweep.py C5 "dyn_sched=1" "dyn_sched=0" > $OUT/sweep1.txt 2>&1; echo "sweep1 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweep1.txt ;;
     *) echo "unknown step $what" ;;
   esac
