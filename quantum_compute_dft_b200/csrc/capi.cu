@@ -50,7 +50,7 @@ CublasHandleWrapper::~CublasHandleWrapper() {
     if (stream) cudaStreamSynchronize(stream);
     xc::comm_destroy(this);
     xc::free_tma_plan(this);
-    dsym.release(); counters.release(); rho.release(); coef.release(); epart.release(); vpart.release(); result.release(); scratch.release();
+    dsym.release(); counters.release(); rho.release(); coef.release(); epart.release(); vpart.release(); result.release(); scratch.release(); repack.release();
     if (h_scalar) cudaFreeHost(h_scalar);
     for (auto& e : ev)
         if (e) cudaEventDestroy(e);
@@ -58,7 +58,7 @@ CublasHandleWrapper::~CublasHandleWrapper() {
 }
 
 size_t CublasHandleWrapper::workspace_bytes() const {
-    return dsym.capacity + rho.capacity + coef.capacity + epart.capacity + vpart.capacity + result.capacity + scratch.capacity;
+    return dsym.capacity + rho.capacity + coef.capacity + epart.capacity + vpart.capacity + result.capacity + scratch.capacity + repack.capacity;
 }
 
 namespace xc {

@@ -96,7 +96,8 @@ struct CublasHandleWrapper {
     DeviceBuffer epart;    // per-CTA partial E_xc
     DeviceBuffer vpart;    // split-K partial V tiles
     DeviceBuffer result;   // packed [V_xc (nao*nao) | E_xc] for the all-reduce / async E
-    DeviceBuffer scratch;  // repacked AO planes etc.
+    DeviceBuffer scratch;  // DFT_EvalAO shell tables; phase-timing records
+    DeviceBuffer repack;   // aligned copy of a y-gradient plane that sits at 8 mod 16 (odd nao x odd ngrid), refreshed every call
     double* h_scalar = nullptr;  // pinned
     void* tma_plan = nullptr;    // cached launch plan of the TMA path (xc_tma.cu)
     int num_sms = 0;

@@ -68,12 +68,16 @@ struct SmallParams {
     double* epart;   // [gridDim.x]
 };
 
-// Every warp is autonomous: it streams its own 8-point tiles (cp.async, double-buffered, private shared memory),
-// takes each through steps 1-5 without a single CTA barrier, and keeps a private (NP x NP) accumulator in
-// registers.  The four lanes of a fragment row evaluate that row's functional redundantly -- 4 x the FP64 work of
-// the point kernel, still a small share of the step -- which keeps rho, the coefficients and E_xc in registers
-// (the coefficients of the points a lane supplies to the M += B^T Phi fragments come by shuffle).
-// shared-memory layout (doubles): Dsym[NP][LDD] | per warp: 2 x { planes[NPL][8 * nao], w[8] }
+// Every warp is autonomous: it streams its own tiles of 8 grid points (cp.async, double-buffered, private shared
+// memory), works on SUPER-BLOCKS of 4 tiles = 32 points without a single CTA barrier, and keeps a private (NP x NP)
+// accumulator in registers:
+//   pass A over the 4 tiles: steps 1 + 2; lane (q, qc) keeps the row sums of row q of tile qc
+//   step 3: the functional, once, every lane its own point (a long dependent FP64 chain: done per tile, with the four
+//           lanes of a row evaluating redundantly, it WAS the kernel's time at 8 warps per SM)
+//   pass B over the same 4 tiles, streamed a second time (from L2: they were read a few microseconds ago): steps 4 + 5,
+//           the coefficients of the points a lane supplies to the fragments arrive by shuffle
+// HBM sees every plane byte once; rho, coefficients and E_xc never leave the registers.
+// shared-memory layout (doubles): Dsym[NP][LDD] | per warp: 2 x planes[NPL][8 * nao] | 8 doubles of slack
 template <int NF, int NPL>
 __global__ void __launch_bounds__(MAXW * 32)
 xc_small_kernel(const SmallParams P) {
@@ -81,41 +85,46 @@ xc_small_kernel(const SmallParams P) {
     extern __shared__ double smd[];
     const int nao = P.nao;
     const int tile_d = TR * nao;                         // doubles per plane tile (even)
-    const int buf_d = NPL * tile_d + TR;                 // + the weights
+    const int buf_d = NPL * tile_d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int q = lane >> 2, qc = lane & 3;
     double* dsym = smd;
     double* buf0 = dsym + NP * LDD + (size_t)warp * 2 * buf_d;
 
-    // ---- Dsym = 1/2 (D + D^T), zero-padded (replaces symmetrize_pad; nao^2 doubles from L2 per CTA)
+    // ---- Dsym = 1/2 (D + D^T), zero-padded (replaces symmetrize_pad; nao^2 doubles from L2 per CTA).  The buffers
+    // are cleared once: the fragment loads below read up to 7 columns past the end of a row (into the next row, the
+    // next plane or the next buffer) instead of testing every column against nao.  What they pick up there is
+    // multiplied by the zero padding of Dsym (steps 1, 2) or lands in rows / columns >= nao of the accumulator that
+    // nobody reads (step 5) -- but it has to be FINITE, which stale tile data is and uninitialised memory is not.
     for (int i = tid; i < NP * LDD; i += blockDim.x) {
         const int r = i / LDD, c = i - r * LDD;
         double v = 0.0;
         if (r < nao && c < nao) v = 0.5 * (__ldg(P.dm + (size_t)r * nao + c) + __ldg(P.dm + (size_t)c * nao + r));
         dsym[i] = v;
     }
+    for (int i = lane; i < 2 * buf_d + (warp == nwarp - 1 ? 8 : 0); i += 32) buf0[i] = 0.0;   // (+ the slack behind the last buffer)
+    __syncwarp();
 
     // ---- asynchronous tile loads: 8 * nao contiguous doubles per plane; rows past the grid are zero-filled
-    auto issue_tile = [&](int blk, double* buf) {
-        const long g0 = (long)blk * TR;
-        const long valid = (long)min((long)TR, (long)P.ngrid - g0) * nao;   // doubles of this tile that exist
+    const uint32_t lane16 = (uint32_t)lane * 16u;
+    auto issue_tile = [&](long g0, double* buf) {
         const uint32_t sb = (uint32_t)__cvta_generic_to_shared(buf);
-        if (P.vec16) {
-            const int n16 = tile_d / 2;
+        if (P.vec16 && g0 + TR <= (long)P.ngrid) {   // the common case: whole tile, 16-byte copies, nothing to test per copy
+            const uint32_t bytes = (uint32_t)tile_d * 8u;
+#pragma unroll
             for (int p = 0; p < NPL; ++p) {
-                const double* src = P.plane[p] + g0 * nao;
-                for (int i = lane; i < n16; i += 32) {
-                    const long rem = valid - 2l * i;
-                    cp_async_16(sb + (uint32_t)(p * tile_d + 2 * i) * 8u, src + 2 * i, rem >= 2 ? 16 : (rem == 1 ? 8 : 0));
-                }
+                const char* src = reinterpret_cast<const char*>(P.plane[p] + g0 * nao);
+                const uint32_t dst = sb + (uint32_t)p * bytes;
+                for (uint32_t o = lane16; o < bytes; o += 512u) cp_async_16(dst + o, src + o, 16);
             }
         } else {
+            long valid = ((long)P.ngrid - g0) * nao;                          // doubles of this tile that exist
+            valid = valid < 0 ? 0 : (valid > tile_d ? tile_d : valid);
             for (int p = 0; p < NPL; ++p) {
-                const double* src = P.plane[p] + g0 * nao;
+                const double* src = P.plane[p] + (valid > 0 ? g0 * nao : 0);
                 for (int i = lane; i < tile_d; i += 32) cp_async_8(sb + (uint32_t)(p * tile_d + i) * 8u, src + i, i < valid ? 8 : 0);
             }
         }
-        if (lane < TR) cp_async_8(sb + (uint32_t)(NPL * tile_d + lane) * 8u, P.w + g0 + lane, g0 + lane < P.ngrid ? 8 : 0);
         cp_async_commit();
     };
 
@@ -127,83 +136,113 @@ xc_small_kernel(const SmallParams P) {
     double e_acc = 0.0;
     const int nk = (nao + 3) / 4;    // k-steps of step 1 that contain real columns
     const int first = blockIdx.x * nwarp + warp, stride = gridDim.x * nwarp;
+    constexpr int SB = 4;            // tiles per super-block
+    const int nsuper = (P.nblocks + SB - 1) / SB;
 
-    if (first < P.nblocks) issue_tile(first, buf0);
-    __syncthreads();                 // Dsym is complete (the only CTA barrier before the final reduction)
-    int it = 0;
-    for (int blk = first; blk < P.nblocks; blk += stride, ++it) {
-        const double* phi = buf0 + (it & 1) * buf_d;
-        cp_async_wait_all();
-        __syncwarp();                // the tile has landed for every lane; every lane is done with the other buffer
-        if (blk + stride < P.nblocks) issue_tile(blk + stride, buf0 + ((it + 1) & 1) * buf_d);
-
-        // ---- step 1: C[8 rows][NP] = Phi . Dsym
-        const double* my_row = phi + (size_t)q * nao;                 // fragment row of this lane
-        double c[NF][2];
-#pragma unroll
-        for (int nf = 0; nf < NF; ++nf) c[nf][0] = c[nf][1] = 0.0;
-        for (int ks = 0; ks < nk; ++ks) {
-            const int k = 4 * ks + qc;
-            const double a = k < nao ? my_row[k] : 0.0;
-            const double* drow = dsym + k * LDD + q;                  // Dsym[k][8 nf + q]
-#pragma unroll
-            for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(c[nf], a, drow[8 * nf]);
+    // L2 prefetch of a whole super-block (its 4 tiles are contiguous: 32 nao doubles per plane).  A warp has ONE tile
+    // (9 KB at benzene size) in flight in shared memory, an SM 8 of them -- far fewer bytes than the HBM latency needs
+    // (v4 of this kernel ran latency-bound at 6 us per tile and warp); prefetching the NEXT super-block into L2 while
+    // the current one is processed costs no shared memory and turns its tile loads into L2 hits.
+    auto prefetch_super = [&](int sblk) {
+        const long gs = (long)sblk * SB * TR;
+        long n = ((long)P.ngrid - gs) * nao;                               // doubles that exist
+        n = n > (long)SB * tile_d ? (long)SB * tile_d : n;
+        for (int p = 0; p < NPL; ++p) {
+            const char* src = reinterpret_cast<const char*>(P.plane[p] + gs * nao);
+            for (long o = (long)lane * 128; o < n * 8; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
         }
-        // ---- step 2: row sums of C o plane; lane holds columns 8 nf + 2 qc + {0, 1} of row q
-        double s[NPL];
+    };
+    if (first < nsuper) issue_tile((long)first * SB * TR, buf0);
+    if (first + stride < nsuper) prefetch_super(first + stride);
+    __syncthreads();                 // Dsym is complete and every buffer is cleared (the only CTA barrier before the final reduction)
+    int it = 0;                      // tile loads consumed so far (selects the buffer)
+    for (int sblk = first; sblk < nsuper; sblk += stride) {
+        const long gs = (long)sblk * SB * TR;                          // first grid point of the super-block
+        if (sblk + 2 * stride < nsuper) prefetch_super(sblk + 2 * stride);
+        double keep[NPL];
 #pragma unroll
-        for (int p = 0; p < NPL; ++p) s[p] = 0.0;
+        for (int p = 0; p < NPL; ++p) keep[p] = 0.0;
+        // ---------------- pass A: C = Phi . Dsym and its row dots, tile by tile
+#pragma unroll 1
+        for (int m = 0; m < SB; ++m, ++it) {
+            const double* phi = buf0 + (it & 1) * buf_d;
+            cp_async_wait_all();
+            __syncwarp();            // the tile has landed for every lane; every lane is done with the other buffer
+            issue_tile(gs + (long)(m + 1 < SB ? m + 1 : 0) * TR, buf0 + ((it + 1) & 1) * buf_d);   // next of pass A, or pass B's first
+            const double* my_row = phi + (size_t)q * nao;             // fragment row of this lane
+            double c[NF][2];
 #pragma unroll
-        for (int nf = 0; nf < NF; ++nf) {
-            const int col = 8 * nf + 2 * qc;
+            for (int nf = 0; nf < NF; ++nf) c[nf][0] = c[nf][1] = 0.0;
+            for (int ks = 0; ks < nk; ++ks) {
+                const int k = 4 * ks + qc;
+                const double a = my_row[k];                           // (k >= nao: finite, times a zero row of Dsym)
+                const double* drow = dsym + k * LDD + q;              // Dsym[k][8 nf + q]
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                if (col + e < nao) {
+                for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(c[nf], a, drow[8 * nf]);
+            }
+            // row sums of C o plane; lane holds columns 8 nf + 2 qc + {0, 1} of row q (columns >= nao: C is zero)
+            double s[NPL];
+#pragma unroll
+            for (int p = 0; p < NPL; ++p) s[p] = 0.0;
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) {
+                const int col = 8 * nf + 2 * qc;
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
 #pragma unroll
                     for (int p = 0; p < NPL; ++p) s[p] = fma(c[nf][e], my_row[p * tile_d + col + e], s[p]);
-                }
+            }
+#pragma unroll
+            for (int p = 0; p < NPL; ++p) {
+                s[p] += __shfl_xor_sync(0xffffffffu, s[p], 1);
+                s[p] += __shfl_xor_sync(0xffffffffu, s[p], 2);
+                if (m == qc) keep[p] = s[p];                          // lane (q, qc) keeps row q of tile qc
             }
         }
+        // ---------------- step 3: the functional; lane (q, qc) evaluates point gs + 8 qc + q
+        const long g = gs + 8 * qc + q;
+        const double wgt = g < (long)P.ngrid ? __ldg(P.w + g) : 0.0;
+        const xcfun::PointCoef pc = NPL == 4 ? eval_mode(P.xc_mode, keep[0], 2.0 * keep[1], 2.0 * keep[2], 2.0 * keep[3], wgt)
+                                             : eval_mode(P.xc_mode, keep[0], 0.0, 0.0, 0.0, wgt);
+        e_acc += pc.exc;
+        // ---------------- pass B: M += B^T Phi, tile by tile (two k-steps of 4 points each)
+#pragma unroll 1
+        for (int m = 0; m < SB; ++m, ++it) {
+            const double* phi = buf0 + (it & 1) * buf_d;
+            cp_async_wait_all();
+            __syncwarp();
+            if (m + 1 < SB) issue_tile(gs + (long)(m + 1) * TR, buf0 + ((it + 1) & 1) * buf_d);
+            else if (sblk + stride < nsuper) issue_tile((long)(sblk + stride) * SB * TR, buf0 + ((it + 1) & 1) * buf_d);
 #pragma unroll
-        for (int p = 0; p < NPL; ++p) {
-            s[p] += __shfl_xor_sync(0xffffffffu, s[p], 1);
-            s[p] += __shfl_xor_sync(0xffffffffu, s[p], 2);
-        }
-        // ---- step 3: the functional of row q (the same in the four lanes of the row)
-        const double wgt = phi[NPL * tile_d + q];
-        const xcfun::PointCoef pc = NPL == 4 ? eval_mode(P.xc_mode, s[0], 2.0 * s[1], 2.0 * s[2], 2.0 * s[3], wgt)
-                                             : eval_mode(P.xc_mode, s[0], 0.0, 0.0, 0.0, wgt);
-        if (qc == 0) e_acc += pc.exc;
-        // ---- steps 4 + 5: M += B^T Phi over the 8 rows (two k-steps of 4 points)
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            const int pt = 4 * ks + qc;                               // the point this lane supplies
-            const double ca = __shfl_sync(0xffffffffu, pc.a, 4 * pt);
-            double cbx = 0.0, cby = 0.0, cbz = 0.0;
-            if (NPL == 4) {
-                cbx = __shfl_sync(0xffffffffu, pc.bx, 4 * pt);
-                cby = __shfl_sync(0xffffffffu, pc.by, 4 * pt);
-                cbz = __shfl_sync(0xffffffffu, pc.bz, 4 * pt);
-            }
-            const double* prow = phi + (size_t)pt * nao;
-            double ph[NF], bb[NF];
-#pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                const int col = 8 * f + q;
-                const bool in = col < nao;
-                ph[f] = in ? prow[col] : 0.0;
-                double v = ca * ph[f];
+            for (int ks = 0; ks < 2; ++ks) {
+                const int pt = 4 * ks + qc;                           // the row of this tile the lane supplies
+                const int src = 4 * pt + m;                           // its coefficients live in lane (q = pt, qc = m)
+                const double ca = __shfl_sync(0xffffffffu, pc.a, src);
+                double cbx = 0.0, cby = 0.0, cbz = 0.0;
                 if (NPL == 4) {
-                    v = fma(cbx, in ? prow[tile_d + col] : 0.0, v);
-                    v = fma(cby, in ? prow[2 * tile_d + col] : 0.0, v);
-                    v = fma(cbz, in ? prow[3 * tile_d + col] : 0.0, v);
+                    cbx = __shfl_sync(0xffffffffu, pc.bx, src);
+                    cby = __shfl_sync(0xffffffffu, pc.by, src);
+                    cbz = __shfl_sync(0xffffffffu, pc.bz, src);
                 }
-                bb[f] = v;
+                const double* prow = phi + (size_t)pt * nao;
+                double ph[NF], bb[NF];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const int col = 8 * f + q;   // (columns >= nao end up in rows / columns of M that nobody reads)
+                    ph[f] = prow[col];
+                    double v = ca * ph[f];
+                    if (NPL == 4) {
+                        v = fma(cbx, prow[tile_d + col], v);
+                        v = fma(cby, prow[2 * tile_d + col], v);
+                        v = fma(cbz, prow[3 * tile_d + col], v);
+                    }
+                    bb[f] = v;
+                }
+#pragma unroll
+                for (int mf = 0; mf < NF; ++mf)
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], bb[mf], ph[nf]);
             }
-#pragma unroll
-            for (int mf = 0; mf < NF; ++mf)
-#pragma unroll
-                for (int nf = 0; nf < NF; ++nf) dmma::mma8x8x4(acc[mf][nf], bb[mf], ph[nf]);
         }
     }
     cp_async_wait_all();
@@ -277,7 +316,7 @@ template <int NF, int NPL>
 static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     constexpr int NP = 8 * NF, LDD = ldd_for(NP);
     const int nao = p.nao;
-    const size_t warp_d = 2 * ((size_t)NPL * TR * nao + TR);          // doubles of one warp's two buffers
+    const size_t warp_d = 2 * (size_t)NPL * TR * nao;                 // doubles of one warp's two buffers
     auto k = xc_small_kernel<NF, NPL>;
     // launch shape of this (instance, nao), worked out ONCE: warps per CTA so that the CTA's shared memory (Dsym + the
     // warps' buffers, at least the NP^2 + 8 doubles of the final reduction) fits, resident CTAs per SM from the
@@ -289,7 +328,7 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     if (sh.nao != nao || sh.per_sm <= 0) {
         int nwarp = MAXW;
         auto smem_for = [&](int nw) {
-            size_t d = (size_t)NP * LDD + (size_t)nw * warp_d;
+            size_t d = (size_t)NP * LDD + (size_t)nw * warp_d + 8;
             if (d < (size_t)NP * NP + 8) d = (size_t)NP * NP + 8;
             return d * sizeof(double);
         };
@@ -303,8 +342,9 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
         sh.nao = nao; sh.nwarp = nwarp; sh.per_sm = per_sm; sh.smem = smem;
     }
     const int nblocks = (p.ngrid + TR - 1) / TR;
+    const int nsuper = (nblocks + 3) / 4;          // the unit of work of a warp: 4 tiles = 32 points
     int grid = nsm * sh.per_sm;
-    if (grid > (nblocks + sh.nwarp - 1) / sh.nwarp) grid = (nblocks + sh.nwarp - 1) / sh.nwarp;
+    if (grid > (nsuper + sh.nwarp - 1) / sh.nwarp) grid = (nsuper + sh.nwarp - 1) / sh.nwarp;
     double* vpart = (double*)ctx->vpart.ensure(sizeof(double) * (size_t)grid * NP * NP, &ctx->failed);
     double* epart = (double*)ctx->epart.ensure(sizeof(double) * grid, &ctx->failed);
     if (ctx->failed) return;

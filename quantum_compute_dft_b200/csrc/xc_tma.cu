@@ -1634,13 +1634,28 @@ bool tma_compatible(const Problem& p) {
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     if (p.nao < 1 || p.ngrid < 1) return false;
     if (!al16(p.ao)) return false;
-    if (p.xc_type != 0 && !(al16(p.gx) && al16(p.gy) && al16(p.gz))) return false;
+    if (p.xc_type != 0) {
+        if (!(al16(p.gx) && al16(p.gz))) return false;
+        // Odd nao with odd ngrid puts the y-gradient plane (grad + ngrid nao) at 8 mod 16.  TMA needs every box to start
+        // on a 16-byte boundary, and in such a plane the rows that do are the OPPOSITE parity of the other planes', so no
+        // tensor map can line it up with them: run_tma copies that one plane to aligned scratch first (one D2D copy per
+        // call, ~6 % of the step at C5 size, against 2.7x for the generic kernels round 1 fell back to).
+        if (!al16(p.gy) && (reinterpret_cast<uintptr_t>(p.gy) & 7u)) return false;
+    }
     if (p.nao > 128 * 16) return false;  // keep the padded D and the slice partials modest
     return tmapath::encode_fn() != nullptr;
 }
 
-void run_tma(CublasHandleWrapper* ctx, const Problem& p) {
+void run_tma(CublasHandleWrapper* ctx, const Problem& p_in) {
     using namespace tmapath;
+    Problem p = p_in;
+    if (p.xc_type != 0 && (reinterpret_cast<uintptr_t>(p.gy) & 15u) != 0) {   // see tma_compatible
+        const size_t bytes = sizeof(double) * (size_t)p.ngrid * p.nao;
+        double* gy2 = (double*)ctx->repack.ensure(bytes, &ctx->failed);
+        if (ctx->failed) return;
+        DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(gy2, p.gy, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        p.gy = gy2;
+    }
     if (!ctx->tma_plan) ctx->tma_plan = new Plan();
     Plan& pl = *static_cast<Plan*>(ctx->tma_plan);
     PlanKey key = make_key(ctx, p);
