@@ -24,5 +24,6 @@ def test_allreduced_result_matches_single_gpu(engine_lib):
            "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1500)
     lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    print(r.stdout[-4000:])
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     assert len(lines) == 4 and all(l["ok"] for l in lines), lines
