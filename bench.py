@@ -356,10 +356,15 @@ def main():
         ev0.record(stream)
         for _ in range(args.steps):
             step()
-            dens_ms += solver.stat("density_ms"); vxc_ms += solver.stat("vxc_ms")
         ev1.record(stream)
         ev1.synchronize()
         total_ms = ev0.elapsed_ms(ev1)
+        # per-kernel durations (the engine's own CUDA events on its stream) for the roofline: read in K further steps
+        # on the same inputs right after the timed region -- reading them costs a handful of driver calls per step,
+        # which inside the region would be charged to the step (visible at 8 GPUs, where a C4 step is 0.5 ms)
+        for _ in range(args.steps):
+            step()
+            dens_ms += solver.stat("density_ms"); vxc_ms += solver.stat("vxc_ms")
     else:
         total_ms = 0.0
         for _ in range(args.steps):

@@ -42,7 +42,7 @@ CublasHandleWrapper::CublasHandleWrapper() {
     DFT_CUDA_CHECK(this, cudaStreamCreateWithFlags(&stream, cudaStreamDefault));
     for (auto& e : ev) DFT_CUDA_CHECK(this, cudaEventCreate(&e));
     DFT_CUDA_CHECK(this, cudaMallocHost(reinterpret_cast<void**>(&h_scalar), 128));
-    if (h_scalar) { h_scalar[8] = 0.0; h_scalar[9] = 1.0; }  // constant sources of the "this rank failed" element
+    if (h_scalar) { h_scalar[8] = 0.0; h_scalar[9] = 1.0; h_scalar[10] = 0.0; h_scalar[11] = 0.0; }  // [8],[9]: constant sources of the "this rank failed" element; [10],[11]: zero-copy {E_xc, seq}
 }
 
 CublasHandleWrapper::~CublasHandleWrapper() {
@@ -148,6 +148,11 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
         // TMA-addressable, the generic kernels otherwise; "path" forces one (a forced path that cannot take the
         // inputs falls through to the next)
         const bool use_small = (ctx->path == PATH_AUTO || ctx->path == PATH_SMALL) && xc::small_compatible(p);
+        if (use_small && !multi && !d_exc_out && ctx->h_scalar) {   // E_xc comes back through mapped pinned memory
+            ctx->zc_seq += 1.0;
+            p.host_exc_slot = ctx->h_scalar + 10;
+            p.host_exc_seq = ctx->zc_seq;
+        }
         const bool use_tma = !use_small && ctx->path != PATH_GENERIC && xc::tma_compatible(p);
         if (use_small) xc::run_small(ctx, p);
         else if (use_tma) xc::run_tma(ctx, p);
@@ -166,6 +171,27 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
     if (d_exc_out) {
         DFT_CUDA_CHECK(ctx, cudaGetLastError());
         return ctx->failed ? nan : 0.0;
+    }
+    if (p.host_exc_slot && !ctx->failed) {
+        // The finalize kernel's last CTA writes {E_xc, seq} once the whole result is in place (device-wide fence before
+        // its count); everything the caller enqueues next is stream-ordered behind that kernel anyway.  Poll the slot;
+        // look at the stream now and then so that a faulted launch cannot leave the host spinning.
+        volatile double* slot = ctx->h_scalar + 10;
+        bool seen = false;
+        for (unsigned long long spins = 1; !seen; ++spins) {
+            seen = slot[1] == ctx->zc_seq;
+            if (!seen && (spins & 0x3fff) == 0) {
+                const cudaError_t q = cudaStreamQuery(ctx->stream);
+                if (q != cudaErrorNotReady) {       // finished (or failed) without publishing: one last look
+                    seen = slot[1] == ctx->zc_seq;
+                    if (!seen) { DFT_CUDA_CHECK(ctx, q); ctx->failed = true; }
+                    break;
+                }
+            }
+        }
+        DFT_CUDA_CHECK(ctx, cudaGetLastError());
+        ctx->times_pending = ctx->timing && !ctx->failed;
+        return (ctx->failed || !seen) ? nan : slot[0];
     }
     DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar, multi ? packed + n2 : p.d_exc, (multi ? 2 : 1) * sizeof(double),
                                         cudaMemcpyDeviceToHost, ctx->stream));

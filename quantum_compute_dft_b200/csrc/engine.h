@@ -98,7 +98,8 @@ struct CublasHandleWrapper {
     DeviceBuffer result;   // packed [V_xc (nao*nao) | E_xc] for the all-reduce / async E
     DeviceBuffer scratch;  // DFT_EvalAO shell tables; phase-timing records
     DeviceBuffer repack;   // aligned copy of a y-gradient plane that sits at 8 mod 16 (odd nao x odd ngrid), refreshed every call
-    double* h_scalar = nullptr;  // pinned
+    double* h_scalar = nullptr;  // pinned (and, with unified addressing, device-accessible through the same pointer)
+    double zc_seq = 0.0;         // sequence number of the last zero-copy E_xc return (h_scalar[10], [11])
     void* tma_plan = nullptr;    // cached launch plan of the TMA path (xc_tma.cu)
     int num_sms = 0;
 
@@ -127,6 +128,8 @@ struct Problem {
     const double* w;
     double* vxc;     // (nao,nao) output
     double* d_exc;   // device scalar output
+    volatile double* host_exc_slot = nullptr;   // small path, blocking calls: mapped pinned {E_xc, sequence number} (see xc_small_finalize)
+    double host_exc_seq = 0.0;
 };
 
 // generic path (any alignment, any nao): xc_generic.cu

@@ -282,9 +282,14 @@ xc_small_kernel(const SmallParams P) {
 // out[i][j] = sum over CTAs of M[i][j] + M[j][i] (raw: 2 M[i][j]); E_xc = sum of the CTA partials.  One WARP per
 // output element: the lanes stride over the CTA partials (all loads in flight at once -- a serial loop over 296
 // partials took 90 us at benzene size), then a shuffle tree.  Fixed order -> bit-reproducible, exactly symmetric.
+// `host_slot` (optional): two doubles of MAPPED PINNED host memory.  The last CTA to finish -- counted with a device
+// atomic after every CTA has fenced its part of V_xc -- writes E_xc and then the call's sequence number there, so the
+// blocking entry point can return E_xc the moment the whole result exists, without a D2H copy and a stream synchronise
+// (at H2O size those two were a fifth of the call).
 __global__ void __launch_bounds__(256)
 xc_small_finalize(int nao, int NP, int ncta, int raw, const double* __restrict__ vpart, const double* __restrict__ epart,
-                  double* __restrict__ vxc, double* __restrict__ d_exc) {
+                  double* __restrict__ vxc, double* __restrict__ d_exc, unsigned int* __restrict__ done_counter,
+                  volatile double* host_slot, double seq) {
     const int lane = threadIdx.x & 31;
     const int idx = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (idx < nao * nao) {
@@ -298,8 +303,9 @@ xc_small_finalize(int nao, int NP, int ncta, int raw, const double* __restrict__
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) vxc[idx] = s;
     }
+    __shared__ double sh[256];
+    __shared__ bool last;
     if (blockIdx.x == 0) {
-        __shared__ double sh[256];
         double e = 0.0;
         for (int k = threadIdx.x; k < ncta; k += 256) e += epart[k];
         sh[threadIdx.x] = e;
@@ -309,6 +315,19 @@ xc_small_finalize(int nao, int NP, int ncta, int raw, const double* __restrict__
             __syncthreads();
         }
         if (threadIdx.x == 0) *d_exc = sh[0];
+    }
+    if (host_slot) {
+        __threadfence();               // this CTA's V_xc (and E_xc) stores are visible device-wide ...
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(done_counter, 1u) == gridDim.x - 1;   // ... before it is counted
+        __syncthreads();
+        if (last && threadIdx.x == 0) {
+            *done_counter = 0u;        // (self-resetting: ready for the next call)
+            __threadfence();
+            host_slot[0] = *reinterpret_cast<volatile double*>(d_exc);
+            __threadfence_system();
+            host_slot[1] = seq;
+        }
     }
 }
 
@@ -364,7 +383,17 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     k<<<grid, sh.nwarp * 32, sh.smem, st>>>(sp);
     if (ctx->timing) { cudaEventRecord(ctx->ev[1], st); cudaEventRecord(ctx->ev[2], st); }
     const int raw = (ctx->raw_convention && p.xc_type == 1) ? 1 : 0;
-    xc_small_finalize<<<(nao * nao + 7) / 8, 256, 0, st>>>(nao, NP, grid, raw, vpart, epart, p.vxc, p.d_exc);
+    // zero-copy return of E_xc (blocking single-GPU calls only: capi.cu sets `host_exc_slot` and then polls it)
+    unsigned int* done = nullptr;
+    if (p.host_exc_slot) {
+        const bool fresh = ctx->counters.ptr == nullptr;
+        done = reinterpret_cast<unsigned int*>(ctx->counters.ensure(6 * sizeof(unsigned long long), &ctx->failed));
+        if (ctx->failed) return;
+        if (fresh) cudaMemsetAsync(done, 0, 6 * sizeof(unsigned long long), st);
+        done += 10;   // (the last 8 bytes of the buffer: the TMA path's statistics and work counter use the first 40)
+    }
+    xc_small_finalize<<<(nao * nao + 7) / 8, 256, 0, st>>>(nao, NP, grid, raw, vpart, epart, p.vxc, p.d_exc, done,
+                                                           p.host_exc_slot, p.host_exc_seq);
     if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
     ctx->stats.launches = 2;
     ctx->stats.path = PATH_SMALL;
