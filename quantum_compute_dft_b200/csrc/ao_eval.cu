@@ -24,6 +24,8 @@
 //   * phase 2, lanes over AOs: a warp takes one point, lane i combines its shell's (e0, e1) with the
 //     distance vector and writes the value and the three gradient components STRAIGHT to global memory:
 //     consecutive lanes -> consecutive AOs, 256 contiguous bytes per warp store, no staging row.
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -80,7 +82,7 @@ struct Tables {
     size_t o_gprim, o_gnprim, o_gmem, o_gnmem, o_mshell, o_mcoef, o_aoshell, o_aocomp;
 };
 
-template <bool DERIV, int G, int NWARPS>
+template <bool DERIV, int G, int NWARPS, bool VEC>
 __global__ void __launch_bounds__(NWARPS * 32)
 eval_kernel(int ngrid, const double* __restrict__ coords, Tables t, int epitch, double cutoff, double* __restrict__ ao,
             double* __restrict__ gout) {
@@ -194,6 +196,62 @@ eval_kernel(int ngrid, const double* __restrict__ coords, Tables t, int epitch, 
         }
         __syncthreads();
         // ---- phase 2: a warp per point, lanes over AOs, results straight to global memory (coalesced)
+        if (VEC) {
+            // 16-byte stores: a lane owns the AO pair (i0, i0 + 1) whose first element sits on a 16-byte boundary of
+            // its row -- row (p0 + r) starts at element (p0 + r) nao, so for odd nao the pairs of odd rows start one
+            // AO earlier (i0 = -1: only the second element exists).  512 contiguous bytes per warp store, half the
+            // store instructions and loop trips of the scalar form.  The y-gradient plane of an odd x odd problem
+            // has the opposite parity: that one plane falls back to two 8-byte stores per pair.
+            for (int r = warp; r < np; r += NWARPS) {
+                const double x = s_pts[3 * r], y = s_pts[3 * r + 1], z = s_pts[3 * r + 2];
+                const double2* erow = e01 + (size_t)r * epitch;
+                const size_t row0 = (size_t)(p0 + r) * nao;
+                const int a = (int)(row0 & 1);
+                const bool vy = ((plane & 1) == 0);                     // gy pairs are 16-byte aligned too
+                for (int i0 = 2 * lane - a; i0 < nao; i0 += 64) {
+                    const bool has0 = i0 >= 0, has1 = i0 + 1 < nao;
+                    double v[2], vx[2], vyv[2], vz[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        int i = i0 + h;
+                        i = i < 0 ? 0 : (i >= nao ? nao - 1 : i);
+                        const int meta = ao_meta[i];
+                        const int sh = meta & 0xffffff, comp = (meta >> 24) - 1;
+                        const double2 e = erow[sh];
+                        const double dx = x - sx[sh], dy = y - sy[sh], dz = z - sz[sh];
+                        double dj = dz;
+                        dj = comp == 1 ? dy : dj;
+                        dj = comp == 0 ? dx : dj;
+                        dj = comp < 0 ? 1.0 : dj;
+                        v[h] = dj * e.x;
+                        if (DERIV) {
+                            const double dj1 = dj * e.y;
+                            vx[h] = fma(dj1, dx, comp == 0 ? e.x : 0.0);
+                            vyv[h] = fma(dj1, dy, comp == 1 ? e.x : 0.0);
+                            vz[h] = fma(dj1, dz, comp == 2 ? e.x : 0.0);
+                        }
+                    }
+                    double* d0 = ao + row0 + i0;
+                    if (has0 && has1) {
+                        *reinterpret_cast<double2*>(d0) = make_double2(v[0], v[1]);
+                        if (DERIV) {
+                            double* d1 = gout + row0 + i0;
+                            *reinterpret_cast<double2*>(d1) = make_double2(vx[0], vx[1]);
+                            if (vy) *reinterpret_cast<double2*>(d1 + plane) = make_double2(vyv[0], vyv[1]);
+                            else { d1[plane] = vyv[0]; d1[plane + 1] = vyv[1]; }
+                            *reinterpret_cast<double2*>(d1 + 2 * plane) = make_double2(vz[0], vz[1]);
+                        }
+                    } else {
+                        const int h = has0 ? 0 : 1;
+                        d0[h] = has0 ? v[0] : v[1];
+                        if (DERIV) {
+                            double* d1 = gout + row0 + i0 + h;
+                            d1[0] = has0 ? vx[0] : vx[1]; d1[plane] = has0 ? vyv[0] : vyv[1]; d1[2 * plane] = has0 ? vz[0] : vz[1];
+                        }
+                    }
+                }
+            }
+        } else {
         for (int r = warp; r < np; r += NWARPS) {
             const double x = s_pts[3 * r], y = s_pts[3 * r + 1], z = s_pts[3 * r + 2];
             const double2* erow = e01 + (size_t)r * epitch;
@@ -201,28 +259,41 @@ eval_kernel(int ngrid, const double* __restrict__ coords, Tables t, int epitch, 
             double* d1 = DERIV ? gout + (size_t)(p0 + r) * nao + lane : nullptr;
             double* d2 = DERIV ? d1 + plane : nullptr;
             double* d3 = DERIV ? d2 + plane : nullptr;
-            for (int i = lane; i < nao; i += 32) {
-                const int meta = ao_meta[i];
-                const int sh = meta & 0xffffff, comp = (meta >> 24) - 1;  // comp: -1 s, 0..2 p_x p_y p_z
-                const double2 e = erow[sh];
-                const double dx = x - sx[sh], dy = y - sy[sh], dz = z - sz[sh];
+            // two AOs per lane and trip (i, i + 32), all their shared-memory loads issued before the first use: the
+            // chain meta -> (e0, e1), centre -> value is two shared-memory latencies long, and with one AO per trip
+            // it was exposed twelve times per point (ncu: short-scoreboard was the top stall of this loop)
+            for (int i = lane; i < nao; i += 64) {
+                const bool h1 = i + 32 < nao;
+                const int meta0 = ao_meta[i], meta1 = ao_meta[h1 ? i + 32 : i];
+                const int sh0 = meta0 & 0xffffff, comp0 = (meta0 >> 24) - 1;  // comp: -1 s, 0..2 p_x p_y p_z
+                const int sh1 = meta1 & 0xffffff, comp1 = (meta1 >> 24) - 1;
+                const double2 e0 = erow[sh0], e1 = erow[sh1];
+                const double dx0 = x - sx[sh0], dy0 = y - sy[sh0], dz0 = z - sz[sh0];
+                const double dx1 = x - sx[sh1], dy1 = y - sy[sh1], dz1 = z - sz[sh1];
                 // (a chain of selects, not nested conditionals: lanes hold different components, and the
                 // nested form compiles to divergent branches)
-                double dj = dz;
-                dj = comp == 1 ? dy : dj;
-                dj = comp == 0 ? dx : dj;
-                dj = comp < 0 ? 1.0 : dj;
-                *d0 = dj * e.x;
+                double dj0 = dz0, dj1 = dz1;
+                dj0 = comp0 == 1 ? dy0 : dj0; dj1 = comp1 == 1 ? dy1 : dj1;
+                dj0 = comp0 == 0 ? dx0 : dj0; dj1 = comp1 == 0 ? dx1 : dj1;
+                dj0 = comp0 < 0 ? 1.0 : dj0;  dj1 = comp1 < 0 ? 1.0 : dj1;
+                d0[0] = dj0 * e0.x;
+                if (h1) d0[32] = dj1 * e1.x;
                 if (DERIV) {
                     // s: e1 d;  p_j: d_j e1 d + e0 delta_j
-                    const double dj1 = dj * e.y;
-                    *d1 = fma(dj1, dx, comp == 0 ? e.x : 0.0);
-                    *d2 = fma(dj1, dy, comp == 1 ? e.x : 0.0);
-                    *d3 = fma(dj1, dz, comp == 2 ? e.x : 0.0);
-                    d1 += 32; d2 += 32; d3 += 32;
+                    const double t0 = dj0 * e0.y, t1 = dj1 * e1.y;
+                    d1[0] = fma(t0, dx0, comp0 == 0 ? e0.x : 0.0);
+                    d2[0] = fma(t0, dy0, comp0 == 1 ? e0.x : 0.0);
+                    d3[0] = fma(t0, dz0, comp0 == 2 ? e0.x : 0.0);
+                    if (h1) {
+                        d1[32] = fma(t1, dx1, comp1 == 0 ? e1.x : 0.0);
+                        d2[32] = fma(t1, dy1, comp1 == 1 ? e1.x : 0.0);
+                        d3[32] = fma(t1, dz1, comp1 == 2 ? e1.x : 0.0);
+                    }
+                    d1 += 64; d2 += 64; d3 += 64;
                 }
-                d0 += 32;
+                d0 += 64;
             }
+        }
         }
     }
 }
@@ -287,6 +358,33 @@ extern "C" int DFT_EvalAO(XCSolver* solver, int ngrid, unsigned long long d_coor
         if (ao_shell[i] < 0) return 3;  // every AO must belong to a shell
     const int ngroup = (int)groups.size();
     if (ngroup > 65535) return 5;
+    // Order of the groups in phase 1.  The two half-warps of a warp work on CONSECUTIVE groups, and a warp pays for the
+    // long path (three exponentials) whenever either of them is inside its cutoff: pair groups that decide alike -- the
+    // same reach sqrt(cutoff / amin) (core shells reach 4 bohr, valence shells 13-19) and neighbouring centres (sorted
+    // along the molecule's longest axis within a reach class).  Shell by shell in input order, a carbon's 1s group sat
+    // next to its own 2sp group, which almost never agree.
+    if (!ctx->ao_input_order) {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (const HGroup& q : groups) {
+            const double c[3] = {q.x, q.y, q.z};
+            for (int d = 0; d < 3; ++d) { lo[d] = c[d] < lo[d] ? c[d] : lo[d]; hi[d] = c[d] > hi[d] ? c[d] : hi[d]; }
+        }
+        int ax = 0;
+        for (int d = 1; d < 3; ++d) if (hi[d] - lo[d] > hi[ax] - lo[ax]) ax = d;
+        std::vector<int> order(ngroup), inv(ngroup);
+        for (int g = 0; g < ngroup; ++g) order[g] = g;
+        auto reach = [&](const HGroup& q) { return (long)(sqrt(exp_cutoff / q.amin) + 0.5); };   // bohr, rounded
+        auto pos = [&](const HGroup& q) { return ax == 0 ? q.x : (ax == 1 ? q.y : q.z); };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const long ra = reach(groups[a]), rb = reach(groups[b]);
+            if (ra != rb) return ra > rb;
+            return pos(groups[a]) < pos(groups[b]);
+        });
+        std::vector<HGroup> sorted(ngroup);
+        for (int g = 0; g < ngroup; ++g) { sorted[g] = groups[order[g]]; inv[order[g]] = g; }
+        groups.swap(sorted);
+        for (int s = 0; s < nshell; ++s) shell_group[s] = inv[shell_group[s]];
+    }
     std::vector<int> mshell(nshell), mcoef(nshell);
     {
         int off = 0;
@@ -346,9 +444,17 @@ extern "C" int DFT_EvalAO(XCSolver* solver, int ngrid, unsigned long long d_coor
     const int epitch = nshell | 1;
     const size_t smem_max = 227 * 1024;
     auto smem_for = [&](int G) { return bytes + sizeof(double) * 6 * G + sizeof(double2) * (size_t)G * epitch + 64; };
+    // ao_shape: 8 | 16 | 32 points per block with 8 | 8 | 16 warps, 17 = 16 points with 16 warps (twice the resident
+    // warps on the same shared memory).  ao_vec_stores: 16-byte stores in phase 2 (a lane owns an aligned AO pair).
+    // Measured at C5 / C4 (profiles/r2_u3_ao_eval_variants.txt): the kernel is bound by instruction issue and
+    // shared-memory latency, not by the number of store instructions -- 3.59 / 0.83 ms with 16-byte stores against
+    // 3.52 / 0.73 ms with 8-byte ones (a warp's 8-byte stores already fill whole 256-byte runs) -- so 8-byte is the default.
     int shape = ctx->ao_shape;
-    if (shape != 8 && shape != 16 && shape != 32) shape = 2 * (smem_for(32) + 1024) <= smem_max ? 32 : 16;
-    const int G = shape, NW = shape == 32 ? 16 : 8;
+    bool vec = ctx->ao_vec_stores;
+    // 16-byte stores need 16-byte aligned output bases (cudaMalloc gives 256)
+    if ((d_ao_ptr & 15ull) || (deriv && (d_ao_grad_ptr & 15ull))) vec = false;
+    if (shape != 8 && shape != 16 && shape != 17 && shape != 32) shape = 2 * (smem_for(32) + 1024) <= smem_max ? 32 : 16;
+    const int G = shape == 17 ? 16 : shape, NW = (shape == 32 || shape == 17) ? 16 : 8;
     const size_t smem = smem_for(G);
     if (smem > smem_max) {
         fprintf(stderr, "[dft_b200] DFT_EvalAO: basis too large for the shared-memory staging (%zu B)\n", smem);
@@ -367,12 +473,18 @@ extern "C" int DFT_EvalAO(XCSolver* solver, int ngrid, unsigned long long d_coor
     if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
 #define DFT_AO_LAUNCH(D_, G_, NW_)                                                                                      \
     do {                                                                                                                \
-        auto k = eval_kernel<D_, G_, NW_>;                                                                              \
-        DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-        k<<<grid, NW_ * 32, smem, ctx->stream>>>(ngrid, coords, t, epitch, exp_cutoff, ao_out, g_out);                  \
+        if (vec) {                                                                                                      \
+            auto k = eval_kernel<D_, G_, NW_, true>;                                                                    \
+            DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+            k<<<grid, NW_ * 32, smem, ctx->stream>>>(ngrid, coords, t, epitch, exp_cutoff, ao_out, g_out);              \
+        } else {                                                                                                        \
+            auto k = eval_kernel<D_, G_, NW_, false>;                                                                   \
+            DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+            k<<<grid, NW_ * 32, smem, ctx->stream>>>(ngrid, coords, t, epitch, exp_cutoff, ao_out, g_out);              \
+        }                                                                                                               \
     } while (0)
-    if (deriv) { if (G == 32) DFT_AO_LAUNCH(true, 32, 16); else if (G == 16) DFT_AO_LAUNCH(true, 16, 8); else DFT_AO_LAUNCH(true, 8, 8); }
-    else { if (G == 32) DFT_AO_LAUNCH(false, 32, 16); else if (G == 16) DFT_AO_LAUNCH(false, 16, 8); else DFT_AO_LAUNCH(false, 8, 8); }
+    if (deriv) { if (G == 32) DFT_AO_LAUNCH(true, 32, 16); else if (NW == 16) DFT_AO_LAUNCH(true, 16, 16); else if (G == 16) DFT_AO_LAUNCH(true, 16, 8); else DFT_AO_LAUNCH(true, 8, 8); }
+    else { if (G == 32) DFT_AO_LAUNCH(false, 32, 16); else if (NW == 16) DFT_AO_LAUNCH(false, 16, 16); else if (G == 16) DFT_AO_LAUNCH(false, 16, 8); else DFT_AO_LAUNCH(false, 8, 8); }
 #undef DFT_AO_LAUNCH
     if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->stream);
     DFT_CUDA_CHECK(ctx, cudaGetLastError());

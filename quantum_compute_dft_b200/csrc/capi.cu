@@ -355,6 +355,8 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "timing")) { c->timing = value != 0.0; return 0; }
     if (!strcmp(key, "l2_prefetch")) { c->l2_prefetch = value != 0.0; return 0; }
     if (!strcmp(key, "ao_shape")) { c->ao_shape = (int)value; return 0; }
+    if (!strcmp(key, "ao_vec_stores")) { c->ao_vec_stores = value != 0.0; return 0; }
+    if (!strcmp(key, "ao_input_order")) { c->ao_input_order = value != 0.0; return 0; }
     if (!strcmp(key, "vxc_skip")) { c->vxc_skip = (int)value; if (c->vxc_skip >= 0) c->vxc_skip_on = c->vxc_skip != 0; return 0; }
     if (!strcmp(key, "density_unit")) { const int v = (int)value; if (v < 0 || v > 2) return 3; c->density_unit = v; return 0; }
     if (!strcmp(key, "stagger_min")) { c->stagger_min = value < 0.0 ? 0 : (int)value; return 0; }
@@ -365,7 +367,7 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
 #endif
     if (!strcmp(key, "vxc_scatter")) { c->vxc_scatter = value != 0.0; return 0; }
     if (!strcmp(key, "vxc_producers")) { c->vxc_producers = value < 1.0 ? 1 : (value > 4.0 ? 4 : (int)value); return 0; }
-    if (!strcmp(key, "vxc_skip_mode")) { const int v = (int)value; if (v != 1 && v != 4) return 3; c->vxc_skip_mode = v; return 0; }
+    if (!strcmp(key, "vxc_skip_mode")) { const int v = (int)value; if (v < 1 || v > 6) return 3; c->vxc_skip_mode = v; return 0; }
     if (!strcmp(key, "raw_convention")) { c->raw_convention = value != 0.0; return 0; }
     if (!strcmp(key, "zero_skip")) { c->zero_skip = value != 0.0; return 0; }
     if (!strcmp(key, "tma_3d")) { c->tma_3d = value != 0.0; return 0; }

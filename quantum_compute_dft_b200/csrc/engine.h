@@ -73,18 +73,20 @@ struct CublasHandleWrapper {
     bool l2_prefetch = false;      // TMA density kernel: short-range L2 prefetch of A tiles and epilogue pieces (measured: no gain)
     int vxc_skip = -1;             // V kernel zero-skipping instance: -1 adaptive (default), 0 never, 1 always
     bool vxc_skip_on = true;       // (adaptive) the zero-skipping V instance is used while the density kernel finds zeros
-    int vxc_skip_mode = 1;         // zero-skipping V instance (128 x 128 tile): 1 per-warp M-side votes (default), 4 staged B with uniform fragment skipping (experimental: measured 12.5 ms against 11.8 ms at C5)
+    int vxc_skip_mode = 2;         // zero-skipping V instance (128 x 128 tile): per-warp M-side votes, 2 = built and voted on for a whole ring stage at once (default, 11.2 ms at C5), 1 = k-step by k-step (round 1, 11.8 ms), 3 = 2 + early Phi fragments, 5 | 6 = 4 x 2 warps with interleaved fragments (12.2-12.4 ms), 4 = staged B with uniform fragment skipping (12.5 ms)
     int vxc_scatter = 1;           // zero-skipping V instances: scatter consecutive ring stages over the grid (golden-ratio stride)
     int density_unit = 0;          // TMA density kernel, unit of work: 0 | 2 = one column tile of a 64-point block (default), 1 = a whole block
     int stagger_min = 8;           // TMA density kernel: consumer group 1 starts half a tile period late when a CTA has more blocks than this
     int dyn_sched = 1;             // TMA density kernel: hand the 64-point blocks out dynamically (one global counter)
     int wait_ns = 0;               // TMA kernels: producer / scanner threads sleep this long between barrier polls
     int debug_nodmma = 0;          // -DDFT_DIAGNOSTICS builds only: TMA kernels skip every DMMA (measures the operand-delivery floor)
-    int vxc_producers = 1;         // TMA V kernel: TMA-issuing threads per CTA (1 | 2)
+    int vxc_producers = 2;         // TMA V kernel: TMA-issuing threads per CTA (1..4)
     bool raw_convention = false;   // GGA only: leave the reference's raw unsymmetrised B^T Phi in d_vxc (dft_solver.cu:616) instead of the symmetric matrix
     bool zero_skip = true;         // TMA kernels: skip k-steps whose operand fragment is all zero (exact: adds nothing)
     bool tma_3d = true;            // TMA V kernel: one 3-D TMA load per plane and stage instead of one per 16-column block
     int ao_shape = 0;              // DFT_EvalAO block shape: 0 = auto, 16 (points, 8 warps) | 32 (points, 16 warps)
+    bool ao_vec_stores = false;    // DFT_EvalAO: 16-byte stores in phase 2 (measured slower than 8-byte ones: not the default)
+    bool ao_input_order = false;   // DFT_EvalAO: keep the exponent-sharing groups in shell input order (round 1) instead of sorting them by reach and position
     int vxc_shape = 0;             // TMA V kernel output tile: 0 = auto, 64 | 128 | 160 (= 160 x 80)
     int vxc_vk = 0;                // TMA V kernel, 128 x 128 tile: grid rows per ring stage (8: 5 stages, 16: 2 stages, 0: auto)
 

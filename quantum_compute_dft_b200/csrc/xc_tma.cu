@@ -171,13 +171,19 @@ struct DensitySmem {
     static constexpr int D_BYTES = NT * 128;
     static constexpr int K_BYTES = A_BYTES + D_BYTES;
     static constexpr int PLANE_BYTES = MB * 128;                          // one plane of a piece
-    static constexpr int PIECE_BYTES = NPL * PLANE_BYTES;
+    // A piece may travel as PSPLIT stages of NPL / PSPLIT planes each.  PSPLIT = 2 for GGA (16 KB stages fit the 24 KB
+    // slot of a k-chunk: a 4-stage ring instead of 3 stages of 32 KB) was measured in round 2 and is SLOWER -- C5
+    // 9.30 against 9.03 ms, C4 1.235 against 1.186 ms (profiles/r2_u4_density_half_pieces.txt): twice the stage
+    // hand-shakes in the epilogue cost more than the deeper ring gains -- so a piece stays one stage.
+    static constexpr int PSPLIT = 1;                                      // stages per piece
+    static constexpr int PPL = NPL / PSPLIT;                              // planes per stage of a piece
+    static constexpr int PIECE_BYTES = PPL * PLANE_BYTES;
     static constexpr int STAGE_BYTES = K_BYTES > PIECE_BYTES ? K_BYTES : PIECE_BYTES;
     static constexpr int FIXED_BYTES = 512 + 1024;                        // barriers, alignment slack
-    static constexpr int STAGES = (232448 - FIXED_BYTES) / (2 * STAGE_BYTES) < 4 ? (232448 - FIXED_BYTES) / (2 * STAGE_BYTES) : 4;
+    static constexpr int STAGES = (232448 - FIXED_BYTES) / (2 * STAGE_BYTES) < 6 ? (232448 - FIXED_BYTES) / (2 * STAGE_BYTES) : 6;
     static_assert(STAGES >= 2, "ring depth");
     static constexpr int NCG = NT / 16;                                   // 16-column groups per tile (= NF2)
-    static constexpr int NPIECES = NCG;
+    static constexpr int NPIECES = NCG * PSPLIT;                          // piece stages per tile
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;               // one group's ring
     static constexpr int BAR_OFF = 2 * RING_BYTES;                        // [2 groups]{full[STAGES], empty[STAGES]}
     static constexpr int BLK_OFF = BAR_OFF + 2 * 2 * STAGES * 8;          // [2 groups][STAGES] block id carried by a stage
@@ -186,6 +192,9 @@ struct DensitySmem {
 
     // piece pc -> column group; consecutive pieces go to different warp columns
     __host__ __device__ static constexpr int piece_cg(int pc) { return (pc & 1) * (NCG / 2) + (pc >> 1); }
+    // piece STAGE ps -> (column group, first plane)
+    __host__ __device__ static constexpr int stage_cg(int ps) { return piece_cg(ps / PSPLIT); }
+    __host__ __device__ static constexpr int stage_pl0(int ps) { return (ps % PSPLIT) * PPL; }
 };
 
 template <int NF2, int NPL>
@@ -269,8 +278,8 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                                 const int span = nk - pc0;
                                 const int lo = ((kc - pc0) * L::NPIECES) / span, hi = ((kc - pc0 + 1) * L::NPIECES) / span;
                                 for (int pc = lo; pc < hi; ++pc)
-                                    for (int p = 0; p < NPL; ++p)
-                                        tma::prefetch_2d(&P.map_e[si][p], nt * NT + 16 * L::piece_cg(pc), blk * MB);
+                                    for (int p = 0; p < L::PPL; ++p)
+                                        tma::prefetch_2d(&P.map_e[si][L::stage_pl0(pc) + p], nt * NT + 16 * L::stage_cg(pc), blk * MB);
                             }
                         }
                         const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
@@ -286,9 +295,9 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                         tma::mbar_wait_relaxed(&empty[s], ph ^ 1u, (uint32_t)P.wait_ns);
                         unsigned char* st = ring + s * L::STAGE_BYTES;
                         tma::mbar_arrive_expect_tx(&full[s], L::PIECE_BYTES);
-                        const int c0 = nt * NT + 16 * L::piece_cg(pc);
-                        for (int p = 0; p < NPL; ++p)
-                            tma::load_2d(st + p * L::PLANE_BYTES, &P.map_e[si][p], c0, blk * MB, &full[s]);
+                        const int c0 = nt * NT + 16 * L::stage_cg(pc);
+                        for (int p = 0; p < L::PPL; ++p)
+                            tma::load_2d(st + p * L::PLANE_BYTES, &P.map_e[si][L::stage_pl0(pc) + p], c0, blk * MB, &full[s]);
                     }
                 }
                 u = un;
@@ -430,37 +439,40 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             if (gw == 0 && lane == 0 && P.phase && n_iv >= 1 && n_iv <= 64) P.phase[65536 + ((size_t)blockIdx.x * 2 + grp) * 128 + 2 * (n_iv - 1)] = t0;
 #endif
             // ---- epilogue: row-dots of C with the plane tiles, straight from the ring
-            for (int pc = 0; pc < L::NPIECES; ++pc, ++it) {
-                const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
-                tma::mbar_wait(&full[s], ph);
-                PHASE_MARK(t_w);
-                const int cg = L::piece_cg(pc);
-                if (cg / (NF2 / 2) == wn) {
-                    // plain shared-memory loads (not asm volatile): the compiler batches them freely
-                    const unsigned char* pbase = ring + s * L::STAGE_BYTES + prow0 * 128;
-                    const int nfp = cg % (NF2 / 2);
+            for (int pcg = 0; pcg < L::NCG; ++pcg) {
+                const int cg = L::piece_cg(pcg);
 #pragma unroll
-                    for (int np = 0; np < NF2 / 2; ++np) {
-                        if (np == nfp) {
+                for (int hs = 0; hs < L::PSPLIT; ++hs, ++it) {   // the stages of this piece: planes hs PPL .. hs PPL + PPL - 1
+                    const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
+                    tma::mbar_wait(&full[s], ph);
+                    PHASE_MARK(t_w);
+                    if (cg / (NF2 / 2) == wn) {
+                        // plain shared-memory loads (not asm volatile): the compiler batches them freely
+                        const unsigned char* pbase = ring + s * L::STAGE_BYTES + prow0 * 128;
+                        const int nfp = cg % (NF2 / 2);
 #pragma unroll
-                            for (int sx = 0; sx < 2; ++sx)
+                        for (int np = 0; np < NF2 / 2; ++np) {
+                            if (np == nfp) {
 #pragma unroll
-                                for (int e = 0; e < 2; ++e)
+                                for (int sx = 0; sx < 2; ++sx)
 #pragma unroll
-                                    for (int mf = 0; mf < 4; ++mf) {
-                                        const double cv = acc[mf][2 * np + sx][e];
-                                        const unsigned char* ad = pbase + mf * 1024 + eoff[e][sx];
+                                    for (int e = 0; e < 2; ++e)
 #pragma unroll
-                                        for (int p = 0; p < NPL; ++p)
-                                            rs[mf][p] = fma(cv, *reinterpret_cast<const double*>(ad + p * L::PLANE_BYTES),
-                                                            rs[mf][p]);
-                                    }
+                                        for (int mf = 0; mf < 4; ++mf) {
+                                            const double cv = acc[mf][2 * np + sx][e];
+                                            const unsigned char* ad = pbase + mf * 1024 + eoff[e][sx];
+#pragma unroll
+                                            for (int p = 0; p < L::PPL; ++p)
+                                                rs[mf][hs * L::PPL + p] = fma(cv, *reinterpret_cast<const double*>(ad + p * L::PLANE_BYTES),
+                                                                              rs[mf][hs * L::PPL + p]);
+                                        }
+                            }
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) tma::mbar_arrive(&empty[s]);
+                    PHASE_MARK(t_m);
                 }
-                __syncwarp();
-                if (lane == 0) tma::mbar_arrive(&empty[s]);
-                PHASE_MARK(t_m);
             }
         }
         // ---- once per block: reduce the partial row sums over the 4 lanes of a fragment row and hand them
@@ -746,8 +758,14 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     // takes groups w and 15 - w instead of 2w and 2w + 1: two halves of one 16-column box (one or two atoms)
     // are zero or non-zero together, while groups from opposite ends of the tile average out, which evens the
     // work of the eight warps that share the ring.
-    constexpr bool MIRROR = SKIP == 1 && WM == 8 && WN == 1 && MF == 2;
-    auto mgroup = [&](int mf) { return MIRROR ? (mf == 0 ? wm : 15 - wm) : ga0 + mf; };
+    constexpr bool MIRROR = (SKIP >= 1 && SKIP <= 3) && WM == 8 && WN == 1 && MF == 2;
+    // 4 x 2 warps on the 128 x 128 tile (round 2): M-group wm takes fragments wm, wm + 4, wm + 8, wm + 12 -- four
+    // samples spread over the whole tile instead of two, so the groups' live counts per stage are closer together
+    // (CPU census at C5: a stage costs max over groups = 0.75 of dense, against 0.86 for the mirrored pairs; the
+    // busiest group's total is 0.65 against 0.76), and the two warps that share an SM sub-partition's tensor pipe
+    // (w, w + 4) hold all the even or all the odd fragments between them.
+    constexpr bool INTERLEAVE = (SKIP >= 1 && SKIP <= 3) && WM == 4 && WN == 2 && MF == 4;
+    auto mgroup = [&](int mf) { return MIRROR ? (mf == 0 ? wm : 15 - wm) : (INTERLEAVE ? wm + 4 * mf : ga0 + mf); };
     uint32_t a_off[KS][MF], b_even[KS], b_odd[KS], c_off[KS];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
@@ -776,6 +794,69 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         t1 = clock64(); t_w += t1 - t0; t0 = t1;
 #endif
         const uint32_t sb = base + s * L::STAGE_BYTES;
+        if constexpr (SKIP == 2 || SKIP == 3) {
+            // Batched variant of the per-fragment votes: the A fragments of ALL the stage's k-steps are built before
+            // the first vote, so the shared loads and FP64 chains of a k-step that turns out to be skipped overlap
+            // with its neighbours' instead of sitting, exposed, between two branches (the loads are `asm volatile`
+            // and never move across a branch by themselves).
+            double a[KS][MF];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const double2 ca = lds_f64x2(sb + c_off[ks]);
+                double2 cb = make_double2(0.0, 0.0);
+                if (NPL == 4) cb = lds_f64x2(sb + c_off[ks] + 16);
+#pragma unroll
+                for (int mf = 0; mf < MF; ++mf) {
+                    const uint32_t ad = sb + a_off[ks][mf];
+                    double v = ca.x * lds_f64(ad);
+                    if (NPL == 4) {
+                        v = fma(ca.y, lds_f64(ad + L::PLANE_BYTES), v);
+                        v = fma(cb.x, lds_f64(ad + 2 * L::PLANE_BYTES), v);
+                        v = fma(cb.y, lds_f64(ad + 3 * L::PLANE_BYTES), v);
+                    }
+                    a[ks][mf] = v;
+                }
+            }
+            // SKIP 3: the Phi fragments of the stage's FIRST k-step are requested before the votes as well (they are
+            // needed whenever any of its fragments is live, three stages in four at C5), so its DMMAs can issue the
+            // moment the votes are in
+            double bf0[NFN];
+            if constexpr (SKIP == 3) {
+#pragma unroll
+                for (int nf = 0; nf < NFN; ++nf)
+                    bf0[nf] = lds_f64(sb + ((nf & 1) ? b_odd[0] + (uint32_t)(((nf - 1) / 2) * L::BOXB)
+                                                     : b_even[0] + (uint32_t)((nf / 2) * L::BOXB)));
+            }
+            unsigned live = 0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int mf = 0; mf < MF; ++mf)
+                    live |= (__any_sync(0xffffffffu, (a[ks][mf] != 0.0) | no_skip) ? 1u : 0u) << (ks * MF + mf);
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const unsigned lk = (live >> (ks * MF)) & ((1u << MF) - 1u);
+                if (lk) {
+                    double bf[NFN];
+                    if (SKIP == 3 && ks == 0) {
+#pragma unroll
+                        for (int nf = 0; nf < NFN; ++nf) bf[nf] = bf0[nf];
+                    } else {
+#pragma unroll
+                    for (int nf = 0; nf < NFN; ++nf)
+                        bf[nf] = lds_f64(sb + ((nf & 1) ? b_odd[ks] + (uint32_t)(((nf - 1) / 2) * L::BOXB)
+                                                        : b_even[ks] + (uint32_t)((nf / 2) * L::BOXB)));
+                    }
+#pragma unroll
+                    for (int mf = 0; mf < MF; ++mf) {
+                        if (lk & (1u << mf)) {
+#pragma unroll
+                            for (int nf = 0; nf < NFN; ++nf) dmma::mma8x8x4(acc[mf][nf], a[ks][mf], bf[nf]);
+                        }
+                    }
+                }
+            }
+        } else {
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
             // A fragments: B[k][m] = a Phi + bx dxPhi + by dyPhi + bz dzPhi, built in registers
@@ -831,6 +912,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
                 }
             }
         }
+        }   // (SKIP 0 | 1)
         __syncwarp();
         if (lane == 0) tma::mbar_arrive(&empty[s]);
 #ifdef DFT_PHASE_TIMING
@@ -1577,6 +1659,15 @@ static void build_plan(CublasHandleWrapper* ctx, const Problem& p, int nsm, Plan
         DFT_PLAN_V(5, 5, 4, 2, NPL, 16, 2);
     } else if (vskip && ctx->vxc_skip_mode == 4) {
         plan_vxc<2, 16, 8, 1, NPL, 8, 5, 4>(ctx, p, g, nsm, coef, pl);
+    } else if (vskip && ctx->vxc_skip_mode == 2) {   // 8 x 1 mirrored pairs, votes batched per stage
+        if (ctx->vxc_vk == 16) plan_vxc<2, 16, 8, 1, NPL, 16, 2, 2>(ctx, p, g, nsm, coef, pl);
+        else plan_vxc<2, 16, 8, 1, NPL, 8, 5, 2>(ctx, p, g, nsm, coef, pl);
+    } else if (vskip && ctx->vxc_skip_mode == 3) {   // the same + the first k-step's Phi fragments requested before the votes
+        plan_vxc<2, 16, 8, 1, NPL, 8, 5, 3>(ctx, p, g, nsm, coef, pl);
+    } else if (vskip && ctx->vxc_skip_mode == 5) {   // 4 x 2 warps, interleaved M fragments, vote per k-step
+        plan_vxc<4, 8, 4, 2, NPL, 8, 5, 1>(ctx, p, g, nsm, coef, pl);
+    } else if (vskip && ctx->vxc_skip_mode == 6) {   // 4 x 2 warps, interleaved M fragments, votes batched per stage
+        plan_vxc<4, 8, 4, 2, NPL, 8, 5, 2>(ctx, p, g, nsm, coef, pl);
     } else {
         // rows per ring stage: 16 (2 stages, fewer barriers) on dense operands; 8 (5 stages) when zero fragments
         // are skipped -- with the stages scattered over the grid, the deeper ring lets the warps drift apart

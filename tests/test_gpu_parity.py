@@ -282,6 +282,8 @@ def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
     for opt in ({"vxc_shape": 64}, {"vxc_shape": 128, "vxc_vk": 8}, {"vxc_shape": 128, "vxc_vk": 16}, {"vxc_shape": 160},
                 {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 4}, {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 1},
                 {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 4, "tma_3d": 0},
+                {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 2}, {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 5},
+                {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 6}, {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 5, "tma_3d": 0},
                 {"vxc_shape": 128, "vxc_skip": 0, "vxc_producers": 3}, {"dyn_sched": 0}, {"density_unit": 1}, {"density_unit": 2},
                 {"density_unit": 2, "dyn_sched": 0}, {"tma_3d": 0}, {"l2_prefetch": 1}):
         e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, dict(opt, path=2))
@@ -362,7 +364,9 @@ def test_vxc_zero_skipping_instances_agree(oracle, engine_lib, functional, ngrid
     assert s0["path"] == 2 and abs(e0 - e_o) <= E_TOL
     np.testing.assert_allclose(0.5 * (v0 + v0.T), oracle.sym(v_o), rtol=0, atol=V_TOL)
     for opt in ({"vxc_skip_mode": 4}, {"vxc_skip_mode": 4, "vxc_scatter": 0}, {"vxc_skip_mode": 1, "vxc_vk": 8},
-                {"vxc_skip_mode": 1, "vxc_vk": 16}):
+                {"vxc_skip_mode": 1, "vxc_vk": 16}, {"vxc_skip_mode": 2}, {"vxc_skip_mode": 5}, {"vxc_skip_mode": 6},
+                {"vxc_skip_mode": 3}, {"vxc_skip_mode": 2, "vxc_vk": 16},
+                {"vxc_skip_mode": 5, "vxc_scatter": 0}):
         opt = dict(opt, vxc_shape=128, vxc_skip=1)
         e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
         assert s1["path"] == 2 and e1 == e0, opt
@@ -432,23 +436,29 @@ def test_ao_evaluation_on_gpu(oracle, engine_lib):
     for name, scale in (("H2O", 0.2), ("H2S", 0.1), ("Benzene", 0.05), ("C33H56N7O17P3S", 0.004)):
         mol = M.load_molecule(name)
         basis = M.sto3g_basis(mol)
-        coords, _, _ = M.make_grid(mol, scale=scale)
-        ao_o, g_o = oracle.eval_ao(coords, basis, deriv=1)
-        d_c = DeviceArray.from_host(coords)
-        d_ao = DeviceArray(ao_o.shape); d_g = DeviceArray(g_o.shape)
-        s.eval_ao(d_c, basis, d_ao, d_g)
-        np.testing.assert_allclose(d_ao.get(), ao_o, rtol=1e-12, atol=1e-15)
-        np.testing.assert_allclose(d_g.get(), g_o, rtol=1e-12, atol=1e-14)
-        d_ao2 = DeviceArray(ao_o.shape)
-        s.eval_ao(d_c, basis, d_ao2, None)
-        np.testing.assert_allclose(d_ao2.get(), d_ao.get(), rtol=1e-14, atol=1e-300)  # deriv=0 kernel contracts FMAs differently
-        for shape in (8, 16, 32):  # every block shape of the kernel writes identical values
-            s.set_option("ao_shape", shape)
-            d_ao3 = DeviceArray(ao_o.shape); d_g3 = DeviceArray(g_o.shape)
-            s.eval_ao(d_c, basis, d_ao3, d_g3)
-            np.testing.assert_array_equal(d_ao3.get(), d_ao.get())
-            np.testing.assert_array_equal(d_g3.get(), d_g.get())
-        s.set_option("ao_shape", 0)
+        coords_all, _, _ = M.make_grid(mol, scale=scale)
+        # both parities of ngrid: with odd nao the 16-byte store pairs of odd rows start one AO early, and odd x odd
+        # puts the y-gradient plane at 8 mod 16 (that plane alone falls back to 8-byte stores)
+        for coords in (coords_all, coords_all[:-1]):
+            ao_o, g_o = oracle.eval_ao(coords, basis, deriv=1)
+            d_c = DeviceArray.from_host(coords)
+            d_ao = DeviceArray(ao_o.shape); d_g = DeviceArray(g_o.shape)
+            s.eval_ao(d_c, basis, d_ao, d_g)
+            np.testing.assert_allclose(d_ao.get(), ao_o, rtol=1e-12, atol=1e-15)
+            np.testing.assert_allclose(d_g.get(), g_o, rtol=1e-12, atol=1e-14)
+            d_ao2 = DeviceArray(ao_o.shape)
+            s.eval_ao(d_c, basis, d_ao2, None)
+            np.testing.assert_allclose(d_ao2.get(), d_ao.get(), rtol=1e-14, atol=1e-300)  # deriv=0 kernel contracts FMAs differently
+            # every block shape of the kernel (8 | 16 | 32 points, 17 = 16 points x 16 warps), both store widths and both
+            # group orders write identical values
+            for shape, vec, order in ((8, 0, 0), (16, 0, 0), (17, 0, 0), (32, 0, 0), (8, 1, 0), (16, 1, 0), (17, 1, 0), (32, 1, 0),
+                                      (0, 0, 1), (16, 1, 1)):
+                s.set_option("ao_shape", shape); s.set_option("ao_vec_stores", vec); s.set_option("ao_input_order", order)
+                d_ao3 = DeviceArray(ao_o.shape); d_g3 = DeviceArray(g_o.shape)
+                s.eval_ao(d_c, basis, d_ao3, d_g3)
+                np.testing.assert_array_equal(d_ao3.get(), d_ao.get())
+                np.testing.assert_array_equal(d_g3.get(), d_g.get())
+            s.set_option("ao_shape", 0); s.set_option("ao_vec_stores", 0); s.set_option("ao_input_order", 0)
 
 
 @pytest.mark.parametrize("workload_name,scale", [("C4", 0.03), ("C5", 0.008)])

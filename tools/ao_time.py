@@ -11,16 +11,19 @@ for wl in sys.argv[1:]:
     dp = workload.device_problem(hp, solver)
     P = 1 if hp.functional == "LDA" else 4
     nbytes = 8.0 * dp.ngrid * dp.nao * P
-    for shape in (0, 8, 16, 32):
-        try:
-            solver.set_option("ao_shape", shape)
-            best = 1e9
-            for _ in range(4):
-                solver.eval_ao(dp.d_coords, hp.basis, dp.d_ao, dp.d_ao_grad)
-                best = min(best, solver.stat("ao_ms"))
-            print(f"{wl} {hp.name} ao_shape={shape}: DFT_EvalAO {best:.3f} ms, {nbytes / 1e9:.2f} GB written, "
-                  f"{nbytes / best / 1e9:.2f} TB/s", flush=True)
-        except Exception as e:   # a shape whose staging does not fit in shared memory
-            print(f"{wl} ao_shape={shape}: {e}", flush=True)
+    for order in (0, 1):
+        solver.set_option("ao_input_order", order)
+        for shape in (0, 17, 100, 117):
+            try:
+                solver.set_option("ao_shape", shape % 100); solver.set_option("ao_vec_stores", 1 if shape >= 100 else 0)
+                best = 1e9
+                for _ in range(4):
+                    solver.eval_ao(dp.d_coords, hp.basis, dp.d_ao, dp.d_ao_grad)
+                    best = min(best, solver.stat("ao_ms"))
+                print(f"{wl} {hp.name} ao_input_order={order} ao_shape={shape}: DFT_EvalAO {best:.3f} ms, {nbytes / 1e9:.2f} GB written, "
+                      f"{nbytes / best / 1e9:.2f} TB/s", flush=True)
+            except Exception as e:   # a shape whose staging does not fit in shared memory
+                print(f"{wl} ao_shape={shape}: {e}", flush=True)
+    solver.set_option("ao_input_order", 0); solver.set_option("ao_vec_stores", 0)
     solver.set_option("ao_shape", 0)
     dp.free()
