@@ -367,7 +367,7 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
 #endif
     if (!strcmp(key, "vxc_scatter")) { c->vxc_scatter = value != 0.0; return 0; }
     if (!strcmp(key, "vxc_producers")) { c->vxc_producers = value < 1.0 ? 1 : (value > 4.0 ? 4 : (int)value); return 0; }
-    if (!strcmp(key, "vxc_skip_mode")) { const int v = (int)value; if (v < 1 || v > 6) return 3; c->vxc_skip_mode = v; return 0; }
+    if (!strcmp(key, "vxc_skip_mode")) { const int v = (int)value; if (v < 1 || v > 7) return 3; c->vxc_skip_mode = v; return 0; }
     if (!strcmp(key, "raw_convention")) { c->raw_convention = value != 0.0; return 0; }
     if (!strcmp(key, "zero_skip")) { c->zero_skip = value != 0.0; return 0; }
     if (!strcmp(key, "tma_3d")) { c->tma_3d = value != 0.0; return 0; }

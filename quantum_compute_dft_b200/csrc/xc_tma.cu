@@ -343,6 +343,18 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             eoff[e][sx] = (uint32_t)(rho * 128 + ((((4 * sx + (nc >> 1)) ^ rho) & 7) << 4) + ((nc & 1) << 3));
     }
     const int prow0 = wm * 32;  // this warp's rows inside a piece
+    // Per-lane fragment offsets, kept in registers behind an opaque move.  (Left to itself the compiler re-derives
+    // them from threadIdx in front of the loads of EVERY k-step -- ten dependent integer instructions between the vote
+    // and the B-fragment loads, on the critical path of each executed k-step; SASS of round 1's instance.)  The four
+    // k-steps of a chunk differ only in the 16-byte chunk index, (2 ks + ..) ^ row: koff[ks] = koff[0] ^ (ks << 5),
+    // and every other term of an operand address is a multiple of 128, so one XOR per k-step does it.
+    uint32_t a_lane = a_row + koff_a[0], b_lane = b_row + koff_b[0];
+    asm volatile("mov.u32 %0, %1;" : "=r"(a_lane) : "r"(a_lane));
+    asm volatile("mov.u32 %0, %1;" : "=r"(b_lane) : "r"(b_lane));
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int sx = 0; sx < 2; ++sx) asm volatile("mov.u32 %0, %1;" : "=r"(eoff[e][sx]) : "r"(eoff[e][sx]));
     const bool no_skip = P.zero_skip == 0;
 #ifdef DFT_DIAGNOSTICS
     const bool dbg_off = P.debug_nodmma != 0;
@@ -400,8 +412,8 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             for (int kc = 0; kc < nk; ++kc, ++it) {
                 const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
                 tma::mbar_wait(&full[s], ph);
-                const uint32_t a_base = ring_u32 + s * L::STAGE_BYTES + a_row;
-                const uint32_t b_base = ring_u32 + s * L::STAGE_BYTES + L::A_BYTES + b_row;
+                const uint32_t a_base = ring_u32 + s * L::STAGE_BYTES + a_lane;              // (k-step 0; ks: ^ (ks << 5))
+                const uint32_t b_base = ring_u32 + s * L::STAGE_BYTES + L::A_BYTES + b_lane;
                 // AO screening at the tensor-core tile level: far from an atom its AOs are EXACT zeros (the
                 // evaluator drops primitives beyond the cutoff), so a k-step whose 32 x 4 Phi fragment is all
                 // zero adds nothing to C and its 32 DMMAs (and B loads) are branched around -- a warp-uniform
@@ -411,19 +423,19 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                 // k-step's A fragments are in flight meanwhile.
                 double a[2][4];
 #pragma unroll
-                for (int mf = 0; mf < 4; ++mf) a[0][mf] = lds_f64(a_base + mf * 1024 + koff_a[0]);
+                for (int mf = 0; mf < 4; ++mf) a[0][mf] = lds_f64(a_base + mf * 1024);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const int cur = ks & 1;
                     if (ks < 3) {
 #pragma unroll
-                        for (int mf = 0; mf < 4; ++mf) a[cur ^ 1][mf] = lds_f64(a_base + mf * 1024 + koff_a[ks + 1]);
+                        for (int mf = 0; mf < 4; ++mf) a[cur ^ 1][mf] = lds_f64((a_base ^ (uint32_t)((ks + 1) << 5)) + mf * 1024);
                     }
                     const bool nz = ((a[cur][0] != 0.0) | (a[cur][1] != 0.0)) | ((a[cur][2] != 0.0) | (a[cur][3] != 0.0));
                     if (__any_sync(0xffffffffu, nz | no_skip) && !dbg_off) {
                         double bf[NF2];
 #pragma unroll
-                        for (int nf = 0; nf < NF2; ++nf) bf[nf] = lds_f64(b_base + nf * 1024 + koff_b[ks]);
+                        for (int nf = 0; nf < NF2; ++nf) bf[nf] = lds_f64((b_base ^ (uint32_t)(ks << 5)) + nf * 1024);
 #pragma unroll
                         for (int mf = 0; mf < 4; ++mf)
 #pragma unroll
@@ -758,7 +770,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     // takes groups w and 15 - w instead of 2w and 2w + 1: two halves of one 16-column box (one or two atoms)
     // are zero or non-zero together, while groups from opposite ends of the tile average out, which evens the
     // work of the eight warps that share the ring.
-    constexpr bool MIRROR = (SKIP >= 1 && SKIP <= 3) && WM == 8 && WN == 1 && MF == 2;
+    constexpr bool MIRROR = ((SKIP >= 1 && SKIP <= 3) || SKIP == 7) && WM == 8 && WN == 1 && MF == 2;
     // 4 x 2 warps on the 128 x 128 tile (round 2): M-group wm takes fragments wm, wm + 4, wm + 8, wm + 12 -- four
     // samples spread over the whole tile instead of two, so the groups' live counts per stage are closer together
     // (CPU census at C5: a stage costs max over groups = 0.75 of dense, against 0.86 for the mirrored pairs; the
@@ -781,10 +793,133 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         b_odd[ks] = (uint32_t)(L::N_OFF + ((gb0 >> 1) + (int)pb) * L::BOXB) + (c0 ^ ((pb ^ 1u) << 6));
         c_off[ks] = (uint32_t)(L::COEF_OFF + row * 32);
     }
+    // The offsets are laundered through an opaque move.  Left to itself the compiler does not keep them: it re-derives
+    // all of them from threadIdx at the top of EVERY ring stage (an S2R and ~30 integer instructions between the
+    // barrier wait and the first fragment load -- on the critical path of the warp that skips least; SASS of round 1's
+    // instances).  Ten registers are cheaper.
+    if constexpr (SKIP != 0 || true) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int mf = 0; mf < MF; ++mf) asm volatile("mov.u32 %0, %1;" : "=r"(a_off[ks][mf]) : "r"(a_off[ks][mf]));
+            asm volatile("mov.u32 %0, %1;" : "=r"(b_even[ks]) : "r"(b_even[ks]));
+            asm volatile("mov.u32 %0, %1;" : "=r"(b_odd[ks]) : "r"(b_odd[ks]));
+            asm volatile("mov.u32 %0, %1;" : "=r"(c_off[ks]) : "r"(c_off[ks]));
+        }
+    }
 
 #ifdef DFT_PHASE_TIMING
     long long t_w = 0, t_c = 0, t_start = clock64(), t0 = t_start, t1;
 #endif
+    if constexpr (SKIP == 7) {
+        // Software-pipelined across ring stages (round 2).  The warp that skips least is the CTA's critical path: it never
+        // waits for data (its next stage is always full already), its partner on the SM sub-partition is usually
+        // ahead and idle, so every latency between its DMMA bursts -- plane loads, the FP64 chain, the votes, the Phi
+        // loads -- is exposed.  Here the raw operands of stage c + 1 are REQUESTED before the DMMAs of stage c issue and
+        // COMBINED after them, k-step by k-step (12 doubles in flight at a time: the register file has no room for a
+        // whole stage's 24), whenever a non-blocking test finds stage c + 1 already delivered; otherwise the warp
+        // falls back to the blocking wait + build of the batched variant (SKIP 2).
+        static_assert(KS == 2, "pipelined V instance: two k-steps per stage");
+        auto build_stage = [&](uint32_t sbx, double (&ax)[KS][MF]) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const double2 ca = lds_f64x2(sbx + c_off[ks]);
+                double2 cb = make_double2(0.0, 0.0);
+                if (NPL == 4) cb = lds_f64x2(sbx + c_off[ks] + 16);
+#pragma unroll
+                for (int mf = 0; mf < MF; ++mf) {
+                    const uint32_t ad = sbx + a_off[ks][mf];
+                    double v = ca.x * lds_f64(ad);
+                    if (NPL == 4) {
+                        v = fma(ca.y, lds_f64(ad + L::PLANE_BYTES), v);
+                        v = fma(cb.x, lds_f64(ad + 2 * L::PLANE_BYTES), v);
+                        v = fma(cb.y, lds_f64(ad + 3 * L::PLANE_BYTES), v);
+                    }
+                    ax[ks][mf] = v;
+                }
+            }
+        };
+        auto vote_stage = [&](const double (&ax)[KS][MF]) {
+            unsigned lv = 0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int mf = 0; mf < MF; ++mf)
+                    lv |= (__any_sync(0xffffffffu, (ax[ks][mf] != 0.0) | no_skip) ? 1u : 0u) << (ks * MF + mf);
+            return lv;
+        };
+        double a[KS][MF];
+        unsigned live = 0;
+        if (nchunks > 0) {
+            tma::mbar_wait(&full[0], 0);
+            build_stage(base, a);
+            live = vote_stage(a);
+        }
+        for (int c = 0; c < nchunks; ++c) {
+            const uint32_t s = c % STAGES;
+            const uint32_t sb = base + s * L::STAGE_BYTES;
+            const bool more = c + 1 < nchunks;
+            const uint32_t s1 = (c + 1) % STAGES, ph1 = ((c + 1) / STAGES) & 1u;
+            const uint32_t sb1 = base + s1 * L::STAGE_BYTES;
+            // (all lanes must have seen the phase complete: each lane's own test is its acquire)
+            const bool pre = more && __all_sync(0xffffffffu, tma::mbar_test_wait(&full[s1], ph1));
+            double an[KS][MF];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                // raw operands of k-step ks of the NEXT stage: requested now, combined after this k-step's DMMAs
+                double2 rca = make_double2(0.0, 0.0), rcb = make_double2(0.0, 0.0);
+                double raw[MF][NPL];
+                if (pre) {
+                    rca = lds_f64x2(sb1 + c_off[ks]);
+                    if (NPL == 4) rcb = lds_f64x2(sb1 + c_off[ks] + 16);
+#pragma unroll
+                    for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+                        for (int pl = 0; pl < NPL; ++pl) raw[mf][pl] = lds_f64(sb1 + a_off[ks][mf] + pl * L::PLANE_BYTES);
+                }
+                const unsigned lk = (live >> (ks * MF)) & ((1u << MF) - 1u);
+                if (lk) {
+                    double bf[NFN];
+#pragma unroll
+                    for (int nf = 0; nf < NFN; ++nf)
+                        bf[nf] = lds_f64(sb + ((nf & 1) ? b_odd[ks] + (uint32_t)(((nf - 1) / 2) * L::BOXB)
+                                                        : b_even[ks] + (uint32_t)((nf / 2) * L::BOXB)));
+#pragma unroll
+                    for (int mf = 0; mf < MF; ++mf) {
+                        if (lk & (1u << mf)) {
+#pragma unroll
+                            for (int nf = 0; nf < NFN; ++nf) dmma::mma8x8x4(acc[mf][nf], a[ks][mf], bf[nf]);
+                        }
+                    }
+                }
+                if (pre) {
+#pragma unroll
+                    for (int mf = 0; mf < MF; ++mf) {
+                        double v = rca.x * raw[mf][0];
+                        if (NPL == 4) {
+                            v = fma(rca.y, raw[mf][1], v);
+                            v = fma(rcb.x, raw[mf][2], v);
+                            v = fma(rcb.y, raw[mf][3], v);
+                        }
+                        an[ks][mf] = v;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(&empty[s]);
+            if (more) {
+                if (!pre) {
+                    tma::mbar_wait(&full[s1], ph1);
+                    build_stage(sb1, an);
+                }
+                live = vote_stage(an);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                    for (int mf = 0; mf < MF; ++mf) a[ks][mf] = an[ks][mf];
+            }
+        }
+    } else {
     // (ptxas software-pipelines the k-steps of a stage by itself: the fragment loads of k-step ks+1 are
     // interleaved with the DMMAs of k-step ks.  Pipelining by hand across stages costs registers and spills.)
     for (int c = 0; c < nchunks; ++c) {
@@ -919,6 +1054,7 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
         t1 = clock64(); t_c += t1 - t0; t0 = t1;
 #endif
     }
+    }   // (SKIP != 7)
     // ---- partial tile out
     double* out = P.vpart + (size_t)blockIdx.y * P.mpv * P.ldv;
 #pragma unroll
@@ -1662,6 +1798,8 @@ static void build_plan(CublasHandleWrapper* ctx, const Problem& p, int nsm, Plan
     } else if (vskip && ctx->vxc_skip_mode == 2) {   // 8 x 1 mirrored pairs, votes batched per stage
         if (ctx->vxc_vk == 16) plan_vxc<2, 16, 8, 1, NPL, 16, 2, 2>(ctx, p, g, nsm, coef, pl);
         else plan_vxc<2, 16, 8, 1, NPL, 8, 5, 2>(ctx, p, g, nsm, coef, pl);
+    } else if (vskip && ctx->vxc_skip_mode == 7) {   // mode 2 software-pipelined across ring stages
+        plan_vxc<2, 16, 8, 1, NPL, 8, 5, 7>(ctx, p, g, nsm, coef, pl);
     } else if (vskip && ctx->vxc_skip_mode == 3) {   // the same + the first k-step's Phi fragments requested before the votes
         plan_vxc<2, 16, 8, 1, NPL, 8, 5, 3>(ctx, p, g, nsm, coef, pl);
     } else if (vskip && ctx->vxc_skip_mode == 5) {   // 4 x 2 warps, interleaved M fragments, vote per k-step

@@ -284,6 +284,7 @@ def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
                 {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 4, "tma_3d": 0},
                 {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 2}, {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 5},
                 {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 6}, {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 5, "tma_3d": 0},
+                {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 7}, {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 1},
                 {"vxc_shape": 128, "vxc_skip": 0, "vxc_producers": 3}, {"dyn_sched": 0}, {"density_unit": 1}, {"density_unit": 2},
                 {"density_unit": 2, "dyn_sched": 0}, {"tma_3d": 0}, {"l2_prefetch": 1}):
         e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, dict(opt, path=2))
@@ -365,7 +366,7 @@ def test_vxc_zero_skipping_instances_agree(oracle, engine_lib, functional, ngrid
     np.testing.assert_allclose(0.5 * (v0 + v0.T), oracle.sym(v_o), rtol=0, atol=V_TOL)
     for opt in ({"vxc_skip_mode": 4}, {"vxc_skip_mode": 4, "vxc_scatter": 0}, {"vxc_skip_mode": 1, "vxc_vk": 8},
                 {"vxc_skip_mode": 1, "vxc_vk": 16}, {"vxc_skip_mode": 2}, {"vxc_skip_mode": 5}, {"vxc_skip_mode": 6},
-                {"vxc_skip_mode": 3}, {"vxc_skip_mode": 2, "vxc_vk": 16},
+                {"vxc_skip_mode": 3}, {"vxc_skip_mode": 2, "vxc_vk": 16}, {"vxc_skip_mode": 7}, {"vxc_skip_mode": 7, "vxc_scatter": 0},
                 {"vxc_skip_mode": 5, "vxc_scatter": 0}):
         opt = dict(opt, vxc_shape=128, vxc_skip=1)
         e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
