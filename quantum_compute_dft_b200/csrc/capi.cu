@@ -41,7 +41,7 @@ CublasHandleWrapper::CublasHandleWrapper() {
     // driver uses (dft.py:178,201,207), so callers need no extra synchronisation.
     DFT_CUDA_CHECK(this, cudaStreamCreateWithFlags(&stream, cudaStreamDefault));
     for (auto& e : ev) DFT_CUDA_CHECK(this, cudaEventCreate(&e));
-    DFT_CUDA_CHECK(this, cudaMallocHost(reinterpret_cast<void**>(&h_scalar), 128));
+    DFT_CUDA_CHECK(this, cudaMallocHost(reinterpret_cast<void**>(&h_scalar), HOST_BLOCK_BYTES));
     if (h_scalar) { h_scalar[8] = 0.0; h_scalar[9] = 1.0; h_scalar[10] = 0.0; h_scalar[11] = 0.0; }  // [8],[9]: constant sources of the "this rank failed" element; [10],[11]: zero-copy {E_xc, seq}
 }
 
@@ -196,9 +196,14 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
     DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar, multi ? packed + n2 : p.d_exc, (multi ? 2 : 1) * sizeof(double),
                                         cudaMemcpyDeviceToHost, ctx->stream));
     const bool have_counters = !bad && ngrid > 0 && ctx->stats.path == PATH_TMA && ctx->counters.ptr;
-    if (have_counters)
+    if (have_counters) {
         DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar + 2, ctx->counters.ptr, 5 * sizeof(unsigned long long),
                                             cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->vxc_rebalance)   // the V kernel's live counts per fragment: next call's deal of the fragments to the warps
+            DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ctx->h_scalar) + HOST_FSTAT_OFF,
+                                                static_cast<unsigned char*>(ctx->counters.ptr) + FSTAT_OFF, FSTAT_BYTES,
+                                                cudaMemcpyDeviceToHost, ctx->stream));
+    }
     DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (multi && ctx->h_scalar[1] != 0.0) {
         if (!ctx->failed) fprintf(stderr, "[dft_b200] rank %d: %d rank(s) failed in this XC build\n", ctx->rank, (int)ctx->h_scalar[1]);
@@ -213,6 +218,7 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
         // adaptive: the zero-skipping V instance pays ~6 % on dense operands; use it only where the density
         // kernel just skipped a real share of its k-steps (the decision takes effect with the next call)
         if (ctx->vxc_skip < 0) ctx->vxc_skip_on = ctx->stats.skip_fraction >= 0.10;
+        if (ctx->vxc_rebalance) xc::tma_rebalance(ctx);
     }
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
     // (the four event intervals are read when DFT_GetStat asks for one: four driver calls per XC build are real money
@@ -366,6 +372,8 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "debug_nodmma")) { c->debug_nodmma = value != 0.0; return 0; }   // results are WRONG: delivery floor
 #endif
     if (!strcmp(key, "vxc_scatter")) { c->vxc_scatter = value != 0.0; return 0; }
+    if (!strcmp(key, "vxc_prefetch")) { c->vxc_prefetch = value < 0.0 ? 0 : (value > 64.0 ? 64 : (int)value); return 0; }
+    if (!strcmp(key, "vxc_rebalance")) { c->vxc_rebalance = value != 0.0; c->fmap_valid = false; return 0; }
     if (!strcmp(key, "vxc_producers")) { c->vxc_producers = value < 1.0 ? 1 : (value > 4.0 ? 4 : (int)value); return 0; }
     if (!strcmp(key, "vxc_skip_mode")) { const int v = (int)value; if (v < 1 || v > 7) return 3; c->vxc_skip_mode = v; return 0; }
     if (!strcmp(key, "raw_convention")) { c->raw_convention = value != 0.0; return 0; }

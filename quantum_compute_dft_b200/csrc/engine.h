@@ -47,6 +47,17 @@ struct DeviceBuffer {
 
 enum XcPath { PATH_AUTO = 0, PATH_GENERIC = 1, PATH_TMA = 2, PATH_SMALL = 3 };
 
+// `counters` workspace: [0,1] density k-steps executed / total, [2,3] V units executed / total, [4] dynamic work counter,
+// [5] small path's finished-CTA counter (6 x 8 bytes, zeroed before every TMA build) | fstat[256] live k-step units per
+// (M tile row, 8-column fragment) of the V kernel (u32, zeroed with the counters) | fmap[256] bytes: which fragments
+// each warp of the V kernel owns (persists across calls)
+constexpr size_t COUNTERS_HEAD_BYTES = 6 * sizeof(unsigned long long);
+constexpr size_t FSTAT_OFF = COUNTERS_HEAD_BYTES, FSTAT_BYTES = 256 * sizeof(unsigned int);
+constexpr size_t FMAP_OFF = FSTAT_OFF + FSTAT_BYTES, FMAP_BYTES = 256;
+constexpr size_t COUNTERS_BYTES = FMAP_OFF + FMAP_BYTES;
+// pinned host block: doubles [0..15] scalars (see capi.cu) | fstat copy (1 KB) | fmap staging (256 B)
+constexpr size_t HOST_FSTAT_OFF = 128, HOST_FMAP_OFF = HOST_FSTAT_OFF + FSTAT_BYTES, HOST_BLOCK_BYTES = HOST_FMAP_OFF + FMAP_BYTES;
+
 struct XcStats {
     float density_ms = 0.f, vxc_ms = 0.f, reduce_ms = 0.f, total_ms = 0.f;
     float ao_ms = 0.f;    // last DFT_EvalAO kernel
@@ -56,6 +67,7 @@ struct XcStats {
     double vxc_skip_fraction = 0.0;  // TMA V kernel, box-bit instances: fraction of (box, k-step) units skipped
     int plans_built = 0;  // TMA path: launch plans (tensor maps, geometry) encoded so far; a steady SCF loop builds one
     int density_units = 0, density_groups = 0;  // TMA density kernel: units of work and consumer groups (2 per CTA) of the last launch
+    int v_tiles_m = 0;    // TMA V kernel: M tile rows of the last launch (rows of the fragment map)
     double dyn_units = 0.0;  // TMA density kernel: draws from the dynamic work counter in the last call (units + consumer groups; 0 = static deal)
 };
 
@@ -80,6 +92,9 @@ struct CublasHandleWrapper {
     int dyn_sched = 1;             // TMA density kernel: hand the 64-point blocks out dynamically (one global counter)
     int wait_ns = 0;               // TMA kernels: producer / scanner threads sleep this long between barrier polls
     int debug_nodmma = 0;          // -DDFT_DIAGNOSTICS builds only: TMA kernels skip every DMMA (measures the operand-delivery floor)
+    bool vxc_rebalance = true;     // TMA V kernel, per-warp-vote instances: re-deal the 8-column M fragments to the warps from the live counts of the previous call (heaviest with lightest, heavy pairs share an SM sub-partition with light ones)
+    bool fmap_valid = false, fmap_dirty = false;   // (state of the fragment map: initialised / host copy newer than the device copy)
+    int vxc_prefetch = 0;          // TMA V kernel: L2 prefetch distance of the producer in ring stages (0: none)
     int vxc_producers = 2;         // TMA V kernel: TMA-issuing threads per CTA (1..4)
     bool raw_convention = false;   // GGA only: leave the reference's raw unsymmetrised B^T Phi in d_vxc (dft_solver.cu:616) instead of the symmetric matrix
     bool zero_skip = true;         // TMA kernels: skip k-steps whose operand fragment is all zero (exact: adds nothing)
@@ -140,6 +155,8 @@ void run_generic(CublasHandleWrapper* ctx, const Problem& p);
 bool tma_compatible(const Problem& p);
 void run_tma(CublasHandleWrapper* ctx, const Problem& p);
 void free_tma_plan(CublasHandleWrapper* ctx);
+// after a blocking TMA build: new fragment map for the V kernel from the live counts the build left in the pinned block
+void tma_rebalance(CublasHandleWrapper* ctx);
 // small-basis single-pass path (nao <= 48): xc_small.cu
 bool small_compatible(const Problem& p);
 void run_small(CublasHandleWrapper* ctx, const Problem& p);

@@ -387,9 +387,9 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     unsigned int* done = nullptr;
     if (p.host_exc_slot) {
         const bool fresh = ctx->counters.ptr == nullptr;
-        done = reinterpret_cast<unsigned int*>(ctx->counters.ensure(6 * sizeof(unsigned long long), &ctx->failed));
+        done = reinterpret_cast<unsigned int*>(ctx->counters.ensure(COUNTERS_BYTES, &ctx->failed));
         if (ctx->failed) return;
-        if (fresh) cudaMemsetAsync(done, 0, 6 * sizeof(unsigned long long), st);
+        if (fresh) cudaMemsetAsync(done, 0, COUNTERS_HEAD_BYTES, st);
         done += 10;   // (the last 8 bytes of the buffer: the TMA path's statistics and work counter use the first 40)
     }
     xc_small_finalize<<<(nao * nao + 7) / 8, 256, 0, st>>>(nao, NP, grid, raw, vpart, epart, p.vxc, p.d_exc, done,

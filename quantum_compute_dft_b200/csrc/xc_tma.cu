@@ -46,6 +46,7 @@
 // generic path (xc_generic.cu).
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 
@@ -105,6 +106,7 @@ struct VxcParams {
     int rem[2];              // columns in the partial block (0: none)
     int use3d, zero_skip;
     int producers;           // TMA-issuing threads per CTA (1..4)
+    int prefetch;            // L2 prefetch distance of the producer in ring stages (0: none)
     int wait_ns;             // producer / scanner threads sleep this long between barrier polls
     int debug_nodmma;        // diagnostic: skip every DMMA (operand-delivery floor; results are wrong)
     int chunk_stride[2];     // per sub-problem: multiplier (coprime to the chunk count) that scatters consecutive stages over the grid
@@ -112,6 +114,8 @@ struct VxcParams {
     const double* coef;
     double* vpart;
     unsigned long long* counters;  // [2]: (box, k-step) units executed / total (box-bit instances)
+    const unsigned char* fmap;     // [tiles_m][16]: 8 x 1 per-warp-vote instances: warp w owns 8-column fragments fmap[tm][2w], [2w+1] of the M tile
+    unsigned int* fstat;           // [tiles_m][16]: live (fragment, k-step) units found by those instances (drives the next call's fmap)
     long long* phase;  // DFT_PHASE_TIMING builds: [CTA][9 warps][4] cycles {wait, work, tail, total}
 };
 
@@ -700,10 +704,26 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
             const int cstep = (int)(((long long)P.slices_per_sub * P.chunk_stride[si]) % total_chunks);
             uint32_t s = 0, ph = 0;
             const int nloop = ops ? nchunks : 0;  // (a thread without transfers has nothing to wait for)
+            // L2 prefetch `P.prefetch` stages ahead (option vxc_prefetch): with the stages scattered over the grid every
+            // chunk is a fresh DRAM access, and a slot that frees up waits the whole DRAM + L2 latency for its refill
+            // while the ring is only five stages deep
+            const int pf = P.prefetch;
+            int pidx = cidx;
+            if (pf > 0 && P.use3d)
+                for (int k = 0; k < pf; ++k) { pidx += cstep; if (pidx >= total_chunks) pidx -= total_chunks; }
             for (int c = 0; c < nloop; ++c) {
                 const int j0 = cidx * VK;
                 cidx += cstep;
                 if (cidx >= total_chunks) cidx -= total_chunks;
+                if (pf > 0 && P.use3d && c + pf < nloop) {
+                    const int jp = pidx * VK;
+                    pidx += cstep;
+                    if (pidx >= total_chunks) pidx -= total_chunks;
+#pragma unroll
+                    for (int p = 0; p < NPL; ++p)
+                        if ((ops & (1u << p)) && fbm == NBM) tma::prefetch_3d(&P.m3[si][p], 0, jp, bm0);
+                    if ((ops & 0x10u) && fbn == NBN) tma::prefetch_3d(&P.n3[si], 0, jp, bn0);
+                }
 #ifdef DFT_PHASE_TIMING
                 t1 = clock64(); t_c += t1 - t0; t0 = t1;
 #endif
@@ -777,7 +797,20 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
     // busiest group's total is 0.65 against 0.76), and the two warps that share an SM sub-partition's tensor pipe
     // (w, w + 4) hold all the even or all the odd fragments between them.
     constexpr bool INTERLEAVE = (SKIP >= 1 && SKIP <= 3) && WM == 4 && WN == 2 && MF == 4;
-    auto mgroup = [&](int mf) { return MIRROR ? (mf == 0 ? wm : 15 - wm) : (INTERLEAVE ? wm + 4 * mf : ga0 + mf); };
+    // (MIRROR: the deal comes from a table the host refreshes from the previous call's live counts -- heaviest fragment
+    // with lightest, heavy pairs on the same SM sub-partition as light ones; it starts as w, 15 - w.  Which warp owns a
+    // fragment does not change a single rounding: every output element is still summed over the stages in order.)
+    int mg[MF];
+#pragma unroll
+    for (int mf = 0; mf < MF; ++mf) mg[mf] = MIRROR ? (mf == 0 ? wm : 15 - wm) : (INTERLEAVE ? wm + 4 * mf : ga0 + mf);
+    if (MIRROR && P.fmap) {
+#pragma unroll
+        for (int mf = 0; mf < MF; ++mf) mg[mf] = (int)P.fmap[tm * 16 + 2 * wm + mf] & 15;
+    }
+    auto mgroup = [&](int mf) { return mg[mf]; };
+    unsigned int n_live[MF];
+#pragma unroll
+    for (int mf = 0; mf < MF; ++mf) n_live[mf] = 0;
     uint32_t a_off[KS][MF], b_even[KS], b_odd[KS], c_off[KS];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
@@ -969,6 +1002,10 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
                 for (int mf = 0; mf < MF; ++mf)
                     live |= (__any_sync(0xffffffffu, (a[ks][mf] != 0.0) | no_skip) ? 1u : 0u) << (ks * MF + mf);
 #pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int mf = 0; mf < MF; ++mf) n_live[mf] += (live >> (ks * MF + mf)) & 1u;
+#pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 const unsigned lk = (live >> (ks * MF)) & ((1u << MF) - 1u);
                 if (lk) {
@@ -1032,6 +1069,8 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
                 unsigned live = 0;
 #pragma unroll
                 for (int mf = 0; mf < MF; ++mf) live |= (__any_sync(0xffffffffu, (a[mf] != 0.0) | no_skip) ? 1u : 0u) << mf;
+#pragma unroll
+                for (int mf = 0; mf < MF; ++mf) n_live[mf] += (live >> mf) & 1u;
                 if (live) {
 #pragma unroll
                     for (int nf = 0; nf < NFN; ++nf)
@@ -1055,6 +1094,10 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
 #endif
     }
     }   // (SKIP != 7)
+    if (MIRROR && P.fstat && lane == 0) {
+#pragma unroll
+        for (int mf = 0; mf < MF; ++mf) atomicAdd(&P.fstat[tm * 16 + mgroup(mf)], n_live[mf]);
+    }
     // ---- partial tile out
     double* out = P.vpart + (size_t)blockIdx.y * P.mpv * P.ldv;
 #pragma unroll
@@ -1576,7 +1619,7 @@ static Geometry make_geometry(int ngrid, int nao) {
 // addresses, so a plan stays valid when the caller rewrites the CONTENTS of its arrays.
 struct PlanKey {
     Problem prob;
-    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, debug_nodmma, wait_ns, dyn_sched, stagger_min, density_unit;
+    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, debug_nodmma, wait_ns, dyn_sched, stagger_min, density_unit, vxc_prefetch, vxc_rebalance;
     const void *dsym, *coef, *epart, *vpart, *rho;  // engine workspaces (grow-only: may move when they grow)
 };
 
@@ -1588,7 +1631,7 @@ struct Plan {
     VxcParams vp;
     const void* dfunc = nullptr;
     const void* vfunc = nullptr;
-    int dgrid = 0, dsmem = 0, vsmem = 0, pgrid = 0, vthreads = NTHREADS;
+    int dgrid = 0, dsmem = 0, vsmem = 0, pgrid = 0, vthreads = NTHREADS, v_tiles_m = 0;
     dim3 vgrid;
     // symmetrize_pad / finalize arguments
     int KP = 0, NP = 0, nsub = 0, ldv = 0, mpv = 0, fin_nt = 0, nsl = 0, shift1 = 0, lda_half = 0;
@@ -1635,7 +1678,7 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
     dp.coef_rows = g.coef_rows; dp.rho = rho;
     // (the counters must exist before `sched` is derived from them: round 1 had these two statements the other
     // way round, so `sched` was always null and the dynamic deal never ran)
-    dp.counters = reinterpret_cast<unsigned long long*>(ctx->counters.ensure(6 * sizeof(unsigned long long), &ctx->failed));
+    dp.counters = reinterpret_cast<unsigned long long*>(ctx->counters.ensure(COUNTERS_BYTES, &ctx->failed));
     if (ctx->failed) return;
     dp.sched = ctx->dyn_sched ? reinterpret_cast<unsigned int*>(dp.counters + 4) : nullptr;
 
@@ -1719,12 +1762,19 @@ static void plan_vxc(CublasHandleWrapper* ctx, const Problem& p, const Geometry&
     vp.use3d = ok3 ? 1 : 0;
     vp.debug_nodmma = ctx->debug_nodmma; vp.wait_ns = ctx->wait_ns;
     vp.producers = ctx->vxc_producers;
+    vp.prefetch = ctx->vxc_prefetch;
     vp.zero_skip = ctx->zero_skip ? 1 : 0;  // (a driver that rejects the 3-D form leaves the per-block 2-D loads)
     vp.sub[0] = g.sub[0]; vp.sub[1] = g.sub[1];
     vp.nsub = g.nsub; vp.tiles_m = tiles_m; vp.tiles_n = tiles_n; vp.lda_half = lda_half;
     vp.rows_per_slice = rows_per_slice; vp.slices_per_sub = nsl; vp.ldv = ldv; vp.mpv = mpv;
     vp.coef = coef; vp.vpart = vpart;
     vp.counters = pl.dp.counters ? pl.dp.counters + 2 : nullptr;
+    if (pl.dp.counters && tiles_m <= 16) {   // fragment deal of the 8 x 1 per-warp-vote instances (see the kernel)
+        unsigned char* cb = reinterpret_cast<unsigned char*>(pl.dp.counters);
+        vp.fmap = cb + FMAP_OFF;
+        vp.fstat = ctx->vxc_rebalance ? reinterpret_cast<unsigned int*>(cb + FSTAT_OFF) : nullptr;
+    }
+    pl.v_tiles_m = tiles_m;
 #ifdef DFT_PHASE_TIMING
     {   // the density kernel's phase record occupies the first 148*8*4 entries of `scratch`
         long long* ph = (long long*)ctx->scratch.ensure(sizeof(long long) * (65536 + 160 * 256), &ctx->failed);
@@ -1825,7 +1875,7 @@ static PlanKey make_key(const CublasHandleWrapper* ctx, const Problem& p) {
     k.prob.vxc = p.vxc; k.prob.d_exc = p.d_exc;
     k.exact = ctx->exact_functionals; k.l2_prefetch = ctx->l2_prefetch; k.tma_3d = ctx->tma_3d;
     k.vxc_shape = ctx->vxc_shape; k.vxc_vk = ctx->vxc_vk; k.zero_skip = ctx->zero_skip; k.vxc_skip_on = ctx->vxc_skip_on; k.vxc_skip_mode = ctx->vxc_skip_mode; k.vxc_scatter = ctx->vxc_scatter;
-    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.stagger_min = ctx->stagger_min; k.density_unit = ctx->density_unit; k.vxc_producers = ctx->vxc_producers;
+    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.stagger_min = ctx->stagger_min; k.density_unit = ctx->density_unit; k.vxc_producers = ctx->vxc_producers; k.vxc_prefetch = ctx->vxc_prefetch; k.vxc_rebalance = ctx->vxc_rebalance;
     k.dsym = ctx->dsym.ptr; k.coef = ctx->coef.ptr; k.epart = ctx->epart.ptr; k.vpart = ctx->vpart.ptr;
     k.rho = ctx->rho.ptr;
     return k;
@@ -1836,7 +1886,21 @@ static void run_plan(CublasHandleWrapper* ctx, const Problem& p, Plan& pl) {
     if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
     symmetrize_pad_tma_kernel<<<dim3((pl.KP + 127) / 128, pl.NP * pl.nsub), 128, 0, st>>>(p.nao, pl.KP, pl.NP, pl.nsub, p.dm,
                                                                                          pl.dsym);
-    if (pl.dp.counters) cudaMemsetAsync(pl.dp.counters, 0, 6 * sizeof(unsigned long long), st);
+    if (pl.dp.counters) {
+        cudaMemsetAsync(pl.dp.counters, 0, COUNTERS_HEAD_BYTES + FSTAT_BYTES, st);
+        unsigned char* h_fmap = reinterpret_cast<unsigned char*>(ctx->h_scalar) + HOST_FMAP_OFF;
+        if (!ctx->fmap_valid) {   // the initial deal: fragments w and 15 - w (opposite ends of the tile)
+            for (int t = 0; t < 16; ++t)
+                for (int w = 0; w < 8; ++w) { h_fmap[t * 16 + 2 * w] = (unsigned char)w; h_fmap[t * 16 + 2 * w + 1] = (unsigned char)(15 - w); }
+            ctx->fmap_valid = true;
+            ctx->fmap_dirty = true;
+        }
+        if (ctx->fmap_dirty) {    // (pinned source; the blocking entry point synchronises before the host touches it again)
+            cudaMemcpyAsync(reinterpret_cast<unsigned char*>(pl.dp.counters) + FMAP_OFF, h_fmap, FMAP_BYTES, cudaMemcpyHostToDevice, st);
+            ctx->fmap_dirty = false;
+        }
+    }
+    ctx->stats.v_tiles_m = pl.v_tiles_m;
     void* dargs[1] = {&pl.dp};
     DFT_CUDA_CHECK(ctx, cudaLaunchKernel(pl.dfunc, dim3(pl.dgrid), dim3(NTHREADS), dargs, (size_t)pl.dsmem, st));
     xc_point_kernel<<<pl.pgrid, POINT_THREADS, 0, st>>>(pl.pp);
@@ -1899,6 +1963,38 @@ void run_tma(CublasHandleWrapper* ctx, const Problem& p_in) {
         ctx->stats.plans_built++;
     }
     run_plan(ctx, p, pl);
+}
+
+// New deal of the V kernel's 8-column M fragments to its warps, per M tile row, from the live (fragment, k-step) counts
+// of the build that just finished: the warp that skips least is the CTA's critical path (phase timing at C5: it waits
+// 9 % of the time, the lightest warp 36 %), so pair the heaviest fragment with the lightest, and put the heaviest pair
+// on the same SM sub-partition (warps w and w + 4 share a tensor pipe) as the lightest pair.  The AO planes do not
+// change during an SCF, so the counts of one iteration describe the next.
+void tma_rebalance(CublasHandleWrapper* ctx) {
+    const int tiles_m = ctx->stats.v_tiles_m;
+    if (!ctx->h_scalar || tiles_m < 1 || tiles_m > 16) return;
+    const unsigned int* fstat = reinterpret_cast<const unsigned int*>(reinterpret_cast<const unsigned char*>(ctx->h_scalar) + HOST_FSTAT_OFF);
+    unsigned char* h_fmap = reinterpret_cast<unsigned char*>(ctx->h_scalar) + HOST_FMAP_OFF;
+    for (int t = 0; t < tiles_m; ++t) {
+        const unsigned int* c = fstat + t * 16;
+        unsigned long long total = 0;
+        for (int i = 0; i < 16; ++i) total += c[i];
+        if (total == 0) continue;   // (an instance that keeps no counts ran: leave the deal alone)
+        int f[16];
+        for (int i = 0; i < 16; ++i) f[i] = i;
+        std::stable_sort(f, f + 16, [&](int a, int b) { return c[a] > c[b]; });
+        int pa[8], pb[8], order[8];
+        unsigned long long load[8];
+        for (int k = 0; k < 8; ++k) { pa[k] = f[k]; pb[k] = f[15 - k]; load[k] = (unsigned long long)c[pa[k]] + c[pb[k]]; order[k] = k; }
+        std::stable_sort(order, order + 8, [&](int a, int b) { return load[a] > load[b]; });
+        unsigned char m[16];
+        for (int s = 0; s < 4; ++s) {   // sub-partition s: warps s and s + 4
+            const int heavy = order[s], light = order[7 - s];
+            m[2 * s] = (unsigned char)pa[heavy]; m[2 * s + 1] = (unsigned char)pb[heavy];
+            m[2 * (s + 4)] = (unsigned char)pa[light]; m[2 * (s + 4) + 1] = (unsigned char)pb[light];
+        }
+        if (memcmp(m, h_fmap + t * 16, 16) != 0) { memcpy(h_fmap + t * 16, m, 16); ctx->fmap_dirty = true; }
+    }
 }
 
 void free_tma_plan(CublasHandleWrapper* ctx) {

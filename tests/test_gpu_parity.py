@@ -378,6 +378,39 @@ def test_vxc_zero_skipping_instances_agree(oracle, engine_lib, functional, ngrid
 
 
 @pytest.mark.parametrize("functional", FUNCS)
+@pytest.mark.parametrize("ngrid,nao", [(24000, 377), (16000, 200), (9001, 129)])
+def test_vxc_fragment_rebalancing_changes_nothing(oracle, engine_lib, functional, ngrid, nao):
+    """The per-warp-vote V instances re-deal their 8-column M fragments to the warps after every blocking call, from the
+    live counts of that call (heaviest with lightest).  Which warp owns a fragment must not change a single bit of the
+    result: call after call on the same inputs, with the re-deal on and off, V_xc and E_xc are identical and equal to
+    the oracle's."""
+    from quantum_compute_dft_b200.cuda_rt import DeviceArray
+    from quantum_compute_dft_b200.solver import DFTSolverWrapper
+    rng = np.random.default_rng(9 * ngrid + nao)
+    dm, ao, w, grad = _screened_case(rng, ngrid, nao)
+    e_o, v_o = oracle.compute_xc(XC[functional], dm, ao, w, grad, mode=0)
+    d_dm, d_ao, d_w = DeviceArray.from_host(dm), DeviceArray.from_host(ao), DeviceArray.from_host(w)
+    d_g = DeviceArray.from_host(grad) if functional != "LDA" else None
+    results = []
+    for mode in (2, 1):
+        for reb in (1, 0):
+            s = DFTSolverWrapper(engine_lib, functional)
+            for k, v in {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": mode, "vxc_rebalance": reb}.items():
+                s.set_option(k, v)
+            d_v = DeviceArray((nao, nao), zero=True)
+            for it in range(4):   # the deal of call k + 1 comes from the counts of call k
+                e = s.compute_xc(ngrid, nao, d_dm, d_ao, d_w, d_v, d_g)
+                results.append((e, d_v.get()))
+            assert s.stat("path") == 2
+    e0, v0 = results[0]
+    assert abs(e0 - e_o) <= E_TOL
+    np.testing.assert_allclose(0.5 * (v0 + v0.T), oracle.sym(v_o), rtol=0, atol=V_TOL)
+    for e, v in results[1:]:
+        assert e == e0
+        np.testing.assert_array_equal(v, v0)
+
+
+@pytest.mark.parametrize("functional", FUNCS)
 def test_launch_plan_reuse(oracle, engine_lib, functional):
     """An SCF loop calls with the same device arrays every iteration: the TMA launch plan (tensor maps,
     geometry) is built once and reused; it caches addresses only, so new CONTENTS behind the same pointers are

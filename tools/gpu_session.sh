@@ -39,6 +39,9 @@ print('DMMA TFLOP/s', l.DFT_MicrobenchDMMA(8192)); print('DFMA TFLOP/s', l.DFT_M
     sweepdef) timeout 600 python tools/vxc_sweep.py C5 "" "vxc_producers=1" "l2_prefetch=1" "stagger_min=100000" > $OUT/sweepdef.txt 2>&1; timeout 600 python tools/vxc_sweep.py C4 "" "vxc_producers=1" "l2_prefetch=1" >> $OUT/sweepdef.txt 2>&1; echo "sweepdef rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweepdef.txt ;;
     sweepv4) timeout 600 python tools/vxc_sweep.py C5 "vxc_skip_mode=2" "vxc_skip_mode=7" "vxc_skip_mode=7,vxc_producers=1" "vxc_skip_mode=7,vxc_scatter=0" "vxc_skip_mode=2" > $OUT/sweepv4.txt 2>&1; echo "sweepv4 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweepv4.txt ;;
     sweepv5) timeout 600 python tools/vxc_sweep.py C5 "" "vxc_skip_mode=1" "vxc_skip_mode=3" "vxc_skip_mode=7" "vxc_skip=0" "zero_skip=0" > $OUT/sweepv5.txt 2>&1; timeout 600 python tools/vxc_sweep.py C4 "" "vxc_skip=1" >> $OUT/sweepv5.txt 2>&1; echo "sweepv5 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweepv5.txt ;;
+    phase:*) A=${what#phase:}; timeout 600 python tools/phase_timing.py C5 $(echo $A | tr ',' ' ') > $OUT/phase_$(echo $A | tr -d '=,').txt 2>&1; echo "phase $A rc=$?" | tee -a $OUT/summary.txt; cat $OUT/phase_$(echo $A | tr -d '=,').txt ;;
+    sweepv6) SWEEP_STEPS=8 timeout 600 python tools/vxc_sweep.py C5 "" "vxc_rebalance=0" "vxc_skip_mode=1" "vxc_skip_mode=1,vxc_rebalance=0" "" > $OUT/sweepv6.txt 2>&1; echo "sweepv6 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweepv6.txt ;;
+    sweepv7) SWEEP_STEPS=8 timeout 600 python tools/vxc_sweep.py C5 "" "vxc_prefetch=4" "vxc_prefetch=8" "vxc_prefetch=16" "vxc_prefetch=8,vxc_scatter=0" "vxc_scatter=0" > $OUT/sweepv7.txt 2>&1; echo "sweepv7 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweepv7.txt ;;
     sweepd)  SWEEP_LIB=diag timeout 600 python tools/vxc_sweep.py C5 "vxc_skip_mode=4" "vxc_skip_mode=4,debug_nodmma=1" "vxc_skip_mode=4,debug_nodmma=1,vxc_scatter=0" > $OUT/sweepd.txt 2>&1; echo "sweepd rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweepd.txt ;;
     sweep1)  timeout 600 python tools/vxc_sweep.py C5 "dyn_sched=1" "dyn_sched=0" > $OUT/sweep1.txt 2>&1; echo "sweep1 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweep1.txt ;;
     *) echo "unknown step $what" ;;

@@ -59,3 +59,10 @@ for i, name in enumerate(("wait full", "fragments+DMMA", "store tile")):
 x = vb[:, 8, :]
 print("V kernel, producer: wait empty %.1f %%, issue %.1f %% of %.3e cycles" % (100 * x[:, 0].mean() / x[:, 3].mean(), 100 * x[:, 1].mean() / x[:, 3].mean(), x[:, 3].mean()))
 print("per-CTA consumer total min/max: %.3e %.3e" % (vb[:, :8, 3].mean(axis=1).min(), vb[:, :8, 3].mean(axis=1).max()))
+# per-warp wait share by tile row (the warp that waits least is the CTA's critical path)
+ntile = int(os.environ.get("V_TILES", "9"))
+tn = int(round(ntile ** 0.5))
+w = vb[:, :8, 0] / np.maximum(vb[:, :8, 3], 1.0)
+for tm in range(tn):
+    sel = [c for c in range(nv) if (c % ntile) // tn == tm]
+    print(f"V kernel, tile row {tm}: per-warp 'wait full' share", w[sel].mean(axis=0).round(3), " least-waiting warp per CTA: mean %.3f" % w[sel].min(axis=1).mean())
