@@ -54,8 +54,9 @@ int DFT_CommDestroy(XCSolver* solver);
 //       0 = chosen from nao)
 //       "vxc_vk" 0|8|16 (tuning: grid rows per ring stage of the 128 x 128 V kernel; 0 = 16 on dense
 //       operands, 8 with zero skipping)
-//       "ao_shape" 0|8|16|17|32 (tuning: grid points per block of DFT_EvalAO -- 8 | 16 | 32 with 8 | 8 | 16 warps,
-//       17 = 16 points with 16 warps; 0 = chosen from the basis size)
+//       "ao_shape" 0|1|8|16|17|32 (tuning: grid points per block of DFT_EvalAO -- 8 | 16 | 32 with 8 | 8 | 16 warps,
+//       17 = 16 points with 16 warps; 0 = chosen from the basis size; 1 = the barrier-free direct kernel, lanes over
+//       AOs throughout, measured slower)
 //       "ao_vec_stores" 0|1 (DFT_EvalAO phase 2: 16-byte stores, a lane owns an aligned AO pair; default 0 -- measured
 //       slower than 8-byte stores, whose warps already fill whole 256-byte runs)
 //       "ao_input_order" 0|1 (DFT_EvalAO: 1 keeps the exponent-sharing shell groups in input order; default 0 sorts them
@@ -64,16 +65,17 @@ int DFT_CommDestroy(XCSolver* solver);
 //       exactly zero are skipped; results are unchanged; default 1)
 //       "vxc_skip" -1|0|1 (the zero-skipping instance of the V kernel: -1 = adaptive, used while the density
 //       kernel of the previous call skipped >= 10 % of its k-steps; default -1)
-//       "vxc_skip_mode" 1..7 (which zero-skipping V instance on the 128 x 128 tile.  Per-warp votes on the M-side
-//       fragments: 2 = built and voted on for a whole ring stage at once (default), 1 = k-step by k-step (round 1),
-//       3 = 2 + the first k-step's Phi fragments requested before the votes, 7 = 2 software-pipelined across stages,
-//       5 | 6 = 4 x 2 warps with interleaved fragments (k-step by k-step | per stage); 4 = staged B: builder warps
-//       combine the planes once per CTA and all MMA warps skip the same all-zero fragments.  C5: 10.8 ms for mode 2,
-//       11.1 for 1, 12.2-12.4 for 5 | 6, 12.5 for 4, 13.2 for 7)
+//       "vxc_skip_mode" 1|2|4 (which zero-skipping V instance on the 128 x 128 tile.  Per-warp votes on the M-side
+//       fragments: 2 = built and voted on for a whole ring stage at once (default, C5 10.8 ms), 1 = k-step by k-step
+//       (round 1, 11.1 ms); 4 = staged B: builder warps combine the planes once per CTA and all MMA warps skip the same
+//       all-zero fragments (12.5 ms).  Diagnostic builds (-DDFT_V_EXPERIMENTS) also carry the measured-and-rejected
+//       variants 3, 5, 6, 7: DESIGN.md 5.2e)
 //       "vxc_rebalance" 0|1 (per-warp-vote instances: after every blocking call re-deal the 8-column M fragments to
 //       the warps from that call's live counts -- heaviest with lightest; results are bit-identical; default 1)
 //       "vxc_prefetch" n (tuning: L2 prefetch distance of the V kernel's producer in ring stages; default 0: measured
 //       no gain)
+//       "density_producers" 1|2 (tuning: TMA-issuing threads per consumer group of the density kernel, default 1:
+//       a helper thread that brings the Dsym chunks and half of a piece's planes measured no gain)
 //       "vxc_producers" 1..4 (tuning: TMA-issuing threads per CTA of the V kernel, default 2)
 //       "vxc_scatter" 0|1 (zero-skipping V instances: scatter consecutive ring stages over the grid, default 1)
 //       "dyn_sched" 0|1 (density kernel: hand the units of work out dynamically, default 1)

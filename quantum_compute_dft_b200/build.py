@@ -65,8 +65,8 @@ def build(verbose=False, force=False, extra=(), tag=""):
 
 if __name__ == "__main__":
     if "--timing" in sys.argv:
-        print(build(verbose="-v" in sys.argv, extra=["-DDFT_PHASE_TIMING", "-DDFT_DIAGNOSTICS"], tag="_timing"))
+        print(build(verbose="-v" in sys.argv, extra=["-DDFT_PHASE_TIMING", "-DDFT_DIAGNOSTICS", "-DDFT_V_EXPERIMENTS"], tag="_timing"))
     elif "--diag" in sys.argv:
-        print(build(verbose="-v" in sys.argv, extra=["-DDFT_DIAGNOSTICS"], tag="_diag"))
+        print(build(verbose="-v" in sys.argv, extra=["-DDFT_DIAGNOSTICS", "-DDFT_V_EXPERIMENTS"], tag="_diag"))
     else:
         print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

@@ -298,6 +298,116 @@ eval_kernel(int ngrid, const double* __restrict__ coords, Tables t, int epitch, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Direct kernel (round 2, option ao_shape 1): lanes over AOs from start to finish, no staging of radial sums, no CTA barrier.
+// ------------------------------------------------------------------------------------------------
+// An experiment with a negative result, kept selectable.  The two-phase kernel above shares the exponentials of a group
+// through shared memory, which costs it 63 KB of [point][shell] staging per CTA (16 resident warps per SM), two CTA
+// barriers per 16 points and a phase 1 whose half-warps diverge on the cutoff (ncu: stalls on barriers and
+// shared-memory latency, 0.76 of the copy bandwidth).  Here a lane owns one AO of one point and evaluates its shell's
+// radial sums itself -- the three AOs of a p shell and the s AO of the same sp group repeat the same exponentials,
+// twice the exp() work overall -- so the only shared memory is the per-AO tables (18 KB at C5), 48 warps are resident
+// per SM, nothing waits on a barrier, and every warp store is still 256 contiguous bytes.  Same arithmetic in the
+// same order: results are bit-identical.  Measured (profiles/r2_u12_ao_direct_kernel.txt): C5 4.31 ms against 3.48,
+// C4 1.02 against 0.75, C2 0.121 against 0.067 -- the doubled exponentials and the mixed live / dead lanes of a
+// 32-AO chunk cost more than the barriers and the occupancy did.
+struct DirectTables {
+    const unsigned char* base;
+    size_t bytes;
+    int nao, nprim;
+    // doubles: cx cy cz amin [nao] | exps coefs [nprim];  ints: poff npr comp [nao]
+    size_t o_cx, o_cy, o_cz, o_amin, o_exp, o_coef, o_poff, o_npr, o_comp;
+};
+
+constexpr int DIRECT_PW = 4;          // consecutive points per warp step
+constexpr int DIRECT_WARPS = 8;
+
+template <bool DERIV>
+__global__ void __launch_bounds__(DIRECT_WARPS * 32)
+eval_direct_kernel(int ngrid, const double* __restrict__ coords, DirectTables t, double cutoff, double* __restrict__ ao,
+                   double* __restrict__ gout) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(t.base);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(smem_raw);
+        for (size_t i = threadIdx.x; i < t.bytes / 8; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();   // (the only one)
+    const double* cx = reinterpret_cast<const double*>(smem_raw + t.o_cx);
+    const double* cy = reinterpret_cast<const double*>(smem_raw + t.o_cy);
+    const double* cz = reinterpret_cast<const double*>(smem_raw + t.o_cz);
+    const double* amin = reinterpret_cast<const double*>(smem_raw + t.o_amin);
+    const double* s_exp = reinterpret_cast<const double*>(smem_raw + t.o_exp);
+    const double* s_coef = reinterpret_cast<const double*>(smem_raw + t.o_coef);
+    const int* poff = reinterpret_cast<const int*>(smem_raw + t.o_poff);
+    const int* npr = reinterpret_cast<const int*>(smem_raw + t.o_npr);
+    const int* compt = reinterpret_cast<const int*>(smem_raw + t.o_comp);
+
+    const int lane = threadIdx.x & 31;
+    const int nao = t.nao;
+    const size_t plane = (size_t)ngrid * nao;
+    const long nstep = ((long)ngrid + DIRECT_PW - 1) / DIRECT_PW;
+    const long wid = (long)blockIdx.x * DIRECT_WARPS + (threadIdx.x >> 5), nw = (long)gridDim.x * DIRECT_WARPS;
+    // coordinates of a step: lanes 0 .. 3 PW - 1 hold one double each (coalesced), the next step's are in flight
+    auto load_pts = [&](long st) {
+        const long e = st * (3 * DIRECT_PW) + lane;
+        return (st < nstep && lane < 3 * DIRECT_PW && e < 3 * (long)ngrid) ? __ldg(coords + e) : 0.0;
+    };
+    double pts_next = load_pts(wid);
+    for (long st = wid; st < nstep; st += nw) {
+        const double pts = pts_next;
+        pts_next = load_pts(st + nw);
+        const long p0 = st * DIRECT_PW;
+#pragma unroll 1
+        for (int r = 0; r < DIRECT_PW; ++r) {
+            if (p0 + r >= ngrid) break;
+            const double x = __shfl_sync(0xffffffffu, pts, 3 * r), y = __shfl_sync(0xffffffffu, pts, 3 * r + 1),
+                         z = __shfl_sync(0xffffffffu, pts, 3 * r + 2);
+            double* d0 = ao + (size_t)(p0 + r) * nao + lane;
+            double* d1 = DERIV ? gout + (size_t)(p0 + r) * nao + lane : nullptr;
+            for (int i = lane; i - lane < nao; i += 32, d0 += 32, d1 += 32) {
+                const bool valid = i < nao;
+                const int ii = valid ? i : nao - 1;
+                const double dx = x - cx[ii], dy = y - cy[ii], dz = z - cz[ii];
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const int comp = compt[ii];
+                // beyond the cutoff of the shell's most diffuse primitive every primitive is dropped: exact zeros
+                const bool live = valid && !(amin[ii] * r2 > cutoff);
+                double e0 = 0.0, e1 = 0.0;
+                if (__any_sync(0xffffffffu, live)) {
+                    const int q0 = poff[ii], nq = live ? npr[ii] : 0;
+                    int nqmax = nq;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) nqmax = max(nqmax, __shfl_xor_sync(0xffffffffu, nqmax, o));
+                    for (int k = 0; k < nqmax; ++k) {
+                        if (k < nq) {
+                            const double al = s_exp[q0 + k];
+                            const double ar2 = al * r2;
+                            if (!(ar2 > cutoff)) {
+                                const double tv = s_coef[q0 + k] * exp_neg(-ar2);
+                                e0 += tv;
+                                e1 = fma(-2.0 * al, tv, e1);
+                            }
+                        }
+                    }
+                }
+                if (!valid) continue;
+                double dj = dz;
+                dj = comp == 1 ? dy : dj;
+                dj = comp == 0 ? dx : dj;
+                dj = comp < 0 ? 1.0 : dj;
+                *d0 = dj * e0;
+                if (DERIV) {
+                    const double dj1 = dj * e1;
+                    d1[0] = fma(dj1, dx, comp == 0 ? e0 : 0.0);
+                    d1[plane] = fma(dj1, dy, comp == 1 ? e0 : 0.0);
+                    d1[2 * plane] = fma(dj1, dz, comp == 2 ? e0 : 0.0);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace ao
 }  // namespace xc
 
@@ -358,6 +468,66 @@ extern "C" int DFT_EvalAO(XCSolver* solver, int ngrid, unsigned long long d_coor
         if (ao_shell[i] < 0) return 3;  // every AO must belong to a shell
     const int ngroup = (int)groups.size();
     if (ngroup > 65535) return 5;
+    double* ao_out = reinterpret_cast<double*>(d_ao_ptr);
+    double* g_out = reinterpret_cast<double*>(d_ao_grad_ptr);
+    const double* coords = reinterpret_cast<const double*>(d_coords_ptr);
+    if (ctx->num_sms <= 0) cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+
+    if (ctx->ao_shape == 1) {
+        // ---- direct kernel (option ao_shape 1; measured slower than the two-phase kernel, see its header): per-AO tables only
+        DirectTables t;
+        memset(&t, 0, sizeof(t));
+        t.nao = nao; t.nprim = nprim_total;
+        size_t off = 0;
+        auto take = [&](size_t nbytes) { const size_t o = off; off += (nbytes + 7) & ~(size_t)7; return o; };
+        t.o_cx = take(8 * (size_t)nao); t.o_cy = take(8 * (size_t)nao); t.o_cz = take(8 * (size_t)nao); t.o_amin = take(8 * (size_t)nao);
+        t.o_exp = take(8 * (size_t)nprim_total); t.o_coef = take(8 * (size_t)nprim_total);
+        t.o_poff = take(4 * (size_t)nao); t.o_npr = take(4 * (size_t)nao); t.o_comp = take(4 * (size_t)nao);
+        const size_t bytes = (off + 15) & ~(size_t)15;
+        if (bytes <= 96 * 1024) {   // (larger bases: the two-phase kernel's shell tables are smaller)
+            std::vector<unsigned char> h(bytes, 0);
+            double* hd = reinterpret_cast<double*>(h.data());
+            for (int i = 0; i < nao; ++i) {
+                const int sh = ao_shell[i];
+                reinterpret_cast<double*>(h.data() + t.o_cx)[i] = shell_xyz[3 * sh];
+                reinterpret_cast<double*>(h.data() + t.o_cy)[i] = shell_xyz[3 * sh + 1];
+                reinterpret_cast<double*>(h.data() + t.o_cz)[i] = shell_xyz[3 * sh + 2];
+                reinterpret_cast<double*>(h.data() + t.o_amin)[i] = groups[shell_group[sh]].amin;
+                reinterpret_cast<int*>(h.data() + t.o_poff)[i] = shell_prim_off[sh];
+                reinterpret_cast<int*>(h.data() + t.o_npr)[i] = shell_nprim[sh];
+                reinterpret_cast<int*>(h.data() + t.o_comp)[i] = ao_comp[i];
+            }
+            (void)hd;
+            memcpy(h.data() + t.o_exp, prim_exp, 8 * (size_t)nprim_total);
+            memcpy(h.data() + t.o_coef, prim_coef, 8 * (size_t)nprim_total);
+            unsigned char* d = (unsigned char*)ctx->scratch.ensure(bytes, &ctx->failed);
+            if (ctx->failed) return 4;
+            DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(d, h.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+            DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // h is pageable: the copy is done now
+            t.base = d; t.bytes = bytes;
+            int per_sm = (int)((227 * 1024) / (bytes + 1024));
+            per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);      // 8 warps per CTA: up to 48 resident warps per SM
+            const long nstep = ((long)ngrid + DIRECT_PW - 1) / DIRECT_PW;
+            const long want = (nstep + DIRECT_WARPS - 1) / DIRECT_WARPS;
+            const int grid = (int)(want < (long)ctx->num_sms * per_sm ? want : (long)ctx->num_sms * per_sm);
+            xc::resolve_times(ctx);
+            if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
+            if (deriv) {
+                auto k = eval_direct_kernel<true>;
+                DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                k<<<grid, DIRECT_WARPS * 32, bytes, ctx->stream>>>(ngrid, coords, t, exp_cutoff, ao_out, g_out);
+            } else {
+                auto k = eval_direct_kernel<false>;
+                DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                k<<<grid, DIRECT_WARPS * 32, bytes, ctx->stream>>>(ngrid, coords, t, exp_cutoff, ao_out, g_out);
+            }
+            if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->stream);
+            DFT_CUDA_CHECK(ctx, cudaGetLastError());
+            DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->timing && !ctx->failed) cudaEventElapsedTime(&ctx->stats.ao_ms, ctx->ev[0], ctx->ev[1]);
+            return ctx->failed ? 6 : 0;
+        }
+    }
     // Order of the groups in phase 1.  The two half-warps of a warp work on CONSECUTIVE groups, and a warp pays for the
     // long path (three exponentials) whenever either of them is inside its cutoff: pair groups that decide alike -- the
     // same reach sqrt(cutoff / amin) (core shells reach 4 bohr, valence shells 13-19) and neighbouring centres (sorted
@@ -460,15 +630,11 @@ extern "C" int DFT_EvalAO(XCSolver* solver, int ngrid, unsigned long long d_coor
         fprintf(stderr, "[dft_b200] DFT_EvalAO: basis too large for the shared-memory staging (%zu B)\n", smem);
         return 5;
     }
-    if (ctx->num_sms <= 0) cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device);
     int per_sm = (int)(smem_max / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 64 / NW) per_sm = 64 / NW;
     const long nblk = ((long)ngrid + G - 1) / G;
     const int grid = (int)(nblk < (long)ctx->num_sms * per_sm ? nblk : (long)ctx->num_sms * per_sm);
-    double* ao_out = reinterpret_cast<double*>(d_ao_ptr);
-    double* g_out = reinterpret_cast<double*>(d_ao_grad_ptr);
-    const double* coords = reinterpret_cast<const double*>(d_coords_ptr);
     xc::resolve_times(ctx);   // (this call reuses the first two timing events)
     if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
 #define DFT_AO_LAUNCH(D_, G_, NW_)                                                                                      \

@@ -372,10 +372,20 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "debug_nodmma")) { c->debug_nodmma = value != 0.0; return 0; }   // results are WRONG: delivery floor
 #endif
     if (!strcmp(key, "vxc_scatter")) { c->vxc_scatter = value != 0.0; return 0; }
+    if (!strcmp(key, "density_producers")) { c->density_producers = value >= 2.0 ? 2 : 1; return 0; }
     if (!strcmp(key, "vxc_prefetch")) { c->vxc_prefetch = value < 0.0 ? 0 : (value > 64.0 ? 64 : (int)value); return 0; }
     if (!strcmp(key, "vxc_rebalance")) { c->vxc_rebalance = value != 0.0; c->fmap_valid = false; return 0; }
     if (!strcmp(key, "vxc_producers")) { c->vxc_producers = value < 1.0 ? 1 : (value > 4.0 ? 4 : (int)value); return 0; }
-    if (!strcmp(key, "vxc_skip_mode")) { const int v = (int)value; if (v < 1 || v > 7) return 3; c->vxc_skip_mode = v; return 0; }
+    if (!strcmp(key, "vxc_skip_mode")) {
+        const int v = (int)value;
+#ifdef DFT_V_EXPERIMENTS
+        if (v < 1 || v > 7) return 3;
+#else
+        if (v != 1 && v != 2 && v != 4) return 3;   // (3, 5, 6, 7: measured variants, diagnostic builds only)
+#endif
+        c->vxc_skip_mode = v;
+        return 0;
+    }
     if (!strcmp(key, "raw_convention")) { c->raw_convention = value != 0.0; return 0; }
     if (!strcmp(key, "zero_skip")) { c->zero_skip = value != 0.0; return 0; }
     if (!strcmp(key, "tma_3d")) { c->tma_3d = value != 0.0; return 0; }

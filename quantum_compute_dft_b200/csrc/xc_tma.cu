@@ -85,6 +85,7 @@ struct DensityParams {
     int stagger_min;   // group 1 starts half a tile period late when the CTA has more than this many blocks to do
     int wait_ns;       // producer threads sleep this long between polls of an `empty` barrier (0: poll back to back)
     int debug_nodmma;  // diagnostic: treat every k-step as zero (measures the operand-delivery floor; results are wrong)
+    int producers2;    // two TMA-issuing threads per consumer group (primary + helper) instead of one
     unsigned long long* counters;  // [2]: k-steps executed, k-steps total (AO screening statistics)
     unsigned int* sched;           // next density block to hand out (dynamic scheduling; reset to 0 before the launch), or null
     double* rho;       // [2 warp columns][coef_rows][4]: partial (rho, drho/2) row sums, summed by the point kernel
@@ -183,7 +184,7 @@ struct DensitySmem {
     static constexpr int PPL = NPL / PSPLIT;                              // planes per stage of a piece
     static constexpr int PIECE_BYTES = PPL * PLANE_BYTES;
     static constexpr int STAGE_BYTES = K_BYTES > PIECE_BYTES ? K_BYTES : PIECE_BYTES;
-    static constexpr int FIXED_BYTES = 512 + 1024;                        // barriers, alignment slack
+    static constexpr int FIXED_BYTES = 640 + 1024;                        // barriers, slots, unit queue, alignment slack
     static constexpr int STAGES = (232448 - FIXED_BYTES) / (2 * STAGE_BYTES) < 6 ? (232448 - FIXED_BYTES) / (2 * STAGE_BYTES) : 6;
     static_assert(STAGES >= 2, "ring depth");
     static constexpr int NCG = NT / 16;                                   // 16-column groups per tile (= NF2)
@@ -191,7 +192,8 @@ struct DensitySmem {
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;               // one group's ring
     static constexpr int BAR_OFF = 2 * RING_BYTES;                        // [2 groups]{full[STAGES], empty[STAGES]}
     static constexpr int BLK_OFF = BAR_OFF + 2 * 2 * STAGES * 8;          // [2 groups][STAGES] block id carried by a stage
-    static constexpr int TOTAL = BLK_OFF + 2 * STAGES * 4 + 8 + 1024;     // + alignment slack
+    static constexpr int UQ_OFF = ((BLK_OFF + 2 * STAGES * 4 + 7) / 8) * 8; // [2 groups][4] (sequence << 32 | unit): primary -> helper issuing thread
+    static constexpr int TOTAL = UQ_OFF + 2 * 4 * 8 + 8 + 1024;           // + alignment slack
     static_assert(TOTAL <= 232448, "shared memory");
 
     // piece pc -> column group; consecutive pieces go to different warp columns
@@ -215,10 +217,11 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
         uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF);
         for (int g = 0; g < 2; ++g)
             for (int s = 0; s < L::STAGES; ++s) {
-                tma::mbar_init(&bars[g * 2 * L::STAGES + s], 1);
+                tma::mbar_init(&bars[g * 2 * L::STAGES + s], P.producers2 ? 2 : 1);   // full: every issuing thread of the group arrives
                 tma::mbar_init(&bars[g * 2 * L::STAGES + L::STAGES + s], GW);
             }
         tma::fence_barrier_init();
+        for (int i = 0; i < 8; ++i) reinterpret_cast<volatile unsigned long long*>(sm + L::UQ_OFF)[i] = 0ull;
     }
     __syncthreads();
 
@@ -246,7 +249,69 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
     if (warp >= NCW) {
         // ===================== producer warpgroup: warps 8 and 9, one elected lane each =====================
         reg_dec<REGS_PRODUCER>();
+        // Optionally two issuing threads per group (option density_producers 2; round 2).  One thread streams only ~21
+        // bytes per clock into shared memory, and the kernel's delivery floor with every DMMA off, 43 B/clk/SM, is
+        // exactly two such threads, while ncu shows the consumers spending a fifth of their samples waiting for stages.
+        // The PRIMARY (lane 0 of warps 8 | 9) draws the units, arms the barriers and brings the Phi chunk / the first
+        // half of a piece's planes; the HELPER (lane 0 of warps 10 | 11) follows the same unit sequence -- handed over
+        // through a 4-entry queue in shared memory when the deal is dynamic -- and brings the Dsym chunk / the second
+        // half of the planes.  (A transfer that lands before the primary has armed the barrier only makes its tx-count
+        // transiently negative.)  MEASURED: no gain -- C5 8.83 against 8.82 ms, C4 1.179 against 1.183
+        // (profiles/r2_u13_density_two_issuers.txt): the waits are not the issue rate.  Default: one thread.
+        const bool two = P.producers2 != 0;
+        volatile unsigned long long* uq = reinterpret_cast<volatile unsigned long long*>(sm + L::UQ_OFF) + 4 * grp;
+        if (warp >= NCW + 2 && lane == 0 && two) {
+            // ===================== helper issuing thread =====================
+            tma::prefetch_map(&P.map_d);
+            uint32_t it = 0;
+            unsigned int kseq = 0;
+            int u = b_first;
+            auto next_unit = [&]() {
+                if (!dyn) { if (kseq) u += b_step; ++kseq; return; }
+                ++kseq;
+                unsigned long long e;
+                uint32_t spins = 0;
+                do { e = uq[(kseq - 1) & 3]; if ((++spins & 1023u) == 0) __nanosleep(64); } while ((unsigned int)(e >> 32) != kseq);
+                u = (int)(unsigned int)(e & 0xffffffffull);
+            };
+            next_unit();
+            while (u < nunits) {
+                const int b = per_tile ? u / ntiles : u;
+                const int nt0 = per_tile ? u - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
+                const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
+                const int blk = b - P.sub[si].blk0;
+                const int drow0 = P.sub[si].shift * P.NP;
+                for (int nt = nt0; nt < nt1; ++nt) {
+                    for (int kc = 0; kc < nk; ++kc, ++it) {
+                        const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
+                        tma::mbar_wait_relaxed(&empty[s], ph ^ 1u, (uint32_t)P.wait_ns);
+                        tma::load_2d(ring + s * L::STAGE_BYTES + L::A_BYTES, &P.map_d, kc * 16, drow0 + nt * NT, &full[s]);
+                        tma::mbar_arrive(&full[s]);
+                    }
+                    // The helper ARRIVES on every stage, also where it has nothing to bring (an LDA piece is one plane):
+                    // waits are by phase parity, and a thread that sat out a stage could be lapped twice on a slot
+                    // between two of its polls and then mistake the slot's previous phase for the one it waits for.
+                    for (int pc = 0; pc < L::NPIECES; ++pc, ++it) {
+                        const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
+                        tma::mbar_wait_relaxed(&empty[s], ph ^ 1u, (uint32_t)P.wait_ns);
+                        unsigned char* st = ring + s * L::STAGE_BYTES;
+                        const int c0 = nt * NT + 16 * L::stage_cg(pc);
+                        if (L::PPL >= 2)
+                            for (int p = L::PPL / 2; p < L::PPL; ++p)
+                                tma::load_2d(st + p * L::PLANE_BYTES, &P.map_e[si][L::stage_pl0(pc) + p], c0, blk * MB, &full[s]);
+                        tma::mbar_arrive(&full[s]);
+                    }
+                }
+                next_unit();
+            }
+            return;
+        }
         if (warp < NCW + 2 && lane == 0) {
+            unsigned int kseq = 0;
+            auto publish = [&](int uu) {   // (dynamic deal: the helper reads the unit sequence from here)
+                ++kseq;
+                if (two && dyn) uq[(kseq - 1) & 3] = ((unsigned long long)kseq << 32) | (unsigned int)uu;
+            };
             tma::prefetch_map(&P.map_a[0]);
             if (P.nsub > 1) tma::prefetch_map(&P.map_a[1]);
             tma::prefetch_map(&P.map_d);
@@ -259,6 +324,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             constexpr int PF = 6;
             const bool pf = P.l2_prefetch != 0;
             int u = dyn ? (int)atomicAdd(P.sched, 1u) : b_first;
+            publish(u);
             while (u < nunits) {
                 const int b = per_tile ? u / ntiles : u;
                 const int nt0 = per_tile ? u - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
@@ -266,6 +332,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                 const int blk = b - P.sub[si].blk0;
                 const int drow0 = P.sub[si].shift * P.NP;
                 const int un = dyn ? (int)atomicAdd(P.sched, 1u) : u + b_step;  // this group's next unit
+                publish(un);
                 const int bn = per_tile ? un / ntiles : un;                      // (its block: L2 prefetch only)
                 const int sin = (P.nsub > 1 && bn >= P.sub[1].blk0) ? 1 : 0;
                 const int blkn = bn - P.sub[sin].blk0;
@@ -292,7 +359,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                         if (nt == nt0 && kc == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(blk_slot + 4 * s), "r"(u) : "memory");
                         tma::mbar_arrive_expect_tx(&full[s], L::K_BYTES);
                         tma::load_2d(st, &P.map_a[si], kc * 16, blk * MB, &full[s]);
-                        tma::load_2d(st + L::A_BYTES, &P.map_d, kc * 16, drow0 + nt * NT, &full[s]);
+                        if (!two) tma::load_2d(st + L::A_BYTES, &P.map_d, kc * 16, drow0 + nt * NT, &full[s]);
                     }
                     for (int pc = 0; pc < L::NPIECES; ++pc, ++it) {
                         const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
@@ -300,7 +367,8 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                         unsigned char* st = ring + s * L::STAGE_BYTES;
                         tma::mbar_arrive_expect_tx(&full[s], L::PIECE_BYTES);
                         const int c0 = nt * NT + 16 * L::stage_cg(pc);
-                        for (int p = 0; p < L::PPL; ++p)
+                        const int pend = (two && L::PPL >= 2) ? L::PPL / 2 : L::PPL;   // (the helper brings the other half)
+                        for (int p = 0; p < pend; ++p)
                             tma::load_2d(st + p * L::PLANE_BYTES, &P.map_e[si][L::stage_pl0(pc) + p], c0, blk * MB, &full[s]);
                     }
                 }
@@ -311,6 +379,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                 tma::mbar_wait_relaxed(&empty[s], ph ^ 1u, (uint32_t)P.wait_ns);
                 asm volatile("st.shared.s32 [%0], %1;" ::"r"(blk_slot + 4 * s), "r"(-1) : "memory");
                 tma::mbar_arrive(&full[s]);
+                if (two) tma::mbar_arrive(&full[s]);   // (the helper never sees this stage)
             }
         }
         return;
@@ -1619,7 +1688,7 @@ static Geometry make_geometry(int ngrid, int nao) {
 // addresses, so a plan stays valid when the caller rewrites the CONTENTS of its arrays.
 struct PlanKey {
     Problem prob;
-    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, debug_nodmma, wait_ns, dyn_sched, stagger_min, density_unit, vxc_prefetch, vxc_rebalance;
+    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, debug_nodmma, wait_ns, dyn_sched, stagger_min, density_unit, vxc_prefetch, vxc_rebalance, density_producers;
     const void *dsym, *coef, *epart, *vpart, *rho;  // engine workspaces (grow-only: may move when they grow)
 };
 
@@ -1675,6 +1744,7 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
     dp.zero_skip = ctx->zero_skip ? 1 : 0;
     dp.debug_nodmma = ctx->debug_nodmma; dp.wait_ns = ctx->wait_ns; dp.stagger_min = ctx->stagger_min;
     dp.per_tile = per_tile ? 1 : 0;
+    dp.producers2 = ctx->density_producers >= 2 ? 1 : 0;
     dp.coef_rows = g.coef_rows; dp.rho = rho;
     // (the counters must exist before `sched` is derived from them: round 1 had these two statements the other
     // way round, so `sched` was always null and the dynamic deal never ran)
@@ -1845,17 +1915,20 @@ static void build_plan(CublasHandleWrapper* ctx, const Problem& p, int nsm, Plan
         DFT_PLAN_V(5, 5, 4, 2, NPL, 16, 2);
     } else if (vskip && ctx->vxc_skip_mode == 4) {
         plan_vxc<2, 16, 8, 1, NPL, 8, 5, 4>(ctx, p, g, nsm, coef, pl);
-    } else if (vskip && ctx->vxc_skip_mode == 2) {   // 8 x 1 mirrored pairs, votes batched per stage
-        if (ctx->vxc_vk == 16) plan_vxc<2, 16, 8, 1, NPL, 16, 2, 2>(ctx, p, g, nsm, coef, pl);
-        else plan_vxc<2, 16, 8, 1, NPL, 8, 5, 2>(ctx, p, g, nsm, coef, pl);
+    } else if (vskip && ctx->vxc_skip_mode == 2) {   // per-warp votes, built and voted on for a whole ring stage at once (default)
+        plan_vxc<2, 16, 8, 1, NPL, 8, 5, 2>(ctx, p, g, nsm, coef, pl);
+#ifdef DFT_V_EXPERIMENTS
+    // Variants that were measured and are NOT faster (profiles/r2_u2_*, r2_u6_*): compiled only into the
+    // diagnostic build (build.py --diag) so that the product library does not carry them.
     } else if (vskip && ctx->vxc_skip_mode == 7) {   // mode 2 software-pipelined across ring stages
         plan_vxc<2, 16, 8, 1, NPL, 8, 5, 7>(ctx, p, g, nsm, coef, pl);
-    } else if (vskip && ctx->vxc_skip_mode == 3) {   // the same + the first k-step's Phi fragments requested before the votes
+    } else if (vskip && ctx->vxc_skip_mode == 3) {   // mode 2 + the first k-step's Phi fragments requested before the votes
         plan_vxc<2, 16, 8, 1, NPL, 8, 5, 3>(ctx, p, g, nsm, coef, pl);
     } else if (vskip && ctx->vxc_skip_mode == 5) {   // 4 x 2 warps, interleaved M fragments, vote per k-step
         plan_vxc<4, 8, 4, 2, NPL, 8, 5, 1>(ctx, p, g, nsm, coef, pl);
     } else if (vskip && ctx->vxc_skip_mode == 6) {   // 4 x 2 warps, interleaved M fragments, votes batched per stage
         plan_vxc<4, 8, 4, 2, NPL, 8, 5, 2>(ctx, p, g, nsm, coef, pl);
+#endif
     } else {
         // rows per ring stage: 16 (2 stages, fewer barriers) on dense operands; 8 (5 stages) when zero fragments
         // are skipped -- with the stages scattered over the grid, the deeper ring lets the warps drift apart
@@ -1875,7 +1948,7 @@ static PlanKey make_key(const CublasHandleWrapper* ctx, const Problem& p) {
     k.prob.vxc = p.vxc; k.prob.d_exc = p.d_exc;
     k.exact = ctx->exact_functionals; k.l2_prefetch = ctx->l2_prefetch; k.tma_3d = ctx->tma_3d;
     k.vxc_shape = ctx->vxc_shape; k.vxc_vk = ctx->vxc_vk; k.zero_skip = ctx->zero_skip; k.vxc_skip_on = ctx->vxc_skip_on; k.vxc_skip_mode = ctx->vxc_skip_mode; k.vxc_scatter = ctx->vxc_scatter;
-    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.stagger_min = ctx->stagger_min; k.density_unit = ctx->density_unit; k.vxc_producers = ctx->vxc_producers; k.vxc_prefetch = ctx->vxc_prefetch; k.vxc_rebalance = ctx->vxc_rebalance;
+    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.stagger_min = ctx->stagger_min; k.density_unit = ctx->density_unit; k.vxc_producers = ctx->vxc_producers; k.vxc_prefetch = ctx->vxc_prefetch; k.vxc_rebalance = ctx->vxc_rebalance; k.density_producers = ctx->density_producers;
     k.dsym = ctx->dsym.ptr; k.coef = ctx->coef.ptr; k.epart = ctx->epart.ptr; k.vpart = ctx->vpart.ptr;
     k.rho = ctx->rho.ptr;
     return k;

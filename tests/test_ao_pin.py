@@ -60,7 +60,7 @@ def test_gpu_evaluator_matches_the_pin(engine_lib):
     s = DFTSolverWrapper(engine_lib, "GGA")
     reps = 37                                   # several blocks of the kernel, ragged tail
     big = np.tile(pts, (reps, 1))
-    for shape in (0, 8, 16, 17, 32):
+    for shape in (0, 1, 8, 16, 17, 32):
         s.set_option("ao_shape", shape)
         d_c = DeviceArray.from_host(big)
         d_ao, d_g = DeviceArray((big.shape[0], 4)), DeviceArray((3, big.shape[0], 4))

@@ -282,11 +282,11 @@ def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
     for opt in ({"vxc_shape": 64}, {"vxc_shape": 128, "vxc_vk": 8}, {"vxc_shape": 128, "vxc_vk": 16}, {"vxc_shape": 160},
                 {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 4}, {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 1},
                 {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 4, "tma_3d": 0},
-                {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 2}, {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 5},
-                {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 6}, {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 5, "tma_3d": 0},
-                {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 7}, {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 1},
+                {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 2}, {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 2, "tma_3d": 0},
+                {"vxc_shape": 128, "vxc_skip": 1, "vxc_skip_mode": 2, "vxc_rebalance": 0, "vxc_prefetch": 6},
                 {"vxc_shape": 128, "vxc_skip": 0, "vxc_producers": 3}, {"dyn_sched": 0}, {"density_unit": 1}, {"density_unit": 2},
-                {"density_unit": 2, "dyn_sched": 0}, {"tma_3d": 0}, {"l2_prefetch": 1}):
+                {"density_unit": 2, "dyn_sched": 0}, {"tma_3d": 0}, {"l2_prefetch": 1}, {"density_producers": 1},
+                {"density_producers": 1, "dyn_sched": 0}, {"density_producers": 2, "dyn_sched": 0, "density_unit": 1}):
         e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, dict(opt, path=2))
         assert s1["path"] == 2, opt
         assert abs(e0 - e1) <= E_TOL * max(1.0, abs(e0) * 1e-3), opt
@@ -365,9 +365,8 @@ def test_vxc_zero_skipping_instances_agree(oracle, engine_lib, functional, ngrid
     assert s0["path"] == 2 and abs(e0 - e_o) <= E_TOL
     np.testing.assert_allclose(0.5 * (v0 + v0.T), oracle.sym(v_o), rtol=0, atol=V_TOL)
     for opt in ({"vxc_skip_mode": 4}, {"vxc_skip_mode": 4, "vxc_scatter": 0}, {"vxc_skip_mode": 1, "vxc_vk": 8},
-                {"vxc_skip_mode": 1, "vxc_vk": 16}, {"vxc_skip_mode": 2}, {"vxc_skip_mode": 5}, {"vxc_skip_mode": 6},
-                {"vxc_skip_mode": 3}, {"vxc_skip_mode": 2, "vxc_vk": 16}, {"vxc_skip_mode": 7}, {"vxc_skip_mode": 7, "vxc_scatter": 0},
-                {"vxc_skip_mode": 5, "vxc_scatter": 0}):
+                {"vxc_skip_mode": 1, "vxc_vk": 16}, {"vxc_skip_mode": 2}, {"vxc_skip_mode": 2, "vxc_scatter": 0},
+                {"vxc_skip_mode": 2, "vxc_producers": 1, "vxc_prefetch": 4}):
         opt = dict(opt, vxc_shape=128, vxc_skip=1)
         e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, opt)
         assert s1["path"] == 2 and e1 == e0, opt
@@ -483,9 +482,10 @@ def test_ao_evaluation_on_gpu(oracle, engine_lib):
             d_ao2 = DeviceArray(ao_o.shape)
             s.eval_ao(d_c, basis, d_ao2, None)
             np.testing.assert_allclose(d_ao2.get(), d_ao.get(), rtol=1e-14, atol=1e-300)  # deriv=0 kernel contracts FMAs differently
-            # every block shape of the kernel (8 | 16 | 32 points, 17 = 16 points x 16 warps), both store widths and both
-            # group orders write identical values
-            for shape, vec, order in ((8, 0, 0), (16, 0, 0), (17, 0, 0), (32, 0, 0), (8, 1, 0), (16, 1, 0), (17, 1, 0), (32, 1, 0),
+            # the direct kernel (shape 1; what 0 = auto picks for bases of this size), every block shape of the two-phase
+            # kernel (8 | 16 | 32 points, 17 = 16 points x 16 warps), both store widths and both group orders write
+            # identical values
+            for shape, vec, order in ((1, 0, 0), (8, 0, 0), (16, 0, 0), (17, 0, 0), (32, 0, 0), (8, 1, 0), (16, 1, 0), (17, 1, 0), (32, 1, 0),
                                       (0, 0, 1), (16, 1, 1)):
                 s.set_option("ao_shape", shape); s.set_option("ao_vec_stores", vec); s.set_option("ao_input_order", order)
                 d_ao3 = DeviceArray(ao_o.shape); d_g3 = DeviceArray(g_o.shape)

@@ -11,9 +11,9 @@ for wl in sys.argv[1:]:
     dp = workload.device_problem(hp, solver)
     P = 1 if hp.functional == "LDA" else 4
     nbytes = 8.0 * dp.ngrid * dp.nao * P
-    for order in (0, 1):
+    for order in (0,):
         solver.set_option("ao_input_order", order)
-        for shape in (0, 17, 100, 117):
+        for shape in (0, 16, 32):
             try:
                 solver.set_option("ao_shape", shape % 100); solver.set_option("ao_vec_stores", 1 if shape >= 100 else 0)
                 best = 1e9

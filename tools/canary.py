@@ -22,10 +22,7 @@ def main():
         for (ngrid, nao), opts in (((3000, 36), {}), ((3000, 36), {"path": 2}), ((4000, 200), {}),
                                    ((4000, 377), {"vxc_skip": 1, "vxc_skip_mode": 4}),
                                    ((4000, 377), {"vxc_skip": 1, "vxc_skip_mode": 1}), ((4000, 377), {"vxc_skip": 0}),
-                                   ((4000, 377), {"vxc_skip": 1, "vxc_skip_mode": 2}), ((4000, 377), {"vxc_skip": 1, "vxc_skip_mode": 5}),
-                                   ((4000, 377), {"vxc_skip": 1, "vxc_skip_mode": 6}), ((4000, 377), {"vxc_skip": 1, "vxc_skip_mode": 3}), ((4000, 377), {"vxc_skip": 1, "vxc_skip_mode": 7}),
-                                   ((20000, 377), {"vxc_skip": 1, "vxc_skip_mode": 7}),
-                                   ((4000, 377), {"vxc_skip": 1, "vxc_skip_mode": 2, "vxc_vk": 16}),
+                                   ((4000, 377), {"vxc_skip": 1, "vxc_skip_mode": 2}), ((20000, 377), {"vxc_skip": 1, "vxc_skip_mode": 2}),
                                    ((3001, 77), {"path": 1})):
             scale = 10 ** rng.uniform(-6, 0, (ngrid, 1))
             ao = rng.standard_normal((ngrid, nao)) * scale
