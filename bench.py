@@ -501,8 +501,10 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
             "per_scf_iter_vxc_ms": ms_step, "e_xc": e_host, "parity": parity,
             "ao_screening": {"density_ksteps_skipped_frac": solver.stat("skip_fraction"),
-                             "note": "share of the density kernel's 32x4 Phi fragments that are exact zeros and "
-                                     "skipped (rank 0); roofline.achieved stays quoted on the DENSE flop count"},
+                             "vxc_fragments_skipped_frac": solver.stat("vxc_skip_fraction"),
+                             "note": "share of the density kernel's 32x4 Phi fragments / of the V kernel's (8-column B "
+                                     "fragment, k-step) units that are exact zeros and skipped (rank 0); "
+                                     "roofline.achieved stays quoted on the DENSE flop count"},
             "ao_eval": None if not ao_ms else {
                 "ms": ao_ms, "bytes_written": 8.0 * n_local * nao * P,
                 "achieved_gbs": 8.0 * n_local * nao * P / (ao_ms * 1e-3) / 1e9,

@@ -1167,6 +1167,13 @@ vxc_tma_kernel(const __grid_constant__ VxcParams P) {
 #pragma unroll
         for (int mf = 0; mf < MF; ++mf) atomicAdd(&P.fstat[tm * 16 + mgroup(mf)], n_live[mf]);
     }
+    if (SKIP != 0 && P.counters && lane == 0) {   // (fragment, k-step) units executed / total: the V kernel's screening statistic
+        unsigned long long done = 0;
+#pragma unroll
+        for (int mf = 0; mf < MF; ++mf) done += n_live[mf];
+        atomicAdd(&P.counters[0], done);
+        atomicAdd(&P.counters[1], (unsigned long long)nchunks * KS * MF);
+    }
     // ---- partial tile out
     double* out = P.vpart + (size_t)blockIdx.y * P.mpv * P.ldv;
 #pragma unroll
