@@ -74,6 +74,9 @@ int DFT_CommDestroy(XCSolver* solver);
 //       the warps from that call's live counts -- heaviest with lightest; results are bit-identical; default 1)
 //       "vxc_prefetch" n (tuning: L2 prefetch distance of the V kernel's producer in ring stages; default 0: measured
 //       no gain)
+//       "density_scatter" 0|1 (density kernel: visit the 64-point blocks in a scattered order -- golden-ratio stride --
+//       instead of grid order, so that the SMs are not all in a sparse or a dense stretch of the grid together; default 0:
+//       measured no gain)
 //       "density_producers" 1|2 (tuning: TMA-issuing threads per consumer group of the density kernel, default 1:
 //       a helper thread that brings the Dsym chunks and half of a piece's planes measured no gain)
 //       "vxc_producers" 1..4 (tuning: TMA-issuing threads per CTA of the V kernel, default 2)

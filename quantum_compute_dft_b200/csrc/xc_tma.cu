@@ -86,6 +86,7 @@ struct DensityParams {
     int wait_ns;       // producer threads sleep this long between polls of an `empty` barrier (0: poll back to back)
     int debug_nodmma;  // diagnostic: treat every k-step as zero (measures the operand-delivery floor; results are wrong)
     int producers2;    // two TMA-issuing threads per consumer group (primary + helper) instead of one
+    int unit_stride;   // visit order of the blocks: k-th draw -> block (k * unit_stride) mod nblocks (<= 1: grid order)
     unsigned long long* counters;  // [2]: k-steps executed, k-steps total (AO screening statistics)
     unsigned int* sched;           // next density block to hand out (dynamic scheduling; reset to 0 before the launch), or null
     double* rho;       // [2 warp columns][coef_rows][4]: partial (rho, drho/2) row sums, summed by the point kernel
@@ -245,6 +246,18 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
     const uint32_t blk_slot = base + L::BLK_OFF + grp * L::STAGES * 4;
     const bool per_tile = P.per_tile != 0;
     const int nunits = per_tile ? nblocks * ntiles : nblocks;
+    // Order in which the units are visited (option density_scatter): the k-th draw is block (k' * stride) mod nblocks,
+    // stride coprime to nblocks (golden ratio), the column tiles of a block still back to back.  In grid order the 296
+    // consumer groups of the GPU work on ~100 neighbouring blocks -- one atom's region -- at any time, so all SMs
+    // are in a sparse (delivery-bound) or a dense (tensor-bound) stretch TOGETHER and their demand on the L2 comes in
+    // chip-wide bursts; scattered, the stretches average out across SMs.  MEASURED: no difference (C5 8.85 against 8.84 ms,
+    // profiles/r2_u16_density_scatter.txt) -- the stage waits are not chip-wide L2 bursts either.  Default: grid order.
+    const int ntl = per_tile ? ntiles : 1;
+    auto unit_of = [&](int draw) {
+        if (P.unit_stride <= 1) return draw;
+        const int bb = draw / ntl, tt = draw - bb * ntl;
+        return (int)(((long long)bb * P.unit_stride) % nblocks) * ntl + tt;
+    };
 
     if (warp >= NCW) {
         // ===================== producer warpgroup: warps 8 and 9, one elected lane each =====================
@@ -276,8 +289,9 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             };
             next_unit();
             while (u < nunits) {
-                const int b = per_tile ? u / ntiles : u;
-                const int nt0 = per_tile ? u - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
+                const int ue = unit_of(u);
+                const int b = per_tile ? ue / ntiles : ue;
+                const int nt0 = per_tile ? ue - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
                 const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
                 const int blk = b - P.sub[si].blk0;
                 const int drow0 = P.sub[si].shift * P.NP;
@@ -326,14 +340,16 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             int u = dyn ? (int)atomicAdd(P.sched, 1u) : b_first;
             publish(u);
             while (u < nunits) {
-                const int b = per_tile ? u / ntiles : u;
-                const int nt0 = per_tile ? u - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
+                const int ue = unit_of(u);
+                const int b = per_tile ? ue / ntiles : ue;
+                const int nt0 = per_tile ? ue - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
                 const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
                 const int blk = b - P.sub[si].blk0;
                 const int drow0 = P.sub[si].shift * P.NP;
                 const int un = dyn ? (int)atomicAdd(P.sched, 1u) : u + b_step;  // this group's next unit
                 publish(un);
-                const int bn = per_tile ? un / ntiles : un;                      // (its block: L2 prefetch only)
+                const int une = un < nunits ? unit_of(un) : un;
+                const int bn = per_tile ? une / ntiles : une;                    // (its block: L2 prefetch only)
                 const int sin = (P.nsub > 1 && bn >= P.sub[1].blk0) ? 1 : 0;
                 const int blkn = bn - P.sub[sin].blk0;
                 for (int nt = nt0; nt < nt1; ++nt) {
@@ -356,7 +372,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                         const uint32_t s = it % L::STAGES, ph = (it / L::STAGES) & 1u;
                         tma::mbar_wait_relaxed(&empty[s], ph ^ 1u, (uint32_t)P.wait_ns);
                         unsigned char* st = ring + s * L::STAGE_BYTES;
-                        if (nt == nt0 && kc == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(blk_slot + 4 * s), "r"(u) : "memory");
+                        if (nt == nt0 && kc == 0) asm volatile("st.shared.s32 [%0], %1;" ::"r"(blk_slot + 4 * s), "r"(ue) : "memory");
                         tma::mbar_arrive_expect_tx(&full[s], L::K_BYTES);
                         tma::load_2d(st, &P.map_a[si], kc * 16, blk * MB, &full[s]);
                         if (!two) tma::load_2d(st + L::A_BYTES, &P.map_d, kc * 16, drow0 + nt * NT, &full[s]);
@@ -459,8 +475,9 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
         } else if (u >= nunits) {
             break;
         }
-        const int b = per_tile ? u / ntiles : u;
-        const int nt0 = per_tile ? u - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
+        const int ue = dyn ? u : unit_of(u);   // (the dynamic deal hands over the unit itself)
+        const int b = per_tile ? ue / ntiles : ue;
+        const int nt0 = per_tile ? ue - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
         const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
         const int blk = b - P.sub[si].blk0;
         double rs[4][NPL];  // per-lane partial row sums of the whole block
@@ -1695,7 +1712,7 @@ static Geometry make_geometry(int ngrid, int nao) {
 // addresses, so a plan stays valid when the caller rewrites the CONTENTS of its arrays.
 struct PlanKey {
     Problem prob;
-    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, debug_nodmma, wait_ns, dyn_sched, stagger_min, density_unit, vxc_prefetch, vxc_rebalance, density_producers;
+    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, debug_nodmma, wait_ns, dyn_sched, stagger_min, density_unit, vxc_prefetch, vxc_rebalance, density_producers, density_scatter;
     const void *dsym, *coef, *epart, *vpart, *rho;  // engine workspaces (grow-only: may move when they grow)
 };
 
@@ -1752,6 +1769,13 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
     dp.debug_nodmma = ctx->debug_nodmma; dp.wait_ns = ctx->wait_ns; dp.stagger_min = ctx->stagger_min;
     dp.per_tile = per_tile ? 1 : 0;
     dp.producers2 = ctx->density_producers >= 2 ? 1 : 0;
+    dp.unit_stride = 1;
+    if (ctx->density_scatter && g.nblocks > 64) {
+        long long st = (long long)(0.6180339887 * (double)g.nblocks) | 1;
+        auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
+        while (gcd(st, g.nblocks) != 1) st += 2;
+        dp.unit_stride = (int)(st % g.nblocks);
+    }
     dp.coef_rows = g.coef_rows; dp.rho = rho;
     // (the counters must exist before `sched` is derived from them: round 1 had these two statements the other
     // way round, so `sched` was always null and the dynamic deal never ran)
@@ -1955,7 +1979,7 @@ static PlanKey make_key(const CublasHandleWrapper* ctx, const Problem& p) {
     k.prob.vxc = p.vxc; k.prob.d_exc = p.d_exc;
     k.exact = ctx->exact_functionals; k.l2_prefetch = ctx->l2_prefetch; k.tma_3d = ctx->tma_3d;
     k.vxc_shape = ctx->vxc_shape; k.vxc_vk = ctx->vxc_vk; k.zero_skip = ctx->zero_skip; k.vxc_skip_on = ctx->vxc_skip_on; k.vxc_skip_mode = ctx->vxc_skip_mode; k.vxc_scatter = ctx->vxc_scatter;
-    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.stagger_min = ctx->stagger_min; k.density_unit = ctx->density_unit; k.vxc_producers = ctx->vxc_producers; k.vxc_prefetch = ctx->vxc_prefetch; k.vxc_rebalance = ctx->vxc_rebalance; k.density_producers = ctx->density_producers;
+    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.stagger_min = ctx->stagger_min; k.density_unit = ctx->density_unit; k.vxc_producers = ctx->vxc_producers; k.vxc_prefetch = ctx->vxc_prefetch; k.vxc_rebalance = ctx->vxc_rebalance; k.density_producers = ctx->density_producers; k.density_scatter = ctx->density_scatter;
     k.dsym = ctx->dsym.ptr; k.coef = ctx->coef.ptr; k.epart = ctx->epart.ptr; k.vpart = ctx->vpart.ptr;
     k.rho = ctx->rho.ptr;
     return k;
