@@ -74,6 +74,8 @@ int DFT_CommDestroy(XCSolver* solver);
 //       the warps from that call's live counts -- heaviest with lightest; results are bit-identical; default 1)
 //       "vxc_prefetch" n (tuning: L2 prefetch distance of the V kernel's producer in ring stages; default 0: measured
 //       no gain)
+//       "density_wide" 0|1 (density kernel: 1 = one consumer group of 8 warps on 128-point blocks with one seven-stage ring,
+//       the Dsym chunk delivered once per 128 rows; 0 = two ping-pong groups of 4 warps on 64-point blocks)
 //       "density_scatter" 0|1 (density kernel: visit the 64-point blocks in a scattered order -- golden-ratio stride --
 //       instead of grid order, so that the SMs are not all in a sparse or a dense stretch of the grid together; default 0:
 //       measured no gain)

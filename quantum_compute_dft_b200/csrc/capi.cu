@@ -372,6 +372,7 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "debug_nodmma")) { c->debug_nodmma = value != 0.0; return 0; }   // results are WRONG: delivery floor
 #endif
     if (!strcmp(key, "vxc_scatter")) { c->vxc_scatter = value != 0.0; return 0; }
+    if (!strcmp(key, "density_wide")) { c->density_wide = value != 0.0; return 0; }
     if (!strcmp(key, "density_scatter")) { c->density_scatter = value != 0.0; return 0; }
     if (!strcmp(key, "density_producers")) { c->density_producers = value >= 2.0 ? 2 : 1; return 0; }
     if (!strcmp(key, "vxc_prefetch")) { c->vxc_prefetch = value < 0.0 ? 0 : (value > 64.0 ? 64 : (int)value); return 0; }

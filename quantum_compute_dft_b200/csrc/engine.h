@@ -94,6 +94,7 @@ struct CublasHandleWrapper {
     int debug_nodmma = 0;          // -DDFT_DIAGNOSTICS builds only: TMA kernels skip every DMMA (measures the operand-delivery floor)
     bool vxc_rebalance = true;     // TMA V kernel, per-warp-vote instances: re-deal the 8-column M fragments to the warps from the live counts of the previous call (heaviest with lightest, heavy pairs share an SM sub-partition with light ones)
     bool fmap_valid = false, fmap_dirty = false;   // (state of the fragment map: initialised / host copy newer than the device copy)
+    int density_wide = 0;          // TMA density kernel: one consumer group of 8 warps on 128-point blocks with one ring (1) instead of two ping-pong groups of 4 on 64-point blocks (0)
     int density_scatter = 0;       // TMA density kernel: visit the 64-point blocks in a scattered order (golden-ratio stride) instead of grid order (measured: no gain)
     int density_producers = 1;     // TMA density kernel: TMA-issuing threads per consumer group (1 | 2; 2 measured no faster: 8.83 against 8.82 ms at C5)
     int vxc_prefetch = 0;          // TMA V kernel: L2 prefetch distance of the producer in ring stages (0: none)

@@ -169,29 +169,39 @@ __device__ __forceinline__ xcfun::PointCoef eval_mode(int mode, double rho, doub
 // independent chains; the cross-lane reduction happens once per block.
 constexpr int GW = 4;                        // warps per consumer group
 
-template <int NF2, int NPL>
+// WIDE (round 2, option density_wide): ONE consumer group of 8 warps (4 x 2) on blocks of 128 grid points with one
+// ring, instead of two ping-pong groups of 4 warps on 64-point blocks with a ring each.  The Dsym chunk -- two thirds of
+// the k-loop's operand bytes -- is then delivered once per 128 rows instead of once per 64 (a third fewer k-loop bytes),
+// and the ring is seven stages of 32 KB deep instead of three; the price is that nobody works on the tensor pipe
+// while the group is in its epilogue.  The per-warp code (fragment maps, votes, row-dot epilogue) is the same.
+template <int NF2, int NPL, bool WIDE = false>
 struct DensitySmem {
     static_assert(NF2 % 2 == 0, "a warp's columns are whole 16-column groups");
     static constexpr int NT = 16 * NF2;
-    static constexpr int A_BYTES = MB * 128;
+    static constexpr int GRPS = WIDE ? 1 : 2;                             // consumer groups (rings) per CTA
+    static constexpr int GWW = NCW / GRPS;                                // warps per group
+    static constexpr int RB = WIDE ? 2 * MB : MB;                         // grid rows per group block
+    static constexpr int A_BYTES = RB * 128;
     static constexpr int D_BYTES = NT * 128;
     static constexpr int K_BYTES = A_BYTES + D_BYTES;
-    static constexpr int PLANE_BYTES = MB * 128;                          // one plane of a piece
-    // A piece may travel as PSPLIT stages of NPL / PSPLIT planes each.  PSPLIT = 2 for GGA (16 KB stages fit the 24 KB
-    // slot of a k-chunk: a 4-stage ring instead of 3 stages of 32 KB) was measured in round 2 and is SLOWER -- C5
-    // 9.30 against 9.03 ms, C4 1.235 against 1.186 ms (profiles/r2_u4_density_half_pieces.txt): twice the stage
-    // hand-shakes in the epilogue cost more than the deeper ring gains -- so a piece stays one stage.
-    static constexpr int PSPLIT = 1;                                      // stages per piece
+    static constexpr int PLANE_BYTES = RB * 128;                          // one plane of a piece
+    // A piece may travel as PSPLIT stages of NPL / PSPLIT planes each.  For the two-group kernel PSPLIT = 2 (16 KB stages
+    // fit the 24 KB slot of a k-chunk: a 4-stage ring instead of 3 stages of 32 KB) was measured in round 2 and is SLOWER
+    // -- C5 9.30 against 9.03 ms, C4 1.235 against 1.186 ms (profiles/r2_u4_density_half_pieces.txt): twice the stage
+    // hand-shakes in the epilogue cost more than the deeper ring gains -- so there a piece stays one stage.  The wide
+    // kernel's 128-row GGA piece is 64 KB and travels as two stages of two planes.
+    static constexpr int PSPLIT = (WIDE && NPL == 4) ? 2 : 1;             // stages per piece
     static constexpr int PPL = NPL / PSPLIT;                              // planes per stage of a piece
     static constexpr int PIECE_BYTES = PPL * PLANE_BYTES;
     static constexpr int STAGE_BYTES = K_BYTES > PIECE_BYTES ? K_BYTES : PIECE_BYTES;
     static constexpr int FIXED_BYTES = 640 + 1024;                        // barriers, slots, unit queue, alignment slack
-    static constexpr int STAGES = (232448 - FIXED_BYTES) / (2 * STAGE_BYTES) < 6 ? (232448 - FIXED_BYTES) / (2 * STAGE_BYTES) : 6;
+    static constexpr int CAP = WIDE ? 8 : 6;
+    static constexpr int STAGES = (232448 - FIXED_BYTES) / (GRPS * STAGE_BYTES) < CAP ? (232448 - FIXED_BYTES) / (GRPS * STAGE_BYTES) : CAP;
     static_assert(STAGES >= 2, "ring depth");
     static constexpr int NCG = NT / 16;                                   // 16-column groups per tile (= NF2)
     static constexpr int NPIECES = NCG * PSPLIT;                          // piece stages per tile
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;               // one group's ring
-    static constexpr int BAR_OFF = 2 * RING_BYTES;                        // [2 groups]{full[STAGES], empty[STAGES]}
+    static constexpr int BAR_OFF = GRPS * RING_BYTES;                     // [groups]{full[STAGES], empty[STAGES]}
     static constexpr int BLK_OFF = BAR_OFF + 2 * 2 * STAGES * 8;          // [2 groups][STAGES] block id carried by a stage
     static constexpr int UQ_OFF = ((BLK_OFF + 2 * STAGES * 4 + 7) / 8) * 8; // [2 groups][4] (sequence << 32 | unit): primary -> helper issuing thread
     static constexpr int TOTAL = UQ_OFF + 2 * 4 * 8 + 8 + 1024;           // + alignment slack
@@ -204,10 +214,10 @@ struct DensitySmem {
     __host__ __device__ static constexpr int stage_pl0(int ps) { return (ps % PSPLIT) * PPL; }
 };
 
-template <int NF2, int NPL>
+template <int NF2, int NPL, bool WIDE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 density_tma_kernel(const __grid_constant__ DensityParams P) {
-    using L = DensitySmem<NF2, NPL>;
+    using L = DensitySmem<NF2, NPL, WIDE>;
     constexpr int NT = L::NT;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (tma::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -216,10 +226,10 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF);
-        for (int g = 0; g < 2; ++g)
+        for (int g = 0; g < L::GRPS; ++g)
             for (int s = 0; s < L::STAGES; ++s) {
                 tma::mbar_init(&bars[g * 2 * L::STAGES + s], P.producers2 ? 2 : 1);   // full: every issuing thread of the group arrives
-                tma::mbar_init(&bars[g * 2 * L::STAGES + L::STAGES + s], GW);
+                tma::mbar_init(&bars[g * 2 * L::STAGES + L::STAGES + s], L::GWW);
             }
         tma::fence_barrier_init();
         for (int i = 0; i < 8; ++i) reinterpret_cast<volatile unsigned long long*>(sm + L::UQ_OFF)[i] = 0ull;
@@ -228,12 +238,12 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
 
     const int nblocks = P.nblocks, ntiles = P.ntiles, nk = P.nk;
     // consumer group / ring of this warp: warps 0-3 -> 0, 4-7 -> 1, producer warps 8 -> 0, 9 -> 1
-    const int grp = warp < NCW ? warp >> 2 : (warp - NCW) & 1;
+    const int grp = WIDE ? 0 : (warp < NCW ? warp >> 2 : (warp - NCW) & 1);
     uint64_t* full = reinterpret_cast<uint64_t*>(sm + L::BAR_OFF) + grp * 2 * L::STAGES;
     uint64_t* empty = full + L::STAGES;
     unsigned char* ring = sm + grp * L::RING_BYTES;
     const uint32_t ring_u32 = base + grp * L::RING_BYTES;
-    const int b_first = 2 * blockIdx.x + grp, b_step = 2 * gridDim.x;
+    const int b_first = L::GRPS * blockIdx.x + grp, b_step = L::GRPS * gridDim.x;
     // Blocks are handed out dynamically (one global counter): a block of points near many atoms costs several
     // times one out in the tail, so a static deal leaves the last groups running alone.  The producer draws
     // the block ids (the next one while the current block streams) and passes each to its consumers in a
@@ -273,7 +283,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
         // (profiles/r2_u13_density_two_issuers.txt): the waits are not the issue rate.  Default: one thread.
         const bool two = P.producers2 != 0;
         volatile unsigned long long* uq = reinterpret_cast<volatile unsigned long long*>(sm + L::UQ_OFF) + 4 * grp;
-        if (warp >= NCW + 2 && lane == 0 && two) {
+        if (warp >= NCW + 2 && warp < NCW + 2 + L::GRPS && lane == 0 && two) {
             // ===================== helper issuing thread =====================
             tma::prefetch_map(&P.map_d);
             uint32_t it = 0;
@@ -290,8 +300,9 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             next_unit();
             while (u < nunits) {
                 const int ue = unit_of(u);
-                const int b = per_tile ? ue / ntiles : ue;
-                const int nt0 = per_tile ? ue - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
+                const int bu = per_tile ? ue / ntiles : ue;                    // unit block (RB rows)
+                const int nt0 = per_tile ? ue - bu * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
+                const int b = WIDE ? 2 * bu : bu;                              // its first 64-row block
                 const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
                 const int blk = b - P.sub[si].blk0;
                 const int drow0 = P.sub[si].shift * P.NP;
@@ -320,7 +331,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             }
             return;
         }
-        if (warp < NCW + 2 && lane == 0) {
+        if (warp < NCW + L::GRPS && lane == 0) {
             unsigned int kseq = 0;
             auto publish = [&](int uu) {   // (dynamic deal: the helper reads the unit sequence from here)
                 ++kseq;
@@ -341,15 +352,16 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             publish(u);
             while (u < nunits) {
                 const int ue = unit_of(u);
-                const int b = per_tile ? ue / ntiles : ue;
-                const int nt0 = per_tile ? ue - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
+                const int bu = per_tile ? ue / ntiles : ue;                    // unit block (RB rows)
+                const int nt0 = per_tile ? ue - bu * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
+                const int b = WIDE ? 2 * bu : bu;                              // its first 64-row block
                 const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
                 const int blk = b - P.sub[si].blk0;
                 const int drow0 = P.sub[si].shift * P.NP;
                 const int un = dyn ? (int)atomicAdd(P.sched, 1u) : u + b_step;  // this group's next unit
                 publish(un);
                 const int une = un < nunits ? unit_of(un) : un;
-                const int bn = per_tile ? une / ntiles : une;                    // (its block: L2 prefetch only)
+                const int bn = (WIDE ? 2 : 1) * (per_tile ? une / ntiles : une);  // (its block: L2 prefetch only)
                 const int sin = (P.nsub > 1 && bn >= P.sub[1].blk0) ? 1 : 0;
                 const int blkn = bn - P.sub[sin].blk0;
                 for (int nt = nt0; nt < nt1; ++nt) {
@@ -359,7 +371,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
                             const int ka = kc + PF;
                             if (ka < nk) tma::prefetch_2d(&P.map_a[si], ka * 16, blk * MB);
                             else if (nt + 1 < nt1) { if (ka - nk < nk) tma::prefetch_2d(&P.map_a[si], (ka - nk) * 16, blk * MB); }
-                            else if (bn < nblocks && ka - nk < nk) tma::prefetch_2d(&P.map_a[sin], (ka - nk) * 16, blkn * MB);
+                            else if (une < nunits && ka - nk < nk) tma::prefetch_2d(&P.map_a[sin], (ka - nk) * 16, blkn * MB);
                             if (kc >= pc0) {
                                 // pieces [lo, hi) of this tile; all of them by the last chunk
                                 const int span = nk - pc0;
@@ -403,8 +415,8 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
 
     // ===================== consumers: 2 groups x (2 x 2 warps), warp tile 32 x (8 NF2) =====================
     reg_inc<REGS_CONSUMER>();
-    const int gw = warp & 3;
-    const int wm = gw >> 1, wn = gw & 1;
+    const int gw = WIDE ? warp : (warp & 3);
+    const int wm = gw >> 1, wn = gw & 1;   // (wide: 4 x 2 warps over 128 rows; else 2 x 2 over 64)
     const int q = lane >> 2, qcol = lane & 3;
     // fragment row -> tile row.  A side: {0,3,4,7 | 1,2,5,6}; B side: {0,2,4,6 | 1,3,5,7}.  Both make
     // the k-loop loads conflict-free under SWIZZLE_128B, and together they make the epilogue loads
@@ -452,7 +464,7 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
 #endif
 
     // group 1 starts half a column-tile period late (only worth it when there are several blocks to do)
-    if (grp == 1 && nblocks > P.stagger_min * (int)gridDim.x) {
+    if (!WIDE && grp == 1 && nblocks > P.stagger_min * (int)gridDim.x) {
         const long long t_start = clock64(), delay = (long long)nk * 2048;
         while (clock64() - t_start < delay) __nanosleep(2000);
     }
@@ -476,8 +488,9 @@ density_tma_kernel(const __grid_constant__ DensityParams P) {
             break;
         }
         const int ue = dyn ? u : unit_of(u);   // (the dynamic deal hands over the unit itself)
-        const int b = per_tile ? ue / ntiles : ue;
-        const int nt0 = per_tile ? ue - b * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
+        const int bu = per_tile ? ue / ntiles : ue;
+        const int nt0 = per_tile ? ue - bu * ntiles : 0, nt1 = per_tile ? nt0 + 1 : ntiles;
+        const int b = WIDE ? 2 * bu : bu;
         const int si = (P.nsub > 1 && b >= P.sub[1].blk0) ? 1 : 0;
         const int blk = b - P.sub[si].blk0;
         double rs[4][NPL];  // per-lane partial row sums of the whole block
@@ -1697,7 +1710,9 @@ static Geometry make_geometry(int ngrid, int nao) {
     for (int s = 0; s < g.nsub; ++s) {
         g.sub[s].blk0 = g.nblocks;
         g.sub[s].coef0 = g.coef_rows;
-        const int nb = (g.sub[s].rows + MB - 1) / MB;
+        // (an even number of 64-row blocks per sub-problem: the wide density kernel takes them in pairs, and a pair must
+        // not straddle the two sub-problems; a padding block is all zero rows)
+        const int nb = 2 * ((g.sub[s].rows + 2 * MB - 1) / (2 * MB));
         g.nblocks += nb;
         g.coef_rows += nb * MB;
     }
@@ -1712,7 +1727,7 @@ static Geometry make_geometry(int ngrid, int nao) {
 // addresses, so a plan stays valid when the caller rewrites the CONTENTS of its arrays.
 struct PlanKey {
     Problem prob;
-    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, debug_nodmma, wait_ns, dyn_sched, stagger_min, density_unit, vxc_prefetch, vxc_rebalance, density_producers, density_scatter;
+    int exact, l2_prefetch, tma_3d, vxc_shape, vxc_vk, zero_skip, vxc_skip_on, vxc_skip_mode, vxc_scatter, vxc_producers, debug_nodmma, wait_ns, dyn_sched, stagger_min, density_unit, vxc_prefetch, vxc_rebalance, density_producers, density_scatter, density_wide;
     const void *dsym, *coef, *epart, *vpart, *rho;  // engine workspaces (grow-only: may move when they grow)
 };
 
@@ -1724,22 +1739,23 @@ struct Plan {
     VxcParams vp;
     const void* dfunc = nullptr;
     const void* vfunc = nullptr;
-    int dgrid = 0, dsmem = 0, vsmem = 0, pgrid = 0, vthreads = NTHREADS, v_tiles_m = 0;
+    int dgrid = 0, dsmem = 0, vsmem = 0, pgrid = 0, vthreads = NTHREADS, v_tiles_m = 0, dgroups = 2;
     dim3 vgrid;
     // symmetrize_pad / finalize arguments
     int KP = 0, NP = 0, nsub = 0, ldv = 0, mpv = 0, fin_nt = 0, nsl = 0, shift1 = 0, lda_half = 0;
     double *dsym = nullptr, *epart = nullptr, *vpart = nullptr;
 };
 
-template <int NF2, int NPL>
+template <int NF2, int NPL, bool WIDE>
 static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geometry& g, int nsm, double* coef, Plan& pl) {
-    using DL = DensitySmem<NF2, NPL>;
+    using DL = DensitySmem<NF2, NPL, WIDE>;
     constexpr int NT = DL::NT;
     const int ngrid = p.ngrid, nao = p.nao;
     const int ntiles = (g.ncols + NT - 1) / NT;
     const int NP = ntiles * NT;
     const int KP = ((g.ncols + 15) / 16) * 16;
-    const int grid1 = (g.nblocks + 1) / 2 < nsm ? (g.nblocks + 1) / 2 : nsm;  // two consumer groups per CTA
+    const int ublocks = WIDE ? g.nblocks / 2 : g.nblocks;                     // unit blocks of DL::RB rows
+    const int grid1 = (ublocks + DL::GRPS - 1) / DL::GRPS < nsm ? (ublocks + DL::GRPS - 1) / DL::GRPS : nsm;  // GRPS consumer groups per CTA
     const int pgrid = (g.coef_rows + POINT_THREADS - 1) / POINT_THREADS;
 
     double* dsym = (double*)ctx->dsym.ensure(sizeof(double) * (size_t)g.nsub * NP * KP, &ctx->failed);
@@ -1756,25 +1772,25 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
     const double* planes[4] = {p.ao, p.gx, p.gy, p.gz};
     bool ok = make_map(&dp.map_d, dsym, (uint64_t)KP, (uint64_t)g.nsub * NP, (uint64_t)KP, NT);
     for (int s = 0; s < g.nsub; ++s) {
-        ok = ok && make_sub_map(&dp.map_a[s], p.ao, ngrid, nao, g.split, s, MB);
+        ok = ok && make_sub_map(&dp.map_a[s], p.ao, ngrid, nao, g.split, s, DL::RB);
         for (int i = 0; i < 4; ++i)
-            ok = ok && make_sub_map(&dp.map_e[s][i], planes[i < NPL ? i : 0], ngrid, nao, g.split, s, MB);
+            ok = ok && make_sub_map(&dp.map_e[s][i], planes[i < NPL ? i : 0], ngrid, nao, g.split, s, DL::RB);
     }
     if (!ok) { ctx->failed = true; return; }
     dp.sub[0] = g.sub[0]; dp.sub[1] = g.sub[1];
     dp.nsub = g.nsub;
-    dp.nblocks = g.nblocks; dp.ntiles = ntiles; dp.nk = KP / 16; dp.NP = NP;
+    dp.nblocks = ublocks; dp.ntiles = ntiles; dp.nk = KP / 16; dp.NP = NP;
     dp.l2_prefetch = ctx->l2_prefetch ? 1 : 0;
     dp.zero_skip = ctx->zero_skip ? 1 : 0;
     dp.debug_nodmma = ctx->debug_nodmma; dp.wait_ns = ctx->wait_ns; dp.stagger_min = ctx->stagger_min;
     dp.per_tile = per_tile ? 1 : 0;
     dp.producers2 = ctx->density_producers >= 2 ? 1 : 0;
     dp.unit_stride = 1;
-    if (ctx->density_scatter && g.nblocks > 64) {
-        long long st = (long long)(0.6180339887 * (double)g.nblocks) | 1;
+    if (ctx->density_scatter && ublocks > 64) {
+        long long st = (long long)(0.6180339887 * (double)ublocks) | 1;
         auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
-        while (gcd(st, g.nblocks) != 1) st += 2;
-        dp.unit_stride = (int)(st % g.nblocks);
+        while (gcd(st, ublocks) != 1) st += 2;
+        dp.unit_stride = (int)(st % ublocks);
     }
     dp.coef_rows = g.coef_rows; dp.rho = rho;
     // (the counters must exist before `sched` is derived from them: round 1 had these two statements the other
@@ -1795,7 +1811,8 @@ static void plan_density(CublasHandleWrapper* ctx, const Problem& p, const Geome
     if (dp.phase) cudaMemsetAsync(dp.phase, 0, sizeof(long long) * 8192, ctx->stream);
 #endif
 
-    auto dk = density_tma_kernel<NF2, NPL>;
+    pl.dgroups = DL::GRPS;
+    auto dk = density_tma_kernel<NF2, NPL, WIDE>;
     DFT_CUDA_CHECK(ctx, cudaFuncSetAttribute(dk, cudaFuncAttributeMaxDynamicSharedMemorySize, DL::TOTAL));
     pl.dfunc = reinterpret_cast<const void*>(dk);
     pl.dgrid = grid1; pl.dsmem = DL::TOTAL;
@@ -1914,13 +1931,16 @@ static void build_plan(CublasHandleWrapper* ctx, const Problem& p, int nsm, Plan
         const int nt = 32 * nf, np = ((g.ncols + nt - 1) / nt) * nt;
         if (np <= best_np) { best_np = np; best_nf = nf; }
     }
+#define DFT_PLAN_D(NF2_) do { if (ctx->density_wide) plan_density<NF2_, NPL, true>(ctx, p, g, nsm, coef, pl); \
+                              else plan_density<NF2_, NPL, false>(ctx, p, g, nsm, coef, pl); } while (0)
     switch (best_nf) {
-        case 1: plan_density<2, NPL>(ctx, p, g, nsm, coef, pl); break;
-        case 2: plan_density<4, NPL>(ctx, p, g, nsm, coef, pl); break;
-        case 3: plan_density<6, NPL>(ctx, p, g, nsm, coef, pl); break;
-        case 4: plan_density<8, NPL>(ctx, p, g, nsm, coef, pl); break;
-        default: plan_density<10, NPL>(ctx, p, g, nsm, coef, pl); break;
+        case 1: DFT_PLAN_D(2); break;
+        case 2: DFT_PLAN_D(4); break;
+        case 3: DFT_PLAN_D(6); break;
+        case 4: DFT_PLAN_D(8); break;
+        default: DFT_PLAN_D(10); break;
     }
+#undef DFT_PLAN_D
     if (ctx->failed) return;
 
     // V output tile: 64 x 64 for narrow matrices, else the cheaper of 128 x 128 and 160 x 80
@@ -1979,7 +1999,7 @@ static PlanKey make_key(const CublasHandleWrapper* ctx, const Problem& p) {
     k.prob.vxc = p.vxc; k.prob.d_exc = p.d_exc;
     k.exact = ctx->exact_functionals; k.l2_prefetch = ctx->l2_prefetch; k.tma_3d = ctx->tma_3d;
     k.vxc_shape = ctx->vxc_shape; k.vxc_vk = ctx->vxc_vk; k.zero_skip = ctx->zero_skip; k.vxc_skip_on = ctx->vxc_skip_on; k.vxc_skip_mode = ctx->vxc_skip_mode; k.vxc_scatter = ctx->vxc_scatter;
-    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.stagger_min = ctx->stagger_min; k.density_unit = ctx->density_unit; k.vxc_producers = ctx->vxc_producers; k.vxc_prefetch = ctx->vxc_prefetch; k.vxc_rebalance = ctx->vxc_rebalance; k.density_producers = ctx->density_producers; k.density_scatter = ctx->density_scatter;
+    k.debug_nodmma = ctx->debug_nodmma; k.wait_ns = ctx->wait_ns; k.dyn_sched = ctx->dyn_sched; k.stagger_min = ctx->stagger_min; k.density_unit = ctx->density_unit; k.vxc_producers = ctx->vxc_producers; k.vxc_prefetch = ctx->vxc_prefetch; k.vxc_rebalance = ctx->vxc_rebalance; k.density_producers = ctx->density_producers; k.density_scatter = ctx->density_scatter; k.density_wide = ctx->density_wide;
     k.dsym = ctx->dsym.ptr; k.coef = ctx->coef.ptr; k.epart = ctx->epart.ptr; k.vpart = ctx->vpart.ptr;
     k.rho = ctx->rho.ptr;
     return k;
@@ -2020,7 +2040,7 @@ static void run_plan(CublasHandleWrapper* ctx, const Problem& p, Plan& pl) {
     ctx->stats.launches = 5;
     ctx->stats.path = PATH_TMA;
     ctx->stats.density_units = pl.dp.per_tile ? pl.dp.nblocks * pl.dp.ntiles : pl.dp.nblocks;
-    ctx->stats.density_groups = 2 * pl.dgrid;
+    ctx->stats.density_groups = pl.dgroups * pl.dgrid;
     ctx->stats.dyn_units = 0.0;
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
 }

@@ -287,7 +287,9 @@ def test_tma_kernel_variants_agree(engine_lib, functional, ngrid, nao):
                 {"vxc_shape": 128, "vxc_skip": 0, "vxc_producers": 3}, {"dyn_sched": 0}, {"density_unit": 1}, {"density_unit": 2},
                 {"density_unit": 2, "dyn_sched": 0}, {"tma_3d": 0}, {"l2_prefetch": 1}, {"density_producers": 1},
                 {"density_producers": 2}, {"density_producers": 2, "dyn_sched": 0, "density_unit": 1}, {"density_scatter": 0},
-                {"density_scatter": 0, "dyn_sched": 0}, {"density_scatter": 1, "dyn_sched": 0, "density_unit": 1}):
+                {"density_scatter": 1}, {"density_scatter": 1, "dyn_sched": 0, "density_unit": 1}, {"density_wide": 1},
+                {"density_wide": 1, "dyn_sched": 0}, {"density_wide": 1, "density_unit": 1}, {"density_wide": 1, "density_producers": 2},
+                {"density_wide": 1, "density_scatter": 1, "l2_prefetch": 1}):
         e1, v1, s1 = _run_engine(engine_lib, functional, dm, ao, w, grad, dict(opt, path=2))
         assert s1["path"] == 2, opt
         assert abs(e0 - e1) <= E_TOL * max(1.0, abs(e0) * 1e-3), opt

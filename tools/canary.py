@@ -23,6 +23,8 @@ def main():
                                    ((4000, 377), {"vxc_skip": 1, "vxc_skip_mode": 4}),
                                    ((4000, 377), {"vxc_skip": 1, "vxc_skip_mode": 1}), ((4000, 377), {"vxc_skip": 0}),
                                    ((4000, 377), {"vxc_skip": 1, "vxc_skip_mode": 2}), ((20000, 377), {"vxc_skip": 1, "vxc_skip_mode": 2}),
+                                   ((4000, 377), {"density_wide": 1}), ((4001, 200), {"density_wide": 1}), ((3000, 36), {"path": 2, "density_wide": 1}),
+                                   ((20000, 152), {"density_wide": 1, "dyn_sched": 0}), ((9000, 377), {"density_wide": 1, "density_unit": 1}),
                                    ((3001, 77), {"path": 1})):
             scale = 10 ** rng.uniform(-6, 0, (ngrid, 1))
             ao = rng.standard_normal((ngrid, nao)) * scale

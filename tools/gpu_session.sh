@@ -45,6 +45,7 @@ print('DMMA TFLOP/s', l.DFT_MicrobenchDMMA(8192)); print('DFMA TFLOP/s', l.DFT_M
     sweep8b) SWEEP_RANKS=8 SWEEP_STEPS=10 timeout 600 python tools/vxc_sweep.py C5 "" "stagger_min=100000" "stagger_min=100000,density_unit=1" "vxc_rebalance=0" "" > $OUT/sweep8b.txt 2>&1; SWEEP_RANKS=8 SWEEP_STEPS=10 timeout 600 python tools/vxc_sweep.py C4 "" "stagger_min=100000" "vxc_shape=128" "vxc_shape=64" >> $OUT/sweep8b.txt 2>&1; echo "sweep8b rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweep8b.txt ;;
     sweepd2) SWEEP_STEPS=8 timeout 600 python tools/vxc_sweep.py C5 "" "density_producers=1" "density_producers=2,dyn_sched=0" "density_producers=2,density_unit=1" "" > $OUT/sweepd2.txt 2>&1; SWEEP_STEPS=8 timeout 600 python tools/vxc_sweep.py C4 "" "density_producers=1" >> $OUT/sweepd2.txt 2>&1;  SWEEP_RANKS=8 SWEEP_STEPS=8 timeout 600 python tools/vxc_sweep.py C5 "" "density_producers=1" >> $OUT/sweepd2.txt 2>&1; echo "sweepd2 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweepd2.txt ;;
     sweepd3) SWEEP_STEPS=8 timeout 600 python tools/vxc_sweep.py C5 "" "density_scatter=0" "density_scatter=1,dyn_sched=0" "density_scatter=1,density_unit=1" "" > $OUT/sweepd3.txt 2>&1; SWEEP_STEPS=8 timeout 600 python tools/vxc_sweep.py C4 "" "density_scatter=0" >> $OUT/sweepd3.txt 2>&1;  SWEEP_RANKS=8 SWEEP_STEPS=8 timeout 600 python tools/vxc_sweep.py C5 "" "density_scatter=0" >> $OUT/sweepd3.txt 2>&1; echo "sweepd3 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweepd3.txt ;;
+    sweepd4) SWEEP_STEPS=8 timeout 600 python tools/vxc_sweep.py C5 "" "density_wide=1" "density_wide=1,density_producers=2" "density_wide=1,dyn_sched=0" "density_wide=1,zero_skip=0" "zero_skip=0" > $OUT/sweepd4.txt 2>&1; SWEEP_STEPS=8 timeout 600 python tools/vxc_sweep.py C4 "" "density_wide=1" >> $OUT/sweepd4.txt 2>&1;  SWEEP_RANKS=8 SWEEP_STEPS=8 timeout 600 python tools/vxc_sweep.py C5 "" "density_wide=1" >> $OUT/sweepd4.txt 2>&1; echo "sweepd4 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweepd4.txt ;;
     sweepd)  SWEEP_LIB=diag timeout 600 python tools/vxc_sweep.py C5 "vxc_skip_mode=4" "vxc_skip_mode=4,debug_nodmma=1" "vxc_skip_mode=4,debug_nodmma=1,vxc_scatter=0" > $OUT/sweepd.txt 2>&1; echo "sweepd rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweepd.txt ;;
     sweep1)  timeout 600 python tools/vxc_sweep.py C5 "dyn_sched=1" "dyn_sched=0" > $OUT/sweep1.txt 2>&1; echo "sweep1 rc=$?" | tee -a $OUT/summary.txt; cat $OUT/sweep1.txt ;;
     *) echo "unknown step $what" ;;

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quantum_compute_dft_b200 import workload  # noqa: E402
 
 DEFAULTS = {"vxc_skip": -1, "vxc_skip_mode": 2, "vxc_vk": 0, "vxc_shape": 0, "zero_skip": 1, "tma_3d": 1,
-            "vxc_scatter": 1, "vxc_producers": 2, "wait_ns": 0, "dyn_sched": 1, "l2_prefetch": 0, "stagger_min": 8, "density_unit": 0, "vxc_rebalance": 1, "vxc_prefetch": 0, "density_producers": 1, "density_scatter": 0}
+            "vxc_scatter": 1, "vxc_producers": 2, "wait_ns": 0, "dyn_sched": 1, "l2_prefetch": 0, "stagger_min": 8, "density_unit": 0, "vxc_rebalance": 1, "vxc_prefetch": 0, "density_producers": 1, "density_scatter": 0, "density_wide": 0}
 
 
 def main():
