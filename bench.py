@@ -314,6 +314,7 @@ def main():
     hp = workload.host_problem(args.workload, scale=args.scale)
     solver = workload.make_solver(hp.functional)
     solver.set_option("path", args.path)
+    solver.set_option("timing", 1)      # (per-kernel CUDA events: on for the AO evaluation and the stat-collection steps only)
     for kv in args.opt:
         k, v = kv.split("=")
         solver.set_option(k, float(v))
@@ -358,6 +359,7 @@ def main():
     sampler.start()
     ev0, ev1 = cuda_rt.Event(), cuda_rt.Event()
     dens_ms = vxc_ms = 0.0
+    solver.set_option("timing", 0)      # the timed regions run the library as a caller would: no per-kernel events
     barrier()
     for _ in range(late_warm):
         e_xc = step()
@@ -368,12 +370,6 @@ def main():
         ev1.record(stream)
         ev1.synchronize()
         total_ms = ev0.elapsed_ms(ev1)
-        # per-kernel durations (the engine's own CUDA events on its stream) for the roofline: read in K further steps
-        # on the same inputs right after the timed region -- reading them costs a handful of driver calls per step,
-        # which inside the region would be charged to the step (visible at 8 GPUs, where a C4 step is 0.5 ms)
-        for _ in range(args.steps):
-            step()
-            dens_ms += solver.stat("density_ms"); vxc_ms += solver.stat("vxc_ms")
     else:
         total_ms = 0.0
         for _ in range(args.steps):
@@ -384,7 +380,18 @@ def main():
             ev1.record(stream)
             ev1.synchronize()
             total_ms += ev0.elapsed_ms(ev1)
-            dens_ms += solver.stat("density_ms"); vxc_ms += solver.stat("vxc_ms")
+    # per-kernel durations (the engine's own CUDA events on its stream) for the roofline: read in K further steps on the
+    # same inputs right after the timed region -- recording and reading them costs a handful of driver calls and event
+    # records per step, which inside the region would be charged to the step (a tenth of it at H2O size; visible at
+    # 8 GPUs, where a C4 step is 0.5 ms)
+    solver.set_option("timing", 1)
+    for _ in range(args.steps):
+        if need_flush:
+            flush_buf.fill_zero()
+            cuda_rt.synchronize()
+        step()
+        dens_ms += solver.stat("density_ms"); vxc_ms += solver.stat("vxc_ms")
+    solver.set_option("timing", 0)
     barrier()
 
     # ---- end-to-end region: host buffers for the per-iteration input (D) and outputs (V_xc, E_xc)

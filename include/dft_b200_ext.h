@@ -96,7 +96,8 @@ int DFT_CommDestroy(XCSolver* solver);
 //       ("debug_nodmma" exists only in -DDFT_DIAGNOSTICS builds, see the end of this header)
 //       "tma_3d" 0|1 (tuning: 3-D tensor maps in the V kernel, one TMA load per plane and stage; default 1)
 //       "l2_prefetch" 0|1 (tuning: short-range L2 prefetch in the density kernel, default 0: measured no gain)
-//       "timing" 0|1 (record the per-kernel CUDA events behind DFT_GetStat, default 1)
+//       "timing" 0|1 (record the per-kernel CUDA events behind DFT_GetStat "*_ms", default 0: at H2O size five event
+//       records are a tenth of a call; bench.py and the tools switch it on where they read the times)
 int DFT_SetOption(XCSolver* solver, const char* key, double value);
 // keys: "density_ms", "vxc_ms", "reduce_ms", "total_ms" (CUDA-event times of the last
 //       DFT_ComputeXC on the engine's stream), "launches" (kernels launched by the last call),

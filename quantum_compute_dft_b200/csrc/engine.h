@@ -81,7 +81,7 @@ struct CublasHandleWrapper {
     // options (DFT_SetOption)
     bool exact_functionals = false;
     int path = PATH_AUTO;
-    bool timing = true;
+    bool timing = false;           // record CUDA events around the kernels of every call (DFT_GetStat "*_ms"); off by default: five event records are a tenth of a call at H2O size
     bool l2_prefetch = false;      // TMA density kernel: short-range L2 prefetch of A tiles and epilogue pieces (measured: no gain)
     int vxc_skip = -1;             // V kernel zero-skipping instance: -1 adaptive (default), 0 never, 1 always
     bool vxc_skip_on = true;       // (adaptive) the zero-skipping V instance is used while the density kernel finds zeros

@@ -128,6 +128,11 @@ __device__ __forceinline__ void load_1d(void* smem_dst, const void* gsrc, uint32
                  : "memory");
 }
 
+// L2 prefetch of a contiguous range (16-byte aligned address, size a multiple of 16)
+__device__ __forceinline__ void prefetch_1d(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes) : "memory");
+}
+
 // L2 prefetch of one box of a tiled tensor (no shared-memory destination, no completion signal)
 __device__ __forceinline__ void prefetch_2d(const CUtensorMap* map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"

@@ -28,6 +28,7 @@
 
 #include "dmma.cuh"
 #include "engine.h"
+#include "tma.cuh"
 #include "xc_functionals.cuh"
 
 namespace xc {
@@ -90,6 +91,14 @@ xc_small_kernel(const SmallParams P) {
     const int q = lane >> 2, qc = lane & 3;
     double* dsym = smd;
     double* buf0 = dsym + NP * LDD + (size_t)warp * 2 * buf_d;
+    // one mbarrier per warp and buffer, behind the last warp's buffers and their slack: whole tiles arrive as four bulk
+    // copies (one per plane, 64 nao contiguous bytes each) issued by lane 0 -- round 2's first version issued them as
+    // 16-byte cp.async from all lanes, 18 per lane and tile plus their address arithmetic, and ncu put a quarter of the
+    // kernel's samples there
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dsym + NP * LDD + (size_t)nwarp * 2 * buf_d + 8) + 2 * warp;
+    if (lane == 0) { tma::mbar_init(&bars[0], 1); tma::mbar_init(&bars[1], 1); tma::fence_barrier_init(); }
+    uint32_t bar_phase = 0;      // bit b: phase of buffer b's barrier
+    uint32_t bar_bulk = 0;       // bit b: the load in flight into buffer b is a bulk copy (else cp.async)
 
     // ---- Dsym = 1/2 (D + D^T), zero-padded (replaces symmetrize_pad; nao^2 doubles from L2 per CTA).  The buffers
     // are cleared once: the fragment loads below read up to 7 columns past the end of a row (into the next row, the
@@ -107,16 +116,18 @@ xc_small_kernel(const SmallParams P) {
 
     // ---- asynchronous tile loads: 8 * nao contiguous doubles per plane; rows past the grid are zero-filled
     const uint32_t lane16 = (uint32_t)lane * 16u;
-    auto issue_tile = [&](long g0, double* buf) {
+    auto issue_tile = [&](long g0, int b) {
+        double* buf = buf0 + b * buf_d;
         const uint32_t sb = (uint32_t)__cvta_generic_to_shared(buf);
-        if (P.vec16 && g0 + TR <= (long)P.ngrid) {   // the common case: whole tile, 16-byte copies, nothing to test per copy
+        if (P.vec16 && g0 + TR <= (long)P.ngrid) {   // the common case: whole tile, one bulk copy per plane
             const uint32_t bytes = (uint32_t)tile_d * 8u;
+            if (lane == 0) {
+                tma::mbar_arrive_expect_tx(&bars[b], NPL * bytes);
 #pragma unroll
-            for (int p = 0; p < NPL; ++p) {
-                const char* src = reinterpret_cast<const char*>(P.plane[p] + g0 * nao);
-                const uint32_t dst = sb + (uint32_t)p * bytes;
-                for (uint32_t o = lane16; o < bytes; o += 512u) cp_async_16(dst + o, src + o, 16);
+                for (int p = 0; p < NPL; ++p)
+                    tma::load_1d(reinterpret_cast<unsigned char*>(buf) + (size_t)p * bytes, P.plane[p] + g0 * nao, bytes, &bars[b]);
             }
+            bar_bulk |= 1u << b;
         } else {
             long valid = ((long)P.ngrid - g0) * nao;                          // doubles of this tile that exist
             valid = valid < 0 ? 0 : (valid > tile_d ? tile_d : valid);
@@ -124,8 +135,19 @@ xc_small_kernel(const SmallParams P) {
                 const double* src = P.plane[p] + (valid > 0 ? g0 * nao : 0);
                 for (int i = lane; i < tile_d; i += 32) cp_async_8(sb + (uint32_t)(p * tile_d + i) * 8u, src + i, i < valid ? 8 : 0);
             }
+            cp_async_commit();
+            bar_bulk &= ~(1u << b);
         }
-        cp_async_commit();
+    };
+    // the load into buffer b has landed for every lane (and every lane is done with what it read before)
+    auto wait_tile = [&](int b) {
+        if (bar_bulk & (1u << b)) {
+            tma::mbar_wait(&bars[b], (bar_phase >> b) & 1u);
+            bar_phase ^= 1u << b;
+        } else {
+            cp_async_wait_all();
+        }
+        __syncwarp();
     };
 
     double acc[NF][NF][2];
@@ -147,12 +169,18 @@ xc_small_kernel(const SmallParams P) {
         const long gs = (long)sblk * SB * TR;
         long n = ((long)P.ngrid - gs) * nao;                               // doubles that exist
         n = n > (long)SB * tile_d ? (long)SB * tile_d : n;
-        for (int p = 0; p < NPL; ++p) {
-            const char* src = reinterpret_cast<const char*>(P.plane[p] + gs * nao);
-            for (long o = (long)lane * 128; o < n * 8; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
+        if (P.vec16 && n == (long)SB * tile_d) {
+            if (lane < NPL) tma::prefetch_1d(P.plane[lane] + gs * nao, (uint32_t)(n * 8));
+        } else {
+            for (int p = 0; p < NPL; ++p) {
+                const char* src = reinterpret_cast<const char*>(P.plane[p] + gs * nao);
+                for (long o = (long)lane * 128; o < n * 8; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
+            }
         }
     };
-    if (first < nsuper) issue_tile((long)first * SB * TR, buf0);
+    tma::fence_proxy_async();        // the cleared buffers (generic proxy) are ordered before the bulk copies (async proxy) into them
+    __syncwarp();                    // (and the barriers are initialised before lane 0 arms one)
+    if (first < nsuper) issue_tile((long)first * SB * TR, 0);
     if (first + stride < nsuper) prefetch_super(first + stride);
     __syncthreads();                 // Dsym is complete and every buffer is cleared (the only CTA barrier before the final reduction)
     int it = 0;                      // tile loads consumed so far (selects the buffer)
@@ -166,9 +194,8 @@ xc_small_kernel(const SmallParams P) {
 #pragma unroll 1
         for (int m = 0; m < SB; ++m, ++it) {
             const double* phi = buf0 + (it & 1) * buf_d;
-            cp_async_wait_all();
-            __syncwarp();            // the tile has landed for every lane; every lane is done with the other buffer
-            issue_tile(gs + (long)(m + 1 < SB ? m + 1 : 0) * TR, buf0 + ((it + 1) & 1) * buf_d);   // next of pass A, or pass B's first
+            wait_tile(it & 1);       // the tile has landed for every lane; every lane is done with the other buffer
+            issue_tile(gs + (long)(m + 1 < SB ? m + 1 : 0) * TR, (it + 1) & 1);   // next of pass A, or pass B's first
             const double* my_row = phi + (size_t)q * nao;             // fragment row of this lane
             double c[NF][2];
 #pragma unroll
@@ -209,10 +236,9 @@ xc_small_kernel(const SmallParams P) {
 #pragma unroll 1
         for (int m = 0; m < SB; ++m, ++it) {
             const double* phi = buf0 + (it & 1) * buf_d;
-            cp_async_wait_all();
-            __syncwarp();
-            if (m + 1 < SB) issue_tile(gs + (long)(m + 1) * TR, buf0 + ((it + 1) & 1) * buf_d);
-            else if (sblk + stride < nsuper) issue_tile((long)(sblk + stride) * SB * TR, buf0 + ((it + 1) & 1) * buf_d);
+            wait_tile(it & 1);
+            if (m + 1 < SB) issue_tile(gs + (long)(m + 1) * TR, (it + 1) & 1);
+            else if (sblk + stride < nsuper) issue_tile((long)(sblk + stride) * SB * TR, (it + 1) & 1);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 const int pt = 4 * ks + qc;                           // the row of this tile the lane supplies
@@ -347,7 +373,7 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     if (sh.nao != nao || sh.per_sm <= 0) {
         int nwarp = MAXW;
         auto smem_for = [&](int nw) {
-            size_t d = (size_t)NP * LDD + (size_t)nw * warp_d + 8;
+            size_t d = (size_t)NP * LDD + (size_t)nw * warp_d + 8 + 2 * (size_t)nw;   // (+ two mbarriers per warp)
             if (d < (size_t)NP * NP + 8) d = (size_t)NP * NP + 8;
             return d * sizeof(double);
         };

@@ -8,6 +8,7 @@ from quantum_compute_dft_b200 import workload  # noqa: E402
 for wl in sys.argv[1:]:
     hp = workload.host_problem(wl)
     solver = workload.make_solver(hp.functional)
+    solver.set_option("timing", 1)
     dp = workload.device_problem(hp, solver)
     P = 1 if hp.functional == "LDA" else 4
     nbytes = 8.0 * dp.ngrid * dp.nao * P

@@ -12,6 +12,7 @@ lib = DEFAULT_LIB.replace("dft.so", "dft_timing.so")
 wl = sys.argv[1]
 hp = workload.host_problem(wl)
 s = DFTSolverWrapper(lib, hp.functional)
+s.set_option("timing", 1)
 for kv in sys.argv[2:]:
     k, v = kv.split("="); s.set_option(k, float(v))
 dp = workload.device_problem(hp, s)

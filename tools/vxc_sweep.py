@@ -27,6 +27,7 @@ def main():
         from quantum_compute_dft_b200.solver import DEFAULT_LIB
         lib_path = DEFAULT_LIB.replace(".so", f"_{lib_tag}.so")
     solver = workload.make_solver(hp.functional, lib_path)
+    solver.set_option("timing", 1)
     # SWEEP_RANKS=N: time rank 0's shard of an N-rank run (the per-GPU problem of a multi-GPU step) on one GPU
     nranks = int(os.environ.get("SWEEP_RANKS", "1"))
     dp = workload.device_problem(hp, solver, 0, nranks)
