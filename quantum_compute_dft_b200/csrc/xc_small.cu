@@ -25,6 +25,7 @@
 // Replaces, for small nao, the same reference code as xc_tma.cu: get_rho[_sigma]_kernel (dft_solver.cu:294-380),
 // *_fused_kernel (:309-513), reduce_sum_kernel (:285-292), cublasDgemm (:580,:616,:663), symmetrize (:515-527).
 #include <cstdio>
+#include <cstring>
 
 #include "dmma.cuh"
 #include "engine.h"
@@ -84,6 +85,9 @@ __global__ void __launch_bounds__(MAXW * 32)
 xc_small_kernel(const SmallParams P) {
     constexpr int NP = 8 * NF, LDD = ldd_for(NP);
     extern __shared__ double smd[];
+    // programmatic dependent launch: the finalize kernel may be scheduled now; it waits (griddepcontrol.wait) until this
+    // whole grid has completed and its partials are visible, so only its launch latency overlaps this kernel
+    asm volatile("griddepcontrol.launch_dependents;");
     const int nao = P.nao;
     const int tile_d = TR * nao;                         // doubles per plane tile (even)
     const int buf_d = NPL * tile_d;
@@ -318,6 +322,7 @@ xc_small_finalize(int nao, int NP, int ncta, int raw, const double* __restrict__
                   volatile double* host_slot, double seq) {
     const int lane = threadIdx.x & 31;
     const int idx = blockIdx.x * 8 + (threadIdx.x >> 5);
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // (a no-op when launched without the PDL attribute)
     if (idx < nao * nao) {
         const int i = idx / nao, j = idx - i * nao;
         const double* a = vpart + (size_t)i * NP + j;
@@ -418,8 +423,18 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
         if (fresh) cudaMemsetAsync(done, 0, COUNTERS_HEAD_BYTES, st);
         done += 10;   // (the last 8 bytes of the buffer: the TMA path's statistics and work counter use the first 40)
     }
-    xc_small_finalize<<<(nao * nao + 7) / 8, 256, 0, st>>>(nao, NP, grid, raw, vpart, epart, p.vxc, p.d_exc, done,
-                                                           p.host_exc_slot, p.host_exc_seq);
+    {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((nao * nao + 7) / 8); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = ctx->timing ? 0 : 1;   // (with the timing events between the two launches there is nothing to overlap)
+        DFT_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, xc_small_finalize, nao, NP, grid, raw, (const double*)vpart, (const double*)epart,
+                                               p.vxc, p.d_exc, done, p.host_exc_slot, p.host_exc_seq));
+    }
     if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
     ctx->stats.launches = 2;
     ctx->stats.path = PATH_SMALL;
