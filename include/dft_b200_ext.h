@@ -54,6 +54,8 @@ int DFT_CommDestroy(XCSolver* solver);
 //       0 = chosen from nao)
 //       "vxc_vk" 0|8|16 (tuning: grid rows per ring stage of the 128 x 128 V kernel; 0 = 16 on dense
 //       operands, 8 with zero skipping)
+//       "small_streaming" 0|1 (small-basis kernel: 1 = always stream tile by tile; default 0 keeps whole 32-point
+//       super-blocks resident in shared memory where two of them fit 16 KB per warp -- nao <= 8 for GGA, <= 32 for LDA)
 //       "ao_shape" 0|1|8|16|17|32 (tuning: grid points per block of DFT_EvalAO -- 8 | 16 | 32 with 8 | 8 | 16 warps,
 //       17 = 16 points with 16 warps; 0 = chosen from the basis size; 1 = the barrier-free direct kernel, lanes over
 //       AOs throughout, measured slower)

@@ -360,6 +360,7 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "path")) { c->path = (int)value; return 0; }
     if (!strcmp(key, "timing")) { c->timing = value != 0.0; return 0; }
     if (!strcmp(key, "l2_prefetch")) { c->l2_prefetch = value != 0.0; return 0; }
+    if (!strcmp(key, "small_streaming")) { c->small_streaming = value != 0.0; return 0; }
     if (!strcmp(key, "ao_shape")) { c->ao_shape = (int)value; return 0; }
     if (!strcmp(key, "ao_vec_stores")) { c->ao_vec_stores = value != 0.0; return 0; }
     if (!strcmp(key, "ao_input_order")) { c->ao_input_order = value != 0.0; return 0; }

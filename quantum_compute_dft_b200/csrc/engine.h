@@ -102,6 +102,7 @@ struct CublasHandleWrapper {
     bool raw_convention = false;   // GGA only: leave the reference's raw unsymmetrised B^T Phi in d_vxc (dft_solver.cu:616) instead of the symmetric matrix
     bool zero_skip = true;         // TMA kernels: skip k-steps whose operand fragment is all zero (exact: adds nothing)
     bool tma_3d = true;            // TMA V kernel: one 3-D TMA load per plane and stage instead of one per 16-column block
+    bool small_streaming = false;  // small-basis kernel: always stream tile by tile (never keep whole super-blocks resident)
     int ao_shape = 0;              // DFT_EvalAO block shape: 0 = auto, 16 (points, 8 warps) | 32 (points, 16 warps)
     bool ao_vec_stores = false;    // DFT_EvalAO: 16-byte stores in phase 2 (measured slower than 8-byte ones: not the default)
     bool ao_input_order = false;   // DFT_EvalAO: keep the exponent-sharing groups in shell input order (round 1) instead of sorting them by reach and position

@@ -63,6 +63,7 @@ __host__ __device__ constexpr int ldd_for(int NP) { return ((NP + 11) / 16) * 16
 
 struct SmallParams {
     int ngrid, nao, xc_mode, nblocks, vec16;
+    int resident;    // a warp's buffer holds a whole super-block (4 tiles), loaded once and used by both passes (small nao)
     const double* dm;
     const double* plane[4];
     const double* w;
@@ -90,7 +91,14 @@ xc_small_kernel(const SmallParams P) {
     asm volatile("griddepcontrol.launch_dependents;");
     const int nao = P.nao;
     const int tile_d = TR * nao;                         // doubles per plane tile (even)
-    const int buf_d = NPL * tile_d;
+    // RESIDENT mode (small nao: H2O): a buffer holds the four tiles of a whole super-block, plane by plane -- one bulk copy
+    // per plane and super-block, double-buffered across super-blocks -- and pass B works from the same buffer.  The
+    // streaming mode (a tile per buffer, pass B's tiles streamed a second time from L2) pays eight load latencies per
+    // super-block in sequence, which at H2O size, where a warp sees one super-block, was a third of the kernel.
+    const bool res = P.resident != 0;
+    constexpr int SBT = 4;                               // tiles per super-block
+    const int ps = res ? SBT * tile_d : tile_d;          // plane stride inside a buffer (doubles)
+    const int buf_d = NPL * ps;                          // doubles per buffer
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int q = lane >> 2, qc = lane & 3;
     double* dsym = smd;
@@ -129,7 +137,7 @@ xc_small_kernel(const SmallParams P) {
                 tma::mbar_arrive_expect_tx(&bars[b], NPL * bytes);
 #pragma unroll
                 for (int p = 0; p < NPL; ++p)
-                    tma::load_1d(reinterpret_cast<unsigned char*>(buf) + (size_t)p * bytes, P.plane[p] + g0 * nao, bytes, &bars[b]);
+                    tma::load_1d(buf + (size_t)p * ps, P.plane[p] + g0 * nao, bytes, &bars[b]);
             }
             bar_bulk |= 1u << b;
         } else {
@@ -137,7 +145,31 @@ xc_small_kernel(const SmallParams P) {
             valid = valid < 0 ? 0 : (valid > tile_d ? tile_d : valid);
             for (int p = 0; p < NPL; ++p) {
                 const double* src = P.plane[p] + (valid > 0 ? g0 * nao : 0);
-                for (int i = lane; i < tile_d; i += 32) cp_async_8(sb + (uint32_t)(p * tile_d + i) * 8u, src + i, i < valid ? 8 : 0);
+                for (int i = lane; i < tile_d; i += 32) cp_async_8(sb + (uint32_t)(p * ps + i) * 8u, src + i, i < valid ? 8 : 0);
+            }
+            cp_async_commit();
+            bar_bulk &= ~(1u << b);
+        }
+    };
+    // resident mode: the whole super-block sblk (32 points = 4 tiles, contiguous per plane) into buffer b
+    auto issue_super = [&](int sblk, int b) {
+        double* buf = buf0 + b * buf_d;
+        const long gs = (long)sblk * SBT * TR;
+        if (P.vec16 && gs + SBT * TR <= (long)P.ngrid) {
+            const uint32_t bytes = (uint32_t)(SBT * tile_d) * 8u;
+            if (lane == 0) {
+                tma::mbar_arrive_expect_tx(&bars[b], NPL * bytes);
+#pragma unroll
+                for (int p = 0; p < NPL; ++p) tma::load_1d(buf + (size_t)p * ps, P.plane[p] + gs * nao, bytes, &bars[b]);
+            }
+            bar_bulk |= 1u << b;
+        } else {
+            const uint32_t sb = (uint32_t)__cvta_generic_to_shared(buf);
+            long valid = ((long)P.ngrid - gs) * nao;
+            valid = valid < 0 ? 0 : (valid > (long)SBT * tile_d ? (long)SBT * tile_d : valid);
+            for (int p = 0; p < NPL; ++p) {
+                const double* src = P.plane[p] + (valid > 0 ? gs * nao : 0);
+                for (int i = lane; i < SBT * tile_d; i += 32) cp_async_8(sb + (uint32_t)(p * ps + i) * 8u, src + i, i < valid ? 8 : 0);
             }
             cp_async_commit();
             bar_bulk &= ~(1u << b);
@@ -184,22 +216,35 @@ xc_small_kernel(const SmallParams P) {
     };
     tma::fence_proxy_async();        // the cleared buffers (generic proxy) are ordered before the bulk copies (async proxy) into them
     __syncwarp();                    // (and the barriers are initialised before lane 0 arms one)
-    if (first < nsuper) issue_tile((long)first * SB * TR, 0);
+    if (first < nsuper) { if (res) issue_super(first, 0); else issue_tile((long)first * SB * TR, 0); }
     if (first + stride < nsuper) prefetch_super(first + stride);
     __syncthreads();                 // Dsym is complete and every buffer is cleared (the only CTA barrier before the final reduction)
     int it = 0;                      // tile loads consumed so far (selects the buffer)
     for (int sblk = first; sblk < nsuper; sblk += stride) {
         const long gs = (long)sblk * SB * TR;                          // first grid point of the super-block
         if (sblk + 2 * stride < nsuper) prefetch_super(sblk + 2 * stride);
+        const double* sbuf = nullptr;
+        if (res) {   // the whole super-block: wait for it, request the next one into the other buffer
+            sbuf = buf0 + (it & 1) * buf_d;
+            wait_tile(it & 1);
+            if (sblk + stride < nsuper) issue_super(sblk + stride, (it + 1) & 1);
+            ++it;
+        }
         double keep[NPL];
 #pragma unroll
         for (int p = 0; p < NPL; ++p) keep[p] = 0.0;
         // ---------------- pass A: C = Phi . Dsym and its row dots, tile by tile
 #pragma unroll 1
-        for (int m = 0; m < SB; ++m, ++it) {
-            const double* phi = buf0 + (it & 1) * buf_d;
-            wait_tile(it & 1);       // the tile has landed for every lane; every lane is done with the other buffer
-            issue_tile(gs + (long)(m + 1 < SB ? m + 1 : 0) * TR, (it + 1) & 1);   // next of pass A, or pass B's first
+        for (int m = 0; m < SB; ++m) {
+            const double* phi;
+            if (res) {
+                phi = sbuf + m * tile_d;
+            } else {
+                phi = buf0 + (it & 1) * buf_d;
+                wait_tile(it & 1);       // the tile has landed for every lane; every lane is done with the other buffer
+                issue_tile(gs + (long)(m + 1 < SB ? m + 1 : 0) * TR, (it + 1) & 1);   // next of pass A, or pass B's first
+                ++it;
+            }
             const double* my_row = phi + (size_t)q * nao;             // fragment row of this lane
             double c[NF][2];
 #pragma unroll
@@ -221,7 +266,7 @@ xc_small_kernel(const SmallParams P) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
 #pragma unroll
-                    for (int p = 0; p < NPL; ++p) s[p] = fma(c[nf][e], my_row[p * tile_d + col + e], s[p]);
+                    for (int p = 0; p < NPL; ++p) s[p] = fma(c[nf][e], my_row[p * ps + col + e], s[p]);
             }
 #pragma unroll
             for (int p = 0; p < NPL; ++p) {
@@ -238,11 +283,17 @@ xc_small_kernel(const SmallParams P) {
         e_acc += pc.exc;
         // ---------------- pass B: M += B^T Phi, tile by tile (two k-steps of 4 points each)
 #pragma unroll 1
-        for (int m = 0; m < SB; ++m, ++it) {
-            const double* phi = buf0 + (it & 1) * buf_d;
-            wait_tile(it & 1);
-            if (m + 1 < SB) issue_tile(gs + (long)(m + 1) * TR, (it + 1) & 1);
-            else if (sblk + stride < nsuper) issue_tile((long)(sblk + stride) * SB * TR, (it + 1) & 1);
+        for (int m = 0; m < SB; ++m) {
+            const double* phi;
+            if (res) {
+                phi = sbuf + m * tile_d;
+            } else {
+                phi = buf0 + (it & 1) * buf_d;
+                wait_tile(it & 1);
+                if (m + 1 < SB) issue_tile(gs + (long)(m + 1) * TR, (it + 1) & 1);
+                else if (sblk + stride < nsuper) issue_tile((long)(sblk + stride) * SB * TR, (it + 1) & 1);
+                ++it;
+            }
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 const int pt = 4 * ks + qc;                           // the row of this tile the lane supplies
@@ -262,9 +313,9 @@ xc_small_kernel(const SmallParams P) {
                     ph[f] = prow[col];
                     double v = ca * ph[f];
                     if (NPL == 4) {
-                        v = fma(cbx, prow[tile_d + col], v);
-                        v = fma(cby, prow[2 * tile_d + col], v);
-                        v = fma(cbz, prow[3 * tile_d + col], v);
+                        v = fma(cbx, prow[ps + col], v);
+                        v = fma(cby, prow[2 * ps + col], v);
+                        v = fma(cbz, prow[3 * ps + col], v);
                     }
                     bb[f] = v;
                 }
@@ -366,16 +417,18 @@ template <int NF, int NPL>
 static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     constexpr int NP = 8 * NF, LDD = ldd_for(NP);
     const int nao = p.nao;
-    const size_t warp_d = 2 * (size_t)NPL * TR * nao;                 // doubles of one warp's two buffers
+    // resident super-blocks (4 tiles per buffer) where two of them stay within 16 KB per warp: nao <= 8 for GGA, 32 for LDA
+    const bool resident = 2 * (size_t)NPL * 4 * TR * nao * sizeof(double) <= 16384 && !ctx->small_streaming;
+    const size_t warp_d = 2 * (size_t)NPL * TR * nao * (resident ? 4 : 1);   // doubles of one warp's two buffers
     auto k = xc_small_kernel<NF, NPL>;
     // launch shape of this (instance, nao), worked out ONCE: warps per CTA so that the CTA's shared memory (Dsym + the
     // warps' buffers, at least the NP^2 + 8 doubles of the final reduction) fits, resident CTAs per SM from the
     // occupancy calculator -- at H2O size the whole call is ~20 us and two driver queries per call were a third of it
     // (function attributes are per device: one slot per device ordinal)
-    struct Shape { int nao, nwarp, per_sm; size_t smem; };
+    struct Shape { int nao, nwarp, per_sm, resident; size_t smem; };
     static Shape cache[16] = {};
     Shape& sh = cache[ctx->device & 15];
-    if (sh.nao != nao || sh.per_sm <= 0) {
+    if (sh.nao != nao || sh.per_sm <= 0 || sh.resident != (resident ? 1 : 0)) {
         int nwarp = MAXW;
         auto smem_for = [&](int nw) {
             size_t d = (size_t)NP * LDD + (size_t)nw * warp_d + 8 + 2 * (size_t)nw;   // (+ two mbarriers per warp)
@@ -389,7 +442,7 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
         DFT_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, nwarp * 32, smem));
         if (per_sm < 1) { ctx->failed = true; return; }
         if (per_sm * nwarp > 16) per_sm = 16 / nwarp > 0 ? 16 / nwarp : 1;   // (more resident warps only add partials)
-        sh.nao = nao; sh.nwarp = nwarp; sh.per_sm = per_sm; sh.smem = smem;
+        sh.nao = nao; sh.nwarp = nwarp; sh.per_sm = per_sm; sh.smem = smem; sh.resident = resident ? 1 : 0;
     }
     const int nblocks = (p.ngrid + TR - 1) / TR;
     const int nsuper = (nblocks + 3) / 4;          // the unit of work of a warp: 4 tiles = 32 points
@@ -400,7 +453,7 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     if (ctx->failed) return;
 
     SmallParams sp;
-    sp.ngrid = p.ngrid; sp.nao = nao; sp.nblocks = nblocks;
+    sp.ngrid = p.ngrid; sp.nao = nao; sp.nblocks = nblocks; sp.resident = resident ? 1 : 0;
     sp.xc_mode = p.xc_type == 2 ? 4 : p.xc_type * 2 + (ctx->exact_functionals ? 1 : 0);
     sp.dm = p.dm; sp.w = p.w;
     sp.plane[0] = p.ao; sp.plane[1] = p.gx; sp.plane[2] = p.gy; sp.plane[3] = p.gz;

@@ -138,6 +138,12 @@ def test_small_basis_shapes_on_every_path(oracle, engine_lib, functional, ngrid,
         assert abs(e - e_o) <= E_TOL, (path, e, e_o)
         np.testing.assert_allclose(0.5 * (v + v.T), oracle.sym(v_o), rtol=0, atol=V_TOL, err_msg=f"path {path}")
         np.testing.assert_array_equal(v, v.T)
+    # the small-basis kernel keeps whole super-blocks resident for small nao (nao <= 8 GGA, <= 32 LDA) and streams tile
+    # by tile otherwise: both modes on every shape (their launch shapes, hence their summation orders, differ)
+    e_s, v_s, st_s = _run_engine(engine_lib, functional, dm, ao, w, grad, {"path": 3, "small_streaming": 1})
+    assert st_s["path"] == 3 and abs(e_s - e_o) <= E_TOL and abs(e_s - e) <= 1e-12 * max(1.0, abs(e))
+    np.testing.assert_allclose(0.5 * (v_s + v_s.T), oracle.sym(v_o), rtol=0, atol=V_TOL, err_msg="streaming mode")
+    np.testing.assert_allclose(v_s, v, rtol=0, atol=1e-12 * max(1.0, np.abs(v).max()))
     ref = _run_reference_so(functional, dm, ao, w, grad)
     if ref is not None:
         assert abs(e - ref[0]) <= E_TOL
