@@ -6,21 +6,22 @@
 // block of 32 grid points goes through EVERYTHING while it sits in shared memory, so every plane byte is read from
 // HBM exactly once per XC build (the algorithmic figure of SURVEY.md 8d):
 //
-//   cp.async (double-buffered)  the block's NPL plane tiles [32 rows][nao] + its 32 weights
-//   step 1  C = Phi_blk . Dsym                        DMMA m8n8k4, warp w owns rows 8w .. 8w+7
+//   bulk copies (double-buffered)  tiles of 8 grid points, NPL planes x [8 rows][nao]: one cp.async.bulk per plane against
+//                                  an mbarrier per warp and buffer (small nao: whole 32-point super-blocks, see the kernel)
+//   step 1  C = Phi_tile . Dsym                       DMMA m8n8k4, a warp per tile
 //   step 2  rho, grad rho / 2 = rowsum(C o plane)     from the accumulator fragments, quad shuffles
-//   step 3  the functional, ONCE per point            one warp, lane = point (all 32 lanes do distinct points);
-//                                                     the evaluating warp rotates from block to block
+//   step 3  the functional, ONCE per point            per super-block of 4 tiles: all 32 lanes on distinct points
 //   step 4  B = a Phi + b . grad Phi                  built in registers as DMMA A fragments
-//   step 5  M += B^T Phi                              DMMA, K = the warp's 8 rows; each warp keeps a private
-//                                                     (NP x NP) accumulator over all the blocks it sees
-//   end     warp accumulators -> CTA partial (fixed order) -> global;  xc_small_finalize sums the CTA
-//           partials in a fixed order, writes M + M^T and E_xc.  Bit-reproducible, two launches per build.
+//   step 5  M += B^T Phi                              DMMA, K = the tile's 8 rows; each warp keeps a private
+//                                                     (NP x NP) accumulator over all the tiles it sees
+//   end     warp accumulators -> CTA partial (fixed order) -> global;  xc_small_finalize (programmatic dependent
+//           launch: its launch latency overlaps the main kernel) sums the CTA partials in a fixed order, writes
+//           M + M^T and E_xc.  Bit-reproducible, two launches per build.
 //
-// CTAs are 4 warps; several are resident per SM (2 at benzene/GGA, where a double-buffered block is 74 KB) so that
-// one CTA's functional evaluation runs under another's tensor work.  Any alignment and any ngrid work: the copies
-// fall back from 16- to 8-byte cp.async when a plane base or the row pitch is not 16-byte aligned, and rows past
-// the end of the grid are zero-filled (zero weight -> zero coefficients).
+// CTAs are 4 or 8 warps; several are resident per SM (2 x 4 warps at benzene/GGA, where a warp's two tile buffers are
+// 18 KB) so that one warp's functional evaluation runs under another's tensor work.  Any alignment and any ngrid work:
+// a ragged last tile, a plane base that is not 16-byte aligned fall back to 8-byte cp.async with zero fill (zero
+// weight -> zero coefficients).
 //
 // Replaces, for small nao, the same reference code as xc_tma.cu: get_rho[_sigma]_kernel (dft_solver.cu:294-380),
 // *_fused_kernel (:309-513), reduce_sum_kernel (:285-292), cublasDgemm (:580,:616,:663), symmetrize (:515-527).
@@ -71,7 +72,7 @@ struct SmallParams {
     double* epart;   // [gridDim.x]
 };
 
-// Every warp is autonomous: it streams its own tiles of 8 grid points (cp.async, double-buffered, private shared
+// Every warp is autonomous: it streams its own tiles of 8 grid points (bulk copies, double-buffered, private shared
 // memory), works on SUPER-BLOCKS of 4 tiles = 32 points without a single CTA barrier, and keeps a private (NP x NP)
 // accumulator in registers:
 //   pass A over the 4 tiles: steps 1 + 2; lane (q, qc) keeps the row sums of row q of tile qc
@@ -80,7 +81,8 @@ struct SmallParams {
 //   pass B over the same 4 tiles, streamed a second time (from L2: they were read a few microseconds ago): steps 4 + 5,
 //           the coefficients of the points a lane supplies to the fragments arrive by shuffle
 // HBM sees every plane byte once; rho, coefficients and E_xc never leave the registers.
-// shared-memory layout (doubles): Dsym[NP][LDD] | per warp: 2 x planes[NPL][8 * nao] | 8 doubles of slack
+// shared-memory layout (doubles): Dsym[NP][LDD] | per warp: 2 x planes[NPL][8 * nao] (resident mode: [NPL][32 * nao]) |
+// 8 doubles of slack | per warp: 2 mbarriers
 template <int NF, int NPL>
 __global__ void __launch_bounds__(MAXW * 32)
 xc_small_kernel(const SmallParams P) {

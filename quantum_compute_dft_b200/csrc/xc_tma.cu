@@ -42,8 +42,9 @@
 // Dsym shifted by (1,1) (row/column 0 zero, so the junk column is annihilated) and accumulates a
 // V matrix shifted by (1,1), which the finalize kernel un-shifts.  Blocks, tiles and slices are
 // always uniform in parity, so the inner loops do not know about any of this.
-// Inputs TMA cannot address at all (misaligned base pointers, odd nao with odd ngrid) take the
-// generic path (xc_generic.cu).
+// Odd nao with odd ngrid puts the y-gradient plane at 8 mod 16: run_tma copies that one plane to aligned scratch per
+// call (see tma_compatible).  Inputs TMA cannot address at all (misaligned base pointers) take the generic path
+// (xc_generic.cu).
 #include <cuda.h>
 
 #include <algorithm>
