@@ -483,6 +483,12 @@ def main():
                         "whole_call_tflops": flops_local / (ms_step * 1e-3) / 1e12,
                         "density_ms": dens_avg, "vxc_ms": vxc_avg,
                         "algorithmic_flops_per_launch": 0.5 * flops_local}
+            # the same with the DMMAs the kernel actually executed (AO screening skips exact-zero fragments): comparable
+            # with ncu's FP64-tensor-pipe utilisation of that kernel
+            skipped = solver.stat("vxc_skip_fraction") if dom == "vxc_kernel" else solver.stat("skip_fraction")
+            if roofline["frac"] is not None and skipped is not None and 0.0 <= skipped < 1.0:
+                roofline["executed_fraction_of_dense_work"] = 1.0 - skipped
+                roofline["frac_executed"] = roofline["frac"] * (1.0 - skipped)
         else:
             bytes_local = workload.algorithmic_bytes(n_local, nao, hp.functional)
             achieved = bytes_local / (ms_step * 1e-3) / 1e9
