@@ -288,6 +288,9 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the parity check of the timed inputs (sweeps, ncu runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 generic, 2 TMA")
+    ap.add_argument("--devices", type=int, default=1,
+                    help="single-process multi-GPU (csrc/fanout.cu): this ONE process holds the whole grid on device 0 "
+                         "exactly like dft.py and DFT_ComputeXC fans out to this many GPUs; not combinable with torchrun")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="engine tuning option passed to DFT_SetOption (e.g. vxc_vk=16, vxc_shape=160, l2_prefetch=0)")
     args = ap.parse_args()
@@ -318,6 +321,10 @@ def main():
     for kv in args.opt:
         k, v = kv.split("=")
         solver.set_option(k, float(v))
+    if args.devices > 1:
+        if world > 1:
+            raise SystemExit("--devices is the single-process mode: launch it without torchrun")
+        solver.set_option("devices", args.devices)
     if world > 1:
         ids = [solver.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -332,6 +339,8 @@ def main():
             solver.eval_ao(dp.d_coords, hp.basis, dp.d_ao, dp.d_ao_grad)
             t_ao = solver.stat("ao_ms")
             ao_ms = t_ao if ao_ms is None else min(ao_ms, t_ao)
+
+    first_call_ms = 0.0
 
     def step():
         return solver.compute_xc(n_local, nao, dp.d_dm, dp.d_ao, dp.d_weights, dp.d_vxc, dp.d_ao_grad)
@@ -349,8 +358,11 @@ def main():
     # K timed steps start on a stream that is already busy: a sub-millisecond step (C4 on 8 GPUs: 0.5 ms) timed right
     # behind a host-side rendezvous measured 0.85 ms against 0.55 ms in the end-to-end loop that follows it
     late_warm = 2 if args.warmup >= 3 else 0
-    for _ in range(args.warmup - late_warm):
+    t_first = time.perf_counter()
+    for i in range(args.warmup - late_warm):
         step()
+        if i == 0:
+            first_call_ms = (time.perf_counter() - t_first) * 1e3    # fan-out: includes cutting the resident shards
     e_xc = step() if late_warm == 0 else None
 
     # ---- device-timed region: K steps, CUDA events on the engine's stream
@@ -465,7 +477,9 @@ def main():
         value = hp.ngrid / (ms_step * 1e-3) / 1e6
         e2e_value = hp.ngrid / (e2e_ms / K * 1e-3) / 1e6
         peaks, peak_src = measured_peaks()
-        flops_local = workload.algorithmic_flops(n_local, nao)
+        fanned = int(solver.stat("fan_active")) == 1
+        ndev = args.devices if fanned else 1
+        flops_local = workload.algorithmic_flops(n_local, nao) / ndev    # (kernel times are the slowest device's)
         dens_avg, vxc_avg = dens_ms / K, vxc_ms / K
         tensor_bound = nao >= 100      # crossover of FP64-tensor and HBM rooflines near nao ~ 100
         if tensor_bound:
@@ -500,12 +514,16 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_port_baseline(hp, args.cpu_sample)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world * ndev, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": bench_config(args, hp, need_flush),
-            "engine": {"path": int(solver.stat("path")), "ranks": world, "points_per_rank": n_local,
-                       "input_gb_per_rank": 8.0 * n_local * P * nao / 1e9, "options": args.opt},
+            "engine": {"path": int(solver.stat("path")), "ranks": world, "points_per_rank": n_local // ndev,
+                       "input_gb_per_rank": 8.0 * n_local * P * nao / 1e9 / ndev, "options": args.opt,
+                       "process_model": "one process per GPU, NCCL all-reduce" if world > 1 else
+                       ("ONE process, DFT_ComputeXC fans out to %d devices (all arrays on device 0 as in dft.py); shards cut "
+                        "%d time(s), first call %.1f ms" % (ndev, int(solver.stat("fan_scatters")), first_call_ms)
+                        if fanned else "one process, one GPU")},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes + 8,
                     "note": "per SCF iteration the driver uploads D (dft.py:200) and downloads V_xc (dft.py:211) + E_xc; "

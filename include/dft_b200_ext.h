@@ -44,6 +44,27 @@ int DFT_CommGetUniqueId(void* out_id_128_bytes);
 int DFT_CommInit(XCSolver* solver, int rank, int nranks, const void* id_128_bytes);
 int DFT_CommDestroy(XCSolver* solver);
 
+// ---- (e) multi-GPU: ONE process, behind the unmodified DFT_ComputeXC (SURVEY.md 8e "process model") ----------
+// The reference's driver holds every array on one device (dft.py:155-176) and calls DFT_ComputeXC from one process.
+// DFT_SetOption(solver, "devices", n) -- or the environment variable DFT_B200_DEVICES=n|all, read by DFT_CreateSolver,
+// for a driver that knows nothing of options -- makes that same call use n GPUs of the box (csrc/fanout.cu): the grid is
+// dealt to one child engine per device in interleaved blocks of 1024 points, each child keeps its shard of
+// (ao, ao_grad, weights) resident on its own device (pulled out of the caller's arrays over NVLink by the copy engines
+// ONCE and reused while the caller passes the same arrays: same pointers, sizes and content fingerprint -- all weights
+// and 2^17 samples per plane), and per call only D (nao^2 doubles) goes out and [V_xc | E_xc] comes back, summed in a
+// fixed order by one kernel on the caller's device through peer loads.  d_vxc, the returned E_xc and the blocking
+// semantics are exactly those of the single-GPU call.
+//   option keys: "devices" n (n <= visible devices; 1 tears the fan-out down), "virtual_devices" n (n children dealt
+//       round-robin over the visible devices: the whole mechanism on a one-GPU box, for tests),
+//       "devices_min_work" x (builds with ngrid * nao^2 < x stay on the caller's device, default 2e9: H2O, benzene),
+//       "ao_cache" 0|1 (default 1; 0 re-cuts the shards on every call), "ao_invalidate" (drop the resident shards now:
+//       for a caller that rewrites its AO arrays in place in a way 2^17 samples per plane might miss).
+//   stat keys: "devices", "fan_active" (the last call was fanned out), "fan_scatters" (times the shards were cut),
+//       "fan_peer_loads" (the reduction reads the children's results through peer loads), "fan_resident_bytes";
+//       "density_ms" / "vxc_ms" / "reduce_ms" are those of the slowest device, "total_ms" the whole call.
+// Points of shard `shard` of that deal (host arithmetic only; -1 on bad arguments).
+int DFT_ShardPoints(int ngrid, int nshards, int shard);
+
 // ---- options / statistics ------------------------------------------------------------------
 // keys: "exact_functionals" 0|1 (0 = reference bug-compatible potentials, default; 1 = potentials
 //       that are the exact derivatives of the energies, i.e. libxc/PySCF numint)

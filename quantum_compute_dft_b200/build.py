@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 OUT = os.path.join(HERE, "weights", "dft.so")
-SOURCES = ["capi.cu", "xc_generic.cu", "xc_tma.cu", "xc_small.cu", "ao_eval.cu", "linalg.cu", "microbench.cu", "comm.cu"]
+SOURCES = ["capi.cu", "xc_generic.cu", "xc_tma.cu", "xc_small.cu", "ao_eval.cu", "linalg.cu", "microbench.cu", "comm.cu", "fanout.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"] + os.environ.get("DFT_EXTRA_NVCC_FLAGS", "").split()
 

@@ -5,6 +5,7 @@
 //   LDASolver::compute_xc :559-584, GGASolver :588-621, B3LYPSolver :625-672
 //   extern "C" block :675-719
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -47,6 +48,7 @@ CublasHandleWrapper::CublasHandleWrapper() {
 
 CublasHandleWrapper::~CublasHandleWrapper() {
     DeviceGuard guard(device);
+    xc::fanout_destroy(this);   // (child engines on the other devices first: they reduce into this one)
     if (stream) cudaStreamSynchronize(stream);
     xc::comm_destroy(this);
     xc::free_tma_plan(this);
@@ -91,10 +93,34 @@ void XCSolver::safe_cublas_dgemm(bool transA, bool transB, int m, int n, int k, 
 }
 
 namespace {
-
 // result = failed ranks > 0 ? NaN : E  (multi-GPU, asynchronous variant: the host never sees the reduced failure count)
 __global__ void publish_exc_kernel(const double* __restrict__ e_and_failed, double* __restrict__ out) {
     out[0] = e_and_failed[1] != 0.0 ? __longlong_as_double(0x7ff8000000000000ll) : e_and_failed[0];
+}
+}  // namespace
+
+namespace xc {
+bool enqueue_counter_readback(CublasHandleWrapper* ctx) {
+    if (!(ctx->stats.path == PATH_TMA && ctx->counters.ptr)) return false;
+    DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar + 2, ctx->counters.ptr, 5 * sizeof(unsigned long long),
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->vxc_rebalance)   // the V kernel's live counts per fragment: next call's deal of the fragments to the warps
+        DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ctx->h_scalar) + HOST_FSTAT_OFF,
+                                            static_cast<unsigned char*>(ctx->counters.ptr) + FSTAT_OFF, FSTAT_BYTES,
+                                            cudaMemcpyDeviceToHost, ctx->stream));
+    return true;
+}
+
+void apply_counters(CublasHandleWrapper* ctx) {
+    unsigned long long c[5];
+    memcpy(c, ctx->h_scalar + 2, sizeof(c));
+    ctx->stats.skip_fraction = c[1] ? 1.0 - (double)c[0] / (double)c[1] : 0.0;
+    ctx->stats.vxc_skip_fraction = c[3] ? 1.0 - (double)c[2] / (double)c[3] : 0.0;
+    ctx->stats.dyn_units = (double)(c[4] & 0xffffffffull);
+    // adaptive: the zero-skipping V instance pays ~6 % on dense operands; use it only where the density
+    // kernel just skipped a real share of its k-steps (the decision takes effect with the next call)
+    if (ctx->vxc_skip < 0) ctx->vxc_skip_on = ctx->stats.skip_fraction >= 0.10;
+    if (ctx->vxc_rebalance) xc::tma_rebalance(ctx);
 }
 
 // One XC build on the engine stream.  When `d_exc_out` is null the call blocks and returns E_xc
@@ -104,10 +130,12 @@ __global__ void publish_exc_kernel(const double* __restrict__ e_and_failed, doub
 // collective, whatever happened locally -- a rank with bad arguments or a failed launch contributes zeros and
 // failed = 1, and every rank returns NaN when the reduced count is non-zero (a rank that left early would leave
 // the others blocked in ncclAllReduce; a rank that contributed an unwritten buffer would corrupt their sums).
-double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const double* d_dm, const double* d_ao,
-              const double* d_ao_grad, const double* d_w, double* d_vxc, double* d_exc_out) {
+double run_build(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const double* d_dm, const double* d_ao,
+                 const double* d_ao_grad, const double* d_w, double* d_vxc, double* d_exc_out) {
     const double nan = std::numeric_limits<double>::quiet_NaN();
     if (!ctx) return nan;
+    if (fanout_wants(ctx, ngrid, nao) && d_dm && d_ao && d_w && d_vxc && (xc_type == 0 || d_ao_grad))
+        return run_fanout(ctx, xc_type, ngrid, nao, d_dm, d_ao, d_ao_grad, d_w, d_vxc, d_exc_out);
     DeviceGuard guard(ctx->device);   // (restores the caller's current device on return)
     ctx->failed = false;
     ctx->times_pending = false;       // (the events are about to be recorded again; unread intervals are dropped)
@@ -195,31 +223,13 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
     }
     DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar, multi ? packed + n2 : p.d_exc, (multi ? 2 : 1) * sizeof(double),
                                         cudaMemcpyDeviceToHost, ctx->stream));
-    const bool have_counters = !bad && ngrid > 0 && ctx->stats.path == PATH_TMA && ctx->counters.ptr;
-    if (have_counters) {
-        DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_scalar + 2, ctx->counters.ptr, 5 * sizeof(unsigned long long),
-                                            cudaMemcpyDeviceToHost, ctx->stream));
-        if (ctx->vxc_rebalance)   // the V kernel's live counts per fragment: next call's deal of the fragments to the warps
-            DFT_CUDA_CHECK(ctx, cudaMemcpyAsync(reinterpret_cast<unsigned char*>(ctx->h_scalar) + HOST_FSTAT_OFF,
-                                                static_cast<unsigned char*>(ctx->counters.ptr) + FSTAT_OFF, FSTAT_BYTES,
-                                                cudaMemcpyDeviceToHost, ctx->stream));
-    }
+    const bool have_counters = !bad && ngrid > 0 && enqueue_counter_readback(ctx);
     DFT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (multi && ctx->h_scalar[1] != 0.0) {
         if (!ctx->failed) fprintf(stderr, "[dft_b200] rank %d: %d rank(s) failed in this XC build\n", ctx->rank, (int)ctx->h_scalar[1]);
         ctx->failed = true;
     }
-    if (have_counters && !ctx->failed) {
-        unsigned long long c[5];
-        memcpy(c, ctx->h_scalar + 2, sizeof(c));
-        ctx->stats.skip_fraction = c[1] ? 1.0 - (double)c[0] / (double)c[1] : 0.0;
-        ctx->stats.vxc_skip_fraction = c[3] ? 1.0 - (double)c[2] / (double)c[3] : 0.0;
-        ctx->stats.dyn_units = (double)(c[4] & 0xffffffffull);
-        // adaptive: the zero-skipping V instance pays ~6 % on dense operands; use it only where the density
-        // kernel just skipped a real share of its k-steps (the decision takes effect with the next call)
-        if (ctx->vxc_skip < 0) ctx->vxc_skip_on = ctx->stats.skip_fraction >= 0.10;
-        if (ctx->vxc_rebalance) xc::tma_rebalance(ctx);
-    }
+    if (have_counters && !ctx->failed) apply_counters(ctx);
     DFT_CUDA_CHECK(ctx, cudaGetLastError());
     // (the four event intervals are read when DFT_GetStat asks for one: four driver calls per XC build are real money
     // at H2O size, where the whole call is ~20 us)
@@ -227,25 +237,28 @@ double run_xc(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const d
     return ctx->failed ? nan : ctx->h_scalar[0];
 }
 
-}  // namespace
+}  // namespace xc
+
+
+
 
 LDASolver::LDASolver() : XCSolver() {}
 double LDASolver::compute_xc(int ngrid, int nao, const double* d_dm, const double* d_ao, const double* d_ao_grad,
                              const double* d_weights, double* d_vxc) {
     (void)d_ao_grad;  // ignored, as in the reference (dft.py:75 passes 0)
-    return run_xc(handle_wrapper.get(), 0, ngrid, nao, d_dm, d_ao, nullptr, d_weights, d_vxc, nullptr);
+    return xc::run_build(handle_wrapper.get(), 0, ngrid, nao, d_dm, d_ao, nullptr, d_weights, d_vxc, nullptr);
 }
 
 GGASolver::GGASolver() : XCSolver() {}
 double GGASolver::compute_xc(int ngrid, int nao, const double* d_dm, const double* d_ao, const double* d_ao_grad,
                              const double* d_weights, double* d_vxc) {
-    return run_xc(handle_wrapper.get(), 1, ngrid, nao, d_dm, d_ao, d_ao_grad, d_weights, d_vxc, nullptr);
+    return xc::run_build(handle_wrapper.get(), 1, ngrid, nao, d_dm, d_ao, d_ao_grad, d_weights, d_vxc, nullptr);
 }
 
 B3LYPSolver::B3LYPSolver() : XCSolver() {}
 double B3LYPSolver::compute_xc(int ngrid, int nao, const double* d_dm, const double* d_ao, const double* d_ao_grad,
                                const double* d_weights, double* d_vxc) {
-    return run_xc(handle_wrapper.get(), 2, ngrid, nao, d_dm, d_ao, d_ao_grad, d_weights, d_vxc, nullptr);
+    return xc::run_build(handle_wrapper.get(), 2, ngrid, nao, d_dm, d_ao, d_ao_grad, d_weights, d_vxc, nullptr);
 }
 
 namespace {
@@ -266,10 +279,20 @@ XCSolver* DFT_CreateSolver(int type) {
         fprintf(stderr, "[dft_b200] no CUDA device: this library has no CPU fallback\n");
         return nullptr;
     }
-    if (type == SOLVER_LDA) return new LDASolver();
-    if (type == SOLVER_GGA) return new GGASolver();
-    if (type == SOLVER_B3LYP) return new B3LYPSolver();
-    return nullptr;
+    XCSolver* s = nullptr;
+    if (type == SOLVER_LDA) s = new LDASolver();
+    else if (type == SOLVER_GGA) s = new GGASolver();
+    else if (type == SOLVER_B3LYP) s = new B3LYPSolver();
+    if (!s) return nullptr;
+    // DFT_B200_DEVICES=<n>|all: the unmodified driver (dft.py:107-116 knows nothing of options) uses n GPUs of the
+    // box from its single process; the same as DFT_SetOption(solver, "devices", n)
+    if (const char* env = getenv("DFT_B200_DEVICES")) {
+        int want = !strcmp(env, "all") ? ndev : atoi(env);
+        if (want > ndev) want = ndev;
+        if (want > 1 && xc::fanout_configure(s->context(), want, false) != 0)
+            fprintf(stderr, "[dft_b200] DFT_B200_DEVICES=%s: multi-GPU fan-out not available, using one device\n", env);
+    }
+    return s;
 }
 
 void DFT_DestroySolver(XCSolver* solver) {
@@ -334,7 +357,7 @@ int DFT_ComputeXCAsync(XCSolver* solver, int ngrid, int nao, unsigned long long 
     if (!solver || !d_exc_ptr) return 1;
     const int t = solver_type(solver);
     if (t < 0) return 2;
-    double r = run_xc(solver->context(), t, ngrid, nao, reinterpret_cast<const double*>(d_dm_ptr),
+    double r = xc::run_build(solver->context(), t, ngrid, nao, reinterpret_cast<const double*>(d_dm_ptr),
                       reinterpret_cast<const double*>(d_ao_ptr),
                       t ? reinterpret_cast<const double*>(d_ao_grad_ptr) : nullptr,
                       reinterpret_cast<const double*>(d_weights_ptr), reinterpret_cast<double*>(d_vxc_ptr),
@@ -355,7 +378,13 @@ unsigned long long DFT_GetStream(XCSolver* solver) {
 
 int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!solver || !key) return 1;
-    CublasHandleWrapper* c = solver->context();
+    return xc::set_option(solver->context(), key, value);
+}
+
+}  // extern "C"
+
+namespace {
+int set_engine_option(CublasHandleWrapper* c, const char* key, double value) {
     if (!strcmp(key, "exact_functionals")) { c->exact_functionals = value != 0.0; return 0; }
     if (!strcmp(key, "path")) { c->path = (int)value; return 0; }
     if (!strcmp(key, "timing")) { c->timing = value != 0.0; return 0; }
@@ -397,10 +426,36 @@ int DFT_SetOption(XCSolver* solver, const char* key, double value) {
     if (!strcmp(key, "deterministic")) { return value != 0.0 ? 0 : 3; }  // reductions are always fixed-order
     return 2;
 }
+}  // namespace
+
+namespace xc {
+// Options of the fan-out itself ("devices", ...) are handled by fanout.cu; every engine option that was accepted is
+// remembered and forwarded to the child engines, so that all devices of a fan-out run the same instances.
+int set_option(CublasHandleWrapper* c, const char* key, double value) {
+    if (!c || !key) return 1;
+    if (!c->is_fan_child) {
+        const int rf = fanout_set_option(c, key, value);
+        if (rf != 2) return rf;
+    }
+    const int rc = set_engine_option(c, key, value);
+    if (rc == 0 && !c->is_fan_child) {
+        c->option_log.emplace_back(key, value);
+        fanout_forward_option(c, key, value);
+    }
+    return rc;
+}
+}  // namespace xc
+
+extern "C" {
 
 double DFT_GetStat(XCSolver* solver, const char* key) {
     if (!solver || !key) return -1.0;
     CublasHandleWrapper* c = solver->context();
+    {
+        bool known = false;
+        const double v = xc::fanout_stat(c, key, &known);
+        if (known) return v;
+    }
     if (strstr(key, "_ms") && strcmp(key, "ao_ms")) xc::resolve_times(c);
     if (!strcmp(key, "density_ms")) return c->stats.density_ms;
     if (!strcmp(key, "vxc_ms")) return c->stats.vxc_ms;

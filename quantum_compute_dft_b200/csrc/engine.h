@@ -10,6 +10,9 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
+#include <string>
+#include <utility>
+#include <vector>
 
 #define DFT_CUDA_CHECK(ctx, call)                                                              \
     do {                                                                                       \
@@ -128,6 +131,11 @@ struct CublasHandleWrapper {
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
 
+    // single-process multi-GPU behind the unmodified ABI (fanout.cu): per-device child engines, their cached AO shards
+    void* fan = nullptr;
+    bool is_fan_child = false;
+    std::vector<std::pair<std::string, double>> option_log;   // every option set so far, replayed onto new child engines
+
     XcStats stats;
 
     CublasHandleWrapper();
@@ -164,6 +172,26 @@ void tma_rebalance(CublasHandleWrapper* ctx);
 // small-basis single-pass path (nao <= 48): xc_small.cu
 bool small_compatible(const Problem& p);
 void run_small(CublasHandleWrapper* ctx, const Problem& p);
+
+// One XC build on ctx's own device and stream (capi.cu).  d_exc_out == nullptr: blocks and returns E_xc; otherwise E_xc
+// stays on the device and the call returns 0 (NaN on failure) at once.  `defer_readback`: the caller reads the TMA
+// path's counters back itself (enqueue_counter_readback / apply_counters) after its own synchronisation.
+double run_build(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const double* d_dm, const double* d_ao,
+                 const double* d_ao_grad, const double* d_w, double* d_vxc, double* d_exc_out);
+bool enqueue_counter_readback(CublasHandleWrapper* ctx);   // async D2H of the TMA path's counters on ctx->stream
+void apply_counters(CublasHandleWrapper* ctx);             // after the stream has drained: statistics, adaptive V instance, re-deal
+int set_option(CublasHandleWrapper* ctx, const char* key, double value);
+
+// single process, several GPUs (fanout.cu): the primary engine deals the caller's grid to one child engine per device
+int fanout_configure(CublasHandleWrapper* ctx, int ndev, bool allow_virtual);   // ndev <= 1 tears the fan-out down
+bool fanout_wants(CublasHandleWrapper* ctx, int ngrid, int nao);
+double run_fanout(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, const double* d_dm, const double* d_ao,
+                  const double* d_ao_grad, const double* d_w, double* d_vxc, double* d_exc_out);
+void fanout_destroy(CublasHandleWrapper* ctx);
+int fanout_set_option(CublasHandleWrapper* ctx, const char* key, double value);   // 2 = not a fan-out key
+double fanout_stat(CublasHandleWrapper* ctx, const char* key, bool* known);
+void fanout_forward_option(CublasHandleWrapper* ctx, const char* key, double value);
+void fanout_invalidate(CublasHandleWrapper* ctx);
 
 // all-reduce of [V | E | failed ranks] over the communicator (comm.cu); no-op when nranks == 1
 int allreduce_result(CublasHandleWrapper* ctx, double* d_packed, double* d_vxc, size_t n2);

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "DFT_EvalAO", "DFT_CommGetUniqueId", "DFT_CommInit", "DFT_CommDestroy",
     "DFT_SetOption", "DFT_GetStat", "DFT_ComputeXCAsync", "DFT_StreamSynchronize", "DFT_GetStream",
     "DFT_MicrobenchDMMA", "DFT_MicrobenchDFMA", "DFT_MicrobenchDMMAWarps", "DFT_B200_Version",
-    "DFT_ComputeCoulombExchange", "DFT_BuildFock", "DFT_SCFEnergies",
+    "DFT_ComputeCoulombExchange", "DFT_BuildFock", "DFT_SCFEnergies", "DFT_ShardPoints",
 ]
 
 _c_dp = ctypes.POINTER(ctypes.c_double)
@@ -78,6 +78,8 @@ def load_library(lib_path=DEFAULT_LIB):
     lib.DFT_MicrobenchDMMAWarps.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.DFT_MicrobenchDMMAWarps.restype = ctypes.c_double
     lib.DFT_B200_Version.restype = ctypes.c_char_p
+    lib.DFT_ShardPoints.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.DFT_ShardPoints.restype = ctypes.c_int
     return lib
 
 
