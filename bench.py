@@ -318,13 +318,13 @@ def main():
     solver = workload.make_solver(hp.functional)
     solver.set_option("path", args.path)
     solver.set_option("timing", 1)      # (per-kernel CUDA events: on for the AO evaluation and the stat-collection steps only)
-    for kv in args.opt:
-        k, v = kv.split("=")
-        solver.set_option(k, float(v))
     if args.devices > 1:
         if world > 1:
             raise SystemExit("--devices is the single-process mode: launch it without torchrun")
         solver.set_option("devices", args.devices)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        solver.set_option(k, float(v))
     if world > 1:
         ids = [solver.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)

@@ -23,9 +23,14 @@
 // Selected by DFT_SetOption(solver, "devices", n) or, for a driver that knows nothing of options, by the environment
 // variable DFT_B200_DEVICES=n|all read in DFT_CreateSolver.  Builds too small to pay for the hand-off
 // (ngrid nao^2 < "devices_min_work", default 2e9: H2O, benzene) stay on the primary device.
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstring>
 #include <limits>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/dft_b200_ext.h"
@@ -44,6 +49,17 @@ struct FanChild {
     cudaEvent_t done = nullptr;
     int nreal = 0, nshard = 0;           // points dealt to the child; the same padded to an even count (zero-weight twin)
     bool have_counters = false;
+    bool job_failed = false;             // outcome of this child's share of the current call
+    std::thread worker;                  // children 1 .. n-1: enqueue their device's work in parallel with the caller's thread
+    std::atomic<unsigned long long> done_seq{0};
+};
+
+// one DFT_ComputeXC call as the workers see it
+struct FanJob {
+    int xc_type = 0, ngrid = 0, nao = 0;
+    const double *dm = nullptr, *ao = nullptr, *grad = nullptr, *w = nullptr;
+    bool stale = false;
+    int primary_device = 0;
 };
 
 struct FanOut {
@@ -60,6 +76,14 @@ struct FanOut {
     DeviceBuffer fp;             // primary device: fingerprint accumulator
     int scatters = 0;            // how many times the shards were (re)built
     bool last_call_fanned = false;
+    // worker threads: a child's share of a call is ~10 driver calls (copy of D, five launches, counter read-back, event),
+    // 40-50 us of host time; issued by one thread the eighth device would start 0.3 ms after the first
+    bool threads = true;         // option "fan_threads"
+    FanJob job;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<unsigned long long> seq{0};
+    std::atomic<bool> quit{false};
 };
 
 struct FanSources {
@@ -155,6 +179,90 @@ bool scatter_plane(CublasHandleWrapper* eng, int dst_dev, int src_dev, double* d
     return e == cudaSuccess;
 }
 
+// One child's share of a call, on the child's device and stream: (shards,) D, the ordinary single-GPU build, the
+// read-back of its counters, the event the primary stream waits for.  Touches only this child's state.
+void enqueue_child(FanOut* f, int c) {
+    const FanJob& j = f->job;
+    FanChild& k = f->kids[c];
+    const int n = (int)f->kids.size();
+    const size_t n2 = (size_t)j.nao * j.nao, plane = (size_t)j.ngrid * j.nao;
+    DeviceGuard child(k.dev);
+    CublasHandleWrapper* e = k.eng;
+    e->failed = false;
+    k.job_failed = true;
+    k.have_counters = false;
+    cudaStream_t st = e->stream;
+    if (j.stale) {
+        int nfull = 0, tail = 0;
+        deal(j.ngrid, n, c, &nfull, &tail);
+        k.nreal = nfull * FAN_BLOCK + tail;
+        k.nshard = k.nreal + (k.nreal & 1);
+        const size_t rows = (size_t)(k.nshard > 0 ? k.nshard : 1);
+        double* ao = (double*)k.ao.ensure(rows * j.nao * sizeof(double), &e->failed);
+        double* gr = j.xc_type ? (double*)k.grad.ensure(3 * rows * j.nao * sizeof(double), &e->failed) : nullptr;
+        double* w = (double*)k.w.ensure(rows * sizeof(double), &e->failed);
+        if (e->failed) return;
+        bool ok = scatter_plane(e, k.dev, j.primary_device, ao, j.ao, j.nao, n, c, nfull, tail, j.ngrid, st);
+        for (int pl = 0; pl < 3 && j.xc_type && ok; ++pl)
+            ok = scatter_plane(e, k.dev, j.primary_device, gr + (size_t)pl * k.nshard * j.nao, j.grad + (size_t)pl * plane,
+                               j.nao, n, c, nfull, tail, j.ngrid, st);
+        ok = ok && scatter_plane(e, k.dev, j.primary_device, w, j.w, 1, n, c, nfull, tail, j.ngrid, st);
+        if (ok && k.nshard > k.nreal) {   // zero-weight twin of the last point: an even number of rows per plane
+            const size_t row = (size_t)j.nao * sizeof(double);
+            cudaMemcpyAsync(ao + (size_t)k.nreal * j.nao, ao + (size_t)(k.nreal - 1) * j.nao, row, cudaMemcpyDeviceToDevice, st);
+            for (int pl = 0; pl < 3 && j.xc_type; ++pl) {
+                double* g = gr + (size_t)pl * k.nshard * j.nao;
+                cudaMemcpyAsync(g + (size_t)k.nreal * j.nao, g + (size_t)(k.nreal - 1) * j.nao, row, cudaMemcpyDeviceToDevice, st);
+            }
+            cudaMemsetAsync(w + k.nreal, 0, sizeof(double), st);
+        }
+        if (!ok) return;
+    }
+    double* dm = (double*)k.dm.ensure(n2 * sizeof(double), &e->failed);
+    double* out = (double*)k.out.ensure((n2 + 1) * sizeof(double), &e->failed);
+    if (!dm || !out) return;
+    DFT_CUDA_CHECK(e, cudaMemcpyAsync(dm, j.dm, n2 * sizeof(double), cudaMemcpyDefault, st));
+    const double r = xc::run_build(e, j.xc_type, k.nshard, j.nao, dm, (const double*)k.ao.ptr, (const double*)k.grad.ptr,
+                                   (const double*)k.w.ptr, out, out + n2);
+    k.have_counters = k.nshard > 0 && !std::isnan(r) && xc::enqueue_counter_readback(e);
+    DFT_CUDA_CHECK(e, cudaEventRecord(k.done, st));
+    k.job_failed = std::isnan(r) || e->failed;
+}
+
+// Worker of child c: spins briefly for the next call (an SCF loop calls every few ms), then sleeps on the condition
+// variable.  `seq` is published with release semantics after the job is written; `done_seq` likewise after the
+// child's state is.
+void worker_main(FanOut* f, int c) {
+    cudaSetDevice(f->kids[c].dev);
+    unsigned long long seen = 0;
+    for (;;) {
+        unsigned long long s = f->seq.load(std::memory_order_acquire);
+        if (s == seen && !f->quit.load(std::memory_order_acquire)) {
+            const auto t0 = std::chrono::steady_clock::now();
+            while ((s = f->seq.load(std::memory_order_acquire)) == seen && !f->quit.load(std::memory_order_acquire)) {
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) {
+                    std::unique_lock<std::mutex> lk(f->mu);
+                    f->cv.wait(lk, [&] { return f->seq.load(std::memory_order_acquire) != seen || f->quit.load(std::memory_order_acquire); });
+                }
+            }
+        }
+        if (f->quit.load(std::memory_order_acquire)) return;
+        seen = s;
+        enqueue_child(f, c);
+        f->kids[c].done_seq.store(s, std::memory_order_release);
+    }
+}
+
+void stop_workers(FanOut* f) {
+    {
+        std::lock_guard<std::mutex> lk(f->mu);
+        f->quit.store(true, std::memory_order_release);
+    }
+    f->cv.notify_all();
+    for (auto& k : f->kids)
+        if (k.worker.joinable()) k.worker.join();
+}
+
 void release_child(FanChild& k) {
     DeviceGuard guard(k.dev);
     if (k.eng && k.eng->stream) cudaStreamSynchronize(k.eng->stream);
@@ -172,6 +280,7 @@ namespace xc {
 void fanout_destroy(CublasHandleWrapper* ctx) {
     if (!ctx || !ctx->fan) return;
     FanOut* f = static_cast<FanOut*>(ctx->fan);
+    stop_workers(f);
     for (auto& k : f->kids) release_child(k);
     {
         DeviceGuard guard(ctx->device);
@@ -211,7 +320,7 @@ int fanout_configure(CublasHandleWrapper* ctx, int ndev, bool allow_virtual) {
     FanOut* f = new FanOut();
     f->min_work = min_work;
     f->cache = cache;
-    f->kids.resize(ndev);
+    f->kids = std::vector<FanChild>(ndev);
     bool ok = true;
     for (int c = 0; c < ndev && ok; ++c) {
         FanChild& k = f->kids[c];
@@ -242,6 +351,8 @@ int fanout_configure(CublasHandleWrapper* ctx, int ndev, bool allow_virtual) {
         }
     }
     ctx->fan = f;
+    if (ok && f->threads)
+        for (int c = 1; c < ndev; ++c) f->kids[c].worker = std::thread(worker_main, f, c);
     if (!ok) {
         fprintf(stderr, "[dft_b200] \"devices\" %d: could not create the per-device engines\n", ndev);
         fanout_destroy(ctx);
@@ -267,6 +378,11 @@ int fanout_set_option(CublasHandleWrapper* ctx, const char* key, double value) {
     if (!strcmp(key, "devices")) return fanout_configure(ctx, (int)value, false);
     if (!strcmp(key, "virtual_devices")) return fanout_configure(ctx, (int)value, true);
     if (!strcmp(key, "ao_invalidate")) { fanout_invalidate(ctx); return 0; }
+    if (!strcmp(key, "fan_threads")) {   // 0: the caller's thread enqueues every device's work itself (measurement)
+        if (!ctx->fan) return 3;
+        static_cast<FanOut*>(ctx->fan)->threads = value != 0.0;   // (idle workers stay parked)
+        return 0;
+    }
     if (!strcmp(key, "devices_min_work") || !strcmp(key, "ao_cache")) {
         if (!ctx->fan) return 3;   // (set "devices" first)
         FanOut* f = static_cast<FanOut*>(ctx->fan);
@@ -342,50 +458,29 @@ double run_fanout(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, con
     const bool stale = !f->cache || !f->valid || f->ao != d_ao || f->grad != d_ao_grad || f->w != d_w || f->ngrid != ngrid ||
                        f->nao != nao || f->xc_type != xc_type || f->fingerprint != *h_fp;
 
-    // 2. every child: (shards), D, the ordinary single-GPU build on its own device and stream
+    // 2. every child: (shards), D, the ordinary single-GPU build on its own device and stream -- child 0 from this
+    //    thread, the others from their worker threads
+    FanJob& j = f->job;
+    j.xc_type = xc_type; j.ngrid = ngrid; j.nao = nao;
+    j.dm = d_dm; j.ao = d_ao; j.grad = d_ao_grad; j.w = d_w;
+    j.stale = stale;
+    j.primary_device = ctx->device;
     bool failed = false;
-    for (int c = 0; c < n; ++c) {
-        FanChild& k = f->kids[c];
-        DeviceGuard child(k.dev);
-        CublasHandleWrapper* e = k.eng;
-        e->failed = false;
-        cudaStream_t st = e->stream;
-        if (stale) {
-            int nfull = 0, tail = 0;
-            deal(ngrid, n, c, &nfull, &tail);
-            k.nreal = nfull * FAN_BLOCK + tail;
-            k.nshard = k.nreal + (k.nreal & 1);
-            const size_t rows = (size_t)(k.nshard > 0 ? k.nshard : 1);
-            double* ao = (double*)k.ao.ensure(rows * nao * sizeof(double), &e->failed);
-            double* gr = xc_type ? (double*)k.grad.ensure(3 * rows * nao * sizeof(double), &e->failed) : nullptr;
-            double* w = (double*)k.w.ensure(rows * sizeof(double), &e->failed);
-            if (e->failed) { failed = true; continue; }
-            bool ok = scatter_plane(e, k.dev, ctx->device, ao, d_ao, nao, n, c, nfull, tail, ngrid, st);
-            for (int pl = 0; pl < 3 && xc_type && ok; ++pl)
-                ok = scatter_plane(e, k.dev, ctx->device, gr + (size_t)pl * k.nshard * nao, d_ao_grad + (size_t)pl * plane,
-                                   nao, n, c, nfull, tail, ngrid, st);
-            ok = ok && scatter_plane(e, k.dev, ctx->device, w, d_w, 1, n, c, nfull, tail, ngrid, st);
-            if (ok && k.nshard > k.nreal) {   // zero-weight twin of the last point: an even number of rows per plane
-                const size_t row = (size_t)nao * sizeof(double);
-                cudaMemcpyAsync(ao + (size_t)k.nreal * nao, ao + (size_t)(k.nreal - 1) * nao, row, cudaMemcpyDeviceToDevice, st);
-                for (int pl = 0; pl < 3 && xc_type; ++pl) {
-                    double* g = gr + (size_t)pl * k.nshard * nao;
-                    cudaMemcpyAsync(g + (size_t)k.nreal * nao, g + (size_t)(k.nreal - 1) * nao, row, cudaMemcpyDeviceToDevice, st);
-                }
-                cudaMemsetAsync(w + k.nreal, 0, sizeof(double), st);
-            }
-            if (!ok) { failed = true; continue; }
+    if (f->threads) {
+        unsigned long long s;
+        {
+            std::lock_guard<std::mutex> lk(f->mu);
+            s = f->seq.load(std::memory_order_relaxed) + 1;
+            f->seq.store(s, std::memory_order_release);
         }
-        double* dm = (double*)k.dm.ensure(n2 * sizeof(double), &e->failed);
-        double* out = (double*)k.out.ensure((n2 + 1) * sizeof(double), &e->failed);
-        if (!dm || !out) { failed = true; continue; }
-        DFT_CUDA_CHECK(e, cudaMemcpyAsync(dm, d_dm, n2 * sizeof(double), cudaMemcpyDefault, st));
-        const double r = run_build(e, xc_type, k.nshard, nao, dm, (const double*)k.ao.ptr, (const double*)k.grad.ptr,
-                                   (const double*)k.w.ptr, out, out + n2);
-        k.have_counters = k.nshard > 0 && !std::isnan(r) && enqueue_counter_readback(e);
-        DFT_CUDA_CHECK(e, cudaEventRecord(k.done, st));
-        if (std::isnan(r) || e->failed) failed = true;
+        f->cv.notify_all();
+        enqueue_child(f, 0);
+        for (int c = 1; c < n; ++c)
+            while (f->kids[c].done_seq.load(std::memory_order_acquire) != s) std::this_thread::yield();
+    } else {
+        for (int c = 0; c < n; ++c) enqueue_child(f, c);
     }
+    for (int c = 0; c < n; ++c) failed = failed || f->kids[c].job_failed;
     if (stale) {
         f->valid = !failed;
         f->ao = d_ao; f->grad = d_ao_grad; f->w = d_w; f->ngrid = ngrid; f->nao = nao; f->xc_type = xc_type;

@@ -25,6 +25,7 @@
 //
 // Replaces, for small nao, the same reference code as xc_tma.cu: get_rho[_sigma]_kernel (dft_solver.cu:294-380),
 // *_fused_kernel (:309-513), reduce_sum_kernel (:285-292), cublasDgemm (:580,:616,:663), symmetrize (:515-527).
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 
@@ -429,6 +430,8 @@ static void launch(CublasHandleWrapper* ctx, const Problem& p, int nsm) {
     // (function attributes are per device: one slot per device ordinal)
     struct Shape { int nao, nwarp, per_sm, resident; size_t smem; };
     static Shape cache[16] = {};
+    static std::mutex cache_mu;   // (solvers on several host threads -- the fan-out's workers -- may share a device slot)
+    std::lock_guard<std::mutex> cache_lock(cache_mu);
     Shape& sh = cache[ctx->device & 15];
     if (sh.nao != nao || sh.per_sm <= 0 || sh.resident != (resident ? 1 : 0)) {
         int nwarp = MAXW;

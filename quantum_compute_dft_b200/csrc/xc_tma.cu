@@ -1624,18 +1624,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // (function-local static with an initialiser: initialised once, thread-safely -- the fan-out's worker threads build
+    // their devices' plans concurrently)
+    static const EncodeTiledFn fn = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        else
-            fprintf(stderr, "[dft_b200] cuTensorMapEncodeTiled not available from the driver\n");
-    }
+            return reinterpret_cast<EncodeTiledFn>(p);
+        fprintf(stderr, "[dft_b200] cuTensorMapEncodeTiled not available from the driver\n");
+        return static_cast<EncodeTiledFn>(nullptr);
+    }();
     return fn;
 }
 
