@@ -59,6 +59,10 @@ int DFT_CommDestroy(XCSolver* solver);
 //       "devices_min_work" x (builds with ngrid * nao^2 < x stay on the caller's device, default 2e9: H2O, benzene),
 //       "ao_cache" 0|1 (default 1; 0 re-cuts the shards on every call), "ao_invalidate" (drop the resident shards now:
 //       for a caller that rewrites its AO arrays in place in a way 2^17 samples per plane might miss).
+//       "fan_threads" 0|1 (default 1: a worker thread per device enqueues that device's share of a call; 0: the caller's
+//       thread does it for all devices in turn -- at 8 devices the last one then starts 0.3 ms after the first).
+//   environment (read in DFT_CreateSolver, for a driver that cannot set options): DFT_B200_DEVICES=n|all,
+//       DFT_B200_VIRTUAL_DEVICES=n, DFT_B200_DEVICES_MIN_WORK=x; DFT_B200_VERBOSE=1 reports every shard cut on stderr.
 //   stat keys: "devices", "fan_active" (the last call was fanned out), "fan_scatters" (times the shards were cut),
 //       "fan_peer_loads" (the reduction reads the children's results through peer loads), "fan_resident_bytes";
 //       "density_ms" / "vxc_ms" / "reduce_ms" are those of the slowest device, "total_ms" the whole call.

@@ -285,12 +285,22 @@ XCSolver* DFT_CreateSolver(int type) {
     else if (type == SOLVER_B3LYP) s = new B3LYPSolver();
     if (!s) return nullptr;
     // DFT_B200_DEVICES=<n>|all: the unmodified driver (dft.py:107-116 knows nothing of options) uses n GPUs of the
-    // box from its single process; the same as DFT_SetOption(solver, "devices", n)
-    if (const char* env = getenv("DFT_B200_DEVICES")) {
-        int want = !strcmp(env, "all") ? ndev : atoi(env);
-        if (want > ndev) want = ndev;
-        if (want > 1 && xc::fanout_configure(s->context(), want, false) != 0)
-            fprintf(stderr, "[dft_b200] DFT_B200_DEVICES=%s: multi-GPU fan-out not available, using one device\n", env);
+    // box from its single process; the same as DFT_SetOption(solver, "devices", n).  DFT_B200_VIRTUAL_DEVICES=<n>
+    // (n children dealt over the visible devices: tests on a one-GPU box) and DFT_B200_DEVICES_MIN_WORK=<x> are the
+    // environment forms of the options "virtual_devices" and "devices_min_work"; DFT_B200_VERBOSE=1 reports every
+    // shard cut on stderr.
+    const char* env = getenv("DFT_B200_DEVICES");
+    const char* venv = getenv("DFT_B200_VIRTUAL_DEVICES");
+    if (env || venv) {
+        int want = venv ? atoi(venv) : (!strcmp(env, "all") ? ndev : atoi(env));
+        if (!venv && want > ndev) want = ndev;
+        if (want > 1) {
+            if (xc::fanout_configure(s->context(), want, venv != nullptr) != 0)
+                fprintf(stderr, "[dft_b200] %s=%s: multi-GPU fan-out not available, using one device\n",
+                        venv ? "DFT_B200_VIRTUAL_DEVICES" : "DFT_B200_DEVICES", venv ? venv : env);
+            else if (const char* mw = getenv("DFT_B200_DEVICES_MIN_WORK"))
+                xc::fanout_set_option(s->context(), "devices_min_work", atof(mw));
+        }
     }
     return s;
 }

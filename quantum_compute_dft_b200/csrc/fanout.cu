@@ -26,6 +26,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <condition_variable>
 #include <cstring>
 #include <limits>
@@ -486,6 +487,9 @@ double run_fanout(CublasHandleWrapper* ctx, int xc_type, int ngrid, int nao, con
         f->ao = d_ao; f->grad = d_ao_grad; f->w = d_w; f->ngrid = ngrid; f->nao = nao; f->xc_type = xc_type;
         f->fingerprint = *h_fp;
         f->scatters += 1;
+        if (getenv("DFT_B200_VERBOSE"))
+            fprintf(stderr, "[dft_b200] fan-out: shards of %d x %d (%s) cut for %d devices (cut #%d)\n", ngrid, nao,
+                    xc_type == 0 ? "LDA" : xc_type == 1 ? "GGA" : "B3LYP", n, f->scatters);
     }
 
     // 3. one reduction on the primary device, straight into the caller's array

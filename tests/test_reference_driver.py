@@ -96,3 +96,26 @@ def test_unmodified_reference_driver_runs_on_this_library(oracle, engine_lib, tm
     assert xc_ms > 0.0
     print(f"{functional} {molecule}: E = {e_driver:.8f} Ha (oracle SCF {e_oracle:.10f}), XC {xc_ms:.3f} ms/iter, "
           f"|E - exact-functional SCF| = {diff:.2e}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("functional", ["LDA", "B3LYP"])
+def test_unmodified_reference_driver_fans_out(oracle, engine_lib, tmp_path, functional):
+    """Single-process multi-GPU behind the unmodified driver (csrc/fanout.cu): the environment alone makes dft.py's own
+    DFT_ComputeXC calls fan out -- here to three virtual devices, so that a one-GPU box runs the whole mechanism.  The
+    driver converges to the same energy, and the shards were cut exactly once for the whole SCF run (the AO arrays are
+    uploaded once, dft.py:155,172; only d_dm changes per iteration, dft.py:200)."""
+    w = _layout(tmp_path, engine_lib)
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "shims"), os.path.join(ROOT, "tests"), ROOT,
+                                         env.get("PYTHONPATH", "")])
+    env.update({"DFT_B200_VIRTUAL_DEVICES": "3", "DFT_B200_DEVICES_MIN_WORK": "0", "DFT_B200_VERBOSE": "1"})
+    r = subprocess.run([sys.executable, "dft.py", functional, "H4"], cwd=w, env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    assert "Converged!" in r.stdout, r.stdout[-3000:]
+    cuts = re.findall(r"fan-out: shards of (\d+) x (\d+) \((\w+)\) cut for 3 devices", r.stderr)
+    assert len(cuts) == 1 and cuts[0][2] == functional, r.stderr[-2000:]
+    e_driver = float(re.search(r"Total Energy: (-?\d+\.\d+) Ha", r.stdout).group(1))
+    body = "".join(open(w / "atom_txt" / "H4.xyz").readlines()[2:])
+    assert abs(e_driver - _oracle_scf(functional, body)) <= 1e-7
