@@ -24,6 +24,7 @@ def main():
         m = re.search(r"Function : (\S+)", line)
         if m:
             name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+            name = name.replace("(anonymous namespace)::", "")
             name = re.sub(r"\(.*", "", name)
             counts[name] = collections.Counter()
             continue
