@@ -32,8 +32,6 @@ class Mole:
         if str(self.basis).lower() != "sto-3g":
             raise NotImplementedError("shim: sto-3g only")
         syms, xyz = _parse_atoms(self.atom)
-        if any(s != "H" for s in syms):
-            raise NotImplementedError("shim: closed-form integrals exist for hydrogen-only molecules (s shells)")
         self._mol = M.Molecule("shim", syms, xyz)
         # PySCF renormalises every contracted function to 1
         self._basis = M.sto3g_basis(self._mol, renormalize=True)
@@ -45,8 +43,13 @@ class Mole:
     def _integrals(self):
         if self._ints is None:
             import scf_driver
-            self._ints = scf_driver.s_integrals(self._mol, self._basis)   # S, Hcore, eri, E_nuc
-            self._kin = scf_driver.s_kinetic(self._mol, self._basis)
+            if np.all(self._basis.shell_l == 0):      # hydrogen chains: closed forms
+                self._ints = scf_driver.s_integrals(self._mol, self._basis)   # S, Hcore, eri, E_nuc
+                self._kin = scf_driver.s_kinetic(self._mol, self._basis)
+            else:                                     # s and p shells (H2O, ...): McMurchie-Davidson, tests/gauss_integrals.py
+                import gauss_integrals
+                self._ints = gauss_integrals.sp_integrals(self._mol, self._basis)
+                self._kin = gauss_integrals.sp_kinetic(self._mol, self._basis)
         return self._ints
 
     def nao_nr(self):

@@ -3,8 +3,8 @@
 `/root/reference/dft.py` (staged byte-for-byte by `make -C oracle ref` into the git-ignored oracle/_ref/driver/,
 because the GPU box has no /root/reference) is executed as a subprocess, `python dft.py <LDA|GGA|B3LYP> <molecule>`,
 in a scratch checkout layout whose ./weights/dft.so is THIS repo's engine.  `cupy` and `pyscf` -- not installable here
--- are the stand-ins of tests/shims (device arrays on the CUDA runtime; closed-form hydrogen integrals, synthetic grid,
-oracle AO evaluation, commutator DIIS).  Everything between `ctypes.CDLL("./weights/dft.so")` and the printed
+-- are the stand-ins of tests/shims (device arrays on the CUDA runtime; closed-form hydrogen integrals and
+McMurchie-Davidson s/p integrals for H2O, synthetic grid, oracle AO evaluation, commutator DIIS).  Everything between `ctypes.CDLL("./weights/dft.so")` and the printed
 "Total Energy" is the reference's own code driving the engine through the reference's own ABI.
 
 Asserted: the driver converges, and its printed total energy equals an independent SCF whose J, K and XC come from the
@@ -39,6 +39,8 @@ def _layout(tmp_path, engine_lib):
     for f in ("dft.py", "grid.py"):
         shutil.copy(os.path.join(DRIVER, f), w / f)
     shutil.copy(os.path.join(DRIVER, "atom_txt", "H2.xyz"), w / "atom_txt" / "H2.xyz")
+    if os.path.exists(os.path.join(DRIVER, "atom_txt", "H2O.xyz")):     # the reference's own water geometry (C1 / C3)
+        shutil.copy(os.path.join(DRIVER, "atom_txt", "H2O.xyz"), w / "atom_txt" / "H2O.xyz")
     (w / "atom_txt" / "H4.xyz").write_text(H4)
     shutil.copy(engine_lib, w / "weights" / "dft.so")
     return w
@@ -48,7 +50,7 @@ def test_staged_driver_is_the_reference_byte_for_byte():
     """Where the reference tree exists (the build container), the staged copy must be identical to it."""
     if not (os.path.exists("/root/reference/dft.py") and os.path.exists(os.path.join(DRIVER, "dft.py"))):
         pytest.skip("needs both /root/reference and the staged copy")
-    for f in ("dft.py", "grid.py", os.path.join("atom_txt", "H2.xyz")):
+    for f in ("dft.py", "grid.py", os.path.join("atom_txt", "H2.xyz"), os.path.join("atom_txt", "H2O.xyz")):
         assert filecmp.cmp(os.path.join("/root/reference", f), os.path.join(DRIVER, f), shallow=False), f
 
 
@@ -71,9 +73,13 @@ def _oracle_scf(functional, xyz_body):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("functional", ["LDA", "GGA", "B3LYP"])
-@pytest.mark.parametrize("molecule", ["H2", "H4"])
+@pytest.mark.parametrize("molecule", ["H2", "H4", "H2O"])
 def test_unmodified_reference_driver_runs_on_this_library(oracle, engine_lib, tmp_path, functional, molecule):
+    """`python dft.py LDA H2O` and `python dft.py B3LYP H2O` are BASELINE.json's configs C1 and C3 verbatim (the
+    reference's own atom_txt/H2O.xyz, STO-3G, level-3-sized grid; s/p integrals from tests/gauss_integrals.py)."""
     w = _layout(tmp_path, engine_lib)
+    if not os.path.exists(w / "atom_txt" / f"{molecule}.xyz"):
+        pytest.skip(f"atom_txt/{molecule}.xyz is not staged (make -C oracle ref)")
     env = dict(os.environ)
     env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "shims"), os.path.join(ROOT, "tests"), ROOT,
                                          env.get("PYTHONPATH", "")])
